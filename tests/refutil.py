@@ -1,0 +1,97 @@
+"""Shared helpers for the test-suite: ctypes access to the CPU oracle (oracle/liboracle.so)
+and, when present, the compiled reference (oracle/_ref). TEST INFRASTRUCTURE ONLY."""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
+REF_BIN = os.path.join(ORACLE_DIR, "_ref", "nnue_data_compression")
+REF_GEN = os.path.join(ORACLE_DIR, "_ref", "gen_ref")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+BIN_TO_BINPACK, BINPACK_TO_BIN, PLAIN_TO_BINPACK, BINPACK_TO_PLAIN, BIN_TO_PLAIN, PLAIN_TO_BIN = range(6)
+MODE_EXT = {
+    BIN_TO_BINPACK: (".bin", ".binpack"),
+    BINPACK_TO_BIN: (".binpack", ".bin"),
+    PLAIN_TO_BINPACK: (".plain", ".binpack"),
+    BINPACK_TO_PLAIN: (".binpack", ".plain"),
+    BIN_TO_PLAIN: (".bin", ".plain"),
+    PLAIN_TO_BIN: (".plain", ".bin"),
+}
+
+_oracle = None
+
+
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "oracle"], check=True)
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(
+            os.path.join(ORACLE_DIR, "oracle.c")
+        ):
+            build_oracle()
+        lib = ctypes.CDLL(ORACLE_SO)
+        lib.orc_convert.restype = ctypes.c_int
+        lib.orc_convert.argtypes = [
+            ctypes.c_int,
+            ctypes.c_char_p,
+            ctypes.c_size_t,
+            ctypes.POINTER(ctypes.c_void_p),
+            ctypes.POINTER(ctypes.c_size_t),
+        ]
+        lib.orc_free.argtypes = [ctypes.c_void_p]
+        lib.orc_sfen_to_fen.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+        lib.orc_fen_to_sfen.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+        lib.orc_is_continuation.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+        lib.orc_binpack_count.restype = ctypes.c_int64
+        lib.orc_binpack_count.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+        _oracle = lib
+    return _oracle
+
+
+def oracle_convert(mode, data):
+    """Returns (rc, bytes)."""
+    lib = oracle()
+    out = ctypes.c_void_p()
+    n = ctypes.c_size_t()
+    rc = lib.orc_convert(mode, bytes(data), len(data), ctypes.byref(out), ctypes.byref(n))
+    res = ctypes.string_at(out, n.value) if n.value else b""
+    lib.orc_free(out)
+    return rc, res
+
+
+def have_ref():
+    return os.access(REF_BIN, os.X_OK) and os.access(REF_GEN, os.X_OK)
+
+
+def ref_convert(mode, data, append_to=None):
+    """Runs the compiled reference CLI on `data`; returns the output file's bytes."""
+    ein, eout = MODE_EXT[mode]
+    with tempfile.TemporaryDirectory() as d:
+        pin, pout = os.path.join(d, "in" + ein), os.path.join(d, "out" + eout)
+        with open(pin, "wb") as f:
+            f.write(data)
+        args = [REF_BIN]
+        if append_to is not None:
+            with open(pout, "wb") as f:
+                f.write(append_to)
+            args.append("-a")
+        subprocess.run(args + [pin, pout], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        if not os.path.exists(pout):
+            return b""
+        with open(pout, "rb") as f:
+            return f.read()
+
+
+def ref_generate(n, plies, seed, mode=0):
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "g.bin")
+        subprocess.run([REF_GEN, p, str(n), str(plies), str(seed), str(mode)], check=True)
+        with open(p, "rb") as f:
+            return f.read()
