@@ -1,0 +1,290 @@
+"""nnue_data_compress_b200 -- B200-native (sm_100a) conversion path for NNUE training data.
+
+Host-side mirror of the reference tool's interface (Sopel97/nnue_data_compress,
+``src/compress_file.cpp:1535-1709``): the six file drivers, ``convert()`` with its
+extension dispatch, and ``main()``/``run()`` with the same flags and messages. Everything
+that touches the data runs in ``libnnuepack.so`` (hand-written CUDA behind the C ABI of
+``include/nnuepack.h``); this module is ctypes plumbing only and raises if the library or a
+GPU is missing -- there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import sys
+
+__all__ = [
+    "NnpError",
+    "lib",
+    "init",
+    "shutdown",
+    "bin_to_binpack",
+    "binpack_to_bin",
+    "plain_to_binpack",
+    "binpack_to_plain",
+    "bin_to_plain",
+    "plain_to_bin",
+    "convert",
+    "main",
+    "STATUS",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnnuepack.so")
+
+STATUS = {
+    0: "NNP_OK",
+    -1: "NNP_ERR_BAD_MAGIC",
+    -2: "NNP_ERR_CHUNK_TOO_LARGE",
+    -3: "NNP_ERR_BAD_SFEN",
+    -4: "NNP_ERR_TRUNCATED",
+    -5: "NNP_ERR_NOMEM",
+    -6: "NNP_ERR_BAD_ARG",
+    -7: "NNP_ERR_BAD_TEXT",
+    -8: "NNP_ERR_CAPACITY",
+    -9: "NNP_ERR_NO_DEVICE",
+    -10: "NNP_ERR_NOT_INITIALISED",
+    -11: "NNP_ERR_CUDA",
+}
+# statuses after which the reference prints a message and still leaves partial output behind
+REFERENCE_ERRORS = (-1, -2, -3)
+
+EXPORTS = [
+    "nnp_init", "nnp_shutdown", "nnp_strerror", "nnp_last_cuda_error", "nnp_kernel_launches",
+    "nnp_host_alloc", "nnp_host_free",
+    "nnp_bin_to_binpack", "nnp_binpack_to_bin", "nnp_plain_to_binpack", "nnp_binpack_to_plain",
+    "nnp_bin_to_plain", "nnp_plain_to_bin",
+    "nnp_bin_to_binpack_dev", "nnp_binpack_to_bin_dev", "nnp_plain_to_binpack_dev",
+    "nnp_binpack_to_plain_dev", "nnp_bin_to_plain_dev", "nnp_plain_to_bin_dev",
+    "nnp_binpack_count_dev", "nnp_generate_bin_dev", "nnp_last_timing",
+]
+
+
+class NnpError(RuntimeError):
+    def __init__(self, status: int, message: str, partial: bytes | None = None):
+        super().__init__(f"{STATUS.get(status, status)}: {message}")
+        self.status = status
+        self.message = message
+        self.partial = partial
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Loads libnnuepack.so (built in-tree by ``__graft_entry__.build()`` / ``csrc/Makefile``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). nnue_data_compress_b200 has no CPU fallback."
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        conv = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        for name in EXPORTS:
+            fn = getattr(L, name)
+            if name.endswith(("_to_binpack", "_to_bin", "_to_plain", "_dev")) and name not in (
+                "nnp_binpack_count_dev",
+                "nnp_generate_bin_dev",
+            ):
+                fn.argtypes = conv
+                fn.restype = ctypes.c_int
+        L.nnp_init.argtypes = [ctypes.c_int]
+        L.nnp_init.restype = ctypes.c_int
+        L.nnp_shutdown.restype = None
+        L.nnp_strerror.argtypes = [ctypes.c_int]
+        L.nnp_strerror.restype = ctypes.c_char_p
+        L.nnp_last_cuda_error.restype = ctypes.c_char_p
+        L.nnp_kernel_launches.restype = ctypes.c_uint64
+        L.nnp_host_alloc.argtypes = [ctypes.c_size_t]
+        L.nnp_host_alloc.restype = ctypes.c_void_p
+        L.nnp_host_free.argtypes = [ctypes.c_void_p]
+        L.nnp_host_free.restype = None
+        L.nnp_binpack_count_dev.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64)]
+        L.nnp_binpack_count_dev.restype = ctypes.c_int
+        L.nnp_generate_bin_dev.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint64]
+        L.nnp_generate_bin_dev.restype = ctypes.c_int
+        L.nnp_last_timing.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
+        L.nnp_last_timing.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+_initialised = False
+
+
+def init(device: int | None = None) -> None:
+    """Binds the process to one GPU (default: LOCAL_RANK, else 0). Raises without a usable B200."""
+    global _initialised
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    rc = lib().nnp_init(device)
+    if rc != 0:
+        raise NnpError(rc, lib().nnp_strerror(rc).decode() + " / " + lib().nnp_last_cuda_error().decode())
+    _initialised = True
+
+
+def shutdown() -> None:
+    global _initialised
+    if _lib is not None:
+        _lib.nnp_shutdown()
+    _initialised = False
+
+
+def _ensure_init():
+    if not _initialised:
+        init()
+
+
+def _strerror(rc: int) -> str:
+    return lib().nnp_strerror(rc).decode()
+
+
+def _convert_host(fn_name: str, data: bytes, allow_partial: bool = False) -> bytes:
+    """Calls one of the six host-buffer drivers: capacity query, then the conversion."""
+    _ensure_init()
+    L = lib()
+    fn = getattr(L, fn_name)
+    src = (ctypes.c_char * len(data)).from_buffer_copy(data) if len(data) else (ctypes.c_char * 1)()
+    need = ctypes.c_size_t(0)
+    rc = fn(src, len(data), None, 0, ctypes.byref(need))
+    if rc != 0 and rc not in REFERENCE_ERRORS:
+        raise NnpError(rc, _strerror(rc))
+    cap = max(int(need.value), 1)
+    dst = (ctypes.c_char * cap)()
+    out_n = ctypes.c_size_t(0)
+    rc = fn(src, len(data), dst, cap, ctypes.byref(out_n))
+    result = bytes(memoryview(dst)[: out_n.value]) if rc in (0,) + REFERENCE_ERRORS else b""
+    if rc != 0:
+        if allow_partial and rc in REFERENCE_ERRORS:
+            raise NnpError(rc, _strerror(rc), partial=result)
+        raise NnpError(rc, _strerror(rc), partial=result if rc in REFERENCE_ERRORS else None)
+    return result
+
+
+# -- the six drivers (compress_file.cpp:1246-1533), in-memory -------------------------------------
+
+def bin_to_binpack(data: bytes) -> bytes:
+    """compressBin (compress_file.cpp:1338-1374)."""
+    return _convert_host("nnp_bin_to_binpack", data)
+
+
+def binpack_to_bin(data: bytes) -> bytes:
+    """decompressBin (compress_file.cpp:1376-1412)."""
+    return _convert_host("nnp_binpack_to_bin", data)
+
+
+def plain_to_binpack(data: bytes) -> bytes:
+    """compressPlain (compress_file.cpp:1246-1297)."""
+    return _convert_host("nnp_plain_to_binpack", data)
+
+
+def binpack_to_plain(data: bytes) -> bytes:
+    """decompressPlain (compress_file.cpp:1299-1335)."""
+    return _convert_host("nnp_binpack_to_plain", data)
+
+
+def bin_to_plain(data: bytes) -> bytes:
+    """convertBinToPlain (compress_file.cpp:1414-1465)."""
+    return _convert_host("nnp_bin_to_plain", data)
+
+
+def plain_to_bin(data: bytes) -> bytes:
+    """convertPlainToBin (compress_file.cpp:1467-1533)."""
+    return _convert_host("nnp_plain_to_bin", data)
+
+
+# -- convert() / run() / main(): the reference CLI (compress_file.cpp:1535-1709) ------------------
+
+PLAIN_EXT, BIN_EXT, BINPACK_EXT = ".plain", ".bin", ".binpack"
+
+_HELP = """Usage:
+    nnue_data_compression [-h] [-a] input_path output_path
+
+-h, --help                show help
+-a, --append              append to the output file instead of truncating it
+
+input_path                the path to the file to process
+output_path               the path to the file to create/append to
+
+Behaviour depends on file extensions. If the input
+file has extension either .bin or .plain
+it will be compressed. The output file has then an implied
+extension of .binpack and it doesn't have to be specified.
+If the input file's extension is .binpack then it will be decompressed
+to either a .bin or .plain file, depending on the extension.
+
+Example usage:
+1. convert from plain to binpack in append mode:
+    nnue_data_compression -a data.plain data
+2. convert from binpack to plain in truncate/replace mode:
+    nnue_data_compression data.binpack data.plain
+"""
+
+
+def _run_driver(driver, label: str, input_path: str, output_path: str, append: bool, out=sys.stdout) -> None:
+    out.write(f"{label} {input_path} to {output_path}\n")
+    with open(input_path, "rb") as f:
+        data = f.read()
+    err = None
+    try:
+        result = driver(data)
+    except NnpError as e:
+        if e.status not in REFERENCE_ERRORS:
+            raise
+        result, err = e.partial or b"", e
+    with open(output_path, "ab" if append else "wb") as f:
+        f.write(result)
+    if err is not None:
+        raise err
+
+
+def convert(input_path: str, output_path: str, append: bool = False, out=sys.stdout, err=sys.stderr) -> None:
+    """convert() (compress_file.cpp:1593-1621): dispatch on the file extensions."""
+    if not os.path.exists(input_path):
+        err.write("Input file doesn't exist.\n")
+        return
+    if input_path.endswith(BIN_EXT) and output_path.endswith(PLAIN_EXT):
+        _run_driver(bin_to_plain, "Converting", input_path, output_path, append, out)
+    elif input_path.endswith(PLAIN_EXT) and output_path.endswith(BIN_EXT):
+        _run_driver(plain_to_bin, "Compressing", input_path, output_path, append, out)
+    elif input_path.endswith(PLAIN_EXT) or input_path.endswith(BIN_EXT):
+        if not output_path.endswith(BINPACK_EXT):
+            output_path += BINPACK_EXT
+        drv = bin_to_binpack if input_path.endswith(BIN_EXT) else plain_to_binpack
+        _run_driver(drv, "Compressing", input_path, output_path, append, out)
+    elif input_path.endswith(BINPACK_EXT):
+        if output_path.endswith(BIN_EXT):
+            _run_driver(binpack_to_bin, "Decompressing", input_path, output_path, append, out)
+        elif output_path.endswith(PLAIN_EXT):
+            _run_driver(binpack_to_plain, "Decompressing", input_path, output_path, append, out)
+        else:
+            err.write("Unrecognized file format. Only .bin and .plain are supported for decompression.")
+    else:
+        err.write("Unsupported extension.")
+
+
+def main(argv: list[str] | None = None, out=sys.stdout, err=sys.stderr) -> int:
+    """main()/run()/readArgs() (compress_file.cpp:1648-1709), including its quirks: any argument
+    starting with '-' is a flag named by the text after the FIRST dash, so ``--append`` is stored
+    as ``-append`` and ignored; reference errors print their message and ``Exiting...`` with exit
+    code 0."""
+    argv = list(sys.argv[1:] if argv is None else argv)
+    flags = {a[1:] for a in argv if a.startswith("-")}
+    pos = [a for a in argv if not a.startswith("-")]
+    if len(pos) == 0 or "help" in flags or "h" in flags:
+        out.write(_HELP)
+        return 0
+    if len(pos) == 2:
+        append = "a" in flags or "append" in flags
+        try:
+            convert(pos[0], pos[1], append, out, err)
+        except NnpError as e:
+            if e.status not in REFERENCE_ERRORS:
+                raise
+            err.write(e.message + "\nExiting...\n")
+        return 0
+    err.write("Invalid arguments.\n")
+    out.write(_HELP)
+    return 1

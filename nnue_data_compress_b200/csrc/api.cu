@@ -1,0 +1,499 @@
+// api.cu -- the C ABI of libnnuepack.so (include/nnuepack.h): context, workspaces and the
+// host-side sequencing of the kernels. No conversion arithmetic happens on the host.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/nnuepack.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nnp {
+
+namespace {
+
+struct Workspace {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+enum WsSlot {
+    WS_CODES = 0, WS_STEMS, WS_TILE_AGG, WS_PAYLOAD, WS_HEAD_OFF, WS_CHUNK_OFF, WS_TOTALS,
+    WS_CHUNK_START, WS_CHUNK_LEN, WS_CHUNK_TILE_BASE, WS_CHUNK_INFO, WS_TILE_COUNT, WS_TILE_PREFIX,
+    WS_CAND_CHUNK, WS_CAND_OFF, WS_CAND_NEXT, WS_CAND_BASE, WS_CHUNK_COUNT, WS_CHUNK_SLOW, WS_CHUNK_BASE,
+    WS_DTOTALS, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
+};
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    Workspace ws[WS_COUNT];
+    void* pinned = nullptr;  // small pinned scratch for read-backs
+    uint64_t launches = 0;
+    std::string last_cuda_error;
+    float last_total_ms = 0.f, last_dominant_ms = 0.f;
+    uint32_t debug_reject_mod = 0;
+};
+
+Context g_ctx;
+std::mutex g_mutex;
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    g_ctx.last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? NNP_ERR_NOMEM : NNP_ERR_CUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);        \
+    } while (0)
+
+int ws_get(WsSlot slot, size_t bytes, void** out)
+{
+    Workspace& w = g_ctx.ws[slot];
+    if (bytes == 0) bytes = 16;
+    if (w.cap < bytes) {
+        if (w.p) {
+            CK(cudaStreamSynchronize(g_ctx.stream));
+            CK(cudaFree(w.p));
+            w.p = nullptr;
+            w.cap = 0;
+        }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&w.p, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&w.p, want);
+        }
+        if (e != cudaSuccess) {
+            w.p = nullptr;
+            return cuda_fail(e, "cudaMalloc(workspace)");
+        }
+        w.cap = want;
+    }
+    *out = w.p;
+    return NNP_OK;
+}
+#define WS(slot, bytes, type, var)                                            \
+    type* var = nullptr;                                                      \
+    do {                                                                      \
+        void* p_ = nullptr;                                                   \
+        int rc_ = ws_get(slot, (size_t)(bytes), &p_);                         \
+        if (rc_ != NNP_OK) return rc_;                                        \
+        var = reinterpret_cast<type*>(p_);                                    \
+    } while (0)
+
+int check_launch(const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    return NNP_OK;
+}
+#define LAUNCHED(n, what)                                    \
+    do {                                                     \
+        g_ctx.launches += (n);                               \
+        int rc_ = check_launch(what);                        \
+        if (rc_ != NNP_OK) return rc_;                       \
+    } while (0)
+
+size_t binpack_capacity_for_records(size_t n)
+{
+    // every record costs at most a stem + numPlies (34 bytes); a continuation ply at most 4
+    const size_t payload = n * 34 + 16;
+    return payload + 8 * (payload / CHUNK_THRESHOLD + 2);
+}
+
+// ---------------------------------------------------------------- .bin -> .binpack
+
+int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    Context& C = g_ctx;
+    const u64 n_all = bin_bytes / 40;  // a short trailing record is dropped (compress_file.cpp:1360)
+    if (!d_out) {
+        *out_bytes = binpack_capacity_for_records(n_all);
+        return NNP_OK;
+    }
+    *out_bytes = 0;
+    if (n_all == 0) return NNP_OK;  // empty input -> empty file
+    if (((uintptr_t)d_bin & 7) || ((uintptr_t)d_out & 7)) return NNP_ERR_BAD_ARG;
+
+    cudaStream_t s = C.stream;
+    WS(WS_CODES, n_all * 4, u32, codes);
+    WS(WS_STEMS, n_all * 32, u32, stems);
+    WS(WS_TILE_AGG, scan_tiles(n_all) * sizeof(Agg), Agg, tile_agg);
+    WS(WS_TOTALS, sizeof(CompressTotals), CompressTotals, d_tot);
+    CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
+
+    h_tot->payload_bytes = 0;
+    h_tot->heads = 0;
+    h_tot->chunks = 0;
+    h_tot->error_index = NO_ERROR_IDX;
+    CK(cudaMemcpyAsync(d_tot, h_tot, sizeof(CompressTotals), cudaMemcpyHostToDevice, s));
+
+    CK(cudaEventRecord(C.ev[0], s));
+    launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, s);
+    LAUNCHED(1, "k_decode_link_encode");
+    CK(cudaEventRecord(C.ev[1], s));
+
+    int status = NNP_OK;
+    u64 n = n_all;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        launch_tile_aggregate(codes, n, tile_agg, s);
+        launch_scan_aggregates(tile_agg, scan_tiles(n), d_tot, s);
+        LAUNCHED(2, "payload scan");
+        CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (attempt == 0 && h_tot->error_index != NO_ERROR_IDX) {
+            // "Improperly encoded bin sfen": the reference stops at the first malformed record and its
+            // writer still flushes everything gathered before it (compress_file.cpp:407-408, :1094-1106)
+            status = NNP_ERR_BAD_SFEN;
+            n = h_tot->error_index;
+            if (n == 0) return status;
+            continue;
+        }
+        break;
+    }
+
+    const u64 payload_bytes = h_tot->payload_bytes, heads = h_tot->heads;
+    const u64 max_chunks = payload_bytes / CHUNK_THRESHOLD + 2;
+    WS(WS_PAYLOAD, payload_bytes + 64, u32, payload);
+    WS(WS_HEAD_OFF, (heads + 1) * 8, u64, head_off);
+    WS(WS_CHUNK_OFF, (max_chunks + 2) * 8, u64, chunk_off);
+    CK(cudaMemsetAsync(payload, 0, payload_bytes + 64, s));
+    launch_write_payload(codes, stems, n, tile_agg, payload, head_off, s);
+    launch_chunk_orbit(head_off, d_tot, chunk_off, max_chunks, s);
+    LAUNCHED(2, "k_write_payload/k_chunk_orbit");
+    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const u64 chunks = h_tot->chunks;
+    const u64 total = payload_bytes + 8 * chunks;
+    *out_bytes = total;
+    if (total > out_cap) return NNP_ERR_CAPACITY;
+    launch_emit_chunks(payload, chunk_off, chunks, d_out, s);
+    LAUNCHED(1, "k_emit_chunks");
+    CK(cudaEventRecord(C.ev[2], s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
+    CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[0], C.ev[1]));
+    return status;
+}
+
+// ---------------------------------------------------------------- .binpack -> .bin
+
+struct DecodePlan {
+    ChunkTable tab;
+    u64 chunks = 0, tiles = 0, ncand = 0, positions = 0;
+    int walk_status = 0;
+    u32 *cand_chunk = nullptr, *cand_off = nullptr, *cand_next = nullptr, *cand_base = nullptr;
+    u32 *chunk_count = nullptr, *chunk_slow = nullptr;
+    u64* chunk_base = nullptr;
+    u64* tile_prefix = nullptr;
+    DecompressTotals* d_tot = nullptr;
+};
+
+// everything up to (and including) the per-chunk position counts
+int decode_plan(const void* d_in, size_t in_bytes, DecodePlan& P)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    WS(WS_CHUNK_INFO, sizeof(ChunkInfo), ChunkInfo, d_info);
+    ChunkInfo* h_info = reinterpret_cast<ChunkInfo*>((char*)C.pinned + 256);
+    u64 table_cap = in_bytes / 65536 + 1024;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        WS(WS_CHUNK_START, (table_cap + 1) * 8, u64, start);
+        WS(WS_CHUNK_LEN, (table_cap + 1) * 4, u32, len);
+        WS(WS_CHUNK_TILE_BASE, (table_cap + 2) * 8, u64, tile_base);
+        P.tab.start = start;
+        P.tab.len = len;
+        P.tab.tile_base = tile_base;
+        P.tab.info = d_info;
+        launch_walk_chunks(d_in, in_bytes, P.tab, table_cap, s);
+        LAUNCHED(1, "k_walk_chunks");
+        CK(cudaMemcpyAsync(h_info, d_info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h_info->chunks <= table_cap) break;
+        table_cap = h_info->chunks + 16;
+    }
+    P.chunks = h_info->chunks;
+    P.tiles = h_info->tiles;
+    P.walk_status = h_info->status;
+    WS(WS_DTOTALS, sizeof(DecompressTotals), DecompressTotals, d_tot);
+    P.d_tot = d_tot;
+    DecompressTotals* h_tot = reinterpret_cast<DecompressTotals*>((char*)C.pinned + 512);
+    h_tot->positions = 0;
+    h_tot->error_chunk = NO_ERROR_IDX;
+    h_tot->slow_chunks = 0;
+    h_tot->candidates = 0;
+    CK(cudaMemcpyAsync(d_tot, h_tot, sizeof(DecompressTotals), cudaMemcpyHostToDevice, s));
+    if (P.chunks == 0) return NNP_OK;
+
+    WS(WS_TILE_COUNT, (P.tiles + 1) * 4, u32, tile_count);
+    WS(WS_TILE_PREFIX, (P.tiles + 2) * 8, u64, tile_prefix);
+    P.tile_prefix = tile_prefix;
+    launch_candidates(false, d_in, P.tab, P.tiles, tile_count, tile_prefix, nullptr, nullptr, C.debug_reject_mod, s);
+    launch_exclusive_sum(tile_count, P.tiles, tile_prefix, s);
+    LAUNCHED(2, "k_candidates<count>");
+    u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+    CK(cudaMemcpyAsync(h_u64, tile_prefix + P.tiles, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    P.ncand = h_u64[0];
+
+    WS(WS_CAND_CHUNK, (P.ncand + 1) * 4, u32, cand_chunk);
+    WS(WS_CAND_OFF, (P.ncand + 1) * 4, u32, cand_off);
+    WS(WS_CAND_NEXT, (P.ncand + 1) * 4, u32, cand_next);
+    WS(WS_CAND_BASE, (P.ncand + 1) * 4, u32, cand_base);
+    WS(WS_CHUNK_COUNT, (P.chunks + 1) * 4, u32, chunk_count);
+    WS(WS_CHUNK_SLOW, (P.chunks + 1) * 4, u32, chunk_slow);
+    WS(WS_CHUNK_BASE, (P.chunks + 2) * 8, u64, chunk_base);
+    P.cand_chunk = cand_chunk; P.cand_off = cand_off; P.cand_next = cand_next; P.cand_base = cand_base;
+    P.chunk_count = chunk_count; P.chunk_slow = chunk_slow; P.chunk_base = chunk_base;
+
+    launch_candidates(true, d_in, P.tab, P.tiles, tile_count, tile_prefix, cand_chunk, cand_off, C.debug_reject_mod, s);
+    launch_probe_chains(d_in, P.tab, cand_chunk, cand_off, P.ncand, cand_next, s);
+    launch_resolve_chunks(d_in, P.tab, P.chunks, tile_prefix, cand_off, cand_next, cand_base, chunk_count, chunk_slow, s);
+    launch_slow_count(d_in, P.tab, P.chunks, chunk_slow, chunk_count, d_tot, s);
+    launch_exclusive_sum(chunk_count, P.chunks, chunk_base, s);
+    LAUNCHED(5, "decode plan");
+    CK(cudaMemcpyAsync(h_u64, chunk_base + P.chunks, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(DecompressTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    P.positions = h_u64[0];
+    if (h_tot->error_chunk != NO_ERROR_IDX) return NNP_ERR_TRUNCATED;
+    return NNP_OK;
+}
+
+// The reference hands its output buffer to the file only once it exceeds 1 MiB
+// (compress_file.cpp:1395-1402), and an exception thrown while fetching chunk k leaves
+// Reader::next() before the last entry of chunk k-1 is returned; this is how many records
+// reach the file in that case.
+u64 committed_bin_records(u64 positions_before_error)
+{
+    if (positions_before_error == 0) return 0;
+    const u64 emitted = positions_before_error - 1;
+    const u64 per_flush = (1048576 / 40) + 1;  // first count whose byte size exceeds 1 MiB
+    return emitted / per_flush * per_flush;
+}
+
+int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    *out_bytes = 0;
+    if (in_bytes == 0) return NNP_OK;
+    CK(cudaEventRecord(C.ev[0], s));
+    DecodePlan P;
+    int rc = decode_plan(d_in, in_bytes, P);
+    if (rc != NNP_OK) return rc;
+    CK(cudaEventRecord(C.ev[1], s));
+    if (!d_out) {
+        *out_bytes = P.positions * 40;
+        return NNP_OK;
+    }
+    if ((uintptr_t)d_out & 7) return NNP_ERR_BAD_ARG;
+    u64 positions = P.positions;
+    *out_bytes = positions * 40;
+    if (positions * 40 > out_cap) return NNP_ERR_CAPACITY;
+    if (P.chunks > 0) {
+        launch_emit_chains(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_base, P.ncand, P.chunk_base, d_out, P.d_tot, s);
+        launch_slow_emit(d_in, P.tab, P.chunks, P.chunk_slow, P.chunk_base, d_out, s);
+        LAUNCHED(2, "k_emit_chains");
+    }
+    CK(cudaEventRecord(C.ev[2], s));
+    DecompressTotals* h_tot = reinterpret_cast<DecompressTotals*>((char*)C.pinned + 512);
+    CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(DecompressTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
+    CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[1], C.ev[2]));
+    if (h_tot->error_chunk != NO_ERROR_IDX) return NNP_ERR_TRUNCATED;
+    if (P.walk_status != 0) {
+        *out_bytes = committed_bin_records(positions) * 40;
+        return P.walk_status;
+    }
+    return NNP_OK;
+}
+
+// ---------------------------------------------------------------- host-buffer wrappers
+
+typedef int (*dev_fn)(const void*, size_t, void*, size_t, size_t*);
+
+int run_host(dev_fn fn, const void* in, size_t in_bytes, void* out, size_t out_cap, size_t* out_bytes, size_t dev_out_cap)
+{
+    Context& C = g_ctx;
+    WS(WS_STAGE_IN, in_bytes + 64, unsigned char, d_in);
+    if (in_bytes) CK(cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, C.stream));
+    if (!out) return fn(d_in, in_bytes, nullptr, 0, out_bytes);
+    size_t need = dev_out_cap;
+    if (need == 0) {
+        int rc = fn(d_in, in_bytes, nullptr, 0, &need);
+        if (rc != NNP_OK) return rc;
+    }
+    WS(WS_STAGE_OUT, need + 64, unsigned char, d_out);
+    size_t produced = 0;
+    int rc = fn(d_in, in_bytes, d_out, need, &produced);
+    *out_bytes = produced;
+    if (rc == NNP_ERR_CAPACITY) return rc;
+    if (produced > out_cap) return NNP_ERR_CAPACITY;
+    if (produced) {
+        CK(cudaMemcpyAsync(out, d_out, produced, cudaMemcpyDeviceToHost, C.stream));
+        CK(cudaStreamSynchronize(C.stream));
+    }
+    return rc;
+}
+
+}  // namespace
+
+}  // namespace nnp
+
+using namespace nnp;
+
+#define REQUIRE_READY()                                              \
+    std::lock_guard<std::mutex> lock_(g_mutex);                      \
+    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;                \
+    if (!out_bytes) return NNP_ERR_BAD_ARG;
+
+extern "C" {
+
+int nnp_init(int device)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (g_ctx.ready) return g_ctx.device == device ? NNP_OK : NNP_ERR_BAD_ARG;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_ctx.last_cuda_error = e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device";
+        (void)cudaGetLastError();
+        return NNP_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) return NNP_ERR_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return NNP_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NNP_ERR_NO_DEVICE;
+    if (prop.major < 10) {
+        g_ctx.last_cuda_error = "libnnuepack is built for sm_100a only";
+        return NNP_ERR_NO_DEVICE;
+    }
+    if (cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking) != cudaSuccess) return NNP_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking) != cudaSuccess) return NNP_ERR_CUDA;
+    for (auto& ev : g_ctx.ev)
+        if (cudaEventCreate(&ev) != cudaSuccess) return NNP_ERR_CUDA;
+    if (cudaMallocHost(&g_ctx.pinned, 4096) != cudaSuccess) return NNP_ERR_NOMEM;
+    const char* dbg = std::getenv("NNP_DEBUG_REJECT_MOD");
+    g_ctx.debug_reject_mod = dbg ? (uint32_t)std::strtoul(dbg, nullptr, 10) : 0u;
+    g_ctx.device = device;
+    g_ctx.ready = true;
+    return NNP_OK;
+}
+
+void nnp_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_ctx.ready) return;
+    cudaStreamSynchronize(g_ctx.stream);
+    for (auto& w : g_ctx.ws) {
+        if (w.p) cudaFree(w.p);
+        w.p = nullptr;
+        w.cap = 0;
+    }
+    if (g_ctx.pinned) cudaFreeHost(g_ctx.pinned);
+    g_ctx.pinned = nullptr;
+    for (auto& ev : g_ctx.ev) {
+        if (ev) cudaEventDestroy(ev);
+        ev = nullptr;
+    }
+    cudaStreamDestroy(g_ctx.stream);
+    cudaStreamDestroy(g_ctx.copy_stream);
+    g_ctx.stream = g_ctx.copy_stream = nullptr;
+    g_ctx.ready = false;
+    g_ctx.device = -1;
+}
+
+const char* nnp_strerror(int status)
+{
+    switch (status) {
+    case NNP_OK: return "ok";
+    case NNP_ERR_BAD_MAGIC: return "Invalid binpack file or chunk.";
+    case NNP_ERR_CHUNK_TOO_LARGE: return "Chunks size larger than supported. Malformed file?";
+    case NNP_ERR_BAD_SFEN: return "Improperly encoded bin sfen";
+    case NNP_ERR_TRUNCATED: return "binpack chunk or movetext is truncated";
+    case NNP_ERR_NOMEM: return "out of memory";
+    case NNP_ERR_BAD_ARG: return "bad argument";
+    case NNP_ERR_BAD_TEXT: return "malformed .plain input";
+    case NNP_ERR_CAPACITY: return "output buffer too small";
+    case NNP_ERR_NO_DEVICE: return "no usable sm_100a CUDA device (libnnuepack has no CPU path)";
+    case NNP_ERR_NOT_INITIALISED: return "nnp_init() has not been called";
+    case NNP_ERR_CUDA: return "CUDA runtime error";
+    default: return "unknown status";
+    }
+}
+
+const char* nnp_last_cuda_error(void) { return g_ctx.last_cuda_error.c_str(); }
+uint64_t nnp_kernel_launches(void) { return g_ctx.launches; }
+
+void* nnp_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void nnp_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int nnp_bin_to_binpack_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    return compress_dev(d_bin, bin_bytes, d_out, out_cap, out_bytes);
+}
+int nnp_binpack_to_bin_dev(const void* d_binpack, size_t binpack_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    return decompress_dev(d_binpack, binpack_bytes, d_out, out_cap, out_bytes);
+}
+int nnp_bin_to_binpack(const void* bin, size_t bin_bytes, void* out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    if (!out) {
+        *out_bytes = binpack_capacity_for_records(bin_bytes / 40);
+        return NNP_OK;
+    }
+    return run_host(compress_dev, bin, bin_bytes, out, out_cap, out_bytes, binpack_capacity_for_records(bin_bytes / 40));
+}
+int nnp_binpack_to_bin(const void* binpack, size_t binpack_bytes, void* out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    return run_host(decompress_dev, binpack, binpack_bytes, out, out_cap, out_bytes, 0);
+}
+
+int nnp_binpack_count_dev(const void* d_binpack, size_t binpack_bytes, uint64_t* n_positions)
+{
+    std::lock_guard<std::mutex> lock_(g_mutex);
+    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    if (!n_positions) return NNP_ERR_BAD_ARG;
+    size_t bytes = 0;
+    int rc = decompress_dev(d_binpack, binpack_bytes, nullptr, 0, &bytes);
+    *n_positions = bytes / 40;
+    return rc;
+}
+
+int nnp_last_timing(float* total_ms, float* dominant_kernel_ms)
+{
+    if (total_ms) *total_ms = g_ctx.last_total_ms;
+    if (dominant_kernel_ms) *dominant_kernel_ms = g_ctx.last_dominant_ms;
+    return NNP_OK;
+}
+
+}  // extern "C"
+
+// ---- entry points implemented in plain.cu / generate.cu are declared there ----

@@ -1,0 +1,725 @@
+// chess.cuh -- device-side position model for the conversion kernels (sm_100a).
+//
+// A position is five 64-bit planes held in registers (white/black occupancy + three
+// bit planes of the piece type) plus a few scalars: everything the path reads fits in
+// 12 registers, comparisons are five XORs, and there is no per-square mailbox to index
+// dynamically. Square numbering follows the reference (a1 = 0 ... h8 = 63,
+// src/chess/Chess.h:593-755); piece codes are type<<1|colour with type order
+// Pawn,Knight,Bishop,Rook,Queen,King and 12 = none (src/chess/Chess.h:74-84, :142-205).
+//
+// Citations are relative to /root/reference.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nnp {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+enum : int { PT_PAWN = 0, PT_KNIGHT, PT_BISHOP, PT_ROOK, PT_QUEEN, PT_KING, PT_NONE };
+enum : int { WHITE = 0, BLACK = 1 };
+enum : int { NO_PIECE = 12, SQ_NONE = 64 };
+enum : int { MT_NORMAL = 0, MT_PROMOTION = 1, MT_CASTLE = 2, MT_ENPASSANT = 3 };  // Chess.h:905-911
+enum : int { CR_WK = 1, CR_WQ = 2, CR_BK = 4, CR_BQ = 8, CR_ALL = 15 };           // Chess.h:1195-1205
+
+constexpr u64 FILE_A = 0x0101010101010101ull;
+constexpr u64 FILE_H = 0x8080808080808080ull;
+constexpr u64 RANK_1 = 0x00000000000000FFull;
+constexpr u64 DIAG_A1H8 = 0x8040201008040201ull;
+constexpr u64 DIAG_H1A8 = 0x0102040810204080ull;
+
+__device__ __forceinline__ u64 bit64(int sq) { return 1ull << sq; }
+__device__ __forceinline__ int popc64(u64 b) { return __popcll(b); }
+__device__ __forceinline__ int lsb64(u64 b) { return __ffsll((long long)b) - 1; }
+__device__ __forceinline__ u64 brev64(u64 b) { return __brevll(b); }
+__device__ __forceinline__ u64 bswap64(u64 b)
+{
+    u32 lo = (u32)b, hi = (u32)(b >> 32);
+    return ((u64)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+}
+// bb::before (Bitboard.h:730-733)
+__device__ __forceinline__ u64 before64(int sq) { return sq >= 64 ? ~0ull : (1ull << sq) - 1ull; }
+
+// usedBitsSafe (compress_file.cpp:600-604): ceil(log2(n)), 0 for n <= 1
+__device__ __forceinline__ int used_bits(u32 n) { return n <= 1 ? 0 : 32 - __clz(n - 1); }
+
+// index of the n-th set bit (nthSetBitIndex, util/ArithmeticUtility.h:186-209), branch-light
+__device__ __forceinline__ int nth_set_bit(u64 v, u32 n)
+{
+    u32 w = (u32)v;
+    int base = 0;
+    u32 c = __popc(w);
+    if (n >= c) { w = (u32)(v >> 32); n -= c; base = 32; }
+    c = __popc(w & 0xFFFFu);
+    if (n >= c) { w >>= 16; n -= c; base += 16; }
+    c = __popc(w & 0xFFu);
+    if (n >= c) { w >>= 8; n -= c; base += 8; }
+    c = __popc(w & 0xFu);
+    if (n >= c) { w >>= 4; n -= c; base += 4; }
+    c = __popc(w & 0x3u);
+    if (n >= c) { w >>= 2; n -= c; base += 2; }
+    if (n >= (w & 1u)) base += 1;
+    return base & 63;
+}
+
+// zigzag (signedToUnsigned / unsignedToSigned, compress_file.cpp:524-546)
+__device__ __forceinline__ u32 zz_enc(int v16)
+{
+    u32 r = (u32)v16 & 0xFFFFu;
+    if (r & 0x8000u) r ^= 0x7FFFu;
+    return ((r << 1) | (r >> 15)) & 0xFFFFu;
+}
+__device__ __forceinline__ int zz_dec(u32 r)
+{
+    r &= 0xFFFFu;
+    r = ((r << 15) | (r >> 1)) & 0xFFFFu;
+    if (r & 0x8000u) r ^= 0x7FFFu;
+    return (int)(short)r;
+}
+
+// ---------------------------------------------------------------- attack sets
+// Table-free, exact equivalents of bb::pseudoAttacks / bb::attacks (Bitboard.h:837-880);
+// the reference's 800 KiB fancy-magic tables (Bitboard.cpp:401-464) are replaced by the
+// o^(o-2r) line trick with a full 64-bit reversal, which needs no memory at all.
+
+__device__ __forceinline__ u64 knight_attacks(int sq)
+{
+    u64 b = bit64(sq);
+    u64 l1 = (b >> 1) & ~FILE_H, l2 = (b >> 2) & 0x3f3f3f3f3f3f3f3full;
+    u64 r1 = (b << 1) & ~FILE_A, r2 = (b << 2) & 0xfcfcfcfcfcfcfcfcull;
+    u64 h1 = l1 | r1, h2 = l2 | r2;
+    return (h1 << 16) | (h1 >> 16) | (h2 << 8) | (h2 >> 8);
+}
+__device__ __forceinline__ u64 king_attacks(int sq)
+{
+    u64 b = bit64(sq);
+    u64 h = ((b >> 1) & ~FILE_H) | ((b << 1) & ~FILE_A);
+    u64 m = h | b;
+    return h | (m << 8) | (m >> 8);
+}
+// bb::pawnAttacks (Bitboard.cpp:500-510)
+__device__ __forceinline__ u64 pawn_attacks(u64 pawns, int color)
+{
+    u64 e = pawns & ~FILE_H, w = pawns & ~FILE_A;
+    return color == WHITE ? ((e << 9) | (w << 7)) : ((e >> 7) | (w >> 9));
+}
+__device__ __forceinline__ u64 line_attacks(u64 occ, u64 mask, int sq)
+{
+    u64 o = occ & mask;
+    u64 fwd = o - 2 * bit64(sq);
+    u64 rev = brev64(brev64(o) - 2 * bit64(63 - sq));
+    return (fwd ^ rev) & mask;
+}
+__device__ __forceinline__ u64 diag_mask(int sq)
+{
+    int d = (sq & 7) - (sq >> 3);
+    return d >= 0 ? (DIAG_A1H8 >> (8 * d)) : (DIAG_A1H8 << (8 * -d));
+}
+__device__ __forceinline__ u64 anti_mask(int sq)
+{
+    int d = (sq & 7) + (sq >> 3) - 7;
+    return d >= 0 ? (DIAG_H1A8 << (8 * d)) : (DIAG_H1A8 >> (8 * -d));
+}
+__device__ __forceinline__ u64 bishop_attacks(int sq, u64 occ)
+{
+    return line_attacks(occ, diag_mask(sq), sq) | line_attacks(occ, anti_mask(sq), sq);
+}
+__device__ __forceinline__ u64 rook_attacks(int sq, u64 occ)
+{
+    return line_attacks(occ, FILE_A << (sq & 7), sq) | line_attacks(occ, RANK_1 << (sq & 56), sq);
+}
+// bb::attacks(pt, sq, occ) (Bitboard.h:864-880); Pawn / None give the empty set
+__device__ __forceinline__ u64 piece_attacks(int pt, int sq, u64 occ)
+{
+    u64 a = 0;
+    if (pt == PT_KNIGHT) a = knight_attacks(sq);
+    else if (pt == PT_KING) a = king_attacks(sq);
+    else {
+        if (pt == PT_BISHOP || pt == PT_QUEEN) a = bishop_attacks(sq, occ);
+        if (pt == PT_ROOK || pt == PT_QUEEN) a |= rook_attacks(sq, occ);
+    }
+    return a;
+}
+
+// ---------------------------------------------------------------- position
+
+struct Pos {
+    u64 occ[2];  // by colour
+    u64 t0, t1, t2;  // piece-type bit planes, zero on empty squares
+    int stm;     // 0 white, 1 black
+    int ep;      // SQ_NONE if none
+    int cr;      // castling rights mask
+    int rule50;  // std::uint8_t in the reference (Position.h:1014)
+    int ply;     // std::uint16_t m_ply (Position.h:1015)
+};
+
+struct Move {
+    int from, to, type, promo;  // promo = piece code or NO_PIECE
+};
+
+__device__ __forceinline__ void pos_clear(Pos& p)  // Position() Position.h:828-836
+{
+    p.occ[0] = p.occ[1] = p.t0 = p.t1 = p.t2 = 0;
+    p.stm = WHITE;
+    p.ep = SQ_NONE;
+    p.cr = CR_ALL;
+    p.rule50 = 0;
+    p.ply = 0;
+}
+__device__ __forceinline__ u64 pos_all(const Pos& p) { return p.occ[0] | p.occ[1]; }
+// colour-indexed occupancy as a select (keeps the planes in registers)
+__device__ __forceinline__ u64 pos_occ(const Pos& p, int c) { return c ? p.occ[1] : p.occ[0]; }
+__device__ __forceinline__ int pos_piece_at(const Pos& p, int sq)
+{
+    u64 all = pos_all(p);
+    if (!((all >> sq) & 1)) return NO_PIECE;
+    int t = (int)((p.t0 >> sq) & 1) | ((int)((p.t1 >> sq) & 1) << 1) | ((int)((p.t2 >> sq) & 1) << 2);
+    return (t << 1) | (int)((p.occ[1] >> sq) & 1);
+}
+__device__ __forceinline__ void pos_remove(Pos& p, int sq)
+{
+    u64 m = ~bit64(sq);
+    p.occ[0] &= m; p.occ[1] &= m; p.t0 &= m; p.t1 &= m; p.t2 &= m;
+}
+__device__ __forceinline__ void pos_put(Pos& p, int sq, int piece)  // Board::place Position.h:260-275
+{
+    pos_remove(p, sq);
+    if (piece == NO_PIECE) return;
+    u64 b = bit64(sq);
+    int t = piece >> 1;
+    if (piece & 1) p.occ[1] |= b; else p.occ[0] |= b;
+    if (t & 1) p.t0 |= b;
+    if (t & 2) p.t1 |= b;
+    if (t & 4) p.t2 |= b;
+}
+__device__ __forceinline__ u64 pos_type_bb(const Pos& p, int t)
+{
+    u64 a = (t & 1) ? p.t0 : ~p.t0;
+    u64 b = (t & 2) ? p.t1 : ~p.t1;
+    u64 c = (t & 4) ? p.t2 : ~p.t2;
+    return a & b & c & pos_all(p);
+}
+__device__ __forceinline__ bool pos_equal(const Pos& a, const Pos& b)  // Position.h:977-984
+{
+    u64 d = (a.occ[0] ^ b.occ[0]) | (a.occ[1] ^ b.occ[1]) | (a.t0 ^ b.t0) | (a.t1 ^ b.t1) | (a.t2 ^ b.t2);
+    return d == 0 && a.stm == b.stm && a.ep == b.ep && a.cr == b.cr;
+}
+
+// bb::isAttackedBySlider (Bitboard.cpp:536-554)
+__device__ __forceinline__ bool attacked_by_slider(int sq, u64 bq, u64 rq, u64 occ)
+{
+    if (bishop_attacks(sq, occ) & bq) return true;
+    return (rook_attacks(sq, occ) & rq) != 0;
+}
+
+// Position::isEpPossible + isEpPossibleColdPath (Position.cpp:824-883), evaluated on the
+// board currently held in `p`: post-move when called from setEpSquare / FEN parsing,
+// PRE-move when called from pos_do_move (Position.cpp:647-657) -- both variants are needed
+// for byte parity.
+static __device__ __noinline__ bool ep_possible_cold(const Pos& p, int ep, u64 attackers, int side)
+{
+    u64 all = pos_all(p);
+    u64 kings = pos_type_bb(p, PT_KING) & pos_occ(p, side);
+    if (!kings) return true;  // outside the parity domain (reference: undefined)
+    int ksq = lsb64(kings);
+    u64 theirs = pos_occ(p, side ^ 1);
+    u64 bq = (pos_type_bb(p, PT_BISHOP) | pos_type_bb(p, PT_QUEEN)) & theirs;
+    u64 rq = (pos_type_bb(p, PT_ROOK) | pos_type_bb(p, PT_QUEEN)) & theirs;
+    u64 queen_lines = bishop_attacks(ksq, 0) | rook_attacks(ksq, 0);
+    if (((bq | rq) & queen_lines) == 0) return true;
+    while (attackers) {
+        int sq = lsb64(attackers);
+        attackers &= attackers - 1;
+        int captured = (ep & 7) | (sq & 56);
+        u64 occ = ((all ^ bit64(sq)) | bit64(ep)) ^ bit64(captured);
+        if (!attacked_by_slider(ksq, bq, rq, occ)) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ bool ep_possible(const Pos& p, int ep, int side)
+{
+    u64 attackers = pawn_attacks(bit64(ep), side ^ 1) & pos_type_bb(p, PT_PAWN) & pos_occ(p, side);
+    if (!attackers) return false;
+    return ep_possible_cold(p, ep, attackers, side);
+}
+
+// detail::lookup::preservedCastlingRights (Position.cpp:605-624)
+__device__ __forceinline__ int preserved_cr(int sq)
+{
+    int m = CR_ALL;
+    if (sq == 4) m = CR_ALL & ~(CR_WK | CR_WQ);
+    if (sq == 60) m = CR_ALL & ~(CR_BK | CR_BQ);
+    if (sq == 7) m = CR_ALL & ~CR_WK;
+    if (sq == 0) m = CR_ALL & ~CR_WQ;
+    if (sq == 63) m = CR_ALL & ~CR_BK;
+    if (sq == 56) m = CR_ALL & ~CR_BQ;
+    return m;
+}
+
+// Board::doMove + doMoveColdPath (Position.h:300-439), mailbox semantics on the planes
+__device__ __forceinline__ void board_do_move(Pos& p, const Move& m)
+{
+    if (m.type == MT_NORMAL) {
+        int pc = pos_piece_at(p, m.from);
+        pos_put(p, m.to, pc);
+        pos_remove(p, m.from);
+    } else if (m.type == MT_PROMOTION) {
+        pos_put(p, m.to, m.promo);
+        pos_remove(p, m.from);
+    } else if (m.type == MT_ENPASSANT) {
+        int pc = pos_piece_at(p, m.from);
+        pos_put(p, m.to, pc);
+        pos_remove(p, m.from);
+        pos_remove(p, (m.to & 7) | (m.from & 56));
+    } else {
+        int rook = pos_piece_at(p, m.to), king = pos_piece_at(p, m.from);
+        int base = (king & 1) ? 56 : 0;  // king.color(); Piece::none() counts as white
+        bool is_short = (m.to & 7) == 7;  // CastlingTraits::moveCastlingType CastlingTraits.h:37-40
+        pos_remove(p, m.to);
+        pos_remove(p, m.from);
+        pos_put(p, base + (is_short ? 5 : 3), rook);  // rookDestination f/d CastlingTraits.h:11
+        pos_put(p, base + (is_short ? 6 : 2), king);  // kingDestination g/c CastlingTraits.h:12
+    }
+}
+
+// Position::doMove (Position.cpp:626-662)
+__device__ __forceinline__ void pos_do_move(Pos& p, const Move& m)
+{
+    int moved = pos_piece_at(p, m.from);
+    int moved_type = moved >> 1;
+    p.ply = (p.ply + 1) & 0xFFFF;
+    p.rule50 = (p.rule50 + 1) & 0xFF;
+    if (m.type != MT_CASTLE && (moved_type == PT_PAWN || ((pos_all(p) >> m.to) & 1))) p.rule50 = 0;
+    p.cr &= preserved_cr(m.from) & preserved_cr(m.to);
+    p.ep = SQ_NONE;
+    if (moved_type == PT_PAWN && ((m.to ^ m.from) == 16)) {
+        int cand = (m.to + m.from) >> 1;
+        if (ep_possible(p, cand, p.stm ^ 1)) p.ep = cand;  // on the PRE-move board
+    }
+    board_do_move(p, m);
+    p.stm ^= 1;
+}
+
+// ---------------------------------------------------------------- .bin record fields
+
+// StockfishMove::toMove (compress_file.cpp:63-83)
+__device__ __forceinline__ Move sfmove_to_move(u32 raw)
+{
+    Move m;
+    m.to = raw & 63;
+    m.from = (raw >> 6) & 63;
+    int flag = (raw >> 14) & 3;
+    m.type = flag == 1 ? MT_PROMOTION : flag == 2 ? MT_ENPASSANT : flag == 3 ? MT_CASTLE : MT_NORMAL;
+    m.promo = NO_PIECE;
+    if (m.type == MT_PROMOTION) m.promo = ((PT_KNIGHT + ((raw >> 12) & 3)) << 1) | ((m.to >> 3) == 7 ? WHITE : BLACK);
+    return m;
+}
+// StockfishMove::fromMove (compress_file.cpp:35-61), same shift/or sequence on 16 bits
+__device__ __forceinline__ u32 move_to_sfmove(const Move& m)
+{
+    u32 flag = m.type == MT_PROMOTION ? 1 : m.type == MT_ENPASSANT ? 2 : m.type == MT_CASTLE ? 3 : 0;
+    u32 promo = m.type == MT_PROMOTION ? (u32)((m.promo >> 1) - PT_KNIGHT) : 0;
+    u32 raw = flag;
+    raw = (raw << 2) & 0xFFFF; raw |= promo;
+    raw = (raw << 6) & 0xFFFF; raw |= (u32)m.from;
+    raw = (raw << 6) & 0xFFFF; raw |= (u32)m.to;
+    return raw & 0xFFFF;
+}
+
+// ---------------------------------------------------------------- sfen (Huffman) codec
+
+// pos_from_packed_sfen (compress_file.cpp:364-446). `W(j)` returns 32-bit word j of the
+// 40-byte record (j < 10; the stream is one little-endian 256-bit integer consumed from
+// bit 0, BitStream :126-185; bits past 256 come from the score/move fields exactly as in
+// the reference's struct, and any decode that gets there fails the cursor check anyway).
+// Returns false for "Improperly encoded bin sfen" (:407-408, :441-442) and for the
+// 3-bit type codes 5..7 on which the reference's table search never terminates (:336-352).
+template <typename WordFn>
+__device__ __forceinline__ bool sfen_decode(WordFn W, Pos& p)
+{
+    pos_clear(p);
+    u32 w0 = W(0);
+    p.stm = w0 & 1;
+    int wk = (w0 >> 1) & 63, bk = (w0 >> 7) & 63;
+    // token ordinal -> stream square (rank 8 first, file a first) skips the king squares
+    int ka = wk ^ 56, kb = bk ^ 56;
+    if (ka > kb) { int t = ka; ka = kb; kb = t; }
+    int ntok = 62;
+    if (ka == kb) { kb = 64; ntok = 63; }
+    int cursor = 13, idx = 0;
+    u64 occ0 = 0, occ1 = 0, t0 = 0, t1 = 0, t2 = 0;
+    while (idx < ntok) {
+        int j = cursor >> 5, sh = cursor & 31;
+        u32 lo = j < 10 ? W(j) : 0u, hi = (j + 1) < 10 ? W(j + 1) : 0u;
+        u32 w = __funnelshift_r(lo, hi, sh);
+        int z = w ? (__ffs((int)w) - 1) : 32;
+        z = min(z, ntok - idx);
+        idx += z;
+        cursor += z;
+        if (idx >= ntok) break;
+        if (z > 27) continue;  // the 5-bit token is cut off by the window: refetch
+        u32 tok = w >> z;
+        int t = (tok >> 1) & 7, c = (tok >> 4) & 1;
+        if (t > PT_QUEEN) return false;
+        int s = idx;
+        s += (s >= ka);
+        s += (s >= kb);
+        u64 b = bit64(s ^ 56);
+        if (c) occ1 |= b; else occ0 |= b;
+        if (t & 1) t0 |= b;
+        if (t & 2) t1 |= b;
+        if (t & 4) t2 |= b;
+        idx += 1;
+        cursor += 5;
+        if (cursor > 256) return false;
+    }
+    p.occ[0] = occ0; p.occ[1] = occ1; p.t0 = t0; p.t1 = t1; p.t2 = t2;
+    // kings: white first, black second (a black king on the same square replaces it, :376-377)
+    pos_put(p, wk, (PT_KING << 1) | WHITE);
+    pos_put(p, bk, (PT_KING << 1) | BLACK);
+    // tail: castling(4) ep(1[+6]) rule50(6) fullmove(8)
+    auto bits = [&](int n) -> u32 {
+        int j = cursor >> 5, sh = cursor & 31;
+        u32 lo = j < 10 ? W(j) : 0u, hi = (j + 1) < 10 ? W(j + 1) : 0u;
+        cursor += n;
+        return __funnelshift_r(lo, hi, sh) & ((1u << n) - 1u);
+    };
+    u32 c4 = bits(4);
+    p.cr = (int)c4;  // WK,WQ,BK,BQ in stream order == CastlingRights bit order (:414-427)
+    if (bits(1)) {
+        int ep = (int)bits(6);
+        p.ep = ep_possible(p, ep, p.stm) ? ep : SQ_NONE;  // setEpSquare Position.h:868-872
+    }
+    p.rule50 = (int)bits(6);
+    int hm = (int)bits(8);
+    p.ply = (2 * hm - 1 + (p.stm == BLACK)) & 0xFFFF;  // setHalfMove Position.h:938-941
+    return cursor <= 256;
+}
+
+// SfenPacker::pack (compress_file.cpp:266-312) into eight 32-bit words out[0..7].
+// Tokens are emitted piece by piece in stream order; `out` may live in registers because
+// the word index only grows (a current-word accumulator is flushed when it is passed).
+__device__ __forceinline__ void sfen_encode(const Pos& p, u32* out /* [8], any address space */)
+{
+    u64 all = pos_all(p);
+    u64 kings = pos_type_bb(p, PT_KING);
+    u64 wkb = kings & p.occ[0], bkb = kings & p.occ[1];
+    int wk = wkb ? lsb64(wkb) : 0, bk = bkb ? lsb64(bkb) : 0;  // kingSquare Position.h:742-745
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    u32 cw = (u32)p.stm | ((u32)wk << 1) | ((u32)bk << 7);
+    int wi = 0;  // index of the word held in cw
+    auto put = [&](u32 v, int pos, int n) {
+        // append n (<= 8) bits of v at absolute bit position pos (positions never decrease)
+        int w = pos >> 5, sh = pos & 31;
+        while (wi < w) { if (wi < 8) out[wi] = cw; cw = 0; ++wi; }
+        cw |= v << sh;
+        if (sh + n > 32) { if (wi < 8) out[wi] = cw; cw = v >> (32 - sh); ++wi; }
+    };
+    // stream order: s = sq ^ 56; every king square (any colour, any count) is skipped (:286-287)
+    u64 s_all = bswap64(all), s_kings = bswap64(kings);
+    u64 s_pieces = s_all & ~s_kings;
+    int npieces = 0;
+    while (s_pieces) {
+        int s = lsb64(s_pieces);
+        s_pieces &= s_pieces - 1;
+        int kings_before = popc64(s_kings & before64(s));
+        int pos = 13 + (s - kings_before) + 4 * npieces;
+        int pc = pos_piece_at(p, s ^ 56);
+        put(1u | ((u32)(pc >> 1) << 1) | ((u32)(pc & 1) << 4), pos, 5);
+        ++npieces;
+    }
+    int cursor = 13 + (64 - popc64(kings)) + 4 * npieces;
+    put((u32)p.cr & 15u, cursor, 4);
+    cursor += 4;
+    if (p.ep == SQ_NONE) {
+        put(0u, cursor, 1);
+        cursor += 1;
+    } else {
+        put(1u | ((u32)(p.ep & 63) << 1), cursor, 7);
+        cursor += 7;
+    }
+    put((u32)p.rule50 & 63u, cursor, 6);
+    cursor += 6;
+    put((u32)(((p.ply + 1) >> 1) & 0xFF), cursor, 8);  // halfMove() Position.h:933-936, 8 bits
+    while (wi < 8) { out[wi] = cw; cw = 0; ++wi; }
+}
+
+// ---------------------------------------------------------------- stem (32-byte chain head)
+
+// Position::compress (Position.h:1374-1406) nibble for one occupied square
+__device__ __forceinline__ int stem_nibble(const Pos& p, int sq, int pc)
+{
+    int t = pc >> 1, c = pc & 1;
+    if (t == PT_PAWN) {
+        if (p.ep != SQ_NONE && (sq & 7) == (p.ep & 7) &&
+            (((sq >> 3) == 3 && p.stm == BLACK) || ((sq >> 3) == 4 && p.stm == WHITE)))
+            return 12;
+        return pc;
+    }
+    if (t == PT_ROOK) {
+        if (c == WHITE && ((sq == 0 && (p.cr & CR_WQ)) || (sq == 7 && (p.cr & CR_WK)))) return 13;
+        if (c == BLACK && ((sq == 56 && (p.cr & CR_BQ)) || (sq == 63 && (p.cr & CR_BK)))) return 14;
+        return pc;
+    }
+    if (t == PT_KING) return c == WHITE ? 10 : (p.stm == WHITE ? 11 : 15);
+    return pc;
+}
+
+// packEntry (compress_file.cpp:997-1020) into eight words that are the stem's bytes 0..31
+// in memory order (little-endian words).
+__device__ __forceinline__ void stem_pack(const Pos& p, const Move& mv, int score, int ply, int result, u32* out /* [8] */)
+{
+    u64 all = pos_all(p);
+    u64 be = bswap64(all);  // big-endian occupancy, Position.h:1245-1257
+    out[0] = (u32)be;
+    out[1] = (u32)(be >> 32);
+    u32 nib[4] = {0, 0, 0, 0};
+    int k = 0;
+    u64 b = all;
+    while (b) {
+        int sq = lsb64(b);
+        b &= b - 1;
+        u32 n = (u32)stem_nibble(p, sq, pos_piece_at(p, sq));
+        u32 v = n << ((k & 7) * 4);
+        int w = k >> 3;
+        if (w == 0) nib[0] |= v; else if (w == 1) nib[1] |= v; else if (w == 2) nib[2] |= v; else nib[3] |= v;
+        ++k;
+    }
+    out[2] = nib[0]; out[3] = nib[1]; out[4] = nib[2]; out[5] = nib[3];
+    u32 cm = 0;  // CompressedMove(Move) Chess.h:1071-1096
+    if (mv.from != mv.to) {
+        cm = ((u32)mv.type << 14) | ((u32)mv.from << 8) | ((u32)mv.to << 2);
+        if (mv.type == MT_PROMOTION) cm |= (u32)((mv.promo >> 1) - PT_KNIGHT);
+        cm &= 0xFFFF;
+    }
+    u32 sc = zz_enc(score);
+    u32 pr = ((u32)ply | (zz_enc(result) << 14)) & 0xFFFF;
+    u32 r50 = (u32)p.rule50 & 0xFF;
+    // bytes 24..27: move hi, move lo, score hi, score lo; 28..31: pr hi, pr lo, 0, rule50
+    out[6] = (cm >> 8) | ((cm & 0xFF) << 8) | ((sc >> 8) << 16) | ((sc & 0xFF) << 24);
+    out[7] = (pr >> 8) | ((pr & 0xFF) << 8) | (0u << 16) | (r50 << 24);
+}
+
+// unpackEntry (compress_file.cpp:1022-1043) + CompressedPosition::decompress
+// (Position.h:1408-1505) + CompressedMove::decompress (Chess.h:1142-1172).
+// `B(i)` returns byte i of the stem.
+template <typename ByteFn>
+__device__ __forceinline__ void stem_unpack(ByteFn B, Pos& p, Move& mv, int& score, int& ply, int& result)
+{
+    pos_clear(p);
+    p.cr = 0;
+    u64 occ = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) occ = (occ << 8) | (u64)B(i);
+    int k = 0;
+    u64 b = occ;
+    while (b) {
+        int sq = lsb64(b);
+        b &= b - 1;
+        int nib = (B(8 + (k >> 1)) >> ((k & 1) * 4)) & 15;
+        ++k;
+        if (nib < 12) {
+            pos_put(p, sq, nib);
+        } else if (nib == 12) {
+            if ((sq >> 3) == 3) { pos_put(p, sq, (PT_PAWN << 1) | WHITE); p.ep = (sq - 8) & 0xFF; }
+            else { pos_put(p, sq, (PT_PAWN << 1) | BLACK); p.ep = (sq + 8) & 0xFF; }
+        } else if (nib == 13) {
+            pos_put(p, sq, (PT_ROOK << 1) | WHITE);
+            p.cr |= (sq == 0) ? CR_WQ : CR_WK;
+        } else if (nib == 14) {
+            pos_put(p, sq, (PT_ROOK << 1) | BLACK);
+            p.cr |= (sq == 56) ? CR_BQ : CR_BK;
+        } else {
+            pos_put(p, sq, (PT_KING << 1) | BLACK);
+            p.stm = BLACK;
+        }
+    }
+    u32 cm = ((u32)B(24) << 8) | (u32)B(25);
+    if (cm == 0) {
+        mv.from = mv.to = SQ_NONE;  // Move::null()
+        mv.type = MT_NORMAL;
+        mv.promo = NO_PIECE;
+    } else {
+        mv.type = (int)(cm >> 14);
+        mv.from = (int)((cm >> 8) & 63);
+        mv.to = (int)((cm >> 2) & 63);
+        mv.promo = NO_PIECE;
+        if (mv.type == MT_PROMOTION) mv.promo = ((PT_KNIGHT + (int)(cm & 3)) << 1) | ((mv.to >> 3) == 0 ? BLACK : WHITE);
+    }
+    score = zz_dec(((u32)B(26) << 8) | (u32)B(27));
+    u32 pr = ((u32)B(28) << 8) | (u32)B(29);
+    ply = (int)(pr & 0x3FFF);
+    p.ply = ply;
+    result = zz_dec(pr >> 14);
+    p.rule50 = (int)B(31);  // setRule50Counter(uint8_t) of a 16-bit big-endian value
+}
+
+// ---------------------------------------------------------------- movetext codec
+
+// destination set of a pawn (addMoveScore :890-919 / nextMoveScore :701-730)
+__device__ __forceinline__ u64 pawn_destinations(const Pos& p, int from, u64 ours, u64 theirs)
+{
+    u64 occ = ours | theirs;
+    u64 targets = theirs;
+    if (p.ep != SQ_NONE) targets |= bit64(p.ep & 63);
+    u64 dest = pawn_attacks(bit64(from), p.stm) & targets;
+    int s1 = p.stm == WHITE ? from + 8 : from - 8;
+    if (s1 >= 0 && s1 < 64 && !((occ >> s1) & 1)) {
+        dest |= bit64(s1);
+        int s2 = p.stm == WHITE ? s1 + 8 : s1 - 8;
+        int start_rank = p.stm == WHITE ? 1 : 6;
+        if ((from >> 3) == start_rank && s2 >= 0 && s2 < 64 && !((occ >> s2) & 1)) dest |= bit64(s2);
+    }
+    return dest;
+}
+
+// PackedMoveScoreList::addMoveScore (compress_file.cpp:877-989) for one continuation ply.
+// Returns the ply's bit string left-aligned in 32 bits; nbits <= 31 (6 + 5 + 20).
+// Field values are masked to their widths (the reference lets an out-of-range id bleed into
+// neighbouring bits, which only happens for stored moves that are not pseudo-legal).
+__device__ __forceinline__ u32 encode_ply(const Pos& p, const Move& mv, int score, int last_score, int& nbits)
+{
+    int stm = p.stm;
+    u64 ours = pos_occ(p, stm), theirs = pos_occ(p, stm ^ 1);
+    u64 occ = ours | theirs;
+    u32 piece_id = (u32)popc64(ours & before64(mv.from));
+    u32 num_moves = 0, move_id = 0;
+    int pc = pos_piece_at(p, mv.from);
+    int pt = pc >> 1;
+    if (pt == PT_PAWN) {
+        u64 dest = pawn_destinations(p, mv.from, ours, theirs);
+        move_id = (u32)popc64(dest & before64(mv.to));
+        num_moves = (u32)popc64(dest);
+        int second_to_last = stm == WHITE ? 6 : 1;
+        if ((mv.from >> 3) == second_to_last) {
+            move_id = move_id * 4 + (u32)((mv.promo >> 1) - PT_KNIGHT);
+            num_moves *= 4;
+        }
+    } else if (pt == PT_KING) {
+        int our_mask = stm == WHITE ? (CR_WK | CR_WQ) : (CR_BK | CR_BQ);
+        u64 att = king_attacks(mv.from) & ~ours;
+        u32 att_n = (u32)popc64(att);
+        num_moves = att_n + (u32)__popc((u32)(p.cr & our_mask));
+        if (mv.type == MT_CASTLE) {
+            int long_right = stm == WHITE ? CR_WQ : CR_BQ;
+            move_id = att_n - 1;
+            if (p.cr & long_right) move_id += 1;
+            if ((mv.to & 7) == 7) move_id += 1;
+        } else {
+            move_id = (u32)popc64(att & before64(mv.to));
+        }
+    } else {
+        u64 att = piece_attacks(pt, mv.from, occ) & ~ours;
+        move_id = (u32)popc64(att & before64(mv.to));
+        num_moves = (u32)popc64(att);
+    }
+    int w1 = used_bits((u32)popc64(ours)), w2 = used_bits(num_moves);
+    u64 acc = 0;  // bits accumulate at the low end, MSB-first order == append order
+    int n = 0;
+    acc = (acc << w1) | (piece_id & ((1u << w1) - 1u)); n += w1;
+    acc = (acc << w2) | (move_id & ((1u << w2) - 1u)); n += w2;
+    // addBitsVle16 (:864-874): 4-bit groups, low group first, continuation flag on top
+    u32 v = zz_enc((int)(short)(score - last_score));
+    for (;;) {
+        u32 block = (v & 15u) | ((v > 15u) ? 16u : 0u);
+        acc = (acc << 5) | block;
+        n += 5;
+        v >>= 4;
+        if (v == 0) break;
+    }
+    nbits = n;
+    return (u32)(acc << (32 - n));
+}
+
+// MSB-first bit reader over a byte span (PackedMoveScoreListReader::extractBitsLE8 :623-648)
+struct BitReader {
+    const unsigned char* p;
+    u32 nbits;   // bits available
+    u32 pos;
+    bool overrun;
+    __device__ __forceinline__ u32 get(int n)
+    {
+        if (n == 0) return 0;
+        if (pos + (u32)n > nbits) { overrun = true; pos += n; return 0; }
+        u32 byte = pos >> 3, sh = pos & 7;
+        u32 v = ((u32)p[byte] << 16);
+        if (((pos + n - 1) >> 3) > byte) v |= ((u32)p[byte + 1] << 8);
+        pos += n;
+        return (v >> (24 - sh - n)) & ((1u << n) - 1u);  // n <= 8
+    }
+};
+
+// PackedMoveScoreListReader::nextMoveScore (compress_file.cpp:685-813).
+// `strict` rejects ids the reference encoder can never produce (used by the speculative
+// chain discovery to kill false candidates early); returns false on such an id.
+__device__ __forceinline__ bool decode_ply(BitReader& r, const Pos& p, int& last_score, Move& mv, int& score, bool strict)
+{
+    int stm = p.stm;
+    u64 ours = pos_occ(p, stm), theirs = pos_occ(p, stm ^ 1);
+    u64 occ = ours | theirs;
+    u32 n_ours = (u32)popc64(ours);
+    u32 piece_id = r.get(used_bits(n_ours));
+    if (strict && piece_id >= n_ours) return false;
+    int from = nth_set_bit(ours, piece_id);
+    int pt = pos_piece_at(p, from) >> 1;
+    mv.from = from;
+    mv.type = MT_NORMAL;
+    mv.promo = NO_PIECE;
+    mv.to = 0;
+    if (pt == PT_PAWN) {
+        u64 dest = pawn_destinations(p, from, ours, theirs);
+        u32 n = (u32)popc64(dest);
+        int promotion_rank = stm == WHITE ? 6 : 1;
+        if ((from >> 3) == promotion_rank) {
+            u32 id = r.get(used_bits(n * 4));
+            if (strict && id >= n * 4) return false;
+            mv.promo = ((PT_KNIGHT + (int)(id & 3)) << 1) | stm;
+            mv.to = nth_set_bit(dest, id >> 2);
+            mv.type = MT_PROMOTION;
+        } else {
+            u32 id = r.get(used_bits(n));
+            if (strict && id >= n) return false;
+            mv.to = nth_set_bit(dest, id);
+            if (mv.to == p.ep) mv.type = MT_ENPASSANT;
+        }
+    } else if (pt == PT_KING) {
+        int our_mask = stm == WHITE ? (CR_WK | CR_WQ) : (CR_BK | CR_BQ);
+        u64 att = king_attacks(from) & ~ours;
+        u32 att_n = (u32)popc64(att);
+        u32 n_cr = (u32)__popc((u32)(p.cr & our_mask));
+        u32 id = r.get(used_bits(att_n + n_cr));
+        if (strict && id >= att_n + n_cr) return false;
+        if (id >= att_n) {
+            int long_right = stm == WHITE ? CR_WQ : CR_BQ;
+            bool is_long = (id - att_n == 0) && (p.cr & long_right);
+            mv.from = stm == WHITE ? 4 : 60;  // Move::castle Chess.h:1029-1040
+            mv.to = (stm == WHITE ? 0 : 56) + (is_long ? 0 : 7);
+            mv.type = MT_CASTLE;
+        } else {
+            mv.to = nth_set_bit(att, id);
+        }
+    } else {
+        u64 att = piece_attacks(pt, from, occ) & ~ours;
+        u32 n = (u32)popc64(att);
+        u32 id = r.get(used_bits(n));
+        if (strict && id >= n) return false;
+        mv.to = nth_set_bit(att, id);
+    }
+    // extractVle16 (:650-667)
+    u32 v = 0;
+    int off = 0;
+    for (;;) {
+        u32 block = r.get(5);
+        v |= (block & 15u) << off;
+        if (!(block >> 4) || r.overrun) break;
+        off += 4;
+        if (off > 28) { if (strict) return false; off = 28; }
+    }
+    score = (int)(short)(last_score + zz_dec(v & 0xFFFFu));
+    last_score = (int)(short)(-score);
+    return !r.overrun;
+}
+
+}  // namespace nnp

@@ -1,0 +1,425 @@
+// compress.cu -- .bin -> .binpack kernels (compressBin, compress_file.cpp:1338-1374, and the
+// CompressedTrainingDataEntryWriter it drives, :1045-1126), restructured for a B200:
+//
+//   k_decode_link_encode  one thread per 40-byte record: Huffman sfen decode (:364-446),
+//                         continuation test against the previous record (:587-593) and, for
+//                         continuation plies, the move/score bit string (:877-989); chain
+//                         heads get their 32-byte stem (:997-1020).
+//   k_tile_aggregate      per-tile summary of the segmented payload scan
+//   k_scan_aggregates     exclusive scan of the tile summaries (+ totals)
+//   k_write_payload       re-scans each tile with its carry-in and writes stems, numPlies
+//                         fields and movetext bits at their final *payload* offsets
+//   k_chunk_orbit         replays the writer's greedy chunk-flush rule (:1076-1080) over the
+//                         chain-head offsets
+//   k_emit_chunks         inserts the 8-byte BINP headers (:486-498)
+//
+// Each record's bit string depends only on its own position/move/score and the previous
+// record's score, so the encode is record-parallel; only bit offsets need a scan.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nnp {
+
+// ------------------------------------------------------------------ K1
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_TILE = K1_THREADS - 1;  // thread 0 decodes the halo record (predecessor of the tile)
+
+struct K1Shared {
+    __align__(16) u32 raw[K1_THREADS * 10 + 4];
+    u64 occ0[K1_THREADS], occ1[K1_THREADS], t0[K1_THREADS], t1[K1_THREADS], t2[K1_THREADS];
+    u32 meta[K1_THREADS];   // stm | ep << 1 | cr << 8 | ok << 16
+    u32 w8[K1_THREADS];     // score | move << 16
+    u32 w9[K1_THREADS];     // gamePly | result << 16
+};
+
+__global__ void __launch_bounds__(K1_THREADS)
+k_decode_link_encode(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ codes,
+                     u32* __restrict__ stems, CompressTotals* tot)
+{
+    __shared__ K1Shared sh;
+    const int t = threadIdx.x;
+    const long long first = (long long)blockIdx.x * K1_TILE - 1;  // record handled by thread 0
+    const long long rec = first + t;
+
+    // coalesced 8-byte loads of the tile (+halo) into shared memory
+    {
+        const u64 lo = first < 0 ? 0ull : (u64)first;
+        u64 hi = (u64)(first + K1_THREADS);
+        if (hi > n) hi = n;
+        const uint2* src = reinterpret_cast<const uint2*>(bin + lo * 40);
+        const int nvec = (int)(hi - lo) * 5;
+        uint2* dst = reinterpret_cast<uint2*>(sh.raw) + (int)((long long)lo - first) * 5;
+        for (int i = t; i < nvec; i += K1_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    const bool valid = rec >= 0 && (u64)rec < n;
+    Pos p;
+    pos_clear(p);
+    bool ok = true;
+    const u32* w = sh.raw + t * 10;
+    u32 w8 = 0, w9 = 0;
+    if (valid) {
+        ok = sfen_decode([&](int j) { return w[j]; }, p);
+        w8 = w[8];
+        w9 = w[9];
+        if (!ok) atomicMin(&tot->error_index, (u64)rec);
+    }
+    sh.occ0[t] = p.occ[0]; sh.occ1[t] = p.occ[1];
+    sh.t0[t] = p.t0; sh.t1[t] = p.t1; sh.t2[t] = p.t2;
+    sh.meta[t] = (u32)p.stm | ((u32)p.ep << 1) | ((u32)p.cr << 8) | ((u32)ok << 16);
+    sh.w8[t] = w8;
+    sh.w9[t] = w9;
+    __syncthreads();
+
+    if (!valid || t == 0) return;
+
+    const int score = (int)(short)(w8 & 0xFFFF);
+    const Move mv = sfmove_to_move(w8 >> 16);
+    const int ply = (int)(w9 & 0xFFFF);
+    const int result = (int)(signed char)((w9 >> 16) & 0xFF);
+
+    bool cont = false;
+    int prev_score = 0;
+    if (rec > 0 && ok) {
+        // isContinuation (compress_file.cpp:587-593), short-circuit order preserved
+        const u32 pw8 = sh.w8[t - 1], pw9 = sh.w9[t - 1], pmeta = sh.meta[t - 1];
+        prev_score = (int)(short)(pw8 & 0xFFFF);
+        const int prev_ply = (int)(pw9 & 0xFFFF);
+        const int prev_result = (int)(signed char)((pw9 >> 16) & 0xFF);
+        if (prev_result == -result && prev_ply + 1 == ply && ((pmeta >> 16) & 1)) {
+            Pos a;
+            a.occ[0] = sh.occ0[t - 1]; a.occ[1] = sh.occ1[t - 1];
+            a.t0 = sh.t0[t - 1]; a.t1 = sh.t1[t - 1]; a.t2 = sh.t2[t - 1];
+            a.stm = pmeta & 1; a.ep = (pmeta >> 1) & 127; a.cr = (pmeta >> 8) & 15;
+            a.rule50 = 0; a.ply = 0;
+            pos_do_move(a, sfmove_to_move(pw8 >> 16));  // Position::afterMove
+            cont = pos_equal(a, p);
+        }
+    }
+    u32 code = 0;
+    if (cont) {
+        int nbits;
+        const int last_score = (int)(short)(-prev_score);  // m_lastScore (:838, :986)
+        const u32 bits = encode_ply(p, mv, score, last_score, nbits);
+        code = bits | (1u << (31 - nbits));  // sentinel-terminated, never zero
+    } else {
+        u32 s[8];
+        stem_pack(p, mv, score, ply, result, s);
+        uint4* d = reinterpret_cast<uint4*>(stems + (u64)rec * 8);
+        d[0] = make_uint4(s[0], s[1], s[2], s[3]);
+        d[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    }
+    codes[rec] = code;
+}
+
+// ------------------------------------------------------------------ payload scan
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int code_bits(u32 code) { return 32 - __ffs((int)code); }  // sentinel position
+
+__device__ __forceinline__ Agg agg_identity()
+{
+    Agg a;
+    a.bytes = 0; a.pre_bits = a.pre_plies = a.post_bits = a.post_plies = a.heads = a.pad = 0;
+    return a;
+}
+__device__ __forceinline__ Agg agg_of_code(u32 code)
+{
+    Agg a = agg_identity();
+    if (code == 0) { a.bytes = 34; a.heads = 1; }
+    else { a.pre_bits = (u32)code_bits(code); a.pre_plies = 1; }
+    return a;
+}
+__device__ __forceinline__ Agg agg_shfl_up(const Agg& a, int delta)
+{
+    Agg r;
+    r.bytes = __shfl_up_sync(0xffffffffu, a.bytes, delta);
+    r.pre_bits = __shfl_up_sync(0xffffffffu, a.pre_bits, delta);
+    r.pre_plies = __shfl_up_sync(0xffffffffu, a.pre_plies, delta);
+    r.post_bits = __shfl_up_sync(0xffffffffu, a.post_bits, delta);
+    r.post_plies = __shfl_up_sync(0xffffffffu, a.post_plies, delta);
+    r.heads = __shfl_up_sync(0xffffffffu, a.heads, delta);
+    r.pad = 0;
+    return r;
+}
+
+// Block-wide exclusive scan of one Agg per thread with the (non-commutative) agg_combine.
+// Returns the exclusive prefix of the calling thread; `total` receives the block aggregate.
+template <int THREADS>
+__device__ __forceinline__ Agg block_exclusive_scan(const Agg& local, Agg& total, Agg* warp_tot /* [THREADS/32] shared */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    Agg inc = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Agg o = agg_shfl_up(inc, d);
+        if (lane >= d) inc = agg_combine(o, inc);
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    Agg wprefix = agg_identity();
+    Agg all = agg_identity();
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) {
+        if (i == wid) wprefix = all;
+        all = agg_combine(all, warp_tot[i]);
+    }
+    total = all;
+    Agg exc = agg_shfl_up(inc, 1);
+    if (lane == 0) exc = agg_identity();
+    __syncthreads();
+    return agg_combine(wprefix, exc);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_tile_aggregate(const u32* __restrict__ codes, u64 n, Agg* __restrict__ tile_agg)
+{
+    __shared__ Agg warp_tot[SCAN_THREADS / 32];
+    const u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    Agg local = agg_identity();
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) local = agg_combine(local, agg_of_code(codes[base + i]));
+    }
+    Agg total;
+    block_exclusive_scan<SCAN_THREADS>(local, total, warp_tot);
+    if (threadIdx.x == 0) tile_agg[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the tile aggregates in place + totals
+constexpr int AGGSCAN_THREADS = 1024;
+__global__ void __launch_bounds__(AGGSCAN_THREADS)
+k_scan_aggregates(Agg* __restrict__ tile_agg, u64 ntiles, CompressTotals* tot)
+{
+    __shared__ Agg warp_tot[AGGSCAN_THREADS / 32];
+    const u64 per = (ntiles + AGGSCAN_THREADS - 1) / AGGSCAN_THREADS;
+    const u64 lo = (u64)threadIdx.x * per;
+    u64 hi = lo + per;
+    if (hi > ntiles) hi = ntiles;
+    Agg local = agg_identity();
+    for (u64 i = lo; i < hi; ++i) local = agg_combine(local, tile_agg[i]);
+    Agg total;
+    Agg run = block_exclusive_scan<AGGSCAN_THREADS>(local, total, warp_tot);
+    for (u64 i = lo; i < hi; ++i) {
+        Agg v = tile_agg[i];
+        tile_agg[i] = run;
+        run = agg_combine(run, v);
+    }
+    if (threadIdx.x == 0) {
+        tot->payload_bytes = total.heads ? total.bytes + ceil8(total.post_bits) : 0;
+        tot->heads = total.heads;
+    }
+}
+
+// ---- byte/bit writers into the zero-initialised payload (all writes are ORs, so ragged
+// edges shared between threads, warps and blocks need no ownership protocol)
+
+__device__ __forceinline__ u32 bswap32(u32 v) { return __byte_perm(v, 0, 0x0123); }
+
+// `code` holds n bits MSB-first, left-aligned; bitpos counts MSB-first bits from payload byte 0
+__device__ __forceinline__ void or_bits(u32* payload, u64 bitpos, u32 code_left, int n)
+{
+    const u64 word = bitpos >> 5;
+    const int k = (int)(bitpos & 31);
+    atomicOr(payload + word, bswap32(code_left >> k));
+    if (k + n > 32) atomicOr(payload + word + 1, bswap32(code_left << (32 - k)));
+}
+__device__ __forceinline__ void or_byte(u32* payload, u64 bytepos, u32 v)
+{
+    atomicOr(payload + (bytepos >> 2), (v & 0xFF) << ((bytepos & 3) * 8));
+}
+// eight memory-order words at an arbitrary byte offset
+__device__ __forceinline__ void or_words8(u32* payload, u64 bytepos, const uint4& a, const uint4& b)
+{
+    const u32 w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    u32* dst = payload + (bytepos >> 2);
+    const int sh = (int)(bytepos & 3) * 8;
+    if (sh == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicOr(dst + i, w[i]);
+    } else {
+        u32 carry = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            atomicOr(dst + i, (w[i] << sh) | carry);
+            carry = w[i] >> (32 - sh);
+        }
+        atomicOr(dst + 8, carry);
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_write_payload(const u32* __restrict__ codes, const u32* __restrict__ stems, u64 n,
+                const Agg* __restrict__ tile_prefix, u32* __restrict__ payload, u64* __restrict__ head_off)
+{
+    __shared__ Agg warp_tot[SCAN_THREADS / 32];
+    const u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    u32 c[SCAN_ITEMS];
+    Agg local = agg_identity();
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        c[i] = 1u << 31;  // harmless zero-bit continuation for out-of-range slots
+        if (base + i < n) {
+            c[i] = codes[base + i];
+            local = agg_combine(local, agg_of_code(c[i]));
+        }
+    }
+    Agg total;
+    const Agg exc = block_exclusive_scan<SCAN_THREADS>(local, total, warp_tot);
+    const Agg st = agg_combine(tile_prefix[blockIdx.x], exc);
+    // running writer state before this thread's first record: movetext start of the open
+    // chain (payload bytes), its bits and plies so far, and the number of heads seen
+    u64 M = st.bytes;
+    u32 ob = st.post_bits, op = st.post_plies;
+    u64 h = st.heads;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        const u64 rec = base + i;
+        if (rec >= n) break;
+        if (c[i] == 0) {
+            u64 P = 0;
+            if (h > 0) {
+                P = M + ceil8(ob);
+                // numPlies of the chain that just ended, big-endian (:1118-1119)
+                or_byte(payload, M - 2, op >> 8);
+                or_byte(payload, M - 1, op);
+            }
+            const uint4* s = reinterpret_cast<const uint4*>(stems + rec * 8);
+            or_words8(payload, P, s[0], s[1]);
+            head_off[h] = P;
+            M = P + 34;
+            ob = 0;
+            op = 0;
+            ++h;
+        } else {
+            const int nb = code_bits(c[i]);
+            or_bits(payload, M * 8 + ob, c[i] & ~(1u << (31 - nb)), nb);
+            ob += nb;
+            op = (op + 1) & 0xFFFF;  // std::uint16_t numPlies
+        }
+        if (rec == n - 1) {  // ~CompressedTrainingDataEntryWriter (:1094-1106): last movelist
+            or_byte(payload, M - 2, op >> 8);
+            or_byte(payload, M - 1, op);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ chunk orbit
+//
+// The writer flushes a chunk when a new chain head arrives and the bytes gathered since the
+// last flush reached 1 MiB (:1076-1080). With P[h] the payload offset of head h that is the
+// orbit b0 = 0, b(k+1) = min{h : P[h] - P[b(k)] >= 2^20}; one warp follows it with a 32-ary
+// search per hop. chunk_off[k] = P[b(k)], chunk_off[K] = payload size.
+__global__ void __launch_bounds__(32)
+k_chunk_orbit(const u64* __restrict__ head_off, CompressTotals* tot, u64* __restrict__ chunk_off, u64 max_chunks)
+{
+    const int lane = threadIdx.x;
+    const u64 H = tot->heads;
+    const u64 total = tot->payload_bytes;
+    u64 k = 0;
+    if (H > 0) {
+        u64 cur = 0;  // head index of the current chunk start
+        for (;;) {
+            if (lane == 0 && k < max_chunks) chunk_off[k] = head_off[cur];
+            ++k;
+            const u64 target = head_off[cur] + CHUNK_THRESHOLD;
+            if (target > total) break;  // no head can reach it (P[h] < total)
+            // first h in (cur, H) with head_off[h] >= target
+            u64 lo = cur + 1, hi = H;  // answer in [lo, hi]; hi == H means none
+            while (lo < hi) {
+                const u64 span = hi - lo;
+                const u64 step = (span + 32) / 33;  // 32 probes split the range into 33 parts
+                const u64 probe = lo + (u64)(lane + 1) * step - 1;
+                const bool ge = probe < hi ? (head_off[probe] >= target) : true;
+                const u32 m = __ballot_sync(0xffffffffu, ge);
+                const int f = __ffs((int)m) - 1;  // first lane whose probe is >= target (always exists)
+                const u64 new_hi = lo + (u64)(f + 1) * step - 1;
+                const u64 new_lo = f == 0 ? lo : lo + (u64)f * step;
+                hi = new_hi < hi ? new_hi : hi;
+                lo = new_lo;
+            }
+            if (lo >= H) break;
+            cur = lo;
+        }
+    }
+    if (lane == 0) {
+        if (k <= max_chunks) chunk_off[k < max_chunks ? k : max_chunks] = total;
+        tot->chunks = k;
+    }
+}
+
+// ------------------------------------------------------------------ chunk emission
+// grid = (EMIT_BLOCKS_PER_CHUNK, chunks): copies payload [chunk_off[k], chunk_off[k+1]) behind
+// its 8-byte header 'B','I','N','P',LE32(size) (:486-498). Source and destination differ by
+// 8(k+1) bytes, so they share their alignment and the body moves as aligned 16-byte vectors.
+constexpr int EMIT_THREADS = 256;
+__global__ void __launch_bounds__(EMIT_THREADS)
+k_emit_chunks(const unsigned char* __restrict__ payload, const u64* __restrict__ chunk_off,
+              unsigned char* __restrict__ out)
+{
+    const u64 k = blockIdx.y;
+    const u64 s0 = chunk_off[k], s1 = chunk_off[k + 1];
+    const u64 size = s1 - s0;
+    unsigned char* dst = out + s0 + 8 * k;
+    if (blockIdx.x == 0 && threadIdx.x < 8) {
+        const unsigned char hdr[8] = {'B', 'I', 'N', 'P', (unsigned char)size, (unsigned char)(size >> 8),
+                                      (unsigned char)(size >> 16), (unsigned char)(size >> 24)};
+        dst[threadIdx.x] = hdr[threadIdx.x];
+    }
+    dst += 8;
+    const unsigned char* src = payload + s0;
+    // head bytes up to 16-byte alignment of src (dst - src = 8(k+1): same alignment mod 8)
+    const u64 tid = (u64)blockIdx.x * EMIT_THREADS + threadIdx.x;
+    const u64 nthreads = (u64)gridDim.x * EMIT_THREADS;
+    u64 head = (8 - ((uintptr_t)src & 7)) & 7;
+    if (head > size) head = size;
+    for (u64 i = tid; i < head; i += nthreads) dst[i] = src[i];
+    const u64 nvec = (size - head) >> 3;
+    const uint2* s8 = reinterpret_cast<const uint2*>(src + head);
+    uint2* d8 = reinterpret_cast<uint2*>(dst + head);
+    for (u64 i = tid; i < nvec; i += nthreads) d8[i] = s8[i];
+    const u64 tail0 = head + (nvec << 3);
+    for (u64 i = tail0 + tid; i < size; i += nthreads) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------ host launchers
+
+void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, cudaStream_t s)
+{
+    if (n == 0) return;
+    const u64 blocks = (n + K1_TILE - 1) / K1_TILE;
+    k_decode_link_encode<<<(unsigned)blocks, K1_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems, tot);
+}
+u64 scan_tiles(u64 n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+void launch_tile_aggregate(const u32* codes, u64 n, Agg* tile_agg, cudaStream_t s)
+{
+    if (n == 0) return;
+    k_tile_aggregate<<<(unsigned)scan_tiles(n), SCAN_THREADS, 0, s>>>(codes, n, tile_agg);
+}
+void launch_scan_aggregates(Agg* tile_agg, u64 ntiles, CompressTotals* tot, cudaStream_t s)
+{
+    k_scan_aggregates<<<1, AGGSCAN_THREADS, 0, s>>>(tile_agg, ntiles, tot);
+}
+void launch_write_payload(const u32* codes, const u32* stems, u64 n, const Agg* tile_prefix, u32* payload,
+                          u64* head_off, cudaStream_t s)
+{
+    if (n == 0) return;
+    k_write_payload<<<(unsigned)scan_tiles(n), SCAN_THREADS, 0, s>>>(codes, stems, n, tile_prefix, payload, head_off);
+}
+void launch_chunk_orbit(const u64* head_off, CompressTotals* tot, u64* chunk_off, u64 max_chunks, cudaStream_t s)
+{
+    k_chunk_orbit<<<1, 32, 0, s>>>(head_off, tot, chunk_off, max_chunks);
+}
+void launch_emit_chunks(const void* payload, const u64* chunk_off, u64 chunks, void* out, cudaStream_t s)
+{
+    if (chunks == 0) return;
+    dim3 grid(8, (unsigned)chunks);
+    k_emit_chunks<<<grid, EMIT_THREADS, 0, s>>>((const unsigned char*)payload, chunk_off, (unsigned char*)out);
+}
+
+}  // namespace nnp

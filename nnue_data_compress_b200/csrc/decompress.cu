@@ -1,0 +1,453 @@
+// decompress.cu -- .binpack -> .bin kernels (decompressBin, compress_file.cpp:1376-1412, and the
+// CompressedTrainingDataEntryReader it drives, :1128-1214).
+//
+// The reference walks a chunk strictly sequentially: chain k+1 starts where chain k's
+// movetext ends, and that length is only known after decoding it (:815-818). Chunk-level
+// parallelism (a few hundred chunks) cannot feed 148 SMs, so the chains are found
+// speculatively instead:
+//
+//   k_walk_chunks      one thread follows the 8-byte BINP headers (:500-521)
+//   k_candidates<0/1>  every byte offset of every chunk is tested for "could be a stem the
+//                      reference writer emits"; pass 0 counts per tile, pass 1 lists the
+//                      survivors in file order
+//   k_probe_chains     one thread per candidate decodes its chain far enough to learn where it
+//                      ends (strict mode: ids the encoder cannot produce kill a false candidate)
+//   k_resolve_chunks   per chunk, follows offset 0 -> next -> next ... through the candidate
+//                      list, marks the real chains and counts their positions; a chunk whose
+//                      walk leaves the candidate set is flagged for the sequential fallback
+//   k_slow_count       sequential per-chunk walk for flagged chunks (correctness net; never
+//                      taken for files the reference itself wrote from legal-move data)
+//   k_emit_chains      one thread per real chain: doMove / nextMoveScore per ply (:669-813) and
+//                      SfenPacker::pack (:266-312) into the final 40-byte records
+//   k_slow_emit        the same, sequentially, for flagged chunks
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nnp {
+
+// ------------------------------------------------------------------ small block scan (u32)
+
+template <int THREADS>
+__device__ __forceinline__ u32 block_exclusive_sum(u32 v, u32& total, u32* warp_tot /* [THREADS/32] shared */)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u32 inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    u32 wprefix = 0, all = 0;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) {
+        if (i == wid) wprefix = all;
+        all += warp_tot[i];
+    }
+    total = all;
+    __syncthreads();
+    return wprefix + inc - v;
+}
+
+// single block: out[i] = sum of in[0..i) as u64, out[n] = total
+constexpr int SUM_THREADS = 1024;
+__global__ void __launch_bounds__(SUM_THREADS)
+k_exclusive_sum(const u32* __restrict__ in, u64 n, u64* __restrict__ out)
+{
+    __shared__ u64 part[SUM_THREADS];
+    const u64 per = (n + SUM_THREADS - 1) / SUM_THREADS;
+    const u64 lo = (u64)threadIdx.x * per;
+    u64 hi = lo + per;
+    if (hi > n) hi = n;
+    u64 s = 0;
+    for (u64 i = lo; i < hi; ++i) s += in[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 run = 0;
+        for (int i = 0; i < SUM_THREADS; ++i) {
+            const u64 v = part[i];
+            part[i] = run;
+            run += v;
+        }
+        out[n] = run;
+    }
+    __syncthreads();
+    u64 run = part[threadIdx.x];
+    for (u64 i = lo; i < hi; ++i) {
+        out[i] = run;
+        run += in[i];
+    }
+}
+
+// ------------------------------------------------------------------ chunk table
+
+__global__ void k_walk_chunks(const unsigned char* __restrict__ in, u64 n, ChunkTable tab, u64 max_chunks)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    u64 pos = 0, k = 0, tiles = 0;
+    int status = 0;
+    while (pos < n) {  // hasNextChunk: peek() / eof (:468-472)
+        if (n - pos < 8 || in[pos] != 'B' || in[pos + 1] != 'I' || in[pos + 2] != 'N' || in[pos + 3] != 'P') {
+            status = -1;  // NNP_ERR_BAD_MAGIC (:504-507)
+            break;
+        }
+        const u32 size = (u32)in[pos + 4] | ((u32)in[pos + 5] << 8) | ((u32)in[pos + 6] << 16) | ((u32)in[pos + 7] << 24);
+        if (size > MAX_CHUNK_SIZE) { status = -2; break; }            // NNP_ERR_CHUNK_TOO_LARGE (:515-518)
+        if (n - pos - 8 < size || size < 34) { status = -4; break; }  // NNP_ERR_TRUNCATED
+        if (k < max_chunks) {
+            tab.start[k] = pos + 8;
+            tab.len[k] = size;
+            tab.tile_base[k] = tiles;
+            tiles += ((u64)size + CAND_TILE - 1) / CAND_TILE;
+        }
+        ++k;
+        pos += 8 + (u64)size;
+    }
+    if (k <= max_chunks) tab.tile_base[k] = tiles;
+    tab.info->chunks = k;
+    tab.info->status = status;
+    tab.info->tiles = tiles;
+}
+
+// ------------------------------------------------------------------ candidate discovery
+
+constexpr int CAND_THREADS = 256;
+constexpr int CAND_ROUNDS = CAND_TILE / CAND_THREADS;  // 16
+
+// Could the 34 bytes at s[0..34) be a stem + numPlies as written by packEntry (:997-1020) from
+// a position with exactly one white and one black king? Everything tested here is guaranteed
+// for such stems: rule50 is a uint8_t stored big-endian in 16 bits (byte 30 == 0), at most 32
+// squares are occupied, unused nibbles stay zero (CompressedPosition() zero-initialises
+// m_packedState, Position.h:1218-1222), nibble 10 appears once and 11/15 together once.
+// A real stem that fails the test (possible only for inputs outside that domain) merely sends
+// its chunk to the sequential fallback.
+__device__ __forceinline__ bool plausible_stem(const unsigned char* s)
+{
+    if (s[30] != 0) return false;
+    u64 occ = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) occ = (occ << 8) | s[i];
+    const int n = popc64(occ);
+    if (n < 2 || n > 32) return false;
+    int wk = 0, bk = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const u32 b = s[8 + i];
+        const int lo = b & 15, hi = b >> 4;
+        if (2 * i < n) { wk += (lo == 10); bk += (lo == 11 || lo == 15); } else if (lo) return false;
+        if (2 * i + 1 < n) { wk += (hi == 10); bk += (hi == 11 || hi == 15); } else if (hi) return false;
+    }
+    return wk == 1 && bk == 1;
+}
+
+__device__ __forceinline__ u64 find_chunk(const u64* base, u64 chunks, u64 tile)
+{
+    u64 lo = 0, hi = chunks;  // last c with base[c] <= tile
+    while (hi - lo > 1) {
+        const u64 mid = (lo + hi) >> 1;
+        if (base[mid] <= tile) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// WRITE == false: tile_count[tile] = number of plausible offsets in the tile
+// WRITE == true : lists them at cand_*[tile_prefix[tile] ...] in ascending offset order
+template <bool WRITE>
+__global__ void __launch_bounds__(CAND_THREADS)
+k_candidates(const unsigned char* __restrict__ in, ChunkTable tab, u32* __restrict__ tile_count,
+             const u64* __restrict__ tile_prefix, u32* __restrict__ cand_chunk, u32* __restrict__ cand_off,
+             u32 debug_reject_mod)
+{
+    __shared__ __align__(16) unsigned char sm[CAND_TILE + 48];
+    __shared__ u32 flags[CAND_TILE / 32];
+    __shared__ u32 warp_tot[CAND_THREADS / 32];
+    const u64 tile = blockIdx.x;
+    const u64 c = find_chunk(tab.tile_base, tab.info->chunks, tile);
+    const u64 clen = tab.len[c];
+    const u64 off0 = (tile - tab.tile_base[c]) * CAND_TILE;
+    const unsigned char* src = in + tab.start[c] + off0;
+    const u64 avail = clen - off0;  // > 0 by construction
+    const int nload = (int)(avail < (u64)(CAND_TILE + 34) ? avail : (u64)(CAND_TILE + 34));
+    for (int i = threadIdx.x; i < nload; i += CAND_THREADS) sm[i] = src[i];
+    __syncthreads();
+    // round j tests offsets j*256 + thread: a warp covers 32 consecutive offsets, and its
+    // ballot is exactly word (j*8 + warp) of the tile's flag bitmap
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll 4
+    for (int j = 0; j < CAND_ROUNDS; ++j) {
+        const int o = j * CAND_THREADS + threadIdx.x;
+        bool ok = false;
+        if ((u64)o + 34 <= avail) {
+            ok = plausible_stem(sm + o);
+            // test hook: drop a pseudo-random subset of candidates to exercise the fallback
+            if (debug_reject_mod && (u32)(((off0 + (u64)o) * 2654435761ull) >> 11) % debug_reject_mod == 0) ok = false;
+        }
+        const u32 b = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) flags[j * (CAND_THREADS / 32) + wid] = b;
+    }
+    __syncthreads();
+    u32 word = threadIdx.x < CAND_TILE / 32 ? flags[threadIdx.x] : 0u;
+    u32 total;
+    const u32 rank0 = block_exclusive_sum<CAND_THREADS>(__popc(word), total, warp_tot);
+    if (!WRITE) {
+        if (threadIdx.x == 0) tile_count[tile] = total;
+        return;
+    }
+    u64 slot = tile_prefix[tile] + rank0;
+    while (word) {
+        const int b = __ffs((int)word) - 1;
+        word &= word - 1;
+        cand_chunk[slot] = (u32)c;
+        cand_off[slot] = (u32)(off0 + (u64)threadIdx.x * 32 + b);
+        ++slot;
+    }
+}
+
+// ------------------------------------------------------------------ chain walking
+
+struct ChainCursor {
+    Pos pos;
+    Move mv;
+    int score, ply, result;
+    int last_score;
+    u32 num_plies;
+};
+
+__device__ __forceinline__ void chain_open(const unsigned char* s, ChainCursor& c)
+{
+    stem_unpack([&](int i) { return (u32)s[i]; }, c.pos, c.mv, c.score, c.ply, c.result);
+    c.num_plies = ((u32)s[32] << 8) | (u32)s[33];
+    c.last_score = (int)(short)(-c.score);  // PackedMoveScoreListReader ctor (:618)
+}
+
+// PackedMoveScoreListReader::nextEntry (:669-678)
+__device__ __forceinline__ bool chain_step(ChainCursor& c, BitReader& r, bool strict)
+{
+    if (strict && (c.mv.from > 63 || c.mv.to > 63)) return false;  // null move followed by plies
+    pos_do_move(c.pos, c.mv);
+    Move m;
+    int sc;
+    if (!decode_ply(r, c.pos, c.last_score, m, sc, strict)) return false;
+    c.mv = m;
+    c.score = sc;
+    c.ply = (c.ply + 1) & 0xFFFF;
+    c.result = (int)(short)(-c.result);
+    return true;
+}
+
+// one thread per candidate: where does its chain end?
+constexpr int PROBE_THREADS = 128;
+__global__ void __launch_bounds__(PROBE_THREADS)
+k_probe_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
+               const u32* __restrict__ cand_off, u64 ncand, u32* __restrict__ cand_next)
+{
+    const u64 i = (u64)blockIdx.x * PROBE_THREADS + threadIdx.x;
+    if (i >= ncand) return;
+    const u32 c = cand_chunk[i], off = cand_off[i];
+    const u32 clen = tab.len[c];
+    const unsigned char* s = in + tab.start[c] + off;
+    ChainCursor cc;
+    chain_open(s, cc);
+    u32 next = off + 34;
+    bool ok = true;
+    if (cc.num_plies > 0) {
+        // the stored first move must start on a piece of the side to move
+        const int pc = cc.mv.from < 64 ? pos_piece_at(cc.pos, cc.mv.from) : NO_PIECE;
+        if (pc == NO_PIECE || (pc & 1) != cc.pos.stm) ok = false;
+        BitReader r;
+        r.p = s + 34;
+        const u64 avail_bits = (u64)(clen - off - 34) * 8;
+        r.nbits = avail_bits > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)avail_bits;
+        r.pos = 0;
+        r.overrun = false;
+        for (u32 k = 0; ok && k < cc.num_plies; ++k) ok = chain_step(cc, r, true);
+        next = off + 34 + ((r.pos + 7) >> 3);  // numReadBytes (:815-818)
+    }
+    cand_next[i] = ok ? next : 0xFFFFFFFFu;
+}
+
+// one thread per chunk: Reader::next / fetchNextChunkIfNeeded (:1154-1213) over the candidates
+constexpr int RESOLVE_THREADS = 64;
+__global__ void __launch_bounds__(RESOLVE_THREADS)
+k_resolve_chunks(const unsigned char* __restrict__ in, ChunkTable tab, const u64* __restrict__ tile_prefix,
+                 const u32* __restrict__ cand_off, const u32* __restrict__ cand_next, u32* __restrict__ cand_base,
+                 u32* __restrict__ chunk_count, u32* __restrict__ chunk_slow)
+{
+    const u64 c = (u64)blockIdx.x * RESOLVE_THREADS + threadIdx.x;
+    if (c >= tab.info->chunks) return;
+    const u64 cb = tile_prefix[tab.tile_base[c]], ce = tile_prefix[tab.tile_base[c + 1]];
+    const u32 clen = tab.len[c];
+    const unsigned char* base = in + tab.start[c];
+    u64 i = cb;
+    u32 cur = 0, count = 0;
+    bool slow = false;
+    while ((u64)cur + 34 <= clen) {
+        while (i < ce && cand_off[i] < cur) { cand_base[i] = 0xFFFFFFFFu; ++i; }  // false positive inside a chain
+        if (i >= ce || cand_off[i] != cur || cand_next[i] == 0xFFFFFFFFu) { slow = true; break; }
+        cand_base[i] = count;
+        count += 1u + (((u32)base[cur + 32] << 8) | (u32)base[cur + 33]);
+        cur = cand_next[i];
+        ++i;
+    }
+    for (; i < ce; ++i) cand_base[i] = 0xFFFFFFFFu;
+    if (slow) {
+        for (u64 k = cb; k < ce; ++k) cand_base[k] = 0xFFFFFFFFu;
+        count = 0;  // filled in by k_slow_count
+    }
+    chunk_count[c] = count;
+    chunk_slow[c] = slow ? 1u : 0u;
+}
+
+// ------------------------------------------------------------------ record emission
+
+__device__ __forceinline__ void emit_bin_record(const ChainCursor& c, unsigned char* out, u64 rec)
+{
+    u32 w[10];
+    sfen_encode(c.pos, w);
+    // trainingDataEntryToPackedSfenValue (:570-585): score, move, gamePly, result, padding 0xFF
+    w[8] = ((u32)c.score & 0xFFFFu) | (move_to_sfmove(c.mv) << 16);
+    w[9] = ((u32)c.ply & 0xFFFFu) | (((u32)c.result & 0xFFu) << 16) | 0xFF000000u;
+    uint2* d = reinterpret_cast<uint2*>(out + rec * 40);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) d[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+}
+
+// walks one chain from its stem, calling emit(cursor, k) for k = 0..numPlies; returns false when
+// the movetext runs off the chunk
+template <typename EmitFn>
+__device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_after_stem, EmitFn emit, u32& consumed)
+{
+    ChainCursor cc;
+    chain_open(s, cc);
+    emit(cc, 0u);
+    BitReader r;
+    r.p = s + 34;
+    const u64 avail_bits = (u64)bytes_after_stem * 8;
+    r.nbits = avail_bits > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)avail_bits;
+    r.pos = 0;
+    r.overrun = false;
+    for (u32 k = 0; k < cc.num_plies; ++k) {
+        if (cc.mv.from > 63 || cc.mv.to > 63) return false;
+        if (!chain_step(cc, r, false)) return false;
+        emit(cc, k + 1);
+    }
+    consumed = 34 + ((r.pos + 7) >> 3);
+    return true;
+}
+
+constexpr int EMITC_THREADS = 128;
+__global__ void __launch_bounds__(EMITC_THREADS)
+k_emit_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
+              const u32* __restrict__ cand_off, const u32* __restrict__ cand_base, u64 ncand,
+              const u64* __restrict__ chunk_base, unsigned char* __restrict__ out, DecompressTotals* tot)
+{
+    const u64 i = (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
+    if (i >= ncand) return;
+    const u32 b = cand_base[i];
+    if (b == 0xFFFFFFFFu) return;
+    const u32 c = cand_chunk[i], off = cand_off[i];
+    const u64 rec0 = chunk_base[c] + b;
+    const unsigned char* s = in + tab.start[c] + off;
+    u32 consumed = 0;
+    const bool ok = walk_chain(s, tab.len[c] - off - 34,
+                               [&](const ChainCursor& cc, u32 k) { emit_bin_record(cc, out, rec0 + k); }, consumed);
+    if (!ok) atomicMin(&tot->error_chunk, (u64)c);
+}
+
+// sequential fallback, one thread per flagged chunk
+__global__ void k_slow_count(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ chunk_slow,
+                             u32* __restrict__ chunk_count, DecompressTotals* tot)
+{
+    const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= tab.info->chunks || !chunk_slow[c]) return;
+    const u32 clen = tab.len[c];
+    const unsigned char* base = in + tab.start[c];
+    u32 cur = 0, count = 0;
+    while ((u64)cur + 34 <= clen) {
+        u32 consumed = 0;
+        const bool ok = walk_chain(base + cur, clen - cur - 34, [&](const ChainCursor&, u32) { ++count; }, consumed);
+        if (!ok) { atomicMin(&tot->error_chunk, (u64)c); break; }
+        cur += consumed;
+    }
+    chunk_count[c] = count;
+    atomicAdd(&tot->slow_chunks, 1ull);
+}
+__global__ void k_slow_emit(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ chunk_slow,
+                            const u64* __restrict__ chunk_base, unsigned char* __restrict__ out)
+{
+    const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= tab.info->chunks || !chunk_slow[c]) return;
+    const u32 clen = tab.len[c];
+    const unsigned char* base = in + tab.start[c];
+    u32 cur = 0;
+    u64 rec = chunk_base[c];
+    const u64 rec_end = chunk_base[c + 1];
+    while ((u64)cur + 34 <= clen) {
+        u32 consumed = 0;
+        const bool ok = walk_chain(base + cur, clen - cur - 34,
+                                   [&](const ChainCursor& cc, u32) { if (rec < rec_end) emit_bin_record(cc, out, rec); ++rec; },
+                                   consumed);
+        if (!ok) break;
+        cur += consumed;
+    }
+}
+
+// ------------------------------------------------------------------ host launchers
+
+void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks, cudaStream_t s)
+{
+    k_walk_chunks<<<1, 32, 0, s>>>((const unsigned char*)d_in, n, tab, max_chunks);
+}
+void launch_candidates(bool write, const void* d_in, ChunkTable tab, u64 tiles, u32* tile_count, const u64* tile_prefix,
+                       u32* cand_chunk, u32* cand_off, u32 debug_reject_mod, cudaStream_t s)
+{
+    if (tiles == 0) return;
+    if (write)
+        k_candidates<true><<<(unsigned)tiles, CAND_THREADS, 0, s>>>((const unsigned char*)d_in, tab, tile_count, tile_prefix,
+                                                                   cand_chunk, cand_off, debug_reject_mod);
+    else
+        k_candidates<false><<<(unsigned)tiles, CAND_THREADS, 0, s>>>((const unsigned char*)d_in, tab, tile_count, tile_prefix,
+                                                                    cand_chunk, cand_off, debug_reject_mod);
+}
+void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s)
+{
+    k_exclusive_sum<<<1, SUM_THREADS, 0, s>>>(in, n, out);
+}
+void launch_probe_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u64 ncand,
+                         u32* cand_next, cudaStream_t s)
+{
+    if (ncand == 0) return;
+    k_probe_chains<<<(unsigned)((ncand + PROBE_THREADS - 1) / PROBE_THREADS), PROBE_THREADS, 0, s>>>(
+        (const unsigned char*)d_in, tab, cand_chunk, cand_off, ncand, cand_next);
+}
+void launch_resolve_chunks(const void* d_in, ChunkTable tab, u64 chunks, const u64* tile_prefix, const u32* cand_off,
+                           const u32* cand_next, u32* cand_base, u32* chunk_count, u32* chunk_slow, cudaStream_t s)
+{
+    if (chunks == 0) return;
+    k_resolve_chunks<<<(unsigned)((chunks + RESOLVE_THREADS - 1) / RESOLVE_THREADS), RESOLVE_THREADS, 0, s>>>(
+        (const unsigned char*)d_in, tab, tile_prefix, cand_off, cand_next, cand_base, chunk_count, chunk_slow);
+}
+void launch_slow_count(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, u32* chunk_count,
+                       DecompressTotals* tot, cudaStream_t s)
+{
+    if (chunks == 0) return;
+    k_slow_count<<<(unsigned)((chunks + 31) / 32), 32, 0, s>>>((const unsigned char*)d_in, tab, chunk_slow, chunk_count, tot);
+}
+void launch_emit_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, const u32* cand_base,
+                        u64 ncand, const u64* chunk_base, void* out, DecompressTotals* tot, cudaStream_t s)
+{
+    if (ncand == 0) return;
+    k_emit_chains<<<(unsigned)((ncand + EMITC_THREADS - 1) / EMITC_THREADS), EMITC_THREADS, 0, s>>>(
+        (const unsigned char*)d_in, tab, cand_chunk, cand_off, cand_base, ncand, chunk_base, (unsigned char*)out, tot);
+}
+void launch_slow_emit(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, const u64* chunk_base, void* out,
+                      cudaStream_t s)
+{
+    if (chunks == 0) return;
+    k_slow_emit<<<(unsigned)((chunks + 31) / 32), 32, 0, s>>>((const unsigned char*)d_in, tab, chunk_slow, chunk_base,
+                                                              (unsigned char*)out);
+}
+
+}  // namespace nnp

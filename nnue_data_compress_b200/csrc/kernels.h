@@ -1,0 +1,48 @@
+// kernels.h -- host-side launchers of the libnnuepack kernels (one per kernel, no logic).
+#pragma once
+#include "common.cuh"
+
+namespace nnp {
+
+// ---- compress (.bin -> .binpack), compress.cu
+void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, cudaStream_t s);
+u64 scan_tiles(u64 n);
+void launch_tile_aggregate(const u32* codes, u64 n, Agg* tile_agg, cudaStream_t s);
+void launch_scan_aggregates(Agg* tile_agg, u64 ntiles, CompressTotals* tot, cudaStream_t s);
+void launch_write_payload(const u32* codes, const u32* stems, u64 n, const Agg* tile_prefix, u32* payload,
+                          u64* head_off, cudaStream_t s);
+void launch_chunk_orbit(const u64* head_off, CompressTotals* tot, u64* chunk_off, u64 max_chunks, cudaStream_t s);
+void launch_emit_chunks(const void* payload, const u64* chunk_off, u64 chunks, void* out, cudaStream_t s);
+
+// ---- decompress (.binpack -> .bin), decompress.cu
+constexpr int CAND_TILE = 4096;  // byte offsets tested per block of the candidate kernels
+
+struct ChunkInfo {
+    u64 chunks;  // chunks found (may exceed the table capacity: then re-walk with a larger table)
+    u64 tiles;   // candidate tiles over all stored chunks
+    int status;  // 0 or the nnp_status of the header that stopped the walk
+    int pad;
+};
+struct ChunkTable {
+    u64* start;      // file offset of the chunk payload
+    u32* len;        // payload bytes
+    u64* tile_base;  // [chunks + 1] exclusive prefix of candidate tiles
+    ChunkInfo* info;
+};
+
+void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks, cudaStream_t s);
+void launch_candidates(bool write, const void* d_in, ChunkTable tab, u64 tiles, u32* tile_count, const u64* tile_prefix,
+                       u32* cand_chunk, u32* cand_off, u32 debug_reject_mod, cudaStream_t s);
+void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s);
+void launch_probe_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u64 ncand,
+                         u32* cand_next, cudaStream_t s);
+void launch_resolve_chunks(const void* d_in, ChunkTable tab, u64 chunks, const u64* tile_prefix, const u32* cand_off,
+                           const u32* cand_next, u32* cand_base, u32* chunk_count, u32* chunk_slow, cudaStream_t s);
+void launch_slow_count(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, u32* chunk_count,
+                       DecompressTotals* tot, cudaStream_t s);
+void launch_emit_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, const u32* cand_base,
+                        u64 ncand, const u64* chunk_base, void* out, DecompressTotals* tot, cudaStream_t s);
+void launch_slow_emit(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, const u64* chunk_base, void* out,
+                      cudaStream_t s);
+
+}  // namespace nnp

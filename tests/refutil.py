@@ -95,3 +95,15 @@ def ref_generate(n, plies, seed, mode=0):
         subprocess.run([REF_GEN, p, str(n), str(plies), str(seed), str(mode)], check=True)
         with open(p, "rb") as f:
             return f.read()
+
+
+def golden(name):
+    """Reads tests/golden/<name>.gz (written by tests/golden/make_golden.py from the reference)."""
+    import gzip
+
+    with gzip.open(os.path.join(GOLDEN, name + ".gz"), "rb") as f:
+        return f.read()
+
+
+GOLDEN_SETS = ["games100", "heads", "long400", "shuffled", "restart", "twochunks"]
+GOLDEN_PLAIN_SETS = ["games100", "heads", "long400"]
