@@ -1,0 +1,483 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the conversion hot path (.bin -> .binpack and .binpack -> .bin).
+
+    python bench.py --gpus N --steps K --warmup W              # our CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
+
+One step = one pass of the hot path over one batch: `positions` synthetic positions
+(random legal-move games, ~100 plies per chain, generated on the device) are compressed
+.bin -> .binpack and the result is decompressed .binpack -> .bin. Both directions count, so
+the metric is (2 * positions) / step time in Mpos/s; per-direction numbers are reported too.
+
+value  : inputs resident in HBM, device pointers through the C ABI (*_dev entry points),
+         timed with CUDA events on the stream the kernels run on, max over ranks.
+e2e    : the same step through the host-buffer entry points (pinned host memory in, pinned
+         host memory out; H2D and D2H inside the timed region).
+roofline, cpu_baseline: see DESIGN.md "Measurement".
+
+N > 1 (torchrun, one rank per GPU): every rank converts its own shard (independent files, what
+the reference does with one run per shard and `-a`), no payload crosses NVLink; the only
+collective is an all-gather of the per-shard byte counts that gives each shard its offset in
+the concatenated output. Weak scaling: `positions` per GPU is fixed.
+"""
+import argparse
+import ctypes
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mpos/s bin->binpack & binpack->bin"
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "nnue_data_compression")
+REF_GEN = os.path.join(ROOT, "oracle", "_ref", "gen_ref")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--positions", type=int, default=100_000_000, help="positions per GPU per step")
+    ap.add_argument("--plies", type=int, default=100, help="maximum plies per chain of the synthetic games")
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="positions of the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {
+            "sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": max(smax) if smax else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's CPU implementation (cpu_baseline leg and --impl reference)
+
+
+def _ref_shard_job(workdir, idx, positions, plies, seed):
+    """Generates one shard with the reference's own chess library (not timed)."""
+    path = os.path.join(workdir, f"shard{idx}.bin")
+    subprocess.run([REF_GEN, path, str(positions), str(plies), str(seed + idx)], check=True)
+    return path
+
+
+def _ref_round_trip(paths):
+    """Runs bin->binpack then binpack->bin with the reference binary, one process per shard, all
+    processes in parallel. Returns (compress_s, decompress_s) wall-clock."""
+    def run_all(cmds):
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen(c, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for c in cmds]
+        for p in procs:
+            if p.wait() != 0:
+                raise RuntimeError("reference binary failed")
+        return time.perf_counter() - t0
+
+    tc = run_all([[REF_BIN, p, p[:-4] + ".binpack"] for p in paths])
+    td = run_all([[REF_BIN, p[:-4] + ".binpack", p[:-4] + ".rt.bin"] for p in paths])
+    return tc, td
+
+
+def reference_available():
+    return os.access(REF_BIN, os.X_OK) and os.access(REF_GEN, os.X_OK)
+
+
+def cpu_reference_measure(positions_total, plies, seed, procs, steps, warmup):
+    """Times the unmodified reference (oracle/_ref, built from /root/reference by oracle/Makefile)
+    on `procs` host processes, each on its own shard of positions_total / procs positions."""
+    workdir = tempfile.mkdtemp(prefix="nnp_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        per = max(positions_total // procs, 1000)
+        gens = [threading.Thread(target=_ref_shard_job, args=(workdir, i, per, plies, seed)) for i in range(procs)]
+        for g in gens:
+            g.start()
+        for g in gens:
+            g.join()
+        paths = [os.path.join(workdir, f"shard{i}.bin") for i in range(procs)]
+        for _ in range(warmup):
+            _ref_round_trip(paths)
+        tcs, tds = [], []
+        for _ in range(steps):
+            tc, td = _ref_round_trip(paths)
+            tcs.append(tc)
+            tds.append(td)
+        n = per * procs
+        tc, td = sum(tcs) / len(tcs), sum(tds) / len(tds)
+        return {
+            "positions": n,
+            "procs": procs,
+            "compress_mpos_s": n / tc / 1e6,
+            "decompress_mpos_s": n / td / 1e6,
+            "value": 2 * n / (tc + td) / 1e6,
+            "ms_per_step": (tc + td) * 1e3,
+        }
+    finally:
+        shutil.rmtree(workdir, ignore_errors=True)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    if not reference_available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (run oracle/Makefile where /root/reference exists)"}))
+        return 0
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    per_proc = 250_000  # ~0.7 s compress + ~0.3 s decompress per process and step
+    r = cpu_reference_measure(per_proc * procs, args.plies, args.seed, procs, max(args.steps, 1), max(args.warmup, 0))
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": r["value"],
+        "unit": "Mpos/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u64",
+        "data": "synthetic",
+        "config": {
+            "workload": f"bin->binpack then binpack->bin, random legal-move games, <= {args.plies} plies per chain",
+            "positions_per_step": r["positions"],
+            "sample": f"{procs} processes x {per_proc} positions (bounded sample of the 100M-position workload)",
+        },
+        "compress_mpos_s": r["compress_mpos_s"],
+        "decompress_mpos_s": r["decompress_mpos_s"],
+        "cpu_baseline": {
+            "value": r["value"], "unit": "Mpos/s", "cores": procs, "kind": "reference",
+            "sample": f"{procs} x {per_proc} positions, reference binary (make release flags, -O2), one process per shard",
+        },
+        "e2e": {"value": r["value"], "unit": "Mpos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import nnue_data_compress_b200 as nnp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the conversion path has no CPU implementation")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    nnp.init(local_rank)
+    L = nnp.lib()
+    stream = torch.cuda.current_stream()
+    L.nnp_set_stream(ctypes.c_void_p(stream.cuda_stream))
+
+    def check(rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: {L.nnp_strerror(rc).decode()} ({L.nnp_last_cuda_error().decode()})")
+
+    n_pos = args.positions
+    bin_bytes = n_pos * 40
+    d_bin = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
+    check(L.nnp_generate_bin_dev(ctypes.c_void_p(d_bin.data_ptr()), n_pos, args.plies, args.seed + 1000 * rank), "generate")
+
+    need = ctypes.c_size_t(0)
+    # the generic capacity bound assumes every record is a chain head (34 B/pos); one sizing pass
+    # gives the real size so that the benchmark buffers are not 3.4 GB of slack
+    cap_guess = bin_bytes // 8 + (1 << 20)
+    d_pack = torch.empty(cap_guess, dtype=torch.uint8, device=dev)
+    rc = L.nnp_bin_to_binpack_dev(ctypes.c_void_p(d_bin.data_ptr()), bin_bytes, ctypes.c_void_p(d_pack.data_ptr()), cap_guess,
+                                  ctypes.byref(need))
+    if rc == -8:  # NNP_ERR_CAPACITY: *out_bytes holds the size required
+        cap_guess = int(need.value) + 4096
+        d_pack = torch.empty(cap_guess, dtype=torch.uint8, device=dev)
+        rc = L.nnp_bin_to_binpack_dev(ctypes.c_void_p(d_bin.data_ptr()), bin_bytes, ctypes.c_void_p(d_pack.data_ptr()),
+                                      cap_guess, ctypes.byref(need))
+    check(rc, "sizing pass")
+    pack_bytes = int(need.value)
+    d_out = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
+
+    t_total = ctypes.c_float(0)
+    t_dom = ctypes.c_float(0)
+
+    def step_device():
+        n1 = ctypes.c_size_t(0)
+        check(L.nnp_bin_to_binpack_dev(ctypes.c_void_p(d_bin.data_ptr()), bin_bytes, ctypes.c_void_p(d_pack.data_ptr()),
+                                       cap_guess, ctypes.byref(n1)), "bin->binpack")
+        L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
+        c_ms, c_dom = t_total.value, t_dom.value
+        n2 = ctypes.c_size_t(0)
+        check(L.nnp_binpack_to_bin_dev(ctypes.c_void_p(d_pack.data_ptr()), n1.value, ctypes.c_void_p(d_out.data_ptr()),
+                                       bin_bytes, ctypes.byref(n2)), "binpack->bin")
+        L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
+        assert n2.value == bin_bytes, (n2.value, bin_bytes)
+        return c_ms, c_dom, t_total.value, t_dom.value, n1.value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    launches0 = L.nnp_kernel_launches()
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    c_ms = c_dom = d_ms = d_dom = 0.0
+    for _ in range(args.steps):
+        a, b, c, d, _n = step_device()
+        c_ms += a
+        c_dom += b
+        d_ms += c
+        d_dom += d
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = int(L.nnp_kernel_launches() - launches0)
+    elapsed_ms = ev0.elapsed_time(ev1)
+    K = max(args.steps, 1)
+    c_ms, c_dom, d_ms, d_dom = c_ms / K, c_dom / K, d_ms / K, d_dom / K
+
+    # ---- e2e: host buffers through the public C ABI, H2D and D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        # pinned host buffers (cudaHostAlloc through torch); nnp_host_alloc() hands out the same kind
+        t_bin = torch.empty(bin_bytes, dtype=torch.uint8, pin_memory=True)
+        t_pack = torch.empty(cap_guess, dtype=torch.uint8, pin_memory=True)
+        t_out = torch.empty(bin_bytes, dtype=torch.uint8, pin_memory=True)
+        t_bin.copy_(d_bin)  # untimed setup: the step's input starts in host memory
+        torch.cuda.synchronize()
+        h_bin, h_pack, h_out = t_bin.data_ptr(), t_pack.data_ptr(), t_out.data_ptr()
+
+        def step_host():
+            n1 = ctypes.c_size_t(0)
+            check(L.nnp_bin_to_binpack(ctypes.c_void_p(h_bin), bin_bytes, ctypes.c_void_p(h_pack), cap_guess,
+                                       ctypes.byref(n1)), "host bin->binpack")
+            n2 = ctypes.c_size_t(0)
+            check(L.nnp_binpack_to_bin(ctypes.c_void_p(h_pack), n1.value, ctypes.c_void_p(h_out), bin_bytes,
+                                       ctypes.byref(n2)), "host binpack->bin")
+            return n1.value, n2.value
+
+        e_steps = max(1, min(args.steps, 3))
+        step_host()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(e_steps):
+            n1, n2 = step_host()
+        e1.record(stream)
+        barrier()
+        e_ms = e0.elapsed_time(e1) / e_steps
+        e2e_local = 2 * n_pos / (e_ms * 1e-3) / 1e6
+        e2e = {"ms": e_ms, "value": e2e_local, "h2d": bin_bytes + n1, "d2h": n1 + n2}
+        del t_bin, t_pack, t_out
+
+    # ---- max over ranks
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    shard_offsets = None
+    if world > 1:
+        # the one exchange step of the multi-GPU path: byte counts -> each shard's output offset
+        mine = torch.tensor([pack_bytes], dtype=torch.int64, device=dev)
+        allc = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        sizes = [int(t.item()) for t in allc]
+        shard_offsets = [sum(sizes[:i]) for i in range(world)]
+
+    elapsed_ms = allmax(elapsed_ms)
+    ms_per_step = elapsed_ms / K
+    total_pos = n_pos * world
+    value = 2 * total_pos / (ms_per_step * 1e-3) / 1e6
+    c_ms_m, d_ms_m = allmax(c_ms), allmax(d_ms)
+    e2e_ms = allmax(e2e["ms"]) if e2e else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak_src = "fallback"
+    peak = 6650.0
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            peaks = json.load(f)
+        if "hbm_gbs" in peaks:
+            peak, peak_src = float(peaks["hbm_gbs"]), "measured"
+
+    # roofline of the dominant kernel (k_decode_link_encode): SURVEY.md 8(d) algorithmic bytes =
+    # |input| + |output| of the direction = 40 B + binpack bytes per position
+    alg_bytes = bin_bytes + pack_bytes
+    achieved = alg_bytes / (c_dom * 1e-3) / 1e9 if c_dom > 0 else None
+    roofline = {
+        "bound": "hbm",
+        "kernel": "k_decode_link_encode",
+        "achieved": achieved,
+        "peak": peak,
+        "peak_source": peak_src + (" MEASURED_PEAKS.json hbm_gbs" if peak_src == "measured" else " B200_PROFILING.md 6.65 TB/s"),
+        "unit": "GB/s",
+        "frac": achieved / peak if achieved else None,
+        "traffic": None,
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "kernel_ms": c_dom,
+        "decompress": {
+            "kernel": "k_emit_chains",
+            "kernel_ms": d_dom,
+            "achieved": alg_bytes / (d_dom * 1e-3) / 1e9 if d_dom > 0 else None,
+            "frac": (alg_bytes / (d_dom * 1e-3) / 1e9) / peak if d_dom > 0 else None,
+        },
+    }
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1 and reference_available():
+        r = cpu_reference_measure(args.cpu_sample, args.plies, args.seed, 1, 1, 0)
+        cpu_baseline = {
+            "value": r["value"], "unit": "Mpos/s", "cores": 1, "kind": "reference",
+            "sample": f"{r['positions']} positions (same generator recipe, {args.plies} plies per chain), reference binary "
+                      f"bin->binpack {r['compress_mpos_s']:.3f} Mpos/s, binpack->bin {r['decompress_mpos_s']:.3f} Mpos/s",
+        }
+    elif not args.no_cpu_baseline and world == 1:
+        cpu_baseline = {"value": None, "unit": "Mpos/s", "cores": 0, "kind": "reference",
+                        "sample": "oracle/_ref missing on this box"}
+
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": "Mpos/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u64",
+        "data": "synthetic",
+        "config": {
+            "workload": f"bin->binpack then binpack->bin of {n_pos} positions per GPU, random legal-move games, "
+                        f"<= {args.plies} plies per chain (BASELINE configs[1]+[2])",
+            "positions_per_gpu": n_pos,
+            "bin_bytes_per_gpu": bin_bytes,
+            "binpack_bytes_per_gpu": pack_bytes,
+            "l2": "inputs (4.0 GB .bin, 0.2 GB .binpack per GPU) are far larger than the 126 MB L2",
+            "sharding": "independent shards per GPU, all-gather of byte counts only" if world > 1 else "single GPU",
+        },
+        "compress_mpos_s": total_pos / (c_ms_m * 1e-3) / 1e6,
+        "decompress_mpos_s": total_pos / (d_ms_m * 1e-3) / 1e6,
+        "compress_ms": c_ms_m,
+        "decompress_ms": d_ms_m,
+        "clocks": clocks,
+        "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if e2e:
+        line["e2e"] = {
+            "value": 2 * total_pos / (e2e_ms * 1e-3) / 1e6,
+            "unit": "Mpos/s",
+            "ms_per_step": e2e_ms,
+            "h2d_bytes_per_step": e2e["h2d"],
+            "d2h_bytes_per_step": e2e["d2h"],
+        }
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
+    if shard_offsets is not None:
+        line["config"]["shard_output_offsets"] = shard_offsets
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -59,6 +59,10 @@ typedef enum nnp_status {
 int nnp_init(int device);
 void nnp_shutdown(void);
 const char* nnp_strerror(int status);
+/* Runs all further work on the caller's CUDA stream (a cudaStream_t of the bound device, e.g.
+ * torch's current stream) so that the caller's events bracket it; NULL restores the library's own
+ * stream. Calls still return only after their result size is known. */
+int nnp_set_stream(void* cuda_stream);
 const char* nnp_last_cuda_error(void);
 /* number of kernel launches issued by this library since nnp_init (for bench accounting) */
 uint64_t nnp_kernel_launches(void);

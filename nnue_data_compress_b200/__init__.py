@@ -50,7 +50,7 @@ STATUS = {
 REFERENCE_ERRORS = (-1, -2, -3)
 
 EXPORTS = [
-    "nnp_init", "nnp_shutdown", "nnp_strerror", "nnp_last_cuda_error", "nnp_kernel_launches",
+    "nnp_init", "nnp_shutdown", "nnp_strerror", "nnp_set_stream", "nnp_last_cuda_error", "nnp_kernel_launches",
     "nnp_host_alloc", "nnp_host_free",
     "nnp_bin_to_binpack", "nnp_binpack_to_bin", "nnp_plain_to_binpack", "nnp_binpack_to_plain",
     "nnp_bin_to_plain", "nnp_plain_to_bin",
@@ -93,6 +93,8 @@ def lib() -> ctypes.CDLL:
         L.nnp_init.argtypes = [ctypes.c_int]
         L.nnp_init.restype = ctypes.c_int
         L.nnp_shutdown.restype = None
+        L.nnp_set_stream.argtypes = [ctypes.c_void_p]
+        L.nnp_set_stream.restype = ctypes.c_int
         L.nnp_strerror.argtypes = [ctypes.c_int]
         L.nnp_strerror.restype = ctypes.c_char_p
         L.nnp_last_cuda_error.restype = ctypes.c_char_p
@@ -288,3 +290,16 @@ def main(argv: list[str] | None = None, out=sys.stdout, err=sys.stderr) -> int:
     err.write("Invalid arguments.\n")
     out.write(_HELP)
     return 1
+
+
+def generate_bin(n_positions: int, max_plies: int = 100, seed: int = 42) -> bytes:
+    """Synthetic .bin input generated on the device (SURVEY.md 8d recipe); torch only provides the
+    device buffer and the copy back to the host."""
+    import torch
+
+    _ensure_init()
+    buf = torch.empty(max(n_positions * 40, 8), dtype=torch.uint8, device="cuda")
+    rc = lib().nnp_generate_bin_dev(ctypes.c_void_p(buf.data_ptr()), n_positions, max_plies, seed)
+    if rc != 0:
+        raise NnpError(rc, _strerror(rc))
+    return buf[: n_positions * 40].cpu().numpy().tobytes()

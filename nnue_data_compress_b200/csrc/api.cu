@@ -24,13 +24,14 @@ enum WsSlot {
     WS_CODES = 0, WS_STEMS, WS_TILE_AGG, WS_PAYLOAD, WS_HEAD_OFF, WS_CHUNK_OFF, WS_TOTALS,
     WS_CHUNK_START, WS_CHUNK_LEN, WS_CHUNK_TILE_BASE, WS_CHUNK_INFO, WS_TILE_COUNT, WS_TILE_PREFIX,
     WS_CAND_CHUNK, WS_CAND_OFF, WS_CAND_NEXT, WS_CAND_BASE, WS_CHUNK_COUNT, WS_CHUNK_SLOW, WS_CHUNK_BASE,
-    WS_DTOTALS, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
+    WS_DTOTALS, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
 };
 
 struct Context {
     bool ready = false;
     int device = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream all kernels and copies are issued on
+    cudaStream_t own_stream = nullptr;  // the library's default stream
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     Workspace ws[WS_COUNT];
@@ -380,7 +381,8 @@ int nnp_init(int device)
         g_ctx.last_cuda_error = "libnnuepack is built for sm_100a only";
         return NNP_ERR_NO_DEVICE;
     }
-    if (cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking) != cudaSuccess) return NNP_ERR_CUDA;
+    if (cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking) != cudaSuccess) return NNP_ERR_CUDA;
+    g_ctx.stream = g_ctx.own_stream;
     if (cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking) != cudaSuccess) return NNP_ERR_CUDA;
     for (auto& ev : g_ctx.ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return NNP_ERR_CUDA;
@@ -408,9 +410,9 @@ void nnp_shutdown(void)
         if (ev) cudaEventDestroy(ev);
         ev = nullptr;
     }
-    cudaStreamDestroy(g_ctx.stream);
+    cudaStreamDestroy(g_ctx.own_stream);
     cudaStreamDestroy(g_ctx.copy_stream);
-    g_ctx.stream = g_ctx.copy_stream = nullptr;
+    g_ctx.stream = g_ctx.own_stream = g_ctx.copy_stream = nullptr;
     g_ctx.ready = false;
     g_ctx.device = -1;
 }
@@ -432,6 +434,15 @@ const char* nnp_strerror(int status)
     case NNP_ERR_CUDA: return "CUDA runtime error";
     default: return "unknown status";
     }
+}
+
+int nnp_set_stream(void* cuda_stream)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    cudaStreamSynchronize(g_ctx.stream);
+    g_ctx.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : g_ctx.own_stream;
+    return NNP_OK;
 }
 
 const char* nnp_last_cuda_error(void) { return g_ctx.last_cuda_error.c_str(); }
@@ -473,7 +484,10 @@ int nnp_bin_to_binpack(const void* bin, size_t bin_bytes, void* out, size_t out_
 int nnp_binpack_to_bin(const void* binpack, size_t binpack_bytes, void* out, size_t out_cap, size_t* out_bytes)
 {
     REQUIRE_READY();
-    return run_host(decompress_dev, binpack, binpack_bytes, out, out_cap, out_bytes, 0);
+    // a continuation ply costs at least 5 bits, a chain head 34 bytes: <= 64 output bytes per input byte
+    size_t bound = binpack_bytes * 64 + 40;
+    if (out && out_cap < bound) bound = out_cap;
+    return run_host(decompress_dev, binpack, binpack_bytes, out, out_cap, out_bytes, out ? bound : 0);
 }
 
 int nnp_binpack_count_dev(const void* d_binpack, size_t binpack_bytes, uint64_t* n_positions)
@@ -485,6 +499,34 @@ int nnp_binpack_count_dev(const void* d_binpack, size_t binpack_bytes, uint64_t*
     int rc = decompress_dev(d_binpack, binpack_bytes, nullptr, 0, &bytes);
     *n_positions = bytes / 40;
     return rc;
+}
+
+int nnp_generate_bin_dev(void* d_out, size_t n_positions, uint32_t max_plies, uint64_t seed)
+{
+    std::lock_guard<std::mutex> lock_(g_mutex);
+    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    if (n_positions == 0) return NNP_OK;
+    if (!d_out || max_plies == 0 || ((uintptr_t)d_out & 7)) return NNP_ERR_BAD_ARG;
+    cudaStream_t s = g_ctx.stream;
+    u64 n_games = n_positions / max_plies + n_positions / ((u64)max_plies * 8) + 64;
+    u64* h_total = reinterpret_cast<u64*>((char*)g_ctx.pinned + 1024);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        WS(WS_GAME_LEN, n_games * 4, u32, game_len);
+        WS(WS_GAME_BASE, (n_games + 1) * 8, u64, game_base);
+        launch_play_games(false, n_games, max_plies, seed, game_len, game_base, nullptr, n_positions, s);
+        launch_exclusive_sum(game_len, n_games, game_base, s);
+        LAUNCHED(2, "k_play_games<count>");
+        CK(cudaMemcpyAsync(h_total, game_base + n_games, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (*h_total >= n_positions) {
+            launch_play_games(true, n_games, max_plies, seed, game_len, game_base, d_out, n_positions, s);
+            LAUNCHED(1, "k_play_games<write>");
+            CK(cudaStreamSynchronize(s));
+            return NNP_OK;
+        }
+        n_games = n_games * 2 + 64;
+    }
+    return NNP_ERR_BAD_ARG;
 }
 
 int nnp_last_timing(float* total_ms, float* dominant_kernel_ms)

@@ -1,0 +1,160 @@
+// cli.cpp -- nnue_data_compression-compatible command line on top of libnnuepack.so.
+//
+// Mirrors readArgs / run / convert / compress / decompress / help of the reference
+// (src/compress_file.cpp:1535-1709): same dispatch by file extension, same flags (including the
+// quirk that "--append" is stored as "-append" and therefore ignored), same messages, same exit
+// codes (0 everywhere except the argument-count error). The conversions themselves run on the
+// GPU through the C ABI; this file only moves files in and out of host memory.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nnuepack.h"
+
+namespace {
+
+const std::string plainExtension = ".plain";
+const std::string binExtension = ".bin";
+const std::string binpackExtension = ".binpack";
+
+typedef int (*driver_fn)(const void*, size_t, void*, size_t, size_t*);
+
+bool endsWith(const std::string& str, const std::string& suffix)
+{
+    return str.size() >= suffix.size() && 0 == str.compare(str.size() - suffix.size(), suffix.size(), suffix);
+}
+
+bool fileExists(const std::string& name)
+{
+    std::ifstream f(name);
+    return f.good();
+}
+
+void runDriver(driver_fn fn, const char* verb, const std::string& inputPath, const std::string& outputPath, bool append)
+{
+    std::cout << verb << " " << inputPath << " to " << outputPath << '\n';
+    std::ifstream in(inputPath, std::ios_base::binary | std::ios_base::ate);
+    const size_t n = in ? static_cast<size_t>(in.tellg()) : 0;
+    char* src = static_cast<char*>(nnp_host_alloc(n + 1));
+    if (!src) throw std::runtime_error("host allocation failed");
+    in.seekg(0);
+    in.read(src, static_cast<std::streamsize>(n));
+
+    size_t need = 0;
+    int rc = fn(src, n, nullptr, 0, &need);
+    if (rc != NNP_OK && rc != NNP_ERR_BAD_MAGIC && rc != NNP_ERR_CHUNK_TOO_LARGE && rc != NNP_ERR_BAD_SFEN) {
+        nnp_host_free(src);
+        throw std::runtime_error(std::string(nnp_strerror(rc)) + " " + nnp_last_cuda_error());
+    }
+    char* dst = static_cast<char*>(nnp_host_alloc(need + 1));
+    if (!dst) throw std::runtime_error("host allocation failed");
+    size_t produced = 0;
+    rc = fn(src, n, dst, need, &produced);
+    const bool referenceError = rc == NNP_ERR_BAD_MAGIC || rc == NNP_ERR_CHUNK_TOO_LARGE || rc == NNP_ERR_BAD_SFEN;
+    if (rc == NNP_OK || referenceError) {
+        std::ofstream out(outputPath, std::ios_base::binary | (append ? std::ios_base::app : std::ios_base::trunc));
+        out.write(dst, static_cast<std::streamsize>(produced));
+    }
+    nnp_host_free(src);
+    nnp_host_free(dst);
+    if (referenceError) throw std::runtime_error(nnp_strerror(rc));  // printed by main, exit code 0
+    if (rc != NNP_OK) {
+        std::cerr << nnp_strerror(rc) << " " << nnp_last_cuda_error() << "\n";
+        std::exit(2);
+    }
+    std::cout << "Processed " << n << " bytes into " << produced << " bytes.\n";
+}
+
+void convert(const std::string& inputPath, std::string outputPath, bool append)
+{
+    if (!fileExists(inputPath)) {
+        std::cerr << "Input file doesn't exist.\n";
+        return;
+    }
+    if (endsWith(inputPath, binExtension) && endsWith(outputPath, plainExtension)) {
+        runDriver(nnp_bin_to_plain, "Converting", inputPath, outputPath, append);
+    } else if (endsWith(inputPath, plainExtension) && endsWith(outputPath, binExtension)) {
+        runDriver(nnp_plain_to_bin, "Compressing", inputPath, outputPath, append);
+    } else if (endsWith(inputPath, plainExtension) || endsWith(inputPath, binExtension)) {
+        if (!endsWith(outputPath, binpackExtension)) outputPath += binpackExtension;
+        runDriver(endsWith(inputPath, binExtension) ? nnp_bin_to_binpack : nnp_plain_to_binpack, "Compressing", inputPath,
+                  outputPath, append);
+    } else if (endsWith(inputPath, binpackExtension)) {
+        if (endsWith(outputPath, binExtension)) {
+            runDriver(nnp_binpack_to_bin, "Decompressing", inputPath, outputPath, append);
+        } else if (endsWith(outputPath, plainExtension)) {
+            runDriver(nnp_binpack_to_plain, "Decompressing", inputPath, outputPath, append);
+        } else {
+            std::cerr << "Unrecognized file format. Only " << binExtension << " and " << plainExtension
+                      << " are supported for decompression.";
+        }
+    } else {
+        std::cerr << "Unsupported extension.";
+    }
+}
+
+void help()
+{
+    std::cout << "Usage:\n";
+    std::cout << "    nnue_data_compression [-h] [-a] input_path output_path\n";
+    std::cout << "\n";
+    std::cout << "-h, --help                show help\n";
+    std::cout << "-a, --append              append to the output file instead of truncating it\n";
+    std::cout << "\n";
+    std::cout << "input_path                the path to the file to process\n";
+    std::cout << "output_path               the path to the file to create/append to\n";
+    std::cout << "\n";
+    std::cout << "Behaviour depends on file extensions. If the input\n";
+    std::cout << "file has extension either " << binExtension << " or " << plainExtension << "\n";
+    std::cout << "it will be compressed. The output file has then an implied\n";
+    std::cout << "extension of " << binpackExtension << " and it doesn't have to be specified.\n";
+    std::cout << "If the input file's extension is " << binpackExtension << " then it will be decompressed\n";
+    std::cout << "to either a " << binExtension << " or " << plainExtension << " file, depending on the extension.\n";
+    std::cout << "\n";
+    std::cout << "Example usage:\n";
+    std::cout << "1. convert from plain to binpack in append mode:\n";
+    std::cout << "    nnue_data_compression -a data.plain data\n";
+    std::cout << "2. convert from binpack to plain in truncate/replace mode:\n";
+    std::cout << "    nnue_data_compression data.binpack data.plain\n";
+}
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    std::set<std::string> flags;
+    std::vector<std::string> pos;
+    for (int i = 1; i < argc; ++i) {
+        if (*argv[i] == '-') flags.emplace(argv[i] + 1);
+        else pos.emplace_back(argv[i]);
+    }
+    if (pos.empty() || flags.count("help") == 1 || flags.count("h") == 1) {
+        help();
+        return 0;
+    }
+    if (pos.size() != 2) {
+        std::cerr << "Invalid arguments.\n";
+        help();
+        return 1;
+    }
+    const bool append = flags.count("a") == 1 || flags.count("append") == 1;
+    const char* dev = std::getenv("NNP_DEVICE");
+    const int rc = nnp_init(dev ? std::atoi(dev) : 0);
+    if (rc != NNP_OK) {
+        std::cerr << nnp_strerror(rc) << " " << nnp_last_cuda_error() << "\n";
+        return 2;
+    }
+    try {
+        convert(pos[0], pos[1], append);
+    } catch (std::runtime_error& e) {
+        std::cerr << e.what() << "\n";
+        std::cerr << "Exiting...\n";
+    }
+    nnp_shutdown();
+    return 0;
+}

@@ -45,4 +45,8 @@ void launch_emit_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk,
 void launch_slow_emit(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, const u64* chunk_base, void* out,
                       cudaStream_t s);
 
+// ---- synthetic input, generate.cu
+void launch_play_games(bool write, u64 n_games, u32 max_plies, u64 seed, u32* game_len, const u64* game_base, void* out,
+                       u64 n_positions, cudaStream_t s);
+
 }  // namespace nnp
