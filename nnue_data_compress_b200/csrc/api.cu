@@ -23,7 +23,7 @@ struct Workspace {
 enum WsSlot {
     WS_CODES = 0, WS_STEMS, WS_TILE_AGG, WS_PAYLOAD, WS_HEAD_OFF, WS_CHUNK_OFF, WS_TOTALS,
     WS_CHUNK_START, WS_CHUNK_LEN, WS_CHUNK_TILE_BASE, WS_CHUNK_INFO, WS_TILE_COUNT, WS_TILE_PREFIX,
-    WS_CAND_CHUNK, WS_CAND_OFF, WS_CAND_NEXT, WS_CAND_BASE, WS_CHUNK_COUNT, WS_CHUNK_SLOW, WS_CHUNK_BASE,
+    WS_CAND_CHUNK, WS_CAND_OFF, WS_CAND_NEXT, WS_CAND_BASE, WS_CAND_CNT, WS_CHUNK_COUNT, WS_CHUNK_SLOW, WS_CHUNK_BASE,
     WS_DTOTALS, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
 };
 
@@ -251,6 +251,7 @@ int decode_plan(const void* d_in, size_t in_bytes, DecodePlan& P)
     WS(WS_CAND_OFF, (P.ncand + 1) * 4, u32, cand_off);
     WS(WS_CAND_NEXT, (P.ncand + 1) * 4, u32, cand_next);
     WS(WS_CAND_BASE, (P.ncand + 1) * 4, u32, cand_base);
+    WS(WS_CAND_CNT, (P.ncand + 1) * 4, u32, cand_cnt);
     WS(WS_CHUNK_COUNT, (P.chunks + 1) * 4, u32, chunk_count);
     WS(WS_CHUNK_SLOW, (P.chunks + 1) * 4, u32, chunk_slow);
     WS(WS_CHUNK_BASE, (P.chunks + 2) * 8, u64, chunk_base);
@@ -258,8 +259,8 @@ int decode_plan(const void* d_in, size_t in_bytes, DecodePlan& P)
     P.chunk_count = chunk_count; P.chunk_slow = chunk_slow; P.chunk_base = chunk_base;
 
     launch_candidates(true, d_in, P.tab, P.tiles, tile_count, tile_prefix, cand_chunk, cand_off, C.debug_reject_mod, s);
-    launch_probe_chains(d_in, P.tab, cand_chunk, cand_off, P.ncand, cand_next, s);
-    launch_resolve_chunks(d_in, P.tab, P.chunks, tile_prefix, cand_off, cand_next, cand_base, chunk_count, chunk_slow, s);
+    launch_probe_chains(d_in, P.tab, cand_chunk, cand_off, P.ncand, cand_next, cand_cnt, s);
+    launch_resolve_chunks(P.tab, P.chunks, tile_prefix, cand_off, cand_next, cand_cnt, cand_base, chunk_count, chunk_slow, s);
     launch_slow_count(d_in, P.tab, P.chunks, chunk_slow, chunk_count, d_tot, s);
     launch_exclusive_sum(chunk_count, P.chunks, chunk_base, s);
     LAUNCHED(5, "decode plan");

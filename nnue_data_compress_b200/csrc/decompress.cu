@@ -241,7 +241,7 @@ __device__ __forceinline__ bool chain_step(ChainCursor& c, BitReader& r, bool st
 constexpr int PROBE_THREADS = 128;
 __global__ void __launch_bounds__(PROBE_THREADS)
 k_probe_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
-               const u32* __restrict__ cand_off, u64 ncand, u32* __restrict__ cand_next)
+               const u32* __restrict__ cand_off, u64 ncand, u32* __restrict__ cand_next, u32* __restrict__ cand_cnt)
 {
     const u64 i = (u64)blockIdx.x * PROBE_THREADS + threadIdx.x;
     if (i >= ncand) return;
@@ -266,38 +266,79 @@ k_probe_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* 
         next = off + 34 + ((r.pos + 7) >> 3);  // numReadBytes (:815-818)
     }
     cand_next[i] = ok ? next : 0xFFFFFFFFu;
+    cand_cnt[i] = 1u + cc.num_plies;
 }
 
-// one thread per chunk: Reader::next / fetchNextChunkIfNeeded (:1154-1213) over the candidates
-constexpr int RESOLVE_THREADS = 64;
-__global__ void __launch_bounds__(RESOLVE_THREADS)
-k_resolve_chunks(const unsigned char* __restrict__ in, ChunkTable tab, const u64* __restrict__ tile_prefix,
-                 const u32* __restrict__ cand_off, const u32* __restrict__ cand_next, u32* __restrict__ cand_base,
+// One warp per chunk: Reader::next / fetchNextChunkIfNeeded (:1154-1213) over the candidate list.
+// The walk "offset 0 -> next -> next ..." is sequential in principle, but on real files every
+// candidate is a real chain and candidate k+1 starts exactly where candidate k ends, so the warp
+// verifies 32 links per step with one ballot and only falls out of lock-step at a false positive.
+constexpr int RESOLVE_WARPS = 4;
+__global__ void __launch_bounds__(RESOLVE_WARPS * 32)
+k_resolve_chunks(ChunkTable tab, const u64* __restrict__ tile_prefix, const u32* __restrict__ cand_off,
+                 const u32* __restrict__ cand_next, const u32* __restrict__ cand_cnt, u32* __restrict__ cand_base,
                  u32* __restrict__ chunk_count, u32* __restrict__ chunk_slow)
 {
-    const u64 c = (u64)blockIdx.x * RESOLVE_THREADS + threadIdx.x;
+    const u64 c = (u64)blockIdx.x * RESOLVE_WARPS + (threadIdx.x >> 5);
     if (c >= tab.info->chunks) return;
+    const int lane = threadIdx.x & 31;
     const u64 cb = tile_prefix[tab.tile_base[c]], ce = tile_prefix[tab.tile_base[c + 1]];
     const u32 clen = tab.len[c];
-    const unsigned char* base = in + tab.start[c];
     u64 i = cb;
     u32 cur = 0, count = 0;
     bool slow = false;
     while ((u64)cur + 34 <= clen) {
-        while (i < ce && cand_off[i] < cur) { cand_base[i] = 0xFFFFFFFFu; ++i; }  // false positive inside a chain
-        if (i >= ce || cand_off[i] != cur || cand_next[i] == 0xFFFFFFFFu) { slow = true; break; }
-        cand_base[i] = count;
-        count += 1u + (((u32)base[cur + 32] << 8) | (u32)base[cur + 33]);
-        cur = cand_next[i];
-        ++i;
+        if (i >= ce) { slow = true; break; }  // the expected chain start is not a candidate
+        const u64 k = i + lane;
+        const bool in = k < ce;
+        const u32 o = in ? cand_off[k] : 0xFFFFFFFFu;
+        const u32 nx = in ? cand_next[k] : 0xFFFFFFFFu;
+        const u32 cn = in ? cand_cnt[k] : 0u;
+        u32 expect = __shfl_up_sync(0xffffffffu, nx, 1);
+        if (lane == 0) expect = cur;
+        // a lane is "linked" when it starts where its predecessor ends, its own chain decodes, and
+        // the predecessor did not already finish the chunk
+        const bool linked = in && o == expect && nx != 0xFFFFFFFFu && (u64)expect + 34 <= clen;
+        const u32 bad = ~__ballot_sync(0xffffffffu, linked);
+        const int good = bad ? (__ffs((int)bad) - 1) : 32;  // lanes [0, good) are real chains
+        // exclusive prefix of the counts over the good lanes
+        u32 inc = lane < good ? cn : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 v = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += v;
+        }
+        if (lane < good) cand_base[k] = count + inc - cn;
+        count += __shfl_sync(0xffffffffu, inc, 31);
+        if (good > 0) cur = __shfl_sync(0xffffffffu, nx, good - 1);
+        i += good;
+        if (good < 32 && (u64)cur + 34 <= clen) {
+            // lane `good` broke the lock-step: candidate i is either a false positive that lies
+            // inside the chain just walked (skip it) or the walk left the candidate set
+            const u32 o_bad = __shfl_sync(0xffffffffu, o, good);
+            const u32 nx_bad = __shfl_sync(0xffffffffu, nx, good);
+            if (i >= ce) { slow = true; break; }
+            if (o_bad < cur) {
+                if (lane == 0) cand_base[i] = 0xFFFFFFFFu;
+                ++i;
+            } else {  // o_bad > cur, or the chain at cur does not decode
+                (void)nx_bad;
+                slow = true;
+                break;
+            }
+        }
     }
-    for (; i < ce; ++i) cand_base[i] = 0xFFFFFFFFu;
+    // whatever is left are false positives behind the last chain
+    for (u64 k = i + lane; k < ce; k += 32) cand_base[k] = 0xFFFFFFFFu;
     if (slow) {
-        for (u64 k = cb; k < ce; ++k) cand_base[k] = 0xFFFFFFFFu;
+        __syncwarp();
+        for (u64 k = cb + lane; k < ce; k += 32) cand_base[k] = 0xFFFFFFFFu;
         count = 0;  // filled in by k_slow_count
     }
-    chunk_count[c] = count;
-    chunk_slow[c] = slow ? 1u : 0u;
+    if (lane == 0) {
+        chunk_count[c] = count;
+        chunk_slow[c] = slow ? 1u : 0u;
+    }
 }
 
 // ------------------------------------------------------------------ record emission
@@ -416,18 +457,18 @@ void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s)
     k_exclusive_sum<<<1, SUM_THREADS, 0, s>>>(in, n, out);
 }
 void launch_probe_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u64 ncand,
-                         u32* cand_next, cudaStream_t s)
+                         u32* cand_next, u32* cand_cnt, cudaStream_t s)
 {
     if (ncand == 0) return;
     k_probe_chains<<<(unsigned)((ncand + PROBE_THREADS - 1) / PROBE_THREADS), PROBE_THREADS, 0, s>>>(
-        (const unsigned char*)d_in, tab, cand_chunk, cand_off, ncand, cand_next);
+        (const unsigned char*)d_in, tab, cand_chunk, cand_off, ncand, cand_next, cand_cnt);
 }
-void launch_resolve_chunks(const void* d_in, ChunkTable tab, u64 chunks, const u64* tile_prefix, const u32* cand_off,
-                           const u32* cand_next, u32* cand_base, u32* chunk_count, u32* chunk_slow, cudaStream_t s)
+void launch_resolve_chunks(ChunkTable tab, u64 chunks, const u64* tile_prefix, const u32* cand_off, const u32* cand_next,
+                           const u32* cand_cnt, u32* cand_base, u32* chunk_count, u32* chunk_slow, cudaStream_t s)
 {
     if (chunks == 0) return;
-    k_resolve_chunks<<<(unsigned)((chunks + RESOLVE_THREADS - 1) / RESOLVE_THREADS), RESOLVE_THREADS, 0, s>>>(
-        (const unsigned char*)d_in, tab, tile_prefix, cand_off, cand_next, cand_base, chunk_count, chunk_slow);
+    k_resolve_chunks<<<(unsigned)((chunks + RESOLVE_WARPS - 1) / RESOLVE_WARPS), RESOLVE_WARPS * 32, 0, s>>>(
+        tab, tile_prefix, cand_off, cand_next, cand_cnt, cand_base, chunk_count, chunk_slow);
 }
 void launch_slow_count(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, u32* chunk_count,
                        DecompressTotals* tot, cudaStream_t s)

@@ -35,9 +35,9 @@ void launch_candidates(bool write, const void* d_in, ChunkTable tab, u64 tiles, 
                        u32* cand_chunk, u32* cand_off, u32 debug_reject_mod, cudaStream_t s);
 void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s);
 void launch_probe_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u64 ncand,
-                         u32* cand_next, cudaStream_t s);
-void launch_resolve_chunks(const void* d_in, ChunkTable tab, u64 chunks, const u64* tile_prefix, const u32* cand_off,
-                           const u32* cand_next, u32* cand_base, u32* chunk_count, u32* chunk_slow, cudaStream_t s);
+                         u32* cand_next, u32* cand_cnt, cudaStream_t s);
+void launch_resolve_chunks(ChunkTable tab, u64 chunks, const u64* tile_prefix, const u32* cand_off, const u32* cand_next,
+                           const u32* cand_cnt, u32* cand_base, u32* chunk_count, u32* chunk_slow, cudaStream_t s);
 void launch_slow_count(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, u32* chunk_count,
                        DecompressTotals* tot, cudaStream_t s);
 void launch_emit_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, const u32* cand_base,

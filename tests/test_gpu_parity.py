@@ -156,3 +156,22 @@ def test_device_generator_vs_reference_binary(nnp):
     want = ref_convert(BIN_TO_BINPACK, b)
     assert nnp.bin_to_binpack(b) == want
     assert nnp.binpack_to_bin(want) == ref_convert(BINPACK_TO_BIN, want)
+
+
+def test_sequential_fallback_is_exact(nnp):
+    """NNP_DEBUG_REJECT_MOD drops a pseudo-random subset of chain-start candidates, which forces
+    the affected chunks through the sequential per-chunk decoder; the output must not change."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.');"
+        "import nnue_data_compress_b200 as n; from refutil import golden;"
+        "n.init(0);"
+        "ok = all(n.binpack_to_bin(golden(s + '.binpack')) == golden(s + '.rt.bin') for s in ('games100', 'twochunks', 'long400'));"
+        "print('FALLBACK_OK' if ok else 'FALLBACK_MISMATCH')"
+    )
+    env = dict(os.environ, NNP_DEBUG_REJECT_MOD="5")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert "FALLBACK_OK" in out.stdout, out.stdout + out.stderr
