@@ -151,7 +151,7 @@ def _convert_host(fn_name: str, data: bytes, allow_partial: bool = False) -> byt
     src = (ctypes.c_char * len(data)).from_buffer_copy(data) if len(data) else (ctypes.c_char * 1)()
     need = ctypes.c_size_t(0)
     rc = fn(src, len(data), None, 0, ctypes.byref(need))
-    if rc != 0 and rc not in REFERENCE_ERRORS:
+    if rc != 0:
         raise NnpError(rc, _strerror(rc))
     cap = max(int(need.value), 1)
     dst = (ctypes.c_char * cap)()

@@ -112,57 +112,21 @@ size_t binpack_capacity_for_records(size_t n)
     return payload + 8 * (payload / CHUNK_THRESHOLD + 2);
 }
 
-// ---------------------------------------------------------------- .bin -> .binpack
+// ---------------------------------------------------------------- shared tail of both compressors
 
-int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+// codes/stems of n records -> payload scan, payload write, chunk orbit, chunk emission
+int compress_tail(const u32* codes, const u32* stems, u64 n, int status, void* d_out, size_t out_cap, size_t* out_bytes)
 {
     Context& C = g_ctx;
-    const u64 n_all = bin_bytes / 40;  // a short trailing record is dropped (compress_file.cpp:1360)
-    if (!d_out) {
-        *out_bytes = binpack_capacity_for_records(n_all);
-        return NNP_OK;
-    }
-    *out_bytes = 0;
-    if (n_all == 0) return NNP_OK;  // empty input -> empty file
-    if (((uintptr_t)d_bin & 7) || ((uintptr_t)d_out & 7)) return NNP_ERR_BAD_ARG;
-
     cudaStream_t s = C.stream;
-    WS(WS_CODES, n_all * 4, u32, codes);
-    WS(WS_STEMS, n_all * 32, u32, stems);
-    WS(WS_TILE_AGG, scan_tiles(n_all) * sizeof(Agg), Agg, tile_agg);
+    WS(WS_TILE_AGG, scan_tiles(n) * sizeof(Agg), Agg, tile_agg);
     WS(WS_TOTALS, sizeof(CompressTotals), CompressTotals, d_tot);
     CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
-
-    h_tot->payload_bytes = 0;
-    h_tot->heads = 0;
-    h_tot->chunks = 0;
-    h_tot->error_index = NO_ERROR_IDX;
-    CK(cudaMemcpyAsync(d_tot, h_tot, sizeof(CompressTotals), cudaMemcpyHostToDevice, s));
-
-    CK(cudaEventRecord(C.ev[0], s));
-    launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, s);
-    LAUNCHED(1, "k_decode_link_encode");
-    CK(cudaEventRecord(C.ev[1], s));
-
-    int status = NNP_OK;
-    u64 n = n_all;
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        launch_tile_aggregate(codes, n, tile_agg, s);
-        launch_scan_aggregates(tile_agg, scan_tiles(n), d_tot, s);
-        LAUNCHED(2, "payload scan");
-        CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        if (attempt == 0 && h_tot->error_index != NO_ERROR_IDX) {
-            // "Improperly encoded bin sfen": the reference stops at the first malformed record and its
-            // writer still flushes everything gathered before it (compress_file.cpp:407-408, :1094-1106)
-            status = NNP_ERR_BAD_SFEN;
-            n = h_tot->error_index;
-            if (n == 0) return status;
-            continue;
-        }
-        break;
-    }
-
+    launch_tile_aggregate(codes, n, tile_agg, s);
+    launch_scan_aggregates(tile_agg, scan_tiles(n), d_tot, s);
+    LAUNCHED(2, "payload scan");
+    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     const u64 payload_bytes = h_tot->payload_bytes, heads = h_tot->heads;
     const u64 max_chunks = payload_bytes / CHUNK_THRESHOLD + 2;
     WS(WS_PAYLOAD, payload_bytes + 64, u32, payload);
@@ -180,28 +144,229 @@ int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_ca
     if (total > out_cap) return NNP_ERR_CAPACITY;
     launch_emit_chunks(payload, chunk_off, chunks, d_out, s);
     LAUNCHED(1, "k_emit_chunks");
+    return status;
+}
+
+int reset_compress_totals(CompressTotals** d_tot_out)
+{
+    Context& C = g_ctx;
+    WS(WS_TOTALS, sizeof(CompressTotals), CompressTotals, d_tot);
+    CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
+    h_tot->payload_bytes = 0;
+    h_tot->heads = 0;
+    h_tot->chunks = 0;
+    h_tot->error_index = NO_ERROR_IDX;
+    CK(cudaMemcpyAsync(d_tot, h_tot, sizeof(CompressTotals), cudaMemcpyHostToDevice, C.stream));
+    *d_tot_out = d_tot;
+    return NNP_OK;
+}
+
+// ---------------------------------------------------------------- .bin -> .binpack
+
+int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    Context& C = g_ctx;
+    const u64 n_all = bin_bytes / 40;  // a short trailing record is dropped (compress_file.cpp:1360)
+    if (!d_out) {
+        *out_bytes = binpack_capacity_for_records(n_all);
+        return NNP_OK;
+    }
+    *out_bytes = 0;
+    if (n_all == 0) return NNP_OK;  // empty input -> empty file
+    if (((uintptr_t)d_bin & 7) || ((uintptr_t)d_out & 7)) return NNP_ERR_BAD_ARG;
+
+    cudaStream_t s = C.stream;
+    WS(WS_CODES, n_all * 4, u32, codes);
+    WS(WS_STEMS, n_all * 32, u32, stems);
+    CompressTotals* d_tot = nullptr;
+    int rc = reset_compress_totals(&d_tot);
+    if (rc != NNP_OK) return rc;
+    CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
+
+    CK(cudaEventRecord(C.ev[0], s));
+    launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, s);
+    LAUNCHED(1, "k_decode_link_encode");
+    CK(cudaEventRecord(C.ev[1], s));
+    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int status = NNP_OK;
+    u64 n = n_all;
+    if (h_tot->error_index != NO_ERROR_IDX) {
+        // "Improperly encoded bin sfen": the reference stops at the first malformed record and its
+        // writer still flushes everything gathered before it (compress_file.cpp:407-408, :1094-1106)
+        status = NNP_ERR_BAD_SFEN;
+        n = h_tot->error_index;
+        if (n == 0) return status;
+    }
+    rc = compress_tail(codes, stems, n, status, d_out, out_cap, out_bytes);
+    if (rc != NNP_OK && rc != NNP_ERR_BAD_SFEN) return rc;
     CK(cudaEventRecord(C.ev[2], s));
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
     CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[0], C.ev[1]));
-    return status;
+    return rc;
 }
 
-// ---------------------------------------------------------------- .binpack -> .bin
+// ---------------------------------------------------------------- .plain -> entries
+
+struct ParsedText {
+    Entry* entries = nullptr;
+    u64 nrec = 0;
+};
+
+// record terminators -> per-record parse; NNP_ERR_BAD_TEXT for layouts the reference would
+// read differently from their line structure (or crash on)
+int parse_plain_dev(const void* d_text, size_t text_bytes, bool count_only, ParsedText& P)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    P.nrec = 0;
+    if (text_bytes == 0) return NNP_OK;
+    const u64 tiles = find_tiles(text_bytes);
+    WS(WS_TILE_COUNT, (tiles + 1) * 4, u32, tile_count);
+    WS(WS_TILE_PREFIX, (tiles + 2) * 8, u64, tile_prefix);
+    WS(WS_DTOTALS, sizeof(PlainTotals) + 64, PlainTotals, d_tot);
+    PlainTotals* h_tot = reinterpret_cast<PlainTotals*>((char*)C.pinned + 1280);
+    h_tot->error_pos = NO_ERROR_IDX;
+    h_tot->committed = 0;
+    CK(cudaMemcpyAsync(d_tot, h_tot, sizeof(PlainTotals), cudaMemcpyHostToDevice, s));
+    launch_find_records(false, d_text, text_bytes, tile_count, tile_prefix, nullptr, d_tot, s);
+    launch_exclusive_sum(tile_count, tiles, tile_prefix, s);
+    LAUNCHED(2, "k_find_records<count>");
+    u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+    CK(cudaMemcpyAsync(h_u64, tile_prefix + tiles, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(PlainTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    P.nrec = h_u64[0];
+    if (h_tot->error_pos != NO_ERROR_IDX) return NNP_ERR_BAD_TEXT;
+    if (count_only || P.nrec == 0) return NNP_OK;
+    WS(WS_TEXT_A, (P.nrec + 1) * 8, u64, rec_pos);
+    WS(WS_TEXT_B, P.nrec * sizeof(Entry), Entry, entries);
+    launch_find_records(true, d_text, text_bytes, tile_count, tile_prefix, rec_pos, d_tot, s);
+    launch_parse_records(d_text, text_bytes, rec_pos, P.nrec, entries, d_tot, s);
+    LAUNCHED(2, "k_parse_records");
+    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(PlainTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h_tot->error_pos != NO_ERROR_IDX) return NNP_ERR_BAD_TEXT;
+    P.entries = entries;
+    return NNP_OK;
+}
+
+int plain_to_binpack_dev(const void* d_text, size_t text_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    *out_bytes = 0;
+    ParsedText P;
+    int rc = parse_plain_dev(d_text, text_bytes, d_out == nullptr, P);
+    if (rc != NNP_OK) return rc;
+    if (!d_out) {
+        *out_bytes = binpack_capacity_for_records(P.nrec);
+        return NNP_OK;
+    }
+    if (P.nrec == 0) return NNP_OK;
+    if ((uintptr_t)d_out & 7) return NNP_ERR_BAD_ARG;
+    WS(WS_CODES, P.nrec * 4, u32, codes);
+    WS(WS_STEMS, P.nrec * 32, u32, stems);
+    CompressTotals* d_tot = nullptr;
+    rc = reset_compress_totals(&d_tot);
+    if (rc != NNP_OK) return rc;
+    launch_entries_link_encode(P.entries, P.nrec, codes, stems, s);
+    LAUNCHED(1, "k_entries_link_encode");
+    rc = compress_tail(codes, stems, P.nrec, NNP_OK, d_out, out_cap, out_bytes);
+    if (rc != NNP_OK) return rc;
+    CK(cudaStreamSynchronize(s));
+    return NNP_OK;
+}
+
+int plain_to_bin_dev(const void* d_text, size_t text_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    *out_bytes = 0;
+    ParsedText P;
+    int rc = parse_plain_dev(d_text, text_bytes, d_out == nullptr, P);
+    if (rc != NNP_OK) return rc;
+    *out_bytes = P.nrec * 40;
+    if (!d_out || P.nrec == 0) return NNP_OK;
+    if ((uintptr_t)d_out & 7) return NNP_ERR_BAD_ARG;
+    if (P.nrec * 40 > out_cap) return NNP_ERR_CAPACITY;
+    launch_entries_to_bin(P.entries, P.nrec, d_out, s);
+    LAUNCHED(1, "k_entries_to_bin");
+    CK(cudaStreamSynchronize(s));
+    return NNP_OK;
+}
+
+// ---------------------------------------------------------------- .bin -> .plain
+
+int bin_to_plain_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    *out_bytes = 0;
+    u64 n = bin_bytes / 40;
+    if (n == 0) return NNP_OK;
+    if ((uintptr_t)d_bin & 7) return NNP_ERR_BAD_ARG;
+    WS(WS_CODES, n * 4, u32, lens);
+    WS(WS_TEXT_A, (n + 2) * 8, u64, offs);
+    WS(WS_TILE_COUNT, (large_sum_tiles(n) + 1) * 4, u32, tile_sum);
+    WS(WS_TILE_PREFIX, (large_sum_tiles(n) + 2) * 8, u64, tile_prefix);
+    CompressTotals* d_tot = nullptr;
+    int rc = reset_compress_totals(&d_tot);
+    if (rc != NNP_OK) return rc;
+    CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
+    launch_bin_text(false, d_bin, n, lens, nullptr, nullptr, d_tot, s);
+    LAUNCHED(1, "k_bin_text<size>");
+    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int status = NNP_OK;
+    if (h_tot->error_index != NO_ERROR_IDX) {
+        status = NNP_ERR_BAD_SFEN;  // convertBinToPlain stops at the first malformed record
+        n = h_tot->error_index;
+        if (n == 0) return status;
+    }
+    launch_exclusive_sum_large(lens, n, offs, tile_sum, tile_prefix, s);
+    LAUNCHED(3, "text offsets");
+    u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+    CK(cudaMemcpyAsync(h_u64, offs + n, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const u64 total = h_u64[0];
+    *out_bytes = total;
+    if (!d_out) return status == NNP_OK ? NNP_OK : status;
+    if (total > out_cap) return NNP_ERR_CAPACITY;
+    launch_bin_text(true, d_bin, n, lens, offs, d_out, d_tot, s);
+    LAUNCHED(1, "k_bin_text<write>");
+    if (status != NNP_OK) {
+        // only what the reference had already flushed survives its exception (:1448-1455)
+        WS(WS_DTOTALS, sizeof(PlainTotals) + 64, PlainTotals, d_pt);
+        launch_text_flush_orbit(d_out, total, 0, &d_pt->committed, s);
+        LAUNCHED(1, "k_text_flush_orbit");
+        CK(cudaMemcpyAsync(h_u64, &d_pt->committed, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        *out_bytes = h_u64[0];
+        return status;
+    }
+    CK(cudaStreamSynchronize(s));
+    return NNP_OK;
+}
+
+// ---------------------------------------------------------------- .binpack -> .bin / .plain
 
 struct DecodePlan {
     ChunkTable tab;
-    u64 chunks = 0, tiles = 0, ncand = 0, positions = 0;
+    u64 chunks = 0, tiles = 0, ncand = 0, positions = 0, text_bytes = 0;
     int walk_status = 0;
     u32 *cand_chunk = nullptr, *cand_off = nullptr, *cand_next = nullptr, *cand_base = nullptr;
+    u64* cand_tbase = nullptr;
     u32 *chunk_count = nullptr, *chunk_slow = nullptr;
     u64* chunk_base = nullptr;
+    u64* chunk_tbase = nullptr;
     u64* tile_prefix = nullptr;
     DecompressTotals* d_tot = nullptr;
 };
 
-// everything up to (and including) the per-chunk position counts
-int decode_plan(const void* d_in, size_t in_bytes, DecodePlan& P)
+// everything up to (and including) the per-chunk position counts (and text sizes when `text`)
+int decode_plan(const void* d_in, size_t in_bytes, bool text, DecodePlan& P)
 {
     Context& C = g_ctx;
     cudaStream_t s = C.stream;
@@ -226,7 +391,7 @@ int decode_plan(const void* d_in, size_t in_bytes, DecodePlan& P)
     P.chunks = h_info->chunks;
     P.tiles = h_info->tiles;
     P.walk_status = h_info->status;
-    WS(WS_DTOTALS, sizeof(DecompressTotals), DecompressTotals, d_tot);
+    WS(WS_DTOTALS, sizeof(DecompressTotals) + 64, DecompressTotals, d_tot);
     P.d_tot = d_tot;
     DecompressTotals* h_tot = reinterpret_cast<DecompressTotals*>((char*)C.pinned + 512);
     h_tot->positions = 0;
@@ -255,19 +420,36 @@ int decode_plan(const void* d_in, size_t in_bytes, DecodePlan& P)
     WS(WS_CHUNK_COUNT, (P.chunks + 1) * 4, u32, chunk_count);
     WS(WS_CHUNK_SLOW, (P.chunks + 1) * 4, u32, chunk_slow);
     WS(WS_CHUNK_BASE, (P.chunks + 2) * 8, u64, chunk_base);
+    u32* cand_tlen = nullptr;
+    u64 *cand_tbase = nullptr, *chunk_tbytes = nullptr, *chunk_tbase = nullptr;
+    if (text) {
+        WS(WS_TEXT_A, (P.ncand + 1) * 4, u32, tl);
+        WS(WS_TEXT_B, (P.ncand + 1) * 8, u64, tb);
+        WS(WS_TEXT_C, (P.chunks + 1) * 8, u64, ctb);
+        WS(WS_TEXT_D, (P.chunks + 2) * 8, u64, ctbase);
+        cand_tlen = tl; cand_tbase = tb; chunk_tbytes = ctb; chunk_tbase = ctbase;
+    }
     P.cand_chunk = cand_chunk; P.cand_off = cand_off; P.cand_next = cand_next; P.cand_base = cand_base;
+    P.cand_tbase = cand_tbase; P.chunk_tbase = chunk_tbase;
     P.chunk_count = chunk_count; P.chunk_slow = chunk_slow; P.chunk_base = chunk_base;
 
     launch_candidates(true, d_in, P.tab, P.tiles, tile_count, tile_prefix, cand_chunk, cand_off, C.debug_reject_mod, s);
-    launch_probe_chains(d_in, P.tab, cand_chunk, cand_off, P.ncand, cand_next, cand_cnt, s);
-    launch_resolve_chunks(P.tab, P.chunks, tile_prefix, cand_off, cand_next, cand_cnt, cand_base, chunk_count, chunk_slow, s);
-    launch_slow_count(d_in, P.tab, P.chunks, chunk_slow, chunk_count, d_tot, s);
+    launch_probe_chains(d_in, P.tab, cand_chunk, cand_off, P.ncand, cand_next, cand_cnt, cand_tlen, s);
+    launch_resolve_chunks(P.tab, P.chunks, tile_prefix, cand_off, cand_next, cand_cnt, cand_base, chunk_count, chunk_slow,
+                          cand_tlen, cand_tbase, chunk_tbytes, s);
+    launch_slow_count(d_in, P.tab, P.chunks, chunk_slow, chunk_count, chunk_tbytes, d_tot, s);
     launch_exclusive_sum(chunk_count, P.chunks, chunk_base, s);
     LAUNCHED(5, "decode plan");
+    if (text) {
+        launch_exclusive_sum64(chunk_tbytes, P.chunks, chunk_tbase, s);
+        LAUNCHED(1, "k_exclusive_sum64");
+        CK(cudaMemcpyAsync(h_u64 + 1, chunk_tbase + P.chunks, 8, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaMemcpyAsync(h_u64, chunk_base + P.chunks, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(DecompressTotals), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     P.positions = h_u64[0];
+    P.text_bytes = text ? h_u64[1] : 0;
     if (h_tot->error_chunk != NO_ERROR_IDX) return NNP_ERR_TRUNCATED;
     return NNP_OK;
 }
@@ -292,7 +474,7 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
     if (in_bytes == 0) return NNP_OK;
     CK(cudaEventRecord(C.ev[0], s));
     DecodePlan P;
-    int rc = decode_plan(d_in, in_bytes, P);
+    int rc = decode_plan(d_in, in_bytes, false, P);
     if (rc != NNP_OK) return rc;
     CK(cudaEventRecord(C.ev[1], s));
     if (!d_out) {
@@ -322,26 +504,68 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
     return NNP_OK;
 }
 
+int binpack_to_plain_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    *out_bytes = 0;
+    if (in_bytes == 0) return NNP_OK;
+    DecodePlan P;
+    int rc = decode_plan(d_in, in_bytes, true, P);
+    if (rc != NNP_OK) return rc;
+    *out_bytes = P.text_bytes;
+    if (!d_out) return NNP_OK;
+    if (P.text_bytes > out_cap) return NNP_ERR_CAPACITY;
+    if (P.chunks > 0) {
+        launch_emit_chains_text(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_base, P.cand_tbase, P.ncand, P.chunk_tbase,
+                                d_out, P.d_tot, s);
+        launch_slow_emit_text(d_in, P.tab, P.chunks, P.chunk_slow, P.chunk_tbase, d_out, s);
+        LAUNCHED(2, "k_emit_chains_text");
+    }
+    DecompressTotals* h_tot = reinterpret_cast<DecompressTotals*>((char*)C.pinned + 512);
+    CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(DecompressTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h_tot->error_chunk != NO_ERROR_IDX) return NNP_ERR_TRUNCATED;
+    if (P.walk_status != 0) {
+        u64 committed = 0;
+        if (P.text_bytes > 0) {
+            WS(WS_TOTALS, sizeof(CompressTotals), CompressTotals, d_scratch);
+            launch_text_flush_orbit(d_out, P.text_bytes, 1, &d_scratch->chunks, s);
+            LAUNCHED(1, "k_text_flush_orbit");
+            u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+            CK(cudaMemcpyAsync(h_u64, &d_scratch->chunks, 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            committed = h_u64[0];
+        }
+        *out_bytes = committed;
+        return P.walk_status;
+    }
+    return NNP_OK;
+}
+
 // ---------------------------------------------------------------- host-buffer wrappers
 
 typedef int (*dev_fn)(const void*, size_t, void*, size_t, size_t*);
 
+bool is_reference_error(int rc) { return rc == NNP_ERR_BAD_MAGIC || rc == NNP_ERR_CHUNK_TOO_LARGE || rc == NNP_ERR_BAD_SFEN; }
+
+// H2D, device driver, D2H. `dev_out_cap` bounds the device-side output buffer; 0 means "the
+// caller's capacity" (callers size their buffer with the out == NULL query).
 int run_host(dev_fn fn, const void* in, size_t in_bytes, void* out, size_t out_cap, size_t* out_bytes, size_t dev_out_cap)
 {
     Context& C = g_ctx;
     WS(WS_STAGE_IN, in_bytes + 64, unsigned char, d_in);
     if (in_bytes) CK(cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, C.stream));
-    if (!out) return fn(d_in, in_bytes, nullptr, 0, out_bytes);
-    size_t need = dev_out_cap;
-    if (need == 0) {
-        int rc = fn(d_in, in_bytes, nullptr, 0, &need);
-        if (rc != NNP_OK) return rc;
+    if (!out) {
+        int rc = fn(d_in, in_bytes, nullptr, 0, out_bytes);
+        return is_reference_error(rc) ? NNP_OK : rc;  // the status is reported by the real call
     }
+    const size_t need = dev_out_cap ? dev_out_cap : out_cap;
     WS(WS_STAGE_OUT, need + 64, unsigned char, d_out);
     size_t produced = 0;
     int rc = fn(d_in, in_bytes, d_out, need, &produced);
     *out_bytes = produced;
-    if (rc == NNP_ERR_CAPACITY) return rc;
+    if (rc != NNP_OK && !is_reference_error(rc)) return rc;
     if (produced > out_cap) return NNP_ERR_CAPACITY;
     if (produced) {
         CK(cudaMemcpyAsync(out, d_out, produced, cudaMemcpyDeviceToHost, C.stream));
@@ -489,6 +713,47 @@ int nnp_binpack_to_bin(const void* binpack, size_t binpack_bytes, void* out, siz
     size_t bound = binpack_bytes * 64 + 40;
     if (out && out_cap < bound) bound = out_cap;
     return run_host(decompress_dev, binpack, binpack_bytes, out, out_cap, out_bytes, out ? bound : 0);
+}
+
+int nnp_plain_to_binpack_dev(const void* d_plain, size_t plain_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    return plain_to_binpack_dev(d_plain, plain_bytes, d_out, out_cap, out_bytes);
+}
+int nnp_plain_to_bin_dev(const void* d_plain, size_t plain_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    return plain_to_bin_dev(d_plain, plain_bytes, d_out, out_cap, out_bytes);
+}
+int nnp_bin_to_plain_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    return bin_to_plain_dev(d_bin, bin_bytes, d_out, out_cap, out_bytes);
+}
+int nnp_binpack_to_plain_dev(const void* d_binpack, size_t binpack_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    return binpack_to_plain_dev(d_binpack, binpack_bytes, d_out, out_cap, out_bytes);
+}
+int nnp_plain_to_binpack(const void* plain, size_t plain_bytes, void* out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    return run_host(plain_to_binpack_dev, plain, plain_bytes, out, out_cap, out_bytes, 0);
+}
+int nnp_plain_to_bin(const void* plain, size_t plain_bytes, void* out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    return run_host(plain_to_bin_dev, plain, plain_bytes, out, out_cap, out_bytes, 0);
+}
+int nnp_bin_to_plain(const void* bin, size_t bin_bytes, void* out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    return run_host(bin_to_plain_dev, bin, bin_bytes, out, out_cap, out_bytes, 0);
+}
+int nnp_binpack_to_plain(const void* binpack, size_t binpack_bytes, void* out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    return run_host(binpack_to_plain_dev, binpack, binpack_bytes, out, out_cap, out_bytes, 0);
 }
 
 int nnp_binpack_count_dev(const void* d_binpack, size_t binpack_bytes, uint64_t* n_positions)

@@ -244,6 +244,20 @@ __device__ __forceinline__ bool ep_possible(const Pos& p, int ep, int side)
     return ep_possible_cold(p, ep, attackers, side);
 }
 
+// Board::isSquareAttacked as used by Position::trySet (Position.cpp:505) and the game generator
+__device__ __forceinline__ bool square_attacked(const Pos& p, int sq, int by, u64 occ)
+{
+    const u64 them = pos_occ(p, by);
+    if (pawn_attacks(bit64(sq), by ^ 1) & pos_type_bb(p, PT_PAWN) & them) return true;
+    if (knight_attacks(sq) & pos_type_bb(p, PT_KNIGHT) & them) return true;
+    if (king_attacks(sq) & pos_type_bb(p, PT_KING) & them) return true;
+    const u64 bq = (pos_type_bb(p, PT_BISHOP) | pos_type_bb(p, PT_QUEEN)) & them;
+    const u64 rq = (pos_type_bb(p, PT_ROOK) | pos_type_bb(p, PT_QUEEN)) & them;
+    if (bq && (bishop_attacks(sq, occ) & bq)) return true;
+    if (rq && (rook_attacks(sq, occ) & rq)) return true;
+    return false;
+}
+
 // detail::lookup::preservedCastlingRights (Position.cpp:605-624)
 __device__ __forceinline__ int preserved_cr(int sq)
 {

@@ -77,4 +77,20 @@ struct DecompressTotals {
     u64 candidates;
 };
 
+// one parsed .plain record (TrainingDataEntry, compress_file.cpp:548-555), 64 bytes
+struct Entry {
+    u64 occ0, occ1, t0, t1, t2;
+    u32 meta;       // stm | ep << 1 | castling << 8 | rule50 << 12
+    u32 pos_ply;    // Position::m_ply
+    u32 mv;         // from | to << 6 | type << 12 | promoted piece << 14
+    u32 score_ply;  // score (int16) | ply << 16
+    u32 result;     // int16
+    u32 pad;
+};
+
+struct PlainTotals {
+    u64 error_pos;  // byte offset of the first construct the parser rejects, or NO_ERROR_IDX
+    u64 committed;  // scratch for the flush-boundary orbit
+};
+
 }  // namespace nnp

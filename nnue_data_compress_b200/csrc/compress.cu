@@ -17,6 +17,7 @@
 // record's score, so the encode is record-parallel; only bit offsets need a scan.
 #include "common.cuh"
 #include "kernels.h"
+#include "link.cuh"
 
 namespace nnp {
 
@@ -75,42 +76,25 @@ k_decode_link_encode(const unsigned char* __restrict__ bin, u64 n, u32* __restri
 
     if (!valid || t == 0) return;
 
-    const int score = (int)(short)(w8 & 0xFFFF);
-    const Move mv = sfmove_to_move(w8 >> 16);
-    const int ply = (int)(w9 & 0xFFFF);
-    const int result = (int)(signed char)((w9 >> 16) & 0xFF);
+    RecordFields cf;
+    cf.score = (int)(short)(w8 & 0xFFFF);
+    cf.mv = sfmove_to_move(w8 >> 16);
+    cf.ply = (int)(w9 & 0xFFFF);
+    cf.result = (int)(signed char)((w9 >> 16) & 0xFF);
 
-    bool cont = false;
-    int prev_score = 0;
-    if (rec > 0 && ok) {
-        // isContinuation (compress_file.cpp:587-593), short-circuit order preserved
-        const u32 pw8 = sh.w8[t - 1], pw9 = sh.w9[t - 1], pmeta = sh.meta[t - 1];
-        prev_score = (int)(short)(pw8 & 0xFFFF);
-        const int prev_ply = (int)(pw9 & 0xFFFF);
-        const int prev_result = (int)(signed char)((pw9 >> 16) & 0xFF);
-        if (prev_result == -result && prev_ply + 1 == ply && ((pmeta >> 16) & 1)) {
-            Pos a;
-            a.occ[0] = sh.occ0[t - 1]; a.occ[1] = sh.occ1[t - 1];
-            a.t0 = sh.t0[t - 1]; a.t1 = sh.t1[t - 1]; a.t2 = sh.t2[t - 1];
-            a.stm = pmeta & 1; a.ep = (pmeta >> 1) & 127; a.cr = (pmeta >> 8) & 15;
-            a.rule50 = 0; a.ply = 0;
-            pos_do_move(a, sfmove_to_move(pw8 >> 16));  // Position::afterMove
-            cont = pos_equal(a, p);
-        }
-    }
-    u32 code = 0;
-    if (cont) {
-        int nbits;
-        const int last_score = (int)(short)(-prev_score);  // m_lastScore (:838, :986)
-        const u32 bits = encode_ply(p, mv, score, last_score, nbits);
-        code = bits | (1u << (31 - nbits));  // sentinel-terminated, never zero
-    } else {
-        u32 s[8];
-        stem_pack(p, mv, score, ply, result, s);
-        uint4* d = reinterpret_cast<uint4*>(stems + (u64)rec * 8);
-        d[0] = make_uint4(s[0], s[1], s[2], s[3]);
-        d[1] = make_uint4(s[4], s[5], s[6], s[7]);
-    }
+    const u32 pw8 = sh.w8[t - 1], pw9 = sh.w9[t - 1], pmeta = sh.meta[t - 1];
+    RecordFields pf;
+    pf.score = (int)(short)(pw8 & 0xFFFF);
+    pf.mv = sfmove_to_move(pw8 >> 16);
+    pf.ply = (int)(pw9 & 0xFFFF);
+    pf.result = (int)(signed char)((pw9 >> 16) & 0xFF);
+    Pos a;
+    a.occ[0] = sh.occ0[t - 1]; a.occ[1] = sh.occ1[t - 1];
+    a.t0 = sh.t0[t - 1]; a.t1 = sh.t1[t - 1]; a.t2 = sh.t2[t - 1];
+    a.stm = pmeta & 1; a.ep = (pmeta >> 1) & 127; a.cr = (pmeta >> 8) & 15;
+    a.rule50 = 0; a.ply = 0;
+    const bool has_prev = rec > 0 && ok && ((pmeta >> 16) & 1);
+    const u32 code = link_and_encode(has_prev, a, pf, p, cf, stems + (u64)rec * 8);
     codes[rec] = code;
 }
 

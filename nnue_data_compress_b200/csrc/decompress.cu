@@ -22,6 +22,7 @@
 //   k_slow_emit        the same, sequentially, for flagged chunks
 #include "common.cuh"
 #include "kernels.h"
+#include "text.cuh"
 
 namespace nnp {
 
@@ -78,6 +79,37 @@ k_exclusive_sum(const u32* __restrict__ in, u64 n, u64* __restrict__ out)
     for (u64 i = lo; i < hi; ++i) {
         out[i] = run;
         run += in[i];
+    }
+}
+
+// single block: out[i] = sum of in[0..i) for u64 input (per-chunk text sizes), out[n] = total
+__global__ void __launch_bounds__(SUM_THREADS)
+k_exclusive_sum64(const u64* __restrict__ in, u64 n, u64* __restrict__ out)
+{
+    __shared__ u64 part[SUM_THREADS];
+    const u64 per = (n + SUM_THREADS - 1) / SUM_THREADS;
+    const u64 lo = (u64)threadIdx.x * per;
+    u64 hi = lo + per;
+    if (hi > n) hi = n;
+    u64 s = 0;
+    for (u64 i = lo; i < hi; ++i) s += in[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 run = 0;
+        for (int i = 0; i < SUM_THREADS; ++i) {
+            const u64 v = part[i];
+            part[i] = run;
+            run += v;
+        }
+        out[n] = run;
+    }
+    __syncthreads();
+    u64 run = part[threadIdx.x];
+    for (u64 i = lo; i < hi; ++i) {
+        const u64 v = in[i];
+        out[i] = run;
+        run += v;
     }
 }
 
@@ -238,10 +270,20 @@ __device__ __forceinline__ bool chain_step(ChainCursor& c, BitReader& r, bool st
 }
 
 // one thread per candidate: where does its chain end?
+__device__ __forceinline__ u32 plain_len(const ChainCursor& c)
+{
+    CountSink s;
+    put_plain_entry(s, c.pos, c.mv, c.score, c.ply, c.result);
+    return s.n;
+}
+
+// TEXT: also sum the .plain size of the chain's records (decompressPlain needs output offsets)
 constexpr int PROBE_THREADS = 128;
+template <bool TEXT>
 __global__ void __launch_bounds__(PROBE_THREADS)
 k_probe_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
-               const u32* __restrict__ cand_off, u64 ncand, u32* __restrict__ cand_next, u32* __restrict__ cand_cnt)
+               const u32* __restrict__ cand_off, u64 ncand, u32* __restrict__ cand_next, u32* __restrict__ cand_cnt,
+               u32* __restrict__ cand_tlen)
 {
     const u64 i = (u64)blockIdx.x * PROBE_THREADS + threadIdx.x;
     if (i >= ncand) return;
@@ -252,6 +294,7 @@ k_probe_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* 
     chain_open(s, cc);
     u32 next = off + 34;
     bool ok = true;
+    u32 tlen = TEXT ? plain_len(cc) : 0u;
     if (cc.num_plies > 0) {
         // the stored first move must start on a piece of the side to move
         const int pc = cc.mv.from < 64 ? pos_piece_at(cc.pos, cc.mv.from) : NO_PIECE;
@@ -262,11 +305,15 @@ k_probe_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* 
         r.nbits = avail_bits > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)avail_bits;
         r.pos = 0;
         r.overrun = false;
-        for (u32 k = 0; ok && k < cc.num_plies; ++k) ok = chain_step(cc, r, true);
+        for (u32 k = 0; ok && k < cc.num_plies; ++k) {
+            ok = chain_step(cc, r, true);
+            if (TEXT && ok) tlen += plain_len(cc);
+        }
         next = off + 34 + ((r.pos + 7) >> 3);  // numReadBytes (:815-818)
     }
     cand_next[i] = ok ? next : 0xFFFFFFFFu;
     cand_cnt[i] = 1u + cc.num_plies;
+    if (TEXT) cand_tlen[i] = tlen;
 }
 
 // One warp per chunk: Reader::next / fetchNextChunkIfNeeded (:1154-1213) over the candidate list.
@@ -277,7 +324,8 @@ constexpr int RESOLVE_WARPS = 4;
 __global__ void __launch_bounds__(RESOLVE_WARPS * 32)
 k_resolve_chunks(ChunkTable tab, const u64* __restrict__ tile_prefix, const u32* __restrict__ cand_off,
                  const u32* __restrict__ cand_next, const u32* __restrict__ cand_cnt, u32* __restrict__ cand_base,
-                 u32* __restrict__ chunk_count, u32* __restrict__ chunk_slow)
+                 u32* __restrict__ chunk_count, u32* __restrict__ chunk_slow, const u32* __restrict__ cand_tlen,
+                 u64* __restrict__ cand_tbase, u64* __restrict__ chunk_tbytes)
 {
     const u64 c = (u64)blockIdx.x * RESOLVE_WARPS + (threadIdx.x >> 5);
     if (c >= tab.info->chunks) return;
@@ -286,6 +334,7 @@ k_resolve_chunks(ChunkTable tab, const u64* __restrict__ tile_prefix, const u32*
     const u32 clen = tab.len[c];
     u64 i = cb;
     u32 cur = 0, count = 0;
+    u64 tbytes = 0;
     bool slow = false;
     while ((u64)cur + 34 <= clen) {
         if (i >= ce) { slow = true; break; }  // the expected chain start is not a candidate
@@ -310,6 +359,17 @@ k_resolve_chunks(ChunkTable tab, const u64* __restrict__ tile_prefix, const u32*
         }
         if (lane < good) cand_base[k] = count + inc - cn;
         count += __shfl_sync(0xffffffffu, inc, 31);
+        if (cand_tlen) {
+            const u64 tl = lane < good ? (u64)cand_tlen[k] : 0ull;
+            u64 tinc = tl;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const u64 v = __shfl_up_sync(0xffffffffu, tinc, d);
+                if (lane >= d) tinc += v;
+            }
+            if (lane < good) cand_tbase[k] = tbytes + tinc - tl;
+            tbytes += __shfl_sync(0xffffffffu, tinc, 31);
+        }
         if (good > 0) cur = __shfl_sync(0xffffffffu, nx, good - 1);
         i += good;
         if (good < 32 && (u64)cur + 34 <= clen) {
@@ -334,10 +394,12 @@ k_resolve_chunks(ChunkTable tab, const u64* __restrict__ tile_prefix, const u32*
         __syncwarp();
         for (u64 k = cb + lane; k < ce; k += 32) cand_base[k] = 0xFFFFFFFFu;
         count = 0;  // filled in by k_slow_count
+        tbytes = 0;
     }
     if (lane == 0) {
         chunk_count[c] = count;
         chunk_slow[c] = slow ? 1u : 0u;
+        if (chunk_tbytes) chunk_tbytes[c] = tbytes;
     }
 }
 
@@ -397,22 +459,45 @@ k_emit_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* _
     if (!ok) atomicMin(&tot->error_chunk, (u64)c);
 }
 
+// the same walk, writing emitPlainEntry text (decompressPlain :1299-1335)
+__global__ void __launch_bounds__(EMITC_THREADS)
+k_emit_chains_text(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
+                   const u32* __restrict__ cand_off, const u32* __restrict__ cand_base, const u64* __restrict__ cand_tbase,
+                   u64 ncand, const u64* __restrict__ chunk_tbase, unsigned char* __restrict__ out, DecompressTotals* tot)
+{
+    const u64 i = (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
+    if (i >= ncand) return;
+    if (cand_base[i] == 0xFFFFFFFFu) return;
+    const u32 c = cand_chunk[i], off = cand_off[i];
+    const unsigned char* s = in + tab.start[c] + off;
+    WriteSink sink{out + chunk_tbase[c] + cand_tbase[i]};
+    u32 consumed = 0;
+    const bool ok = walk_chain(s, tab.len[c] - off - 34,
+                               [&](const ChainCursor& cc, u32) { put_plain_entry(sink, cc.pos, cc.mv, cc.score, cc.ply, cc.result); },
+                               consumed);
+    if (!ok) atomicMin(&tot->error_chunk, (u64)c);
+}
+
 // sequential fallback, one thread per flagged chunk
 __global__ void k_slow_count(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ chunk_slow,
-                             u32* __restrict__ chunk_count, DecompressTotals* tot)
+                             u32* __restrict__ chunk_count, u64* __restrict__ chunk_tbytes, DecompressTotals* tot)
 {
     const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= tab.info->chunks || !chunk_slow[c]) return;
     const u32 clen = tab.len[c];
     const unsigned char* base = in + tab.start[c];
     u32 cur = 0, count = 0;
+    u64 tbytes = 0;
     while ((u64)cur + 34 <= clen) {
         u32 consumed = 0;
-        const bool ok = walk_chain(base + cur, clen - cur - 34, [&](const ChainCursor&, u32) { ++count; }, consumed);
+        const bool ok = walk_chain(base + cur, clen - cur - 34,
+                                   [&](const ChainCursor& cc, u32) { ++count; if (chunk_tbytes) tbytes += plain_len(cc); },
+                                   consumed);
         if (!ok) { atomicMin(&tot->error_chunk, (u64)c); break; }
         cur += consumed;
     }
     chunk_count[c] = count;
+    if (chunk_tbytes) chunk_tbytes[c] = tbytes;
     atomicAdd(&tot->slow_chunks, 1ull);
 }
 __global__ void k_slow_emit(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ chunk_slow,
@@ -429,6 +514,28 @@ __global__ void k_slow_emit(const unsigned char* __restrict__ in, ChunkTable tab
         u32 consumed = 0;
         const bool ok = walk_chain(base + cur, clen - cur - 34,
                                    [&](const ChainCursor& cc, u32) { if (rec < rec_end) emit_bin_record(cc, out, rec); ++rec; },
+                                   consumed);
+        if (!ok) break;
+        cur += consumed;
+    }
+}
+
+__global__ void k_slow_emit_text(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ chunk_slow,
+                                 const u64* __restrict__ chunk_tbase, unsigned char* __restrict__ out)
+{
+    const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= tab.info->chunks || !chunk_slow[c]) return;
+    const u32 clen = tab.len[c];
+    const unsigned char* base = in + tab.start[c];
+    u32 cur = 0;
+    WriteSink sink{out + chunk_tbase[c]};
+    unsigned char* const end = out + chunk_tbase[c + 1];
+    while ((u64)cur + 34 <= clen) {
+        u32 consumed = 0;
+        const bool ok = walk_chain(base + cur, clen - cur - 34,
+                                   [&](const ChainCursor& cc, u32) {
+                                       if (sink.p + plain_len(cc) <= end) put_plain_entry(sink, cc.pos, cc.mv, cc.score, cc.ply, cc.result);
+                                   },
                                    consumed);
         if (!ok) break;
         cur += consumed;
@@ -456,25 +563,51 @@ void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s)
 {
     k_exclusive_sum<<<1, SUM_THREADS, 0, s>>>(in, n, out);
 }
+void launch_exclusive_sum64(const u64* in, u64 n, u64* out, cudaStream_t s)
+{
+    k_exclusive_sum64<<<1, SUM_THREADS, 0, s>>>(in, n, out);
+}
 void launch_probe_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u64 ncand,
-                         u32* cand_next, u32* cand_cnt, cudaStream_t s)
+                         u32* cand_next, u32* cand_cnt, u32* cand_tlen, cudaStream_t s)
 {
     if (ncand == 0) return;
-    k_probe_chains<<<(unsigned)((ncand + PROBE_THREADS - 1) / PROBE_THREADS), PROBE_THREADS, 0, s>>>(
-        (const unsigned char*)d_in, tab, cand_chunk, cand_off, ncand, cand_next, cand_cnt);
+    const unsigned blocks = (unsigned)((ncand + PROBE_THREADS - 1) / PROBE_THREADS);
+    if (cand_tlen)
+        k_probe_chains<true><<<blocks, PROBE_THREADS, 0, s>>>((const unsigned char*)d_in, tab, cand_chunk, cand_off, ncand,
+                                                             cand_next, cand_cnt, cand_tlen);
+    else
+        k_probe_chains<false><<<blocks, PROBE_THREADS, 0, s>>>((const unsigned char*)d_in, tab, cand_chunk, cand_off, ncand,
+                                                              cand_next, cand_cnt, cand_tlen);
 }
 void launch_resolve_chunks(ChunkTable tab, u64 chunks, const u64* tile_prefix, const u32* cand_off, const u32* cand_next,
-                           const u32* cand_cnt, u32* cand_base, u32* chunk_count, u32* chunk_slow, cudaStream_t s)
+                           const u32* cand_cnt, u32* cand_base, u32* chunk_count, u32* chunk_slow, const u32* cand_tlen,
+                           u64* cand_tbase, u64* chunk_tbytes, cudaStream_t s)
 {
     if (chunks == 0) return;
     k_resolve_chunks<<<(unsigned)((chunks + RESOLVE_WARPS - 1) / RESOLVE_WARPS), RESOLVE_WARPS * 32, 0, s>>>(
-        tab, tile_prefix, cand_off, cand_next, cand_cnt, cand_base, chunk_count, chunk_slow);
+        tab, tile_prefix, cand_off, cand_next, cand_cnt, cand_base, chunk_count, chunk_slow, cand_tlen, cand_tbase, chunk_tbytes);
 }
 void launch_slow_count(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, u32* chunk_count,
-                       DecompressTotals* tot, cudaStream_t s)
+                       u64* chunk_tbytes, DecompressTotals* tot, cudaStream_t s)
 {
     if (chunks == 0) return;
-    k_slow_count<<<(unsigned)((chunks + 31) / 32), 32, 0, s>>>((const unsigned char*)d_in, tab, chunk_slow, chunk_count, tot);
+    k_slow_count<<<(unsigned)((chunks + 31) / 32), 32, 0, s>>>((const unsigned char*)d_in, tab, chunk_slow, chunk_count,
+                                                               chunk_tbytes, tot);
+}
+void launch_emit_chains_text(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, const u32* cand_base,
+                             const u64* cand_tbase, u64 ncand, const u64* chunk_tbase, void* out, DecompressTotals* tot,
+                             cudaStream_t s)
+{
+    if (ncand == 0) return;
+    k_emit_chains_text<<<(unsigned)((ncand + EMITC_THREADS - 1) / EMITC_THREADS), EMITC_THREADS, 0, s>>>(
+        (const unsigned char*)d_in, tab, cand_chunk, cand_off, cand_base, cand_tbase, ncand, chunk_tbase, (unsigned char*)out, tot);
+}
+void launch_slow_emit_text(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, const u64* chunk_tbase,
+                           void* out, cudaStream_t s)
+{
+    if (chunks == 0) return;
+    k_slow_emit_text<<<(unsigned)((chunks + 31) / 32), 32, 0, s>>>((const unsigned char*)d_in, tab, chunk_slow, chunk_tbase,
+                                                                   (unsigned char*)out);
 }
 void launch_emit_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, const u32* cand_base,
                         u64 ncand, const u64* chunk_base, void* out, DecompressTotals* tot, cudaStream_t s)

@@ -34,16 +34,37 @@ void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks,
 void launch_candidates(bool write, const void* d_in, ChunkTable tab, u64 tiles, u32* tile_count, const u64* tile_prefix,
                        u32* cand_chunk, u32* cand_off, u32 debug_reject_mod, cudaStream_t s);
 void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s);
+void launch_exclusive_sum64(const u64* in, u64 n, u64* out, cudaStream_t s);
 void launch_probe_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u64 ncand,
-                         u32* cand_next, u32* cand_cnt, cudaStream_t s);
+                         u32* cand_next, u32* cand_cnt, u32* cand_tlen, cudaStream_t s);
 void launch_resolve_chunks(ChunkTable tab, u64 chunks, const u64* tile_prefix, const u32* cand_off, const u32* cand_next,
-                           const u32* cand_cnt, u32* cand_base, u32* chunk_count, u32* chunk_slow, cudaStream_t s);
+                           const u32* cand_cnt, u32* cand_base, u32* chunk_count, u32* chunk_slow, const u32* cand_tlen,
+                           u64* cand_tbase, u64* chunk_tbytes, cudaStream_t s);
 void launch_slow_count(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, u32* chunk_count,
-                       DecompressTotals* tot, cudaStream_t s);
+                       u64* chunk_tbytes, DecompressTotals* tot, cudaStream_t s);
+void launch_emit_chains_text(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, const u32* cand_base,
+                             const u64* cand_tbase, u64 ncand, const u64* chunk_tbase, void* out, DecompressTotals* tot,
+                             cudaStream_t s);
+void launch_slow_emit_text(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, const u64* chunk_tbase,
+                           void* out, cudaStream_t s);
 void launch_emit_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, const u32* cand_base,
                         u64 ncand, const u64* chunk_base, void* out, DecompressTotals* tot, cudaStream_t s);
 void launch_slow_emit(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, const u64* chunk_base, void* out,
                       cudaStream_t s);
+
+// ---- .plain text, plain.cu
+u64 large_sum_tiles(u64 n);
+void launch_exclusive_sum_large(const u32* in, u64 n, u64* out, u32* tile_sum, u64* tile_prefix, cudaStream_t s);
+u64 find_tiles(u64 n);
+void launch_find_records(bool write, const void* text, u64 n, u32* tile_count, const u64* tile_prefix, u64* rec_pos,
+                         PlainTotals* tot, cudaStream_t s);
+void launch_parse_records(const void* text, u64 n, const u64* rec_pos, u64 nrec, Entry* entries, PlainTotals* tot,
+                          cudaStream_t s);
+void launch_entries_link_encode(const Entry* entries, u64 n, u32* codes, u32* stems, cudaStream_t s);
+void launch_entries_to_bin(const Entry* entries, u64 n, void* out, cudaStream_t s);
+void launch_bin_text(bool write, const void* bin, u64 n, u32* lens, const u64* offs, void* out, CompressTotals* tot,
+                     cudaStream_t s);
+void launch_text_flush_orbit(const void* text, u64 limit, int drop_last, u64* committed, cudaStream_t s);
 
 // ---- synthetic input, generate.cu
 void launch_play_games(bool write, u64 n_games, u32 max_plies, u64 seed, u32* game_len, const u64* game_base, void* out,

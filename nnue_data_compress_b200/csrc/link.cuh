@@ -1,0 +1,43 @@
+// link.cuh -- the per-record half of CompressedTrainingDataEntryWriter::addTrainingDataEntry
+// (compress_file.cpp:1061-1092), shared by the .bin and the .plain compressors: decide whether a
+// record continues its predecessor (isContinuation :587-593) and produce either its movetext bit
+// string (addMoveScore :877-989) or its 32-byte stem (packEntry :997-1020).
+#pragma once
+#include "chess.cuh"
+
+namespace nnp {
+
+struct RecordFields {
+    Move mv;
+    int score;   // int16
+    int ply;     // uint16
+    int result;  // int16 (int8 widened on the .bin path)
+};
+
+// Returns the record's code word: 0 for a chain head (its stem is stored at `stem_out`, 8 words),
+// otherwise the ply's bits left-aligned and terminated by a single 1 bit (never zero), so that the
+// bit count is 32 - ffs(code).
+__device__ __forceinline__ u32 link_and_encode(bool has_prev, const Pos& prev, const RecordFields& pf, const Pos& cur,
+                                               const RecordFields& cf, u32* stem_out)
+{
+    bool cont = false;
+    if (has_prev && pf.result == -cf.result && pf.ply + 1 == cf.ply) {  // short-circuit order of :589-592
+        Pos a = prev;
+        pos_do_move(a, pf.mv);  // Position::afterMove
+        cont = pos_equal(a, cur);
+    }
+    if (cont) {
+        int nbits;
+        const int last_score = (int)(short)(-pf.score);  // m_lastScore (:838, :986)
+        const u32 bits = encode_ply(cur, cf.mv, cf.score, last_score, nbits);
+        return bits | (1u << (31 - nbits));
+    }
+    u32 s[8];
+    stem_pack(cur, cf.mv, cf.score, cf.ply, cf.result, s);
+    uint4* d = reinterpret_cast<uint4*>(stem_out);
+    d[0] = make_uint4(s[0], s[1], s[2], s[3]);
+    d[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    return 0u;
+}
+
+}  // namespace nnp

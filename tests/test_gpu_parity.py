@@ -175,3 +175,99 @@ def test_sequential_fallback_is_exact(nnp):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert "FALLBACK_OK" in out.stdout, out.stdout + out.stderr
+
+
+# ---------------------------------------------------------------------------------------------
+# .plain path (compressPlain / decompressPlain / convertBinToPlain / convertPlainToBin)
+
+from refutil import BIN_TO_PLAIN, BINPACK_TO_PLAIN, GOLDEN_PLAIN_SETS, PLAIN_TO_BIN, PLAIN_TO_BINPACK  # noqa: E402
+
+
+@pytest.mark.parametrize("name", GOLDEN_PLAIN_SETS)
+def test_golden_plain_directions(nnp, name):
+    assert nnp.binpack_to_plain(golden(name + ".binpack")) == golden(name + ".plain")
+    assert nnp.plain_to_binpack(golden(name + ".plain")) == golden(name + ".p.binpack")
+    assert nnp.bin_to_plain(golden(name + ".bin")) == golden(name + ".b.plain")
+    assert nnp.plain_to_bin(golden(name + ".b.plain")) == golden(name + ".p.bin")
+
+
+def test_kat_plain(nnp):
+    expect = bytes.fromhex(
+        "42494e5026000000ffff00000000ffff2d844ad200000000111111113e955be30c7000328000000000024299a040"
+    )
+    assert nnp.plain_to_binpack(golden("kat.plain")) == expect
+    assert nnp.binpack_to_plain(expect) == golden("kat.rt.plain")
+    assert nnp.plain_to_bin(golden("kat.plain")) == oracle_convert(PLAIN_TO_BIN, golden("kat.plain"))[1]
+
+
+@pytest.mark.parametrize("n,plies,seed", [(120_000, 100, 21), (40_000, 1, 22), (60_000, 400, 23)])
+def test_oracle_parity_plain(nnp, n, plies, seed):
+    b = nnp.generate_bin(n, plies, seed)
+    rc, bp = oracle_convert(BIN_TO_BINPACK, b)
+    assert rc == 0
+    rc, pl = oracle_convert(BINPACK_TO_PLAIN, bp)
+    assert rc == 0
+    assert nnp.binpack_to_plain(bp) == pl
+    rc, bp2 = oracle_convert(PLAIN_TO_BINPACK, pl)
+    assert rc == 0
+    assert nnp.plain_to_binpack(pl) == bp2
+    rc, bpl = oracle_convert(BIN_TO_PLAIN, b)
+    assert rc == 0
+    assert nnp.bin_to_plain(b) == bpl
+    rc, b2 = oracle_convert(PLAIN_TO_BIN, bpl)
+    assert rc == 0
+    assert nnp.plain_to_bin(bpl) == b2
+
+
+def test_plain_layout_variants(nnp):
+    """Key order, unknown keys, inherited fields, blank lines, CR before LF on the terminator, no
+    trailing newline: everything the reference tokeniser reads line by line."""
+    base = golden("kat.plain").decode()
+    recs = base.strip().split("e\n")
+    recs = [r for r in recs if r.strip()]
+    shuffled = ""
+    for r in recs:
+        lines = r.strip().split("\n")
+        shuffled += "\n".join(reversed(lines)) + "\ncomment ignored by the parser\n\n  e  \n"
+    inherited = recs[0] + "e\n" + "move e2e3\ne\n" + "fen " + recs[1].split("fen ")[1] + "e"
+    for text in (shuffled, inherited):
+        data = text.encode()
+        for mode, fn in ((PLAIN_TO_BINPACK, nnp.plain_to_binpack), (PLAIN_TO_BIN, nnp.plain_to_bin)):
+            rc, want = oracle_convert(mode, data)
+            assert rc == 0
+            assert fn(data) == want
+    assert nnp.plain_to_bin(b"") == b"" and nnp.plain_to_binpack(b"\n\n") == b""
+
+
+def test_plain_rejected_layouts(nnp):
+    for text in (b"fen\nrnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1\nmove e2e4\nscore 1\nply 0\nresult 0\ne\n",
+                 b"fen rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1\nmove e2e4\nscore x\nply 0\nresult 0\ne\n",
+                 b"fen rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1\nmove e2e4\nscore 1\nply 0\nresult 0\ne fen x\n"):
+        with pytest.raises(nnp.NnpError) as ei:
+            nnp.plain_to_binpack(text)
+        assert ei.value.status == -7
+
+
+def test_plain_error_partial_outputs(nnp):
+    """bad sfen in .bin -> .plain and bad chunk in .binpack -> .plain: only what the reference had
+    flushed (1 MiB buffer rule) survives."""
+    b = nnp.generate_bin(30_000, 100, 31)
+    bits = [0] + [0] * 6 + [1, 0, 0, 0, 0, 0] + [1, 0, 0, 0, 0] * 49
+    sfen = bytearray(32)
+    for i, v in enumerate(bits[:256]):
+        sfen[i // 8] |= v << (i & 7)
+    bad = bytes(sfen) + bytes(8)
+    data = b[: 40 * 25_000] + bad + b[40 * 25_000:]
+    rc, want = oracle_convert(BIN_TO_PLAIN, data)
+    assert rc == -3 and len(want) > 1 << 20
+    with pytest.raises(nnp.NnpError) as ei:
+        nnp.bin_to_plain(data)
+    assert ei.value.status == -3 and ei.value.partial == want
+    bp = golden("twochunks.binpack")
+    second = 8 + int.from_bytes(bp[4:8], "little")
+    data = bp[:second] + b"BINX" + bp[second + 4:]
+    rc, want = oracle_convert(BINPACK_TO_PLAIN, data)
+    assert rc == -1 and len(want) > 1 << 20
+    with pytest.raises(nnp.NnpError) as ei:
+        nnp.binpack_to_plain(data)
+    assert ei.value.status == -1 and ei.value.partial == want
