@@ -1,0 +1,136 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/nnuepack.h declares, it
+refuses to run without a GPU (no CPU fallback), and the host-side mirrors of the reference CLI
+dispatch exactly like compress_file.cpp:1593-1709. No compute calls are made here."""
+import ctypes
+import io
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "nnuepack.h")
+LIB = os.path.join(ROOT, "nnue_data_compress_b200", "libnnuepack.so")
+CLI = os.path.join(ROOT, "nnue_data_compress_b200", "nnue_data_compression")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nnp_[a-z0-9_]+)\s*\(", text)))
+
+
+def have_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(LIB), "build with python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(LIB)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), name
+    import nnue_data_compress_b200 as pkg
+
+    assert sorted(pkg.EXPORTS) == names
+
+
+def test_error_strings_are_the_reference_messages():
+    lib = ctypes.CDLL(LIB)
+    lib.nnp_strerror.restype = ctypes.c_char_p
+    assert lib.nnp_strerror(-1) == b"Invalid binpack file or chunk."  # compress_file.cpp:506
+    assert lib.nnp_strerror(-2) == b"Chunks size larger than supported. Malformed file?"  # :517
+    assert lib.nnp_strerror(-3) == b"Improperly encoded bin sfen"  # :408, :442
+
+
+@pytest.mark.skipif(have_gpu(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    lib = ctypes.CDLL(LIB)
+    n = ctypes.c_size_t(0)
+    buf = ctypes.create_string_buffer(64)
+    # not initialised: every driver refuses
+    for name in ("nnp_bin_to_binpack", "nnp_binpack_to_bin", "nnp_plain_to_binpack", "nnp_binpack_to_plain",
+                 "nnp_bin_to_plain", "nnp_plain_to_bin"):
+        assert getattr(lib, name)(buf, 40, buf, 64, ctypes.byref(n)) == -10
+    assert lib.nnp_init(0) == -9  # NNP_ERR_NO_DEVICE
+    import nnue_data_compress_b200 as pkg
+
+    with pytest.raises(pkg.NnpError) as ei:
+        pkg.bin_to_binpack(b"\0" * 40)
+    assert ei.value.status == -9
+
+
+def _run_main(pkg, argv, monkeypatch, calls):
+    for name in ("bin_to_binpack", "binpack_to_bin", "plain_to_binpack", "binpack_to_plain", "bin_to_plain", "plain_to_bin"):
+        monkeypatch.setattr(pkg, name, (lambda nm: (lambda data: calls.append(nm) or nm.encode()))(name))
+    out, err = io.StringIO(), io.StringIO()
+    rc = pkg.main(argv, out=out, err=err)
+    return rc, out.getvalue(), err.getvalue()
+
+
+def test_cli_mirror_dispatch(tmp_path, monkeypatch):
+    import nnue_data_compress_b200 as pkg
+
+    calls = []
+    rc, out, err = _run_main(pkg, [], monkeypatch, calls)
+    assert rc == 0 and out.startswith("Usage:")
+    rc, out, err = _run_main(pkg, ["a", "b", "c"], monkeypatch, calls)
+    assert rc == 1 and err == "Invalid arguments.\n"
+    rc, out, err = _run_main(pkg, [str(tmp_path / "missing.bin"), "x"], monkeypatch, calls)
+    assert rc == 0 and err == "Input file doesn't exist.\n"
+
+    table = [("a.bin", "o", "bin_to_binpack", "o.binpack"), ("a.plain", "o.binpack", "plain_to_binpack", "o.binpack"),
+             ("a.binpack", "o.bin", "binpack_to_bin", "o.bin"), ("a.binpack", "o.plain", "binpack_to_plain", "o.plain"),
+             ("a.bin", "o.plain", "bin_to_plain", "o.plain"), ("a.plain", "o.bin", "plain_to_bin", "o.bin")]
+    for src, dst, fn, produced in table:
+        (tmp_path / src).write_bytes(b"x")
+        calls.clear()
+        rc, out, err = _run_main(pkg, [str(tmp_path / src), str(tmp_path / dst)], monkeypatch, calls)
+        assert rc == 0 and calls == [fn]
+        assert (tmp_path / produced).read_bytes() == fn.encode()
+    # -a appends, --append is silently ignored (stored as "-append", compress_file.cpp:1684-1687)
+    (tmp_path / "o.binpack").write_bytes(b"bin_to_binpack")
+    rc, _, _ = _run_main(pkg, ["-a", str(tmp_path / "a.bin"), str(tmp_path / "o")], monkeypatch, calls)
+    assert (tmp_path / "o.binpack").read_bytes() == b"bin_to_binpack" * 2
+    rc, _, _ = _run_main(pkg, ["--append", str(tmp_path / "a.bin"), str(tmp_path / "o")], monkeypatch, calls)
+    assert (tmp_path / "o.binpack").read_bytes() == b"bin_to_binpack"
+    (tmp_path / "a.txt").write_bytes(b"x")
+    rc, out, err = _run_main(pkg, [str(tmp_path / "a.txt"), "o"], monkeypatch, calls)
+    assert rc == 0 and err == "Unsupported extension."
+
+
+def test_cli_mirror_reference_error(tmp_path, monkeypatch):
+    """A reference-style error writes the partial output, prints the message and 'Exiting...',
+    and still exits 0 (compress_file.cpp:1697-1709)."""
+    import nnue_data_compress_b200 as pkg
+
+    def boom(data):
+        raise pkg.NnpError(-1, "Invalid binpack file or chunk.", partial=b"partial")
+
+    monkeypatch.setattr(pkg, "binpack_to_bin", boom)
+    (tmp_path / "a.binpack").write_bytes(b"x")
+    out, err = io.StringIO(), io.StringIO()
+    rc = pkg.main([str(tmp_path / "a.binpack"), str(tmp_path / "o.bin")], out=out, err=err)
+    assert rc == 0
+    assert err.getvalue() == "Invalid binpack file or chunk.\nExiting...\n"
+    assert (tmp_path / "o.bin").read_bytes() == b"partial"
+
+
+def test_native_cli_argument_handling():
+    assert os.access(CLI, os.X_OK)
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("Usage:")
+    r = subprocess.run([CLI, "-h", "a", "b"], capture_output=True, text=True)
+    assert r.returncode == 0 and "nnue_data_compression [-h] [-a] input_path output_path" in r.stdout
+    r = subprocess.run([CLI, "a", "b", "c"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("Invalid arguments.")
+    if not have_gpu():
+        r = subprocess.run([CLI, "a.bin", "b"], capture_output=True, text=True)
+        assert r.returncode == 2 and "no usable sm_100a CUDA device" in r.stderr

@@ -1,0 +1,101 @@
+"""CPU suite: the multi-rank path (world_size 2, gloo). Each rank converts its own shard --
+with the oracle standing in for the CUDA converter -- exchanges byte counts with the same
+all-gather the GPU path uses, and the shard outputs assembled at the gathered offsets must equal
+what the reference semantics prescribe (one run per shard, appended)."""
+import os
+import socket
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, tmpdir):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from nnue_data_compress_b200.sharding import chunk_bounds_binpack, exchange_offsets, shard_bounds
+    from refutil import BIN_TO_BINPACK, BINPACK_TO_BIN, golden, oracle_convert
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b = golden("twochunks.bin")
+        n = len(b) // 40
+        lo, hi = shard_bounds(n, world, rank)
+        rc, mine = oracle_convert(BIN_TO_BINPACK, b[lo * 40:hi * 40])
+        assert rc == 0
+        off, total, sizes = exchange_offsets(len(mine))
+        assert sizes[rank] == len(mine) and total == sum(sizes)
+        with open(os.path.join(tmpdir, f"pack{rank}"), "wb") as f:
+            f.write(off.to_bytes(8, "little") + mine)
+        # decompression shards by chunk ranges of the full file
+        full = golden("twochunks.binpack")
+        chunks = chunk_bounds_binpack(full)
+        clo, chi = shard_bounds(len(chunks), world, rank)
+        part = b"".join(full[o:o + l] for o, l in chunks[clo:chi])
+        rc, rec = oracle_convert(BINPACK_TO_BIN, part)
+        assert rc == 0
+        off2, total2, _ = exchange_offsets(len(rec))
+        with open(os.path.join(tmpdir, f"bin{rank}"), "wb") as f:
+            f.write(off2.to_bytes(8, "little") + rec)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_shards_assemble(tmp_path):
+    import torch.multiprocessing as mp
+
+    from refutil import BIN_TO_BINPACK, golden, oracle_convert
+    from nnue_data_compress_b200.sharding import shard_bounds
+
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+
+    b = golden("twochunks.bin")
+    n = len(b) // 40
+    expect = b""
+    for r in range(world):
+        lo, hi = shard_bounds(n, world, r)
+        expect += oracle_convert(BIN_TO_BINPACK, b[lo * 40:hi * 40])[1]  # reference: one run per shard, -a
+    out = bytearray(len(expect))
+    for r in range(world):
+        raw = (tmp_path / f"pack{r}").read_bytes()
+        off = int.from_bytes(raw[:8], "little")
+        out[off:off + len(raw) - 8] = raw[8:]
+    assert bytes(out) == expect
+
+    full_bin = golden("twochunks.rt.bin")
+    out = bytearray(len(full_bin))
+    for r in range(world):
+        raw = (tmp_path / f"bin{r}").read_bytes()
+        off = int.from_bytes(raw[:8], "little")
+        out[off:off + len(raw) - 8] = raw[8:]
+    assert bytes(out) == full_bin  # chunk-sharded decompression is exact
+
+
+def test_shard_bounds_cover_everything():
+    from nnue_data_compress_b200.sharding import offsets_from_sizes, shard_bounds
+
+    for n in (0, 1, 7, 8, 9, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    assert offsets_from_sizes([3, 0, 5]) == [0, 3, 3]
