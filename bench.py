@@ -39,6 +39,14 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "nnue_data_compression")
 REF_GEN = os.path.join(ROOT, "oracle", "_ref", "gen_ref")
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    """progress on stderr (the JSON line is the only thing on stdout)"""
+    print(f"[bench +{time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -260,9 +268,11 @@ def main():
 
     n_pos = args.positions
     bin_bytes = n_pos * 40
+    log(f"rank {rank}: generating {n_pos} positions on the device")
     d_bin = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
     check(L.nnp_generate_bin_dev(ctypes.c_void_p(d_bin.data_ptr()), n_pos, args.plies, args.seed + 1000 * rank), "generate")
 
+    log("generated; sizing pass")
     need = ctypes.c_size_t(0)
     # the generic capacity bound assumes every record is a chain head (34 B/pos); one sizing pass
     # gives the real size so that the benchmark buffers are not 3.4 GB of slack
@@ -300,8 +310,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    log(f"binpack is {pack_bytes} bytes; warm-up")
     for _ in range(args.warmup):
         step_device()
+    log("timed region")
     sampler = ClockSampler(local_rank)
     launches0 = L.nnp_kernel_launches()
     barrier()
@@ -323,6 +335,7 @@ def main():
     K = max(args.steps, 1)
     c_ms, c_dom, d_ms, d_dom = c_ms / K, c_dom / K, d_ms / K, d_dom / K
 
+    log(f"device-resident: {elapsed_ms / max(args.steps, 1):.2f} ms/step")
     # ---- e2e: host buffers through the public C ABI, H2D and D2H inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -344,7 +357,9 @@ def main():
             return n1.value, n2.value
 
         e_steps = max(1, min(args.steps, 3))
+        log("e2e warm-up")
         step_host()
+        log("e2e timed")
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -419,6 +434,7 @@ def main():
         },
     }
 
+    log("cpu baseline")
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1 and reference_available():
         r = cpu_reference_measure(args.cpu_sample, args.plies, args.seed, 1, 1, 0)

@@ -317,15 +317,15 @@ k_chunk_orbit(const u64* __restrict__ head_off, CompressTotals* tot, u64* __rest
             u64 lo = cur + 1, hi = H;  // answer in [lo, hi]; hi == H means none
             while (lo < hi) {
                 const u64 span = hi - lo;
-                const u64 step = (span + 32) / 33;  // 32 probes split the range into 33 parts
+                const u64 step = (span + 31) / 32;  // 32 probes; the last one reaches hi - 1 or beyond
                 const u64 probe = lo + (u64)(lane + 1) * step - 1;
                 const bool ge = probe < hi ? (head_off[probe] >= target) : true;
                 const u32 m = __ballot_sync(0xffffffffu, ge);
-                const int f = __ffs((int)m) - 1;  // first lane whose probe is >= target (always exists)
+                if (m == 0) { lo = hi; break; }  // every head below hi is too small
+                const int f = __ffs((int)m) - 1;  // first lane whose probe is >= target
                 const u64 new_hi = lo + (u64)(f + 1) * step - 1;
-                const u64 new_lo = f == 0 ? lo : lo + (u64)f * step;
+                lo = lo + (u64)f * step;
                 hi = new_hi < hi ? new_hi : hi;
-                lo = new_lo;
             }
             if (lo >= H) break;
             cur = lo;

@@ -70,6 +70,17 @@ def test_oracle_parity_synthetic(nnp, n, plies, seed, mode):
     assert nnp.binpack_to_bin(want) == want_bin
 
 
+@pytest.mark.parametrize("n,plies", [(1_500_000, 1), (2_500_000, 3)])
+def test_many_chunks(nnp, n, plies):
+    """Dozens of chunks: the chunk-flush orbit (compress) and the chunk table (decompress)."""
+    b = nnp.generate_bin(n, plies, 8)
+    rc, want = oracle_convert(BIN_TO_BINPACK, b)
+    assert rc == 0 and want.count(b"BINP") >= 30
+    got = nnp.bin_to_binpack(b)
+    assert got == want
+    assert nnp.binpack_to_bin(got) == oracle_convert(BINPACK_TO_BIN, want)[1]
+
+
 def test_reference_parity_1m(nnp):
     """BASELINE config 1: 1M positions, ~100 plies per chain, against the reference binary."""
     b = _synthetic(1_000_000, 100, 42)
