@@ -349,66 +349,105 @@ __device__ __forceinline__ u32 move_to_sfmove(const Move& m)
 // the reference's struct, and any decode that gets there fails the cursor check anyway).
 // Returns false for "Improperly encoded bin sfen" (:407-408, :441-442) and for the
 // 3-bit type codes 5..7 on which the reference's table search never terminates (:336-352).
+// One half of the board (32 stream squares). `wlo:whi` is a 64-bit window of the stream with
+// `avail` valid bits, refilled one 32-bit word at a time; runs of empty squares are consumed with one
+// count-trailing-zeros, every piece sets one bit in each of the planes it belongs to. The planes of
+// this half are 32-bit registers: stream square s (rank 8 first) is square s ^ 56, i.e. bit
+// (s ^ 24) & 31 of the other 32-bit half.
+template <typename WordFn>
+__device__ __forceinline__ void sfen_decode_half(WordFn W, u32& wlo, u32& whi, int& avail, int& nextw, int& idx,
+                                                 const int idx_end, const int ka, const int kb, u32& err, u32& o0,
+                                                 u32& o1, u32& q0, u32& q1, u32& q2)
+{
+    while (idx < idx_end) {
+        if (avail < 32) {  // insert the next word above the valid bits
+            const u32 nw = nextw < 10 ? W(nextw) : 0u;
+            ++nextw;
+            wlo |= nw << avail;
+            whi |= __funnelshift_l(nw, 0u, avail);
+            avail += 32;
+        }
+        int z = __clz(__brev(wlo));  // empty squares ahead (32 when the low word is all zero)
+        z = min(z, idx_end - idx);
+        idx += z;
+        wlo = __funnelshift_rc(wlo, whi, z);
+        whi = __funnelshift_rc(whi, 0u, z);
+        avail -= z;
+        if (idx >= idx_end) break;
+        if (avail < 5) continue;  // the 5-bit token is not in the window yet
+        const u32 tok = wlo;      // 1, type (3 bits, LSB first), colour
+        err |= ((tok >> 1) & 7u) > (u32)PT_QUEEN ? 1u : 0u;
+        int s = idx;              // token ordinal -> stream square: skip the king squares
+        s += (s >= ka);
+        s += (s >= kb);
+        const u32 b = 1u << ((s ^ 24) & 31);
+        if (tok & 16u) o1 |= b; else o0 |= b;
+        if (tok & 2u) q0 |= b;
+        if (tok & 4u) q1 |= b;
+        if (tok & 8u) q2 |= b;
+        idx += 1;
+        wlo = __funnelshift_rc(wlo, whi, 5);
+        whi >>= 5;
+        avail -= 5;
+    }
+}
+
 template <typename WordFn>
 __device__ __forceinline__ bool sfen_decode(WordFn W, Pos& p)
 {
-    pos_clear(p);
-    u32 w0 = W(0);
+    const u32 w0 = W(0), w1 = W(1);
     p.stm = w0 & 1;
-    int wk = (w0 >> 1) & 63, bk = (w0 >> 7) & 63;
+    const int wk = (w0 >> 1) & 63, bk = (w0 >> 7) & 63;
     // token ordinal -> stream square (rank 8 first, file a first) skips the king squares
     int ka = wk ^ 56, kb = bk ^ 56;
     if (ka > kb) { int t = ka; ka = kb; kb = t; }
     int ntok = 62;
     if (ka == kb) { kb = 64; ntok = 63; }
-    int cursor = 13, idx = 0;
-    u64 occ0 = 0, occ1 = 0, t0 = 0, t1 = 0, t2 = 0;
-    while (idx < ntok) {
-        int j = cursor >> 5, sh = cursor & 31;
-        u32 lo = j < 10 ? W(j) : 0u, hi = (j + 1) < 10 ? W(j + 1) : 0u;
-        u32 w = __funnelshift_r(lo, hi, sh);
-        int z = w ? (__ffs((int)w) - 1) : 32;
-        z = min(z, ntok - idx);
-        idx += z;
-        cursor += z;
-        if (idx >= ntok) break;
-        if (z > 27) continue;  // the 5-bit token is cut off by the window: refetch
-        u32 tok = w >> z;
-        int t = (tok >> 1) & 7, c = (tok >> 4) & 1;
-        if (t > PT_QUEEN) return false;
-        int s = idx;
-        s += (s >= ka);
-        s += (s >= kb);
-        u64 b = bit64(s ^ 56);
-        if (c) occ1 |= b; else occ0 |= b;
-        if (t & 1) t0 |= b;
-        if (t & 2) t1 |= b;
-        if (t & 4) t2 |= b;
-        idx += 1;
-        cursor += 5;
-        if (cursor > 256) return false;
-    }
-    p.occ[0] = occ0; p.occ[1] = occ1; p.t0 = t0; p.t1 = t1; p.t2 = t2;
+    // number of token squares among stream squares 0..31 (ranks 8..5)
+    const int half_tok = 32 - (ka < 32) - (kb < 32);
+    u32 wlo = __funnelshift_r(w0, w1, 13), whi = w1 >> 13;
+    int avail = 51, nextw = 2, idx = 0;
+    u32 err = 0;
+    u32 o0h = 0, o1h = 0, q0h = 0, q1h = 0, q2h = 0;  // squares 32..63 (ranks 5..8)
+    u32 o0l = 0, o1l = 0, q0l = 0, q1l = 0, q2l = 0;  // squares 0..31  (ranks 1..4)
+    sfen_decode_half(W, wlo, whi, avail, nextw, idx, half_tok, ka, kb, err, o0h, o1h, q0h, q1h, q2h);
+    sfen_decode_half(W, wlo, whi, avail, nextw, idx, ntok, ka, kb, err, o0l, o1l, q0l, q1l, q2l);
+    p.occ[0] = ((u64)o0h << 32) | o0l;
+    p.occ[1] = ((u64)o1h << 32) | o1l;
+    p.t0 = ((u64)q0h << 32) | q0l;
+    p.t1 = ((u64)q1h << 32) | q1l;
+    p.t2 = ((u64)q2h << 32) | q2l;
+    p.ep = SQ_NONE;
     // kings: white first, black second (a black king on the same square replaces it, :376-377)
     pos_put(p, wk, (PT_KING << 1) | WHITE);
     pos_put(p, bk, (PT_KING << 1) | BLACK);
-    // tail: castling(4) ep(1[+6]) rule50(6) fullmove(8)
-    auto bits = [&](int n) -> u32 {
-        int j = cursor >> 5, sh = cursor & 31;
-        u32 lo = j < 10 ? W(j) : 0u, hi = (j + 1) < 10 ? W(j + 1) : 0u;
-        cursor += n;
-        return __funnelshift_r(lo, hi, sh) & ((1u << n) - 1u);
-    };
-    u32 c4 = bits(4);
-    p.cr = (int)c4;  // WK,WQ,BK,BQ in stream order == CastlingRights bit order (:414-427)
-    if (bits(1)) {
-        int ep = (int)bits(6);
-        p.ep = ep_possible(p, ep, p.stm) ? ep : SQ_NONE;  // setEpSquare Position.h:868-872
+    // tail: castling(4) ep(1[+6]) rule50(6) fullmove(8) = at most 25 bits
+    if (avail < 32) {
+        const u32 nw = nextw < 10 ? W(nextw) : 0u;
+        ++nextw;
+        wlo |= nw << avail;
+        whi |= __funnelshift_l(nw, 0u, avail);
+        avail += 32;
     }
-    p.rule50 = (int)bits(6);
-    int hm = (int)bits(8);
+    u32 tail = wlo;
+    int used = 0;
+    p.cr = (int)(tail & 15u);  // WK,WQ,BK,BQ in stream order == CastlingRights bit order (:414-427)
+    tail >>= 4; used += 4;
+    if (tail & 1u) {
+        const int ep = (int)((tail >> 1) & 63u);
+        tail >>= 7; used += 7;
+        p.ep = ep_possible(p, ep, p.stm) ? ep : SQ_NONE;  // setEpSquare Position.h:868-872
+    } else {
+        tail >>= 1; used += 1;
+    }
+    p.rule50 = (int)(tail & 63u);
+    const int hm = (int)((tail >> 6) & 255u);
+    used += 14;
     p.ply = (2 * hm - 1 + (p.stm == BLACK)) & 0xFFFF;  // setHalfMove Position.h:938-941
-    return cursor <= 256;
+    const int cursor = 32 * nextw - avail + used;
+    // the reference checks the cursor after every piece and at the end (:407-408, :441-442); it only
+    // grows, so the final value decides. Type codes 5..7 never terminate its table search (:336-352).
+    return cursor <= 256 && err == 0;
 }
 
 // SfenPacker::pack (compress_file.cpp:266-312) into eight 32-bit words out[0..7].

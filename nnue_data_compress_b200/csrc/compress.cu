@@ -29,12 +29,28 @@ constexpr int K1_TILE = K1_THREADS - 1;  // thread 0 decodes the halo record (pr
 struct K1Shared {
     __align__(16) u32 raw[K1_THREADS * 10 + 4];
     u64 occ0[K1_THREADS], occ1[K1_THREADS], t0[K1_THREADS], t1[K1_THREADS], t2[K1_THREADS];
-    u32 meta[K1_THREADS];   // stm | ep << 1 | cr << 8 | ok << 16
+    u32 meta[K1_THREADS];   // stm | ep << 1 | cr << 8 | ok << 16 | rule50 << 17
     u32 w8[K1_THREADS];     // score | move << 16
     u32 w9[K1_THREADS];     // gamePly | result << 16
+    u32 heads[K1_THREADS];  // threads whose record starts a chain
+    u32 nheads;
 };
 
-__global__ void __launch_bounds__(K1_THREADS)
+__device__ __forceinline__ void k1_load(const K1Shared& sh, int t, Pos& p, RecordFields& f, bool& ok)
+{
+    const u32 w8 = sh.w8[t], w9 = sh.w9[t], meta = sh.meta[t];
+    p.occ[0] = sh.occ0[t]; p.occ[1] = sh.occ1[t];
+    p.t0 = sh.t0[t]; p.t1 = sh.t1[t]; p.t2 = sh.t2[t];
+    p.stm = meta & 1; p.ep = (meta >> 1) & 127; p.cr = (meta >> 8) & 15;
+    p.rule50 = (meta >> 17) & 255; p.ply = 0;
+    ok = (meta >> 16) & 1;
+    f.score = (int)(short)(w8 & 0xFFFF);
+    f.mv = sfmove_to_move(w8 >> 16);
+    f.ply = (int)(w9 & 0xFFFF);
+    f.result = (int)(signed char)((w9 >> 16) & 0xFF);
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 3)
 k_decode_link_encode(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ codes,
                      u32* __restrict__ stems, CompressTotals* tot)
 {
@@ -42,6 +58,7 @@ k_decode_link_encode(const unsigned char* __restrict__ bin, u64 n, u32* __restri
     const int t = threadIdx.x;
     const long long first = (long long)blockIdx.x * K1_TILE - 1;  // record handled by thread 0
     const long long rec = first + t;
+    if (t == 0) sh.nheads = 0;
 
     // coalesced 8-byte loads of the tile (+halo) into shared memory
     {
@@ -69,33 +86,37 @@ k_decode_link_encode(const unsigned char* __restrict__ bin, u64 n, u32* __restri
     }
     sh.occ0[t] = p.occ[0]; sh.occ1[t] = p.occ[1];
     sh.t0[t] = p.t0; sh.t1[t] = p.t1; sh.t2[t] = p.t2;
-    sh.meta[t] = (u32)p.stm | ((u32)p.ep << 1) | ((u32)p.cr << 8) | ((u32)ok << 16);
+    sh.meta[t] = (u32)p.stm | ((u32)p.ep << 1) | ((u32)p.cr << 8) | ((u32)ok << 16) | (((u32)p.rule50 & 255u) << 17);
     sh.w8[t] = w8;
     sh.w9[t] = w9;
     __syncthreads();
 
-    if (!valid || t == 0) return;
-
-    RecordFields cf;
-    cf.score = (int)(short)(w8 & 0xFFFF);
-    cf.mv = sfmove_to_move(w8 >> 16);
-    cf.ply = (int)(w9 & 0xFFFF);
-    cf.result = (int)(signed char)((w9 >> 16) & 0xFF);
-
-    const u32 pw8 = sh.w8[t - 1], pw9 = sh.w9[t - 1], pmeta = sh.meta[t - 1];
-    RecordFields pf;
-    pf.score = (int)(short)(pw8 & 0xFFFF);
-    pf.mv = sfmove_to_move(pw8 >> 16);
-    pf.ply = (int)(pw9 & 0xFFFF);
-    pf.result = (int)(signed char)((pw9 >> 16) & 0xFF);
-    Pos a;
-    a.occ[0] = sh.occ0[t - 1]; a.occ[1] = sh.occ1[t - 1];
-    a.t0 = sh.t0[t - 1]; a.t1 = sh.t1[t - 1]; a.t2 = sh.t2[t - 1];
-    a.stm = pmeta & 1; a.ep = (pmeta >> 1) & 127; a.cr = (pmeta >> 8) & 15;
-    a.rule50 = 0; a.ply = 0;
-    const bool has_prev = rec > 0 && ok && ((pmeta >> 16) & 1);
-    const u32 code = link_and_encode(has_prev, a, pf, p, cf, stems + (u64)rec * 8);
-    codes[rec] = code;
+    if (valid && t > 0) {
+        RecordFields cf, pf;
+        cf.score = (int)(short)(w8 & 0xFFFF);
+        cf.mv = sfmove_to_move(w8 >> 16);
+        cf.ply = (int)(w9 & 0xFFFF);
+        cf.result = (int)(signed char)((w9 >> 16) & 0xFF);
+        Pos a;
+        bool prev_ok;
+        k1_load(sh, t - 1, a, pf, prev_ok);
+        const bool has_prev = rec > 0 && ok && prev_ok;
+        const u32 code = link_code(has_prev, a, pf, p, cf);
+        codes[rec] = code;
+        if (code == 0u) sh.heads[atomicAdd(&sh.nheads, 1u)] = (u32)t;
+    }
+    __syncthreads();
+    // chain heads are rare (about one record in a hundred): pack their stems with full warps
+    // instead of letting one lane per warp diverge into stem_pack
+    const u32 nheads = sh.nheads;
+    for (u32 h = t; h < nheads; h += K1_THREADS) {
+        const int th = (int)sh.heads[h];
+        Pos hp;
+        RecordFields hf;
+        bool hok;
+        k1_load(sh, th, hp, hf, hok);
+        store_stem(hp, hf, stems + (u64)(first + th) * 8);
+    }
 }
 
 // ------------------------------------------------------------------ payload scan

@@ -14,11 +14,10 @@ struct RecordFields {
     int result;  // int16 (int8 widened on the .bin path)
 };
 
-// Returns the record's code word: 0 for a chain head (its stem is stored at `stem_out`, 8 words),
-// otherwise the ply's bits left-aligned and terminated by a single 1 bit (never zero), so that the
-// bit count is 32 - ffs(code).
-__device__ __forceinline__ u32 link_and_encode(bool has_prev, const Pos& prev, const RecordFields& pf, const Pos& cur,
-                                               const RecordFields& cf, u32* stem_out)
+// Returns the record's code word: 0 for a chain head, otherwise the ply's bits left-aligned and
+// terminated by a single 1 bit (never zero), so that the bit count is 32 - ffs(code).
+__device__ __forceinline__ u32 link_code(bool has_prev, const Pos& prev, const RecordFields& pf, const Pos& cur,
+                                         const RecordFields& cf)
 {
     bool cont = false;
     if (has_prev && pf.result == -cf.result && pf.ply + 1 == cf.ply) {  // short-circuit order of :589-592
@@ -26,18 +25,29 @@ __device__ __forceinline__ u32 link_and_encode(bool has_prev, const Pos& prev, c
         pos_do_move(a, pf.mv);  // Position::afterMove
         cont = pos_equal(a, cur);
     }
-    if (cont) {
-        int nbits;
-        const int last_score = (int)(short)(-pf.score);  // m_lastScore (:838, :986)
-        const u32 bits = encode_ply(cur, cf.mv, cf.score, last_score, nbits);
-        return bits | (1u << (31 - nbits));
-    }
+    if (!cont) return 0u;
+    int nbits;
+    const int last_score = (int)(short)(-pf.score);  // m_lastScore (:838, :986)
+    const u32 bits = encode_ply(cur, cf.mv, cf.score, last_score, nbits);
+    return bits | (1u << (31 - nbits));
+}
+
+// packEntry (:997-1020) of a chain head into 8 words at `stem_out` (32-byte aligned)
+__device__ __forceinline__ void store_stem(const Pos& cur, const RecordFields& cf, u32* stem_out)
+{
     u32 s[8];
     stem_pack(cur, cf.mv, cf.score, cf.ply, cf.result, s);
     uint4* d = reinterpret_cast<uint4*>(stem_out);
     d[0] = make_uint4(s[0], s[1], s[2], s[3]);
     d[1] = make_uint4(s[4], s[5], s[6], s[7]);
-    return 0u;
+}
+
+__device__ __forceinline__ u32 link_and_encode(bool has_prev, const Pos& prev, const RecordFields& pf, const Pos& cur,
+                                               const RecordFields& cf, u32* stem_out)
+{
+    const u32 code = link_code(has_prev, prev, pf, cur, cf);
+    if (code == 0u) store_stem(cur, cf, stem_out);
+    return code;
 }
 
 }  // namespace nnp
