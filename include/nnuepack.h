@@ -109,6 +109,19 @@ int nnp_binpack_count_dev(const void* d_binpack, size_t binpack_bytes, uint64_t*
  * Deterministic in (n_positions, max_plies, seed). Not a reference driver: bench/test input. */
 int nnp_generate_bin_dev(void* d_out, size_t n_positions, uint32_t max_plies, uint64_t seed);
 
+/* Diagnostics of the .binpack decoder: out14[0] = decodes finished by the
+ * optimistic single walk, [1] = decodes that fell back to the exhaustive walk, [2] = chain-start
+ * candidates of the last decode, [3] = positions their headers claim, [4] = walk violations of the
+ * last optimistic attempt (~0 when it was not attempted), [5] = candidates the last exhaustive walk
+ * found not to be chain starts, [6..13] = the first of those as chunk << 32 | offset. */
+int nnp_decode_stats(uint64_t* out14);
+
+/* Test hooks (the environment variables NNP_DEBUG_EXHAUSTIVE / NNP_DEBUG_REJECT_MOD set the same
+ * switches at nnp_init): "exhaustive" != 0 skips the optimistic decode strategy; "reject_mod" = m
+ * drops the chain-start candidates whose hashed offset is 0 mod m (0 = off), which forces the
+ * fallback strategies. Results never depend on these switches. */
+int nnp_debug_config(const char* key, uint64_t value);
+
 /* Timing of the last *_dev call, measured with CUDA events on the library's stream:
  * total milliseconds, and the slice spent in the dominant kernel of that direction. */
 int nnp_last_timing(float* total_ms, float* dominant_kernel_ms);

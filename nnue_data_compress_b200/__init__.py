@@ -30,7 +30,7 @@ __all__ = [
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnnuepack.so")
+LIB_PATH = os.environ.get("NNP_LIB", os.path.join(_HERE, "libnnuepack.so"))  # NNP_LIB: experiment builds
 
 STATUS = {
     0: "NNP_OK",
@@ -56,7 +56,8 @@ EXPORTS = [
     "nnp_bin_to_plain", "nnp_plain_to_bin",
     "nnp_bin_to_binpack_dev", "nnp_binpack_to_bin_dev", "nnp_plain_to_binpack_dev",
     "nnp_binpack_to_plain_dev", "nnp_bin_to_plain_dev", "nnp_plain_to_bin_dev",
-    "nnp_binpack_count_dev", "nnp_generate_bin_dev", "nnp_last_timing",
+    "nnp_binpack_count_dev", "nnp_generate_bin_dev", "nnp_last_timing", "nnp_decode_stats",
+    "nnp_debug_config",
 ]
 
 
@@ -107,6 +108,10 @@ def lib() -> ctypes.CDLL:
         L.nnp_binpack_count_dev.restype = ctypes.c_int
         L.nnp_generate_bin_dev.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint64]
         L.nnp_generate_bin_dev.restype = ctypes.c_int
+        L.nnp_debug_config.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
+        L.nnp_debug_config.restype = ctypes.c_int
+        L.nnp_decode_stats.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
+        L.nnp_decode_stats.restype = ctypes.c_int
         L.nnp_last_timing.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
         L.nnp_last_timing.restype = ctypes.c_int
         _lib = L
@@ -290,6 +295,14 @@ def main(argv: list[str] | None = None, out=sys.stdout, err=sys.stderr) -> int:
     err.write("Invalid arguments.\n")
     out.write(_HELP)
     return 1
+
+
+def decode_stats() -> dict:
+    """Diagnostics of the .binpack decoder (nnp_decode_stats)."""
+    a = (ctypes.c_uint64 * 14)()
+    lib().nnp_decode_stats(a)
+    return {"optimistic_hits": a[0], "optimistic_misses": a[1], "candidates": a[2], "tentative_positions": a[3],
+            "violations": a[4], "false_candidates": a[5], "false_sample": [(v >> 32, v & 0xFFFFFFFF) for v in a[6:14]]}
 
 
 def generate_bin(n_positions: int, max_plies: int = 100, seed: int = 42) -> bytes:

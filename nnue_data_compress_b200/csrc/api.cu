@@ -24,7 +24,7 @@ enum WsSlot {
     WS_CODES = 0, WS_STEMS, WS_TILE_AGG, WS_PAYLOAD, WS_HEAD_OFF, WS_CHUNK_OFF, WS_TOTALS,
     WS_CHUNK_START, WS_CHUNK_LEN, WS_CHUNK_TILE_BASE, WS_CHUNK_INFO, WS_TILE_COUNT, WS_TILE_PREFIX,
     WS_CAND_CHUNK, WS_CAND_OFF, WS_CAND_NEXT, WS_CAND_BASE, WS_CAND_CNT, WS_CHUNK_COUNT, WS_CHUNK_SLOW, WS_CHUNK_BASE,
-    WS_DTOTALS, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
+    WS_DTOTALS, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
 };
 
 struct Context {
@@ -40,6 +40,11 @@ struct Context {
     std::string last_cuda_error;
     float last_total_ms = 0.f, last_dominant_ms = 0.f;
     uint32_t debug_reject_mod = 0;
+    bool debug_exhaustive = false;     // NNP_DEBUG_EXHAUSTIVE: skip the optimistic decode strategy
+    uint64_t optimistic_misses = 0;    // optimistic decodes that had to be redone exhaustively
+    uint64_t optimistic_hits = 0;
+    uint64_t last_candidates = 0, last_tentative_positions = 0, last_violations = 0, last_false = 0;
+    uint64_t last_false_sample[8] = {0};
 };
 
 Context g_ctx;
@@ -356,7 +361,7 @@ struct DecodePlan {
     ChunkTable tab;
     u64 chunks = 0, tiles = 0, ncand = 0, positions = 0, text_bytes = 0;
     int walk_status = 0;
-    u32 *cand_chunk = nullptr, *cand_off = nullptr, *cand_next = nullptr, *cand_base = nullptr;
+    u32 *cand_chunk = nullptr, *cand_off = nullptr, *cand_next = nullptr, *cand_base = nullptr, *cand_cnt = nullptr;
     u64* cand_tbase = nullptr;
     u32 *chunk_count = nullptr, *chunk_slow = nullptr;
     u64* chunk_base = nullptr;
@@ -365,8 +370,8 @@ struct DecodePlan {
     DecompressTotals* d_tot = nullptr;
 };
 
-// everything up to (and including) the per-chunk position counts (and text sizes when `text`)
-int decode_plan(const void* d_in, size_t in_bytes, bool text, DecodePlan& P)
+// chunk table + candidate list: the part both decode strategies share
+int decode_front(const void* d_in, size_t in_bytes, DecodePlan& P)
 {
     Context& C = g_ctx;
     cudaStream_t s = C.stream;
@@ -394,19 +399,18 @@ int decode_plan(const void* d_in, size_t in_bytes, bool text, DecodePlan& P)
     WS(WS_DTOTALS, sizeof(DecompressTotals) + 64, DecompressTotals, d_tot);
     P.d_tot = d_tot;
     DecompressTotals* h_tot = reinterpret_cast<DecompressTotals*>((char*)C.pinned + 512);
-    h_tot->positions = 0;
+    std::memset(h_tot, 0, sizeof(DecompressTotals));
     h_tot->error_chunk = NO_ERROR_IDX;
-    h_tot->slow_chunks = 0;
-    h_tot->candidates = 0;
     CK(cudaMemcpyAsync(d_tot, h_tot, sizeof(DecompressTotals), cudaMemcpyHostToDevice, s));
     if (P.chunks == 0) return NNP_OK;
 
     WS(WS_TILE_COUNT, (P.tiles + 1) * 4, u32, tile_count);
     WS(WS_TILE_PREFIX, (P.tiles + 2) * 8, u64, tile_prefix);
+    WS(WS_TILE_FLAGS, P.tiles * (CAND_TILE / 32) * 4, u32, tile_flags);
     P.tile_prefix = tile_prefix;
-    launch_candidates(false, d_in, P.tab, P.tiles, tile_count, tile_prefix, nullptr, nullptr, C.debug_reject_mod, s);
+    launch_candidates_scan(d_in, in_bytes, P.tab, P.tiles, tile_count, tile_flags, C.debug_reject_mod, s);
     launch_exclusive_sum(tile_count, P.tiles, tile_prefix, s);
-    LAUNCHED(2, "k_candidates<count>");
+    LAUNCHED(2, "k_candidates_scan");
     u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
     CK(cudaMemcpyAsync(h_u64, tile_prefix + P.tiles, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -414,9 +418,33 @@ int decode_plan(const void* d_in, size_t in_bytes, bool text, DecodePlan& P)
 
     WS(WS_CAND_CHUNK, (P.ncand + 1) * 4, u32, cand_chunk);
     WS(WS_CAND_OFF, (P.ncand + 1) * 4, u32, cand_off);
+    WS(WS_CAND_CNT, (P.ncand + 1) * 4, u32, cand_cnt);
+    P.cand_chunk = cand_chunk; P.cand_off = cand_off; P.cand_cnt = cand_cnt;
+    launch_candidates_list(d_in, P.tab, P.tiles, tile_flags, tile_prefix, cand_chunk, cand_off, cand_cnt, s);
+    LAUNCHED(1, "k_candidates_list");
+    return NNP_OK;
+}
+
+// Exhaustive strategy after decode_front: probe every candidate, resolve the reader's walk per
+// chunk (false candidates are skipped, unresolvable chunks go to the sequential kernels) and
+// produce the per-chunk position counts (and text sizes when `text`).
+int decode_plan(const void* d_in, size_t in_bytes, bool text, DecodePlan& P, bool have_front = false)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    if (!have_front) {
+        int rc = decode_front(d_in, in_bytes, P);
+        if (rc != NNP_OK) return rc;
+    }
+    if (P.chunks == 0) return NNP_OK;
+    DecompressTotals* d_tot = P.d_tot;
+    DecompressTotals* h_tot = reinterpret_cast<DecompressTotals*>((char*)C.pinned + 512);
+    u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+    u32 *cand_chunk = P.cand_chunk, *cand_off = P.cand_off, *cand_cnt = P.cand_cnt;
+    u64* tile_prefix = P.tile_prefix;
+
     WS(WS_CAND_NEXT, (P.ncand + 1) * 4, u32, cand_next);
     WS(WS_CAND_BASE, (P.ncand + 1) * 4, u32, cand_base);
-    WS(WS_CAND_CNT, (P.ncand + 1) * 4, u32, cand_cnt);
     WS(WS_CHUNK_COUNT, (P.chunks + 1) * 4, u32, chunk_count);
     WS(WS_CHUNK_SLOW, (P.chunks + 1) * 4, u32, chunk_slow);
     WS(WS_CHUNK_BASE, (P.chunks + 2) * 8, u64, chunk_base);
@@ -429,17 +457,16 @@ int decode_plan(const void* d_in, size_t in_bytes, bool text, DecodePlan& P)
         WS(WS_TEXT_D, (P.chunks + 2) * 8, u64, ctbase);
         cand_tlen = tl; cand_tbase = tb; chunk_tbytes = ctb; chunk_tbase = ctbase;
     }
-    P.cand_chunk = cand_chunk; P.cand_off = cand_off; P.cand_next = cand_next; P.cand_base = cand_base;
+    P.cand_next = cand_next; P.cand_base = cand_base;
     P.cand_tbase = cand_tbase; P.chunk_tbase = chunk_tbase;
     P.chunk_count = chunk_count; P.chunk_slow = chunk_slow; P.chunk_base = chunk_base;
 
-    launch_candidates(true, d_in, P.tab, P.tiles, tile_count, tile_prefix, cand_chunk, cand_off, C.debug_reject_mod, s);
     launch_probe_chains(d_in, P.tab, cand_chunk, cand_off, P.ncand, cand_next, cand_cnt, cand_tlen, s);
     launch_resolve_chunks(P.tab, P.chunks, tile_prefix, cand_off, cand_next, cand_cnt, cand_base, chunk_count, chunk_slow,
                           cand_tlen, cand_tbase, chunk_tbytes, s);
     launch_slow_count(d_in, P.tab, P.chunks, chunk_slow, chunk_count, chunk_tbytes, d_tot, s);
     launch_exclusive_sum(chunk_count, P.chunks, chunk_base, s);
-    LAUNCHED(5, "decode plan");
+    LAUNCHED(4, "decode plan");
     if (text) {
         launch_exclusive_sum64(chunk_tbytes, P.chunks, chunk_tbase, s);
         LAUNCHED(1, "k_exclusive_sum64");
@@ -472,16 +499,61 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
     cudaStream_t s = C.stream;
     *out_bytes = 0;
     if (in_bytes == 0) return NNP_OK;
+    if (d_out && ((uintptr_t)d_out & 7)) return NNP_ERR_BAD_ARG;
     CK(cudaEventRecord(C.ev[0], s));
     DecodePlan P;
-    int rc = decode_plan(d_in, in_bytes, false, P);
+    int rc = decode_front(d_in, in_bytes, P);
+    if (rc != NNP_OK) return rc;
+    DecompressTotals* h_tot = reinterpret_cast<DecompressTotals*>((char*)C.pinned + 512);
+    u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+
+    // Optimistic strategy: on files the reference wrote, the candidates are exactly the chains, so
+    // every chain can be emitted at the record index its header count implies while the kernel
+    // verifies the reader's walk link by link. Any violation reruns the exhaustive strategy.
+    if (d_out && P.chunks > 0 && P.ncand > 0 && !C.debug_exhaustive) {
+        WS(WS_CAND_REC, (P.ncand + 2) * 8, u64, cand_rec);
+        WS(WS_LSUM_A, (large_sum_tiles(P.ncand) + 1) * 4, u32, lsum_a);
+        WS(WS_LSUM_B, (large_sum_tiles(P.ncand) + 2) * 8, u64, lsum_b);
+        launch_mark_conflicts(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_cnt, P.ncand, s);
+        launch_exclusive_sum_large(P.cand_cnt, P.ncand, cand_rec, lsum_a, lsum_b, s);
+        LAUNCHED(4, "candidate record offsets");
+        CK(cudaMemcpyAsync(h_u64, cand_rec + P.ncand, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const u64 positions = h_u64[0];
+        C.last_candidates = P.ncand;
+        C.last_tentative_positions = positions;
+        C.last_violations = ~0ull;
+        if (positions * 40 <= out_cap) {
+            CK(cudaEventRecord(C.ev[1], s));
+            launch_emit_chains_verify(d_in, P.tab, P.chunks, P.tile_prefix, P.cand_chunk, P.cand_off, P.cand_cnt, cand_rec, P.ncand, d_out,
+                                      &P.d_tot->violations, s);
+            LAUNCHED(2, "k_emit_chains_verify");
+            CK(cudaEventRecord(C.ev[2], s));
+            CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(DecompressTotals), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            C.last_violations = h_tot->violations;
+            if (h_tot->violations == 0) {  // no violation: the output is the reader's
+                ++C.optimistic_hits;
+                CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
+                CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[1], C.ev[2]));
+                *out_bytes = positions * 40;
+                if (P.walk_status != 0) {
+                    *out_bytes = committed_bin_records(positions) * 40;
+                    return P.walk_status;
+                }
+                return NNP_OK;
+            }
+        }
+        ++C.optimistic_misses;
+    }
+
+    rc = decode_plan(d_in, in_bytes, false, P, true);
     if (rc != NNP_OK) return rc;
     CK(cudaEventRecord(C.ev[1], s));
     if (!d_out) {
         *out_bytes = P.positions * 40;
         return NNP_OK;
     }
-    if ((uintptr_t)d_out & 7) return NNP_ERR_BAD_ARG;
     u64 positions = P.positions;
     *out_bytes = positions * 40;
     if (positions * 40 > out_cap) return NNP_ERR_CAPACITY;
@@ -491,11 +563,13 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
         LAUNCHED(2, "k_emit_chains");
     }
     CK(cudaEventRecord(C.ev[2], s));
-    DecompressTotals* h_tot = reinterpret_cast<DecompressTotals*>((char*)C.pinned + 512);
     CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(DecompressTotals), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
     CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[1], C.ev[2]));
+    C.last_candidates = P.ncand;
+    C.last_false = h_tot->false_candidates;
+    for (int i = 0; i < 8; ++i) C.last_false_sample[i] = h_tot->false_sample[i];
     if (h_tot->error_chunk != NO_ERROR_IDX) return NNP_ERR_TRUNCATED;
     if (P.walk_status != 0) {
         *out_bytes = committed_bin_records(positions) * 40;
@@ -614,6 +688,8 @@ int nnp_init(int device)
     if (cudaMallocHost(&g_ctx.pinned, 4096) != cudaSuccess) return NNP_ERR_NOMEM;
     const char* dbg = std::getenv("NNP_DEBUG_REJECT_MOD");
     g_ctx.debug_reject_mod = dbg ? (uint32_t)std::strtoul(dbg, nullptr, 10) : 0u;
+    const char* dbg2 = std::getenv("NNP_DEBUG_EXHAUSTIVE");
+    g_ctx.debug_exhaustive = dbg2 && dbg2[0] == '1';
     g_ctx.device = device;
     g_ctx.ready = true;
     return NNP_OK;
@@ -793,6 +869,29 @@ int nnp_generate_bin_dev(void* d_out, size_t n_positions, uint32_t max_plies, ui
         n_games = n_games * 2 + 64;
     }
     return NNP_ERR_BAD_ARG;
+}
+
+int nnp_debug_config(const char* key, uint64_t value)
+{
+    std::lock_guard<std::mutex> lock_(g_mutex);
+    if (!key) return NNP_ERR_BAD_ARG;
+    if (!std::strcmp(key, "exhaustive")) g_ctx.debug_exhaustive = value != 0;
+    else if (!std::strcmp(key, "reject_mod")) g_ctx.debug_reject_mod = (uint32_t)value;
+    else return NNP_ERR_BAD_ARG;
+    return NNP_OK;
+}
+
+int nnp_decode_stats(uint64_t* out14)
+{
+    if (!out14) return NNP_ERR_BAD_ARG;
+    out14[0] = g_ctx.optimistic_hits;
+    out14[1] = g_ctx.optimistic_misses;
+    out14[2] = g_ctx.last_candidates;
+    out14[3] = g_ctx.last_tentative_positions;
+    out14[4] = g_ctx.last_violations;
+    out14[5] = g_ctx.last_false;
+    for (int i = 0; i < 8; ++i) out14[6 + i] = g_ctx.last_false_sample[i];
+    return NNP_OK;
 }
 
 int nnp_last_timing(float* total_ms, float* dominant_kernel_ms)

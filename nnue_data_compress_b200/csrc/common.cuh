@@ -74,7 +74,9 @@ struct DecompressTotals {
     u64 positions;
     u64 error_chunk;   // first chunk with a decode error (truncated movetext), or NO_ERROR_IDX
     u64 slow_chunks;   // chunks that needed the sequential fallback
-    u64 candidates;
+    u64 violations;    // links of the optimistic walk that did not hold
+    u64 false_candidates;      // candidates the exhaustive walk found not to be chain starts
+    u64 false_sample[8];       // the first few of them: chunk << 32 | offset (diagnostics)
 };
 
 // one parsed .plain record (TrainingDataEntry, compress_file.cpp:548-555), 64 bytes

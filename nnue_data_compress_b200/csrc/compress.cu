@@ -23,7 +23,10 @@ namespace nnp {
 
 // ------------------------------------------------------------------ K1
 
-constexpr int K1_THREADS = 256;
+#ifndef K1_THREADS_N
+#define K1_THREADS_N 256
+#endif
+constexpr int K1_THREADS = K1_THREADS_N;
 constexpr int K1_TILE = K1_THREADS - 1;  // thread 0 decodes the halo record (predecessor of the tile)
 
 struct K1Shared {
@@ -50,7 +53,10 @@ __device__ __forceinline__ void k1_load(const K1Shared& sh, int t, Pos& p, Recor
     f.result = (int)(signed char)((w9 >> 16) & 0xFF);
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 3)
+#ifndef K1_MIN_BLOCKS
+#define K1_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
 k_decode_link_encode(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ codes,
                      u32* __restrict__ stems, CompressTotals* tot)
 {

@@ -146,15 +146,18 @@ __global__ void k_walk_chunks(const unsigned char* __restrict__ in, u64 n, Chunk
 // ------------------------------------------------------------------ candidate discovery
 
 constexpr int CAND_THREADS = 256;
-constexpr int CAND_ROUNDS = CAND_TILE / CAND_THREADS;  // 16
+static_assert(CAND_TILE == CAND_THREADS * 16, "stage 1 of k_candidates_scan tests 16 offsets per thread");
 
-// Could the 34 bytes at s[0..34) be a stem + numPlies as written by packEntry (:997-1020) from
-// a position with exactly one white and one black king? Everything tested here is guaranteed
-// for such stems: rule50 is a uint8_t stored big-endian in 16 bits (byte 30 == 0), at most 32
-// squares are occupied, unused nibbles stay zero (CompressedPosition() zero-initialises
-// m_packedState, Position.h:1218-1222), nibble 10 appears once and 11/15 together once.
-// A real stem that fails the test (possible only for inputs outside that domain) merely sends
-// its chunk to the sequential fallback.
+// Could the 34 bytes at s[0..34) be a stem + numPlies as written by packEntry (:997-1020)?
+// Two groups of tests. (1) Properties every stem of the reference writer has, whatever the input:
+// rule50 is a uint8_t stored big-endian in 16 bits (byte 30 == 0); unused nibbles stay zero
+// (CompressedPosition() zero-initialises m_packedState, Position.h:1218-1222); nibble 13/14 only on
+// the corner squares that carry the castling right, nibble 12 only on rank 4/5 matching the side to
+// move (Position.h:1274-1333); a non-null move has from != to and promotion bits only with type
+// Promotion (Chess.h:1071-1096). (2) Properties of stems made from legal chess positions: exactly
+// one king per side, at most 32 pieces, no pawn on rank 1/8, the stored move starts on a piece of
+// the side to move and does not land on an own piece. A real stem that fails group (2) (possible
+// only for inputs outside that domain) merely sends the file through the exhaustive path.
 __device__ __forceinline__ bool plausible_stem(const unsigned char* s)
 {
     if (s[30] != 0) return false;
@@ -163,15 +166,41 @@ __device__ __forceinline__ bool plausible_stem(const unsigned char* s)
     for (int i = 0; i < 8; ++i) occ = (occ << 8) | s[i];
     const int n = popc64(occ);
     if (n < 2 || n > 32) return false;
-    int wk = 0, bk = 0;
+    int wk = 0, bk = 0, stm = WHITE;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const u32 b = s[8 + i];
         const int lo = b & 15, hi = b >> 4;
-        if (2 * i < n) { wk += (lo == 10); bk += (lo == 11 || lo == 15); } else if (lo) return false;
-        if (2 * i + 1 < n) { wk += (hi == 10); bk += (hi == 11 || hi == 15); } else if (hi) return false;
+        if (2 * i < n) { wk += (lo == 10); bk += (lo == 11 || lo == 15); stm |= (lo == 15); } else if (lo) return false;
+        if (2 * i + 1 < n) { wk += (hi == 10); bk += (hi == 11 || hi == 15); stm |= (hi == 15); } else if (hi) return false;
     }
-    return wk == 1 && bk == 1;
+    if (wk != 1 || bk != 1) return false;
+    // per-square checks (reached by about one offset in 10^5)
+    const u32 cm = ((u32)s[24] << 8) | s[25];
+    const int mtype = (int)(cm >> 14), from = (int)((cm >> 8) & 63), to = (int)((cm >> 2) & 63);
+    if (cm != 0 && (from == to || ((cm & 3u) && mtype != MT_PROMOTION))) return false;
+    int k = 0, n12 = 0, from_nib = -1, to_nib = -1;
+    for (u64 b = occ; b; b &= b - 1, ++k) {
+        const int sq = lsb64(b);
+        const int nib = (s[8 + (k >> 1)] >> ((k & 1) * 4)) & 15;
+        const int rank = sq >> 3;
+        if (nib == 13 && sq != 0 && sq != 7) return false;
+        if (nib == 14 && sq != 56 && sq != 63) return false;
+        if (nib == 12) {
+            if (++n12 > 1) return false;
+            if (!((rank == 3 && stm == BLACK) || (rank == 4 && stm == WHITE))) return false;
+        }
+        if ((nib <= 1 || nib == 12) && (rank == 0 || rank == 7)) return false;
+        if (sq == from) from_nib = nib;
+        if (sq == to) to_nib = nib;
+    }
+    if (cm != 0) {
+        // colour of a nibble: 12 is the pawn that just moved (the side NOT to move), 13 white, 14/15 black
+        auto colour = [&](int nib) { return nib < 12 ? (nib & 1) : nib == 12 ? (stm ^ 1) : nib == 13 ? WHITE : BLACK; };
+        if (from_nib < 0 || colour(from_nib) != stm) return false;
+        if (to_nib >= 0 && colour(to_nib) == stm && mtype != MT_CASTLE) return false;
+    }
+    return true;
 }
 
 __device__ __forceinline__ u64 find_chunk(const u64* base, u64 chunks, u64 tile)
@@ -184,17 +213,32 @@ __device__ __forceinline__ u64 find_chunk(const u64* base, u64 chunks, u64 tile)
     return lo;
 }
 
-// WRITE == false: tile_count[tile] = number of plausible offsets in the tile
-// WRITE == true : lists them at cand_*[tile_prefix[tile] ...] in ascending offset order
-template <bool WRITE>
-__global__ void __launch_bounds__(CAND_THREADS)
-k_candidates(const unsigned char* __restrict__ in, ChunkTable tab, u32* __restrict__ tile_count,
-             const u64* __restrict__ tile_prefix, u32* __restrict__ cand_chunk, u32* __restrict__ cand_off,
-             u32 debug_reject_mod)
+// 16 bytes at p, zero-filled outside [lo, hi)
+__device__ __forceinline__ uint4 load16_clipped(const unsigned char* p, const unsigned char* lo, const unsigned char* hi)
 {
-    __shared__ __align__(16) unsigned char sm[CAND_TILE + 48];
+    if (p >= lo && p + 16 <= hi) return *reinterpret_cast<const uint4*>(p);  // p is 16-byte aligned by construction
+    u32 w[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 16; ++i)
+        if (p + i >= lo && p + i < hi) w[i >> 2] |= (u32)p[i] << ((i & 3) * 8);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// pass 0: tests every offset of the tile, stores the tile's flag bitmap (CAND_TILE / 32 words) and
+//         tile_count[tile].
+// Stage 1 looks at one byte per offset -- the high byte of the stem's rule50 field, which packEntry
+// always writes as zero -- 16 offsets per thread with byte-parallel compares, and queues the
+// survivors (about 7 % of the offsets of real movetext); stage 2 runs the full test on the queue
+// with dense warps.
+__global__ void __launch_bounds__(CAND_THREADS)
+k_candidates_scan(const unsigned char* __restrict__ in, u64 n_in, ChunkTable tab, u32* __restrict__ tile_count,
+                  u32* __restrict__ tile_flags, u32 debug_reject_mod)
+{
+    __shared__ __align__(16) unsigned char sm[CAND_TILE + 96];  // the tile from its 16-byte aligned base
     __shared__ u32 flags[CAND_TILE / 32];
+    __shared__ unsigned short queue[CAND_TILE];
     __shared__ u32 warp_tot[CAND_THREADS / 32];
+    __shared__ u32 nq;
+    const int t = threadIdx.x, lane = t & 31;
     const u64 tile = blockIdx.x;
     const u64 c = find_chunk(tab.tile_base, tab.info->chunks, tile);
     const u64 clen = tab.len[c];
@@ -202,37 +246,98 @@ k_candidates(const unsigned char* __restrict__ in, ChunkTable tab, u32* __restri
     const unsigned char* src = in + tab.start[c] + off0;
     const u64 avail = clen - off0;  // > 0 by construction
     const int nload = (int)(avail < (u64)(CAND_TILE + 34) ? avail : (u64)(CAND_TILE + 34));
-    for (int i = threadIdx.x; i < nload; i += CAND_THREADS) sm[i] = src[i];
+    const unsigned char* base = reinterpret_cast<const unsigned char*>((uintptr_t)src & ~(uintptr_t)15);
+    const int delta = (int)(src - base);
+    const int nvec = (delta + nload + 15) >> 4;
+    for (int i = t; i < nvec; i += CAND_THREADS)
+        reinterpret_cast<uint4*>(sm)[i] = load16_clipped(base + 16 * i, in, in + n_in);
+    if (t < CAND_TILE / 32) flags[t] = 0;
+    if (t == 0) nq = 0;
     __syncthreads();
-    // round j tests offsets j*256 + thread: a warp covers 32 consecutive offsets, and its
-    // ballot is exactly word (j*8 + warp) of the tile's flag bitmap
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll 4
-    for (int j = 0; j < CAND_ROUNDS; ++j) {
-        const int o = j * CAND_THREADS + threadIdx.x;
-        bool ok = false;
-        if ((u64)o + 34 <= avail) {
-            ok = plausible_stem(sm + o);
-            // test hook: drop a pseudo-random subset of candidates to exercise the fallback
-            if (debug_reject_mod && (u32)(((off0 + (u64)o) * 2654435761ull) >> 11) % debug_reject_mod == 0) ok = false;
+    const unsigned char* s0 = sm + delta;  // s0[o] = byte at chunk offset off0 + o
+
+    // stage 1: offsets 16t .. 16t+15, byte s0[o + 30]
+    {
+        const int A = delta + 30 + 16 * t;
+        const u32* wp = reinterpret_cast<const u32*>(sm) + (A >> 2);
+        const int sh = (A & 3) * 8;
+        u32 x[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) x[i] = wp[i];
+        u32 mask = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const u32 y = __funnelshift_r(x[i], x[i + 1], sh);
+            const u32 z = __vcmpeq4(y, 0u);  // 0xFF in every zero byte
+            mask |= (((z & 0x08040201u) * 0x01010101u) >> 24) << (4 * i);
         }
-        const u32 b = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) flags[j * (CAND_THREADS / 32) + wid] = b;
+        // offsets with a whole stem + numPlies inside the chunk
+        const long long last = (long long)avail - 34 - 16 * t;  // last valid local bit index
+        if (last < 15) mask &= last < 0 ? 0u : ((2u << (int)last) - 1u);
+        const u32 cnt = __popc(mask);
+        u32 inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        u32 wbase = 0;
+        if (lane == 31 && inc) wbase = atomicAdd(&nq, inc);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        u32 slot = wbase + inc - cnt;
+        while (mask) {
+            const int bit = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            queue[slot++] = (unsigned short)(16 * t + bit);
+        }
     }
     __syncthreads();
-    u32 word = threadIdx.x < CAND_TILE / 32 ? flags[threadIdx.x] : 0u;
-    u32 total;
-    const u32 rank0 = block_exclusive_sum<CAND_THREADS>(__popc(word), total, warp_tot);
-    if (!WRITE) {
-        if (threadIdx.x == 0) tile_count[tile] = total;
-        return;
+    // stage 2: the full test on the survivors
+    const u32 n_queued = nq;
+    for (u32 q = t; q < n_queued; q += CAND_THREADS) {
+        const int o = queue[q];
+        bool ok = plausible_stem(s0 + o);
+        // test hook: drop a pseudo-random subset of candidates to exercise the fallbacks
+        if (debug_reject_mod && (u32)(((off0 + (u64)o) * 2654435761ull) >> 11) % debug_reject_mod == 0) ok = false;
+        if (ok) atomicOr(&flags[o >> 5], 1u << (o & 31));
     }
+    __syncthreads();
+    u32 mine = 0;
+    if (t < CAND_TILE / 32) {
+        const u32 word = flags[t];
+        tile_flags[tile * (CAND_TILE / 32) + t] = word;
+        mine = __popc(word);
+    }
+    u32 total;
+    block_exclusive_sum<CAND_THREADS>(mine, total, warp_tot);
+    if (t == 0) tile_count[tile] = total;
+}
+
+// pass 1: lists the flagged offsets at cand_*[tile_prefix[tile] ...] in ascending offset order,
+//         with the position count 1 + numPlies read from the chain header (:1175)
+constexpr int LIST_THREADS = CAND_TILE / 32;  // one thread per bitmap word
+__global__ void __launch_bounds__(LIST_THREADS)
+k_candidates_list(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ tile_flags,
+                  const u64* __restrict__ tile_prefix, u32* __restrict__ cand_chunk, u32* __restrict__ cand_off,
+                  u32* __restrict__ cand_cnt)
+{
+    __shared__ u32 warp_tot[LIST_THREADS / 32];
+    const u64 tile = blockIdx.x;
+    if (tile_prefix[tile + 1] == tile_prefix[tile]) return;
+    const u64 c = find_chunk(tab.tile_base, tab.info->chunks, tile);
+    const u64 off0 = (tile - tab.tile_base[c]) * CAND_TILE;
+    const unsigned char* src = in + tab.start[c] + off0;
+    u32 word = tile_flags[tile * (CAND_TILE / 32) + threadIdx.x];
+    u32 total;
+    const u32 rank0 = block_exclusive_sum<LIST_THREADS>(__popc(word), total, warp_tot);
     u64 slot = tile_prefix[tile] + rank0;
     while (word) {
         const int b = __ffs((int)word) - 1;
         word &= word - 1;
+        const u32 o = threadIdx.x * 32 + b;
         cand_chunk[slot] = (u32)c;
-        cand_off[slot] = (u32)(off0 + (u64)threadIdx.x * 32 + b);
+        cand_off[slot] = (u32)(off0 + o);
+        cand_cnt[slot] = 1u + (((u32)src[o + 32] << 8) | (u32)src[o + 33]);
         ++slot;
     }
 }
@@ -279,8 +384,11 @@ __device__ __forceinline__ u32 plain_len(const ChainCursor& c)
 
 // TEXT: also sum the .plain size of the chain's records (decompressPlain needs output offsets)
 constexpr int PROBE_THREADS = 128;
+#ifndef PROBE_MIN_BLOCKS
+#define PROBE_MIN_BLOCKS 8
+#endif
 template <bool TEXT>
-__global__ void __launch_bounds__(PROBE_THREADS)
+__global__ void __launch_bounds__(PROBE_THREADS, PROBE_MIN_BLOCKS)
 k_probe_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
                const u32* __restrict__ cand_off, u64 ncand, u32* __restrict__ cand_next, u32* __restrict__ cand_cnt,
                u32* __restrict__ cand_tlen)
@@ -440,8 +548,11 @@ __device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_aft
     return true;
 }
 
+#ifndef EMIT_MIN_BLOCKS
+#define EMIT_MIN_BLOCKS 8
+#endif
 constexpr int EMITC_THREADS = 128;
-__global__ void __launch_bounds__(EMITC_THREADS)
+__global__ void __launch_bounds__(EMITC_THREADS, EMIT_MIN_BLOCKS)
 k_emit_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
               const u32* __restrict__ cand_off, const u32* __restrict__ cand_base, u64 ncand,
               const u64* __restrict__ chunk_base, unsigned char* __restrict__ out, DecompressTotals* tot)
@@ -449,14 +560,89 @@ k_emit_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* _
     const u64 i = (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
     if (i >= ncand) return;
     const u32 b = cand_base[i];
-    if (b == 0xFFFFFFFFu) return;
     const u32 c = cand_chunk[i], off = cand_off[i];
+    if (b == 0xFFFFFFFFu) {
+        const u64 k = atomicAdd(&tot->false_candidates, 1ull);
+        if (k < 8) tot->false_sample[k] = ((u64)c << 32) | off;
+        return;
+    }
     const u64 rec0 = chunk_base[c] + b;
     const unsigned char* s = in + tab.start[c] + off;
     u32 consumed = 0;
     const bool ok = walk_chain(s, tab.len[c] - off - 34,
                                [&](const ChainCursor& cc, u32 k) { emit_bin_record(cc, out, rec0 + k); }, consumed);
     if (!ok) atomicMin(&tot->error_chunk, (u64)c);
+}
+
+// Two candidates less than 34 bytes apart overlap, so at most one of them starts a chain. (This is
+// how the rare false candidate arises in practice: 27 bytes before a real stem whose occupancy has
+// empty middle ranks, the bytes "ff ff 00 00 00 00 ff" land on the score / ply / rule50 / numPlies
+// fields.) The thread of the lower one decides: offset 0 always starts a chain; otherwise the
+// chain of the candidate before the pair is walked to see which of the two it ends on. The loser
+// gets cand_cnt = 0 (a chain holds at least one position), which takes it out of the prefix sum
+// and of the walk below. Anything this heuristic gets wrong is caught by k_emit_chains_verify.
+__global__ void __launch_bounds__(128)
+k_mark_conflicts(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
+                 const u32* __restrict__ cand_off, u32* __restrict__ cand_cnt, u64 ncand)
+{
+    const u64 i = (u64)blockIdx.x * 128 + threadIdx.x;
+    if (i + 1 >= ncand) return;
+    const u32 c = cand_chunk[i];
+    if (cand_chunk[i + 1] != c) return;
+    const u32 off = cand_off[i], off2 = cand_off[i + 1];
+    if (off2 - off >= 34) return;
+    if (i == 0 || cand_chunk[i - 1] != c) {
+        if (off == 0) cand_cnt[i + 1] = 0;
+        return;
+    }
+    const u32 poff = cand_off[i - 1];
+    u32 consumed = 0;
+    if (!walk_chain(in + tab.start[c] + poff, tab.len[c] - poff - 34, [](const ChainCursor&, u32) {}, consumed)) return;
+    const u32 end = poff + consumed;
+    if (end == off) cand_cnt[i + 1] = 0;
+    else if (end == off2) cand_cnt[i] = 0;
+}
+
+// Optimistic single walk: assume every (unmarked) candidate is a real chain. Each thread emits its
+// chain at the record index given by the prefix sum of the header counts and then verifies its link
+// of the reader's walk (Reader::next / fetchNextChunkIfNeeded, :1154-1213): the chunk's first
+// candidate sits at offset 0, every chain ends exactly where the next candidate starts, and
+// after the last chain fewer than 34 bytes remain. If every link of every chunk holds, the
+// candidates ARE the reader's chains and the output is final; otherwise *violations is raised
+// and the caller reruns the file through the exhaustive path (probe / resolve / emit).
+__global__ void __launch_bounds__(EMITC_THREADS, EMIT_MIN_BLOCKS)
+k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
+                     const u32* __restrict__ cand_off, const u32* __restrict__ cand_cnt, const u64* __restrict__ cand_rec,
+                     u64 ncand, unsigned char* __restrict__ out, u64* __restrict__ violations)
+{
+    const u64 i = (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
+    if (i >= ncand) return;
+    if (cand_cnt[i] == 0) return;  // marked by k_mark_conflicts
+    const u32 c = cand_chunk[i], off = cand_off[i];
+    const u32 clen = tab.len[c];
+    const u64 rec0 = cand_rec[i];
+    const unsigned char* s = in + tab.start[c] + off;
+    u32 consumed = 0;
+    bool ok = walk_chain(s, clen - off - 34, [&](const ChainCursor& cc, u32 k) { emit_bin_record(cc, out, rec0 + k); },
+                         consumed);
+    const u32 end = off + consumed;
+    u64 prev = i, next = i + 1;  // neighbours in the chunk, skipping marked candidates
+    while (prev > 0 && cand_chunk[prev - 1] == c && cand_cnt[prev - 1] == 0) --prev;
+    while (next < ncand && cand_chunk[next] == c && cand_cnt[next] == 0) ++next;
+    const bool first = prev == 0 || cand_chunk[prev - 1] != c;
+    const bool last = next == ncand || cand_chunk[next] != c;
+    if (first && off != 0) ok = false;
+    if (last) { if ((u64)end + 34 <= clen) ok = false; }
+    else if (cand_off[next] != end) ok = false;
+    if (!ok) atomicAdd(violations, 1ull);
+}
+
+// every chunk needs at least one candidate (its first chain); chunks without any are violations
+__global__ void k_check_chunks(ChunkTable tab, const u64* __restrict__ tile_prefix, u64* __restrict__ violations)
+{
+    const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= tab.info->chunks) return;
+    if (tile_prefix[tab.tile_base[c]] == tile_prefix[tab.tile_base[c + 1]]) atomicAdd(violations, 1ull);
 }
 
 // the same walk, writing emitPlainEntry text (decompressPlain :1299-1335)
@@ -548,16 +734,36 @@ void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks,
 {
     k_walk_chunks<<<1, 32, 0, s>>>((const unsigned char*)d_in, n, tab, max_chunks);
 }
-void launch_candidates(bool write, const void* d_in, ChunkTable tab, u64 tiles, u32* tile_count, const u64* tile_prefix,
-                       u32* cand_chunk, u32* cand_off, u32 debug_reject_mod, cudaStream_t s)
+void launch_candidates_scan(const void* d_in, u64 n_in, ChunkTable tab, u64 tiles, u32* tile_count, u32* tile_flags,
+                            u32 debug_reject_mod, cudaStream_t s)
 {
     if (tiles == 0) return;
-    if (write)
-        k_candidates<true><<<(unsigned)tiles, CAND_THREADS, 0, s>>>((const unsigned char*)d_in, tab, tile_count, tile_prefix,
-                                                                   cand_chunk, cand_off, debug_reject_mod);
-    else
-        k_candidates<false><<<(unsigned)tiles, CAND_THREADS, 0, s>>>((const unsigned char*)d_in, tab, tile_count, tile_prefix,
-                                                                    cand_chunk, cand_off, debug_reject_mod);
+    k_candidates_scan<<<(unsigned)tiles, CAND_THREADS, 0, s>>>((const unsigned char*)d_in, n_in, tab, tile_count, tile_flags,
+                                                             debug_reject_mod);
+}
+void launch_mark_conflicts(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u32* cand_cnt,
+                           u64 ncand, cudaStream_t s)
+{
+    if (ncand < 2) return;
+    k_mark_conflicts<<<(unsigned)((ncand + 127) / 128), 128, 0, s>>>((const unsigned char*)d_in, tab, cand_chunk, cand_off,
+                                                                    cand_cnt, ncand);
+}
+void launch_candidates_list(const void* d_in, ChunkTable tab, u64 tiles, const u32* tile_flags, const u64* tile_prefix,
+                            u32* cand_chunk, u32* cand_off, u32* cand_cnt, cudaStream_t s)
+{
+    if (tiles == 0) return;
+    k_candidates_list<<<(unsigned)tiles, LIST_THREADS, 0, s>>>((const unsigned char*)d_in, tab, tile_flags, tile_prefix,
+                                                             cand_chunk, cand_off, cand_cnt);
+}
+void launch_emit_chains_verify(const void* d_in, ChunkTable tab, u64 chunks, const u64* tile_prefix, const u32* cand_chunk,
+                               const u32* cand_off, const u32* cand_cnt, const u64* cand_rec, u64 ncand, void* out,
+                               u64* violations, cudaStream_t s)
+{
+    if (chunks == 0) return;
+    k_check_chunks<<<(unsigned)((chunks + 127) / 128), 128, 0, s>>>(tab, tile_prefix, violations);
+    if (ncand == 0) return;
+    k_emit_chains_verify<<<(unsigned)((ncand + EMITC_THREADS - 1) / EMITC_THREADS), EMITC_THREADS, 0, s>>>(
+        (const unsigned char*)d_in, tab, cand_chunk, cand_off, cand_cnt, cand_rec, ncand, (unsigned char*)out, violations);
 }
 void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s)
 {

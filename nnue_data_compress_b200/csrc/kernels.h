@@ -31,8 +31,15 @@ struct ChunkTable {
 };
 
 void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks, cudaStream_t s);
-void launch_candidates(bool write, const void* d_in, ChunkTable tab, u64 tiles, u32* tile_count, const u64* tile_prefix,
-                       u32* cand_chunk, u32* cand_off, u32 debug_reject_mod, cudaStream_t s);
+void launch_candidates_scan(const void* d_in, u64 n_in, ChunkTable tab, u64 tiles, u32* tile_count, u32* tile_flags,
+                            u32 debug_reject_mod, cudaStream_t s);
+void launch_mark_conflicts(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u32* cand_cnt,
+                           u64 ncand, cudaStream_t s);
+void launch_candidates_list(const void* d_in, ChunkTable tab, u64 tiles, const u32* tile_flags, const u64* tile_prefix,
+                            u32* cand_chunk, u32* cand_off, u32* cand_cnt, cudaStream_t s);
+void launch_emit_chains_verify(const void* d_in, ChunkTable tab, u64 chunks, const u64* tile_prefix, const u32* cand_chunk,
+                               const u32* cand_off, const u32* cand_cnt, const u64* cand_rec, u64 ncand, void* out,
+                               u64* violations, cudaStream_t s);
 void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s);
 void launch_exclusive_sum64(const u64* in, u64 n, u64* out, cudaStream_t s);
 void launch_probe_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u64 ncand,

@@ -169,22 +169,28 @@ def test_device_generator_vs_reference_binary(nnp):
     assert nnp.binpack_to_bin(want) == ref_convert(BINPACK_TO_BIN, want)
 
 
-def test_sequential_fallback_is_exact(nnp):
-    """NNP_DEBUG_REJECT_MOD drops a pseudo-random subset of chain-start candidates, which forces
-    the affected chunks through the sequential per-chunk decoder; the output must not change."""
+@pytest.mark.parametrize("env", [{"NNP_DEBUG_REJECT_MOD": "5"}, {"NNP_DEBUG_EXHAUSTIVE": "1"}])
+def test_decode_fallbacks_are_exact(nnp, env):
+    """binpack -> bin has three strategies: the optimistic single walk (default), the exhaustive
+    probe/resolve walk (NNP_DEBUG_EXHAUSTIVE=1, or whenever the optimistic walk sees a violation)
+    and the sequential per-chunk decoder. NNP_DEBUG_REJECT_MOD drops a pseudo-random subset of
+    chain-start candidates, which fails the optimistic walk and forces the affected chunks through
+    the sequential decoder. The output must not change."""
     import subprocess
     import sys
 
     code = (
         "import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.');"
-        "import nnue_data_compress_b200 as n; from refutil import golden;"
+        "import nnue_data_compress_b200 as n; from refutil import golden, GOLDEN_SETS;"
         "n.init(0);"
-        "ok = all(n.binpack_to_bin(golden(s + '.binpack')) == golden(s + '.rt.bin') for s in ('games100', 'twochunks', 'long400'));"
+        "ok = all(n.binpack_to_bin(golden(s + '.binpack')) == golden(s + '.rt.bin') for s in GOLDEN_SETS);"
+        "b = n.generate_bin(300000, 100, 99); p = n.bin_to_binpack(b); r = n.binpack_to_bin(p);"
+        "ok = ok and len(r) == len(b) and n.bin_to_binpack(r) == p;"
         "print('FALLBACK_OK' if ok else 'FALLBACK_MISMATCH')"
     )
-    env = dict(os.environ, NNP_DEBUG_REJECT_MOD="5")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True,
+                         timeout=600)
     assert "FALLBACK_OK" in out.stdout, out.stdout + out.stderr
 
 
