@@ -10,7 +10,11 @@
 // Citations are relative to /root/reference.
 #pragma once
 #include <cstdint>
+#ifdef NNP_HOST_SIM
+#include "host_sim.h"  // tests/host_sim: CPU stand-ins for the intrinsics, test harness only
+#else
 #include <cuda_runtime.h>
+#endif
 
 namespace nnp {
 

@@ -22,6 +22,7 @@
 //   k_slow_emit        the same, sequentially, for flagged chunks
 #include "common.cuh"
 #include "kernels.h"
+#include "stream.cuh"
 #include "text.cuh"
 
 namespace nnp {
@@ -513,22 +514,11 @@ k_resolve_chunks(ChunkTable tab, const u64* __restrict__ tile_prefix, const u32*
 
 // ------------------------------------------------------------------ record emission
 
-__device__ __forceinline__ void emit_bin_record(const ChainCursor& c, unsigned char* out, u64 rec)
-{
-    u32 w[10];
-    sfen_encode(c.pos, w);
-    // trainingDataEntryToPackedSfenValue (:570-585): score, move, gamePly, result, padding 0xFF
-    w[8] = ((u32)c.score & 0xFFFFu) | (move_to_sfmove(c.mv) << 16);
-    w[9] = ((u32)c.ply & 0xFFFFu) | (((u32)c.result & 0xFFu) << 16) | 0xFF000000u;
-    uint2* d = reinterpret_cast<uint2*>(out + rec * 40);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) d[i] = make_uint2(w[2 * i], w[2 * i + 1]);
-}
-
-// walks one chain from its stem, calling emit(cursor, k) for k = 0..numPlies; returns false when
-// the movetext runs off the chunk
-template <typename EmitFn>
-__device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_after_stem, EmitFn emit, u32& consumed)
+// walks one chain from its stem, calling emit(cursor, k) for k = 0..numPlies and before_move(cursor)
+// just before the cursor's move is made; returns false when the movetext runs off the chunk
+template <typename MoveFn, typename EmitFn>
+__device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_after_stem, MoveFn before_move, EmitFn emit,
+                                           u32& consumed)
 {
     ChainCursor cc;
     chain_open(s, cc);
@@ -541,15 +531,49 @@ __device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_aft
     r.overrun = false;
     for (u32 k = 0; k < cc.num_plies; ++k) {
         if (cc.mv.from > 63 || cc.mv.to > 63) return false;
+        before_move(cc);
         if (!chain_step(cc, r, false)) return false;
         emit(cc, k + 1);
     }
     consumed = 34 + ((r.pos + 7) >> 3);
     return true;
 }
+template <typename EmitFn>
+__device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_after_stem, EmitFn emit, u32& consumed)
+{
+    return walk_chain(s, bytes_after_stem, [](const ChainCursor&) {}, emit, consumed);
+}
+
+// walk_chain writing 40-byte .bin records rec0, rec0 + 1, ... (below rec_limit). The Huffman stream
+// of the position is carried along the chain (stream.cuh): built once for the chain head, then
+// spliced per move. `col` is the thread's 8-word scratch column in shared memory.
+__device__ __forceinline__ bool emit_chain_bin(const unsigned char* s, u32 bytes_after_stem, unsigned char* out, u64 rec0,
+                                               u64 rec_limit, u32* col, int stride, u32& consumed)
+{
+    u32 W[8];
+    bool spliced = false;
+    return walk_chain(
+        s, bytes_after_stem, [&](const ChainCursor& cc) { spliced = stream_apply_move(W, cc.pos, cc.mv); },
+        [&](const ChainCursor& cc, u32 k) {
+            const int end = (k == 0 || !spliced) ? stream_from_pos(cc.pos, col, stride, W) : stream_board_end(cc.pos);
+            if (rec0 + k >= rec_limit) return;
+            u32 w[8];
+            stream_with_tail(W, end, cc.pos, w);
+            // trainingDataEntryToPackedSfenValue (:570-585): score, move, gamePly, result, padding 0xFF
+            const u32 w8 = ((u32)cc.score & 0xFFFFu) | (move_to_sfmove(cc.mv) << 16);
+            const u32 w9 = ((u32)cc.ply & 0xFFFFu) | (((u32)cc.result & 0xFFu) << 16) | 0xFF000000u;
+            uint2* d = reinterpret_cast<uint2*>(out + (rec0 + k) * 40);
+            d[0] = make_uint2(w[0], w[1]);
+            d[1] = make_uint2(w[2], w[3]);
+            d[2] = make_uint2(w[4], w[5]);
+            d[3] = make_uint2(w[6], w[7]);
+            d[4] = make_uint2(w8, w9);
+        },
+        consumed);
+}
 
 #ifndef EMIT_MIN_BLOCKS
-#define EMIT_MIN_BLOCKS 8
+#define EMIT_MIN_BLOCKS 6
 #endif
 constexpr int EMITC_THREADS = 128;
 __global__ void __launch_bounds__(EMITC_THREADS, EMIT_MIN_BLOCKS)
@@ -557,6 +581,7 @@ k_emit_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* _
               const u32* __restrict__ cand_off, const u32* __restrict__ cand_base, u64 ncand,
               const u64* __restrict__ chunk_base, unsigned char* __restrict__ out, DecompressTotals* tot)
 {
+    __shared__ u32 scratch[8 * EMITC_THREADS];
     const u64 i = (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
     if (i >= ncand) return;
     const u32 b = cand_base[i];
@@ -569,8 +594,7 @@ k_emit_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* _
     const u64 rec0 = chunk_base[c] + b;
     const unsigned char* s = in + tab.start[c] + off;
     u32 consumed = 0;
-    const bool ok = walk_chain(s, tab.len[c] - off - 34,
-                               [&](const ChainCursor& cc, u32 k) { emit_bin_record(cc, out, rec0 + k); }, consumed);
+    const bool ok = emit_chain_bin(s, tab.len[c] - off - 34, out, rec0, ~0ull, scratch + threadIdx.x, EMITC_THREADS, consumed);
     if (!ok) atomicMin(&tot->error_chunk, (u64)c);
 }
 
@@ -615,6 +639,7 @@ k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const
                      const u32* __restrict__ cand_off, const u32* __restrict__ cand_cnt, const u64* __restrict__ cand_rec,
                      u64 ncand, unsigned char* __restrict__ out, u64* __restrict__ violations)
 {
+    __shared__ u32 scratch[8 * EMITC_THREADS];
     const u64 i = (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
     if (i >= ncand) return;
     if (cand_cnt[i] == 0) return;  // marked by k_mark_conflicts
@@ -623,8 +648,7 @@ k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const
     const u64 rec0 = cand_rec[i];
     const unsigned char* s = in + tab.start[c] + off;
     u32 consumed = 0;
-    bool ok = walk_chain(s, clen - off - 34, [&](const ChainCursor& cc, u32 k) { emit_bin_record(cc, out, rec0 + k); },
-                         consumed);
+    bool ok = emit_chain_bin(s, clen - off - 34, out, rec0, ~0ull, scratch + threadIdx.x, EMITC_THREADS, consumed);
     const u32 end = off + consumed;
     u64 prev = i, next = i + 1;  // neighbours in the chunk, skipping marked candidates
     while (prev > 0 && cand_chunk[prev - 1] == c && cand_cnt[prev - 1] == 0) --prev;
@@ -689,6 +713,7 @@ __global__ void k_slow_count(const unsigned char* __restrict__ in, ChunkTable ta
 __global__ void k_slow_emit(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ chunk_slow,
                             const u64* __restrict__ chunk_base, unsigned char* __restrict__ out)
 {
+    __shared__ u32 scratch[8 * 32];  // launched with 32 threads per block
     const u64 c = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= tab.info->chunks || !chunk_slow[c]) return;
     const u32 clen = tab.len[c];
@@ -698,10 +723,9 @@ __global__ void k_slow_emit(const unsigned char* __restrict__ in, ChunkTable tab
     const u64 rec_end = chunk_base[c + 1];
     while ((u64)cur + 34 <= clen) {
         u32 consumed = 0;
-        const bool ok = walk_chain(base + cur, clen - cur - 34,
-                                   [&](const ChainCursor& cc, u32) { if (rec < rec_end) emit_bin_record(cc, out, rec); ++rec; },
-                                   consumed);
-        if (!ok) break;
+        const u32 plies = ((u32)base[cur + 32] << 8) | (u32)base[cur + 33];
+        if (!emit_chain_bin(base + cur, clen - cur - 34, out, rec, rec_end, scratch + threadIdx.x, 32, consumed)) break;
+        rec += 1 + plies;
         cur += consumed;
     }
 }

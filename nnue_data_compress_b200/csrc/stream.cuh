@@ -1,0 +1,191 @@
+// stream.cuh -- the PackedSfen Huffman stream (SfenPacker::pack, compress_file.cpp:266-312) kept
+// up to date along a chain instead of being rebuilt for every position.
+//
+// Layout of the 256-bit little-endian stream: stm(1) wK(6) bK(6), then one token per non-king
+// square in stream order (square ^ 56: rank 8 first, file a first): '0' for an empty square,
+// 1 + type(3) + colour(1) for a piece; then castling(4) ep(1[+6]) rule50(6) fullmove(8).
+// A move changes two to four tokens, so the board part of the next record's stream is the current
+// one with those tokens replaced and everything above them shifted by the width difference:
+// a few dozen word operations instead of a loop over all pieces. The tail is re-appended for every
+// record. Moves outside the domain of the splice (no or several kings of a colour, king captures,
+// degenerate castling / en-passant geometry: nothing the reference writer emits from legal games)
+// make stream_apply_move return false and the caller rebuilds the stream with stream_from_pos.
+#pragma once
+#include "chess.cuh"
+
+namespace nnp {
+
+// bits of 32-bit word k that lie below stream position p
+__device__ __forceinline__ u32 stream_low_mask(int p, int k)
+{
+    const int t = max(p - 32 * k, 0);
+    return __funnelshift_lc(0xffffffffu, 0u, (u32)t);  // clamps the shift to 32
+}
+
+// Replaces the `wo` bits at stream position X by the `wn` low bits of `val` (wo, wn <= 5); all bits
+// above move by wn - wo. Bits pushed beyond position 255 are dropped.
+__device__ __forceinline__ void stream_edit(u32 (&W)[8], int X, int wo, int wn, u32 val)
+{
+    const u32 up = (u32)(wn - wo + 8);  // 3 .. 13: shift up, applied to the stream moved down one byte
+    const int wi = X >> 5, sb = X & 31;
+    const u32 vlo = val << sb, vhi = __funnelshift_l(val, 0u, sb);
+    u32 N[8];
+    u32 below = W[0] << 24;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const u32 next = k < 7 ? W[k + 1] : 0u;
+        const u32 b8 = __byte_perm(W[k], next, 0x4321);   // stream bits 32k+8 .. 32k+39
+        const u32 sh = __funnelshift_l(below, b8, up);     // bit i of the result = old bit i - (wn - wo)
+        below = b8;
+        const u32 m1 = stream_low_mask(X, k), m2 = stream_low_mask(X + wn, k);
+        u32 v = (W[k] & m1) | (sh & ~m2);
+        if (k == wi) v |= vlo;
+        if (k == wi + 1) v |= vhi;
+        N[k] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) W[k] = N[k];
+}
+
+__device__ __forceinline__ u32 stream_token(int piece) { return 1u | ((u32)(piece >> 1) << 1) | ((u32)(piece & 1) << 4); }
+
+// end of the board part for a position with one king per side
+__device__ __forceinline__ int stream_board_end(const Pos& p) { return 13 + 62 + 4 * (popc64(pos_all(p)) - 2); }
+
+// Header + board tokens of `p` built from scratch into W; returns the bit length. `col` is a
+// per-thread scratch column of 8 words with the given stride (shared memory: the word index of a
+// token is data dependent).
+__device__ __forceinline__ int stream_from_pos(const Pos& p, u32* col, int stride, u32 (&W)[8])
+{
+    const u64 all = pos_all(p);
+    const u64 kings = pos_type_bb(p, PT_KING);
+    const u64 wkb = kings & p.occ[0], bkb = kings & p.occ[1];
+    const int wk = wkb ? lsb64(wkb) : 0, bk = bkb ? lsb64(bkb) : 0;  // kingSquare Position.h:742-745
+#pragma unroll
+    for (int k = 1; k < 8; ++k) col[k * stride] = 0;
+    col[0] = (u32)p.stm | ((u32)wk << 1) | ((u32)bk << 7);
+    const u64 s_k = bswap64(kings);
+    u64 s_np = bswap64(all) & ~s_k;
+    int np = 0;
+    while (s_np) {
+        const int s = lsb64(s_np);
+        s_np &= s_np - 1;
+        const int pos = 13 + s - popc64(s_k & before64(s)) + 4 * np;
+        const u32 tok = stream_token(pos_piece_at(p, s ^ 56));
+        const int wi = pos >> 5, sb = pos & 31;
+        if (wi < 8) col[wi * stride] |= tok << sb;
+        if (sb > 27 && wi < 7) col[(wi + 1) * stride] |= tok >> (32 - sb);
+        ++np;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) W[k] = col[k * stride];
+    return 13 + (64 - popc64(kings)) + 4 * np;
+}
+
+// Applies move `m`, made in position `p` (the position BEFORE the move), to the stream of `p`.
+// The token changes mirror Board::doMove (Position.h:300-439) as restated in board_do_move.
+__device__ __forceinline__ bool stream_apply_move(u32 (&W)[8], const Pos& p, const Move& m)
+{
+    const u64 all = pos_all(p);
+    const u64 kings = pos_type_bb(p, PT_KING);
+    const u64 wkb = kings & p.occ[0], bkb = kings & p.occ[1];
+    if (popc64(wkb) != 1 || popc64(bkb) != 1 || popc64(all) > 34) return false;
+    const int from = m.from, to = m.to;
+    if (from > 63 || to > 63 || from == to) return false;
+    const int pc = pos_piece_at(p, from);
+    if (pc == NO_PIECE) return false;
+    const bool king_moves = (pc >> 1) == PT_KING;
+    auto occupied = [&](int sq) { return (int)((all >> sq) & 1); };
+    auto has_king = [&](int sq) { return (int)((kings >> sq) & 1); };
+
+    int es[4], ewo[4], ewn[4], n = 2;
+    u32 ev[4];
+    es[2] = es[3] = 0; ewo[2] = ewo[3] = ewn[2] = ewn[3] = 0; ev[2] = ev[3] = 0;
+    int new_king_sq = -1;
+    if (m.type == MT_CASTLE) {
+        const int rook = pos_piece_at(p, to);
+        if (!king_moves || rook == NO_PIECE || (rook >> 1) == PT_KING) return false;
+        const int base = (pc & 1) ? 56 : 0;
+        const bool is_short = (to & 7) == 7;
+        const int rt = base + (is_short ? 5 : 3), kt = base + (is_short ? 6 : 2);
+        if (rt == from || rt == to || kt == from || kt == to || has_king(rt) || has_king(kt)) return false;
+        es[0] = from ^ 56; ewo[0] = 0; ewn[0] = 1; ev[0] = 0;
+        es[1] = to ^ 56; ewo[1] = 5; ewn[1] = 1; ev[1] = 0;
+        es[2] = rt ^ 56; ewo[2] = occupied(rt) ? 5 : 1; ewn[2] = 5; ev[2] = stream_token(rook);
+        es[3] = kt ^ 56; ewo[3] = occupied(kt) ? 5 : 1; ewn[3] = 0; ev[3] = 0;
+        n = 4;
+        new_king_sq = kt;
+    } else {
+        if (has_king(to)) return false;
+        const int wto = occupied(to) ? 5 : 1;
+        if (king_moves) {
+            if (m.type != MT_NORMAL) return false;
+            es[0] = from ^ 56; ewo[0] = 0; ewn[0] = 1; ev[0] = 0;
+            es[1] = to ^ 56; ewo[1] = wto; ewn[1] = 0; ev[1] = 0;
+            new_king_sq = to;
+        } else {
+            const int placed = m.type == MT_PROMOTION ? m.promo : pc;
+            if (placed == NO_PIECE) return false;
+            es[0] = from ^ 56; ewo[0] = 5; ewn[0] = 1; ev[0] = 0;
+            es[1] = to ^ 56; ewo[1] = wto; ewn[1] = 5; ev[1] = stream_token(placed);
+            if (m.type == MT_ENPASSANT) {
+                const int cap = (to & 7) | (from & 56);
+                if ((pc >> 1) != PT_PAWN || cap == from || cap == to || has_king(cap)) return false;
+                if (occupied(cap)) {
+                    es[2] = cap ^ 56; ewo[2] = 5; ewn[2] = 1; ev[2] = 0;
+                    n = 3;
+                }
+            }
+        }
+    }
+    const u64 s_all = bswap64(all);
+    const int ks1 = lsb64(wkb) ^ 56, ks2 = lsb64(bkb) ^ 56;
+    int X[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        // position of stream square s in the stream of `p`: 13 + non-king squares before it
+        // + 4 bits for every non-king piece before it
+        const int s = es[j];
+        const int ab = popc64(s_all & before64(s));
+        const int kb = (s > ks1) + (s > ks2);
+        int x = 13 + s + 4 * ab - 5 * kb;
+#pragma unroll
+        for (int i = 0; i < j; ++i)  // edits already applied below this one moved it
+            if (i < n && es[i] < s) x += ewn[i] - ewo[i];
+        X[j] = x;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (j < n) stream_edit(W, X[j], ewo[j], ewn[j], ev[j]);
+    u32 w0 = W[0] ^ 1u;  // side to move
+    if (new_king_sq >= 0) {
+        const int f = (pc & 1) ? 7 : 1;
+        w0 = (w0 & ~(63u << f)) | ((u32)new_king_sq << f);
+    }
+    W[0] = w0;
+    return true;
+}
+
+// W (header + board, `end` bits) followed by castling / ep / rule50 / fullmove of `p` (:290-311)
+__device__ __forceinline__ void stream_with_tail(const u32 (&W)[8], int end, const Pos& p, u32 (&out)[8])
+{
+    u32 T = (u32)p.cr & 15u;
+    int n = 5;
+    if (p.ep != SQ_NONE) {
+        T |= 16u | ((u32)(p.ep & 63) << 5);
+        n = 11;
+    }
+    T |= ((u32)p.rule50 & 63u) << n;
+    T |= (u32)(((p.ply + 1) >> 1) & 0xFF) << (n + 6);  // halfMove() Position.h:933-936, 8 bits
+    const int wi = end >> 5, sb = end & 31;
+    const u32 lo = T << sb, hi = __funnelshift_l(T, 0u, sb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        u32 v = W[k];
+        if (k == wi) v |= lo;
+        if (k == wi + 1) v |= hi;
+        out[k] = v;
+    }
+}
+
+}  // namespace nnp

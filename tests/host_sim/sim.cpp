@@ -1,0 +1,119 @@
+// sim.cpp -- TEST INFRASTRUCTURE ONLY (see host_sim.h). Runs device functions of chess.cuh /
+// stream.cuh on the CPU over a .bin record array so that the CPU suite can check them against the
+// oracle and the golden vectors.
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+#include "host_sim.h"
+#include "../../nnue_data_compress_b200/csrc/chess.cuh"
+#include "../../nnue_data_compress_b200/csrc/stream.cuh"
+
+using namespace nnp;
+
+namespace {
+struct Rec {
+    u32 w[10];
+};
+Rec load(const unsigned char* bin, size_t i)
+{
+    Rec r;
+    std::memcpy(r.w, bin + 40 * i, 40);
+    return r;
+}
+}  // namespace
+
+extern "C" {
+
+// For every record: decode, re-encode from scratch with sfen_encode and with stream_from_pos +
+// stream_with_tail; count disagreements between the two encoders (-> *enc_mismatch).
+// For every consecutive pair (i, i+1): apply record i's move to record i's position with
+// stream_apply_move (+ pos_do_move) and compare with sfen_encode of the resulting position
+// (-> *splice_mismatch); *spliced counts the moves inside the splice domain.
+int sim_stream_check(const unsigned char* bin, size_t n, uint64_t* enc_mismatch, uint64_t* splice_mismatch,
+                     uint64_t* spliced, uint64_t* first_bad)
+{
+    *enc_mismatch = *splice_mismatch = *spliced = 0;
+    *first_bad = ~0ull;
+    u32 col[8];
+    for (size_t i = 0; i < n; ++i) {
+        const Rec r = load(bin, i);
+        Pos p;
+        pos_clear(p);
+        if (!sfen_decode([&](int j) { return r.w[j]; }, p)) continue;
+        u32 a[8], W[8], b[8];
+        sfen_encode(p, a);
+        const int end = stream_from_pos(p, col, 1, W);
+        stream_with_tail(W, end, p, b);
+        if (std::memcmp(a, b, 32) != 0) {
+            ++*enc_mismatch;
+            if (*first_bad == ~0ull) *first_bad = i;
+        }
+        const Move m = sfmove_to_move(r.w[8] >> 16);
+        u32 W2[8];
+        std::memcpy(W2, W, 32);
+        const bool ok = stream_apply_move(W2, p, m);
+        if (!ok) continue;
+        ++*spliced;
+        Pos q = p;
+        pos_do_move(q, m);
+        u32 c[8], d[8];
+        sfen_encode(q, c);
+        stream_with_tail(W2, stream_board_end(q), q, d);
+        if (std::memcmp(c, d, 32) != 0) {
+            ++*splice_mismatch;
+            if (*first_bad == ~0ull) *first_bad = i;
+        }
+    }
+    return 0;
+}
+
+// The same splice check with pseudo-random (mostly illegal) moves of all four types on every
+// position: whenever stream_apply_move accepts a move, the result must equal the from-scratch
+// encoding of pos_do_move's result. Returns the number of accepted moves; *mismatch counts errors.
+uint64_t sim_stream_fuzz(const unsigned char* bin, size_t n, int moves_per_pos, uint64_t seed, uint64_t* mismatch)
+{
+    *mismatch = 0;
+    uint64_t accepted = 0, x = seed * 2862933555777941757ull + 3037000493ull;
+    u32 col[8];
+    for (size_t i = 0; i < n; ++i) {
+        const Rec r = load(bin, i);
+        Pos p;
+        pos_clear(p);
+        if (!sfen_decode([&](int j) { return r.w[j]; }, p)) continue;
+        u32 W[8];
+        stream_from_pos(p, col, 1, W);
+        for (int k = 0; k < moves_per_pos; ++k) {
+            x = x * 6364136223846793005ull + 1442695040888963407ull;
+            const u32 v = (u32)(x >> 33);
+            Move m;
+            m.from = v & 63;
+            m.to = (v >> 6) & 63;
+            m.type = (v >> 12) & 3;
+            m.promo = NO_PIECE;
+            // bias towards moves that start on a piece and towards castling-like geometry
+            if ((v >> 20) & 1) {
+                u64 all = pos_all(p);
+                m.from = nth_set_bit(all, (v >> 21) % (u32)popc64(all));
+            }
+            if (m.type == MT_CASTLE && ((v >> 14) & 1)) {
+                m.from = ((v >> 15) & 1) ? 4 : 60;
+                m.to = (m.from & 56) + (((v >> 16) & 1) ? 7 : 0);
+            }
+            if (m.type == MT_PROMOTION) m.promo = ((PT_KNIGHT + (int)((v >> 17) & 3)) << 1) | (int)((v >> 19) & 1);
+            u32 W2[8];
+            std::memcpy(W2, W, 32);
+            if (!stream_apply_move(W2, p, m)) continue;
+            ++accepted;
+            Pos q = p;
+            pos_do_move(q, m);
+            u32 c[8], d[8];
+            sfen_encode(q, c);
+            stream_with_tail(W2, stream_board_end(q), q, d);
+            if (std::memcmp(c, d, 32) != 0) ++*mismatch;
+        }
+    }
+    return accepted;
+}
+
+}  // extern "C"
