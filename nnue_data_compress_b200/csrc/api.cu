@@ -24,7 +24,7 @@ enum WsSlot {
     WS_CODES = 0, WS_STEMS, WS_TILE_AGG, WS_PAYLOAD, WS_HEAD_OFF, WS_CHUNK_OFF, WS_TOTALS,
     WS_CHUNK_START, WS_CHUNK_LEN, WS_CHUNK_TILE_BASE, WS_CHUNK_INFO, WS_TILE_COUNT, WS_TILE_PREFIX,
     WS_CAND_CHUNK, WS_CAND_OFF, WS_CAND_NEXT, WS_CAND_BASE, WS_CAND_CNT, WS_CHUNK_COUNT, WS_CHUNK_SLOW, WS_CHUNK_BASE,
-    WS_DTOTALS, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
+    WS_DTOTALS, WS_PARK_A, WS_PARK_B, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
 };
 
 struct Context {
@@ -40,6 +40,7 @@ struct Context {
     std::string last_cuda_error;
     float last_total_ms = 0.f, last_dominant_ms = 0.f;
     uint32_t debug_reject_mod = 0;
+    bool debug_k1_per_record = false;  // "k1_per_record": the record-parallel K1 instead of the chain walk
     bool debug_exhaustive = false;     // NNP_DEBUG_EXHAUSTIVE: skip the optimistic decode strategy
     uint64_t optimistic_misses = 0;    // optimistic decodes that had to be redone exhaustively
     uint64_t optimistic_hits = 0;
@@ -161,6 +162,7 @@ int reset_compress_totals(CompressTotals** d_tot_out)
     h_tot->heads = 0;
     h_tot->chunks = 0;
     h_tot->error_index = NO_ERROR_IDX;
+    h_tot->parked[0] = h_tot->parked[1] = 0;
     CK(cudaMemcpyAsync(d_tot, h_tot, sizeof(CompressTotals), cudaMemcpyHostToDevice, C.stream));
     *d_tot_out = d_tot;
     return NNP_OK;
@@ -189,11 +191,29 @@ int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_ca
     CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
 
     CK(cudaEventRecord(C.ev[0], s));
-    launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, s);
-    LAUNCHED(1, "k_decode_link_encode");
+    if (C.debug_k1_per_record) {
+        launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, s);
+        LAUNCHED(1, "k_decode_link_encode");
+        CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    } else {
+        if (n_all >= 0xFFFFFFFFull) return NNP_ERR_BAD_ARG;  // record indices travel as 32 bits
+        WS(WS_PARK_A, (walk_runs(n_all) + 1) * 4, u32, park_a);
+        WS(WS_PARK_B, (walk_runs(n_all) + 1) * 4, u32, park_b);
+        u32* lists[2] = {park_a, park_b};
+        launch_walk_runs(d_bin, n_all, codes, stems, d_tot, lists[0], &d_tot->parked[0], s);
+        LAUNCHED(1, "k_walk_runs");
+        for (int cur = 0;; cur ^= 1) {
+            CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            const u64 n_items = h_tot->parked[cur];
+            if (n_items == 0) break;
+            CK(cudaMemsetAsync(&d_tot->parked[cur ^ 1], 0, 8, s));
+            launch_walk_items(d_bin, n_all, codes, stems, d_tot, lists[cur], n_items, lists[cur ^ 1], &d_tot->parked[cur ^ 1], s);
+            LAUNCHED(1, "k_walk_items");
+        }
+    }
     CK(cudaEventRecord(C.ev[1], s));
-    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
     int status = NNP_OK;
     u64 n = n_all;
     if (h_tot->error_index != NO_ERROR_IDX) {
@@ -876,6 +896,7 @@ int nnp_debug_config(const char* key, uint64_t value)
     std::lock_guard<std::mutex> lock_(g_mutex);
     if (!key) return NNP_ERR_BAD_ARG;
     if (!std::strcmp(key, "exhaustive")) g_ctx.debug_exhaustive = value != 0;
+    else if (!std::strcmp(key, "k1_per_record")) g_ctx.debug_k1_per_record = value != 0;
     else if (!std::strcmp(key, "reject_mod")) g_ctx.debug_reject_mod = (uint32_t)value;
     else return NNP_ERR_BAD_ARG;
     return NNP_OK;

@@ -68,6 +68,7 @@ struct CompressTotals {
     u64 heads;          // number of chains
     u64 chunks;         // written by the chunk-orbit kernel
     u64 error_index;    // first record whose sfen is malformed, or NO_ERROR_IDX
+    u64 parked[2];      // chain heads parked by the current / next round of the chain walk
 };
 
 struct DecompressTotals {

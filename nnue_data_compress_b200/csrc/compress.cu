@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "link.cuh"
+#include "walk.cuh"
 
 namespace nnp {
 
@@ -123,6 +124,76 @@ k_decode_link_encode(const unsigned char* __restrict__ bin, u64 n, u32* __restri
         k1_load(sh, th, hp, hf, hok);
         store_stem(hp, hf, stems + (u64)(first + th) * 8);
     }
+}
+
+// ------------------------------------------------------------------ K1, chain-walking form
+//
+// k_walk_runs: every thread owns a run of KW_RUN consecutive records and walks it with walk_item
+// (walk.cuh): one from-scratch decode of the record before the run, then splice-and-compare per
+// record. A chain head met on the way (the ply / result fields say so without decoding anything)
+// ends the thread's walk and is appended to a global list; k_walk_items then works the list off
+// with one thread per parked head -- decode it, emit its stem, walk the rest of its run -- which
+// may park again (a second head in the same run), so the host repeats k_walk_items until a round
+// parks nothing. Every round runs dense warps; heads never make a warp diverge into the decoder.
+
+#ifndef KW_THREADS_N
+#define KW_THREADS_N 128
+#endif
+#ifndef KW_RUN_N
+#define KW_RUN_N 16
+#endif
+#ifndef KW_MIN_BLOCKS
+#define KW_MIN_BLOCKS 6
+#endif
+constexpr int KW_THREADS = KW_THREADS_N;
+constexpr int KW_RUN = KW_RUN_N;
+constexpr u32 KW_NONE = 0xFFFFFFFFu;
+
+// appends the parked records of a warp with one atomic
+__device__ __forceinline__ void park_append(u32 parked, u32* __restrict__ list, u64* count)
+{
+    const u32 m = __ballot_sync(0xffffffffu, parked != KW_NONE);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    u64 base = 0;
+    if (lane == __ffs((int)m) - 1) base = atomicAdd(count, (u64)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs((int)m) - 1);
+    if (parked != KW_NONE) list[base + __popc(m & ((1u << lane) - 1u))] = parked;
+}
+
+__global__ void __launch_bounds__(KW_THREADS, KW_MIN_BLOCKS)
+k_walk_runs(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ codes, u32* __restrict__ stems,
+            CompressTotals* tot, u32* __restrict__ park_list, u64* park_count)
+{
+    const u64 r0 = ((u64)blockIdx.x * KW_THREADS + threadIdx.x) * KW_RUN;
+    u32 parked = KW_NONE;
+    if (r0 < n) {
+        const u64 e = r0 + KW_RUN < n ? r0 + KW_RUN : n;
+        bool head = r0 == 0;
+        if (!head) {
+            const u32* w = reinterpret_cast<const u32*>(bin + (r0 - 1) * 40);
+            head = !fields_link(w[9], w[19]);
+        }
+        walk_item(bin, head ? r0 : r0 - 1, head, e, codes, stems, [&](u64 rec) { atomicMin(&tot->error_index, rec); },
+                  [&](u64 rec) { parked = (u32)rec; });
+    }
+    park_append(parked, park_list, park_count);
+}
+
+__global__ void __launch_bounds__(KW_THREADS, KW_MIN_BLOCKS)
+k_walk_items(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ codes, u32* __restrict__ stems,
+             CompressTotals* tot, const u32* __restrict__ items, u64 n_items, u32* __restrict__ park_list, u64* park_count)
+{
+    const u64 i = (u64)blockIdx.x * KW_THREADS + threadIdx.x;
+    u32 parked = KW_NONE;
+    if (i < n_items) {
+        const u64 rec = items[i];
+        u64 e = (rec / KW_RUN + 1) * KW_RUN;
+        if (e > n) e = n;
+        walk_item(bin, rec, true, e, codes, stems, [&](u64 r) { atomicMin(&tot->error_index, r); },
+                  [&](u64 r) { parked = (u32)r; });
+    }
+    park_append(parked, park_list, park_count);
 }
 
 // ------------------------------------------------------------------ payload scan
@@ -405,6 +476,22 @@ void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems,
     if (n == 0) return;
     const u64 blocks = (n + K1_TILE - 1) / K1_TILE;
     k_decode_link_encode<<<(unsigned)blocks, K1_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems, tot);
+}
+u64 walk_runs(u64 n) { return (n + KW_RUN - 1) / KW_RUN; }
+void launch_walk_runs(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u32* park_list, u64* park_count,
+                      cudaStream_t s)
+{
+    if (n == 0) return;
+    const u64 blocks = (walk_runs(n) + KW_THREADS - 1) / KW_THREADS;
+    k_walk_runs<<<(unsigned)blocks, KW_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems, tot, park_list, park_count);
+}
+void launch_walk_items(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, const u32* items, u64 n_items,
+                       u32* park_list, u64* park_count, cudaStream_t s)
+{
+    if (n_items == 0) return;
+    const u64 blocks = (n_items + KW_THREADS - 1) / KW_THREADS;
+    k_walk_items<<<(unsigned)blocks, KW_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems, tot, items, n_items,
+                                                        park_list, park_count);
 }
 u64 scan_tiles(u64 n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
 void launch_tile_aggregate(const u32* codes, u64 n, Agg* tile_agg, cudaStream_t s)

@@ -6,6 +6,11 @@ namespace nnp {
 
 // ---- compress (.bin -> .binpack), compress.cu
 void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, cudaStream_t s);
+u64 walk_runs(u64 n);  // number of runs = upper bound of the parked heads of any round
+void launch_walk_runs(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u32* park_list, u64* park_count,
+                      cudaStream_t s);
+void launch_walk_items(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, const u32* items, u64 n_items,
+                       u32* park_list, u64* park_count, cudaStream_t s);
 u64 scan_tiles(u64 n);
 void launch_tile_aggregate(const u32* codes, u64 n, Agg* tile_agg, cudaStream_t s);
 void launch_scan_aggregates(Agg* tile_agg, u64 ntiles, CompressTotals* tot, cudaStream_t s);

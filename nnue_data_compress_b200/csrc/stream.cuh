@@ -28,6 +28,8 @@ __device__ __forceinline__ void stream_edit(u32 (&W)[8], int X, int wo, int wn, 
 {
     const u32 up = (u32)(wn - wo + 8);  // 3 .. 13: shift up, applied to the stream moved down one byte
     const int wi = X >> 5, sb = X & 31;
+    const u32 field = (1u << wn) - 1u;  // the inserted bits: cleared in the shifted stream, then set
+    const u32 clo = field << sb, chi = __funnelshift_l(field, 0u, sb);
     const u32 vlo = val << sb, vhi = __funnelshift_l(val, 0u, sb);
     u32 N[8];
     u32 below = W[0] << 24;
@@ -37,10 +39,10 @@ __device__ __forceinline__ void stream_edit(u32 (&W)[8], int X, int wo, int wn, 
         const u32 b8 = __byte_perm(W[k], next, 0x4321);   // stream bits 32k+8 .. 32k+39
         const u32 sh = __funnelshift_l(below, b8, up);     // bit i of the result = old bit i - (wn - wo)
         below = b8;
-        const u32 m1 = stream_low_mask(X, k), m2 = stream_low_mask(X + wn, k);
-        u32 v = (W[k] & m1) | (sh & ~m2);
-        if (k == wi) v |= vlo;
-        if (k == wi + 1) v |= vhi;
+        const u32 m = stream_low_mask(X, k);
+        u32 v = (W[k] & m) | (sh & ~m);
+        if (k == wi) v = (v & ~clo) | vlo;
+        if (k == wi + 1) v = (v & ~chi) | vhi;
         N[k] = v;
     }
 #pragma unroll
@@ -98,9 +100,10 @@ __device__ __forceinline__ bool stream_apply_move(u32 (&W)[8], const Pos& p, con
     auto occupied = [&](int sq) { return (int)((all >> sq) & 1); };
     auto has_king = [&](int sq) { return (int)((kings >> sq) & 1); };
 
-    int es[4], ewo[4], ewn[4], n = 2;
-    u32 ev[4];
-    es[2] = es[3] = 0; ewo[2] = ewo[3] = ewn[2] = ewn[3] = 0; ev[2] = ev[3] = 0;
+    // up to four token edits, packed as stream square | old width << 6 | new width << 9 | new bits << 12
+    auto edit = [](int sq, int wo, int wn, u32 v) { return (u32)(sq ^ 56) | ((u32)wo << 6) | ((u32)wn << 9) | (v << 12); };
+    u32 e0, e1, e2 = 0, e3 = 0;
+    int n = 2;
     int new_king_sq = -1;
     if (m.type == MT_CASTLE) {
         const int rook = pos_piece_at(p, to);
@@ -109,10 +112,10 @@ __device__ __forceinline__ bool stream_apply_move(u32 (&W)[8], const Pos& p, con
         const bool is_short = (to & 7) == 7;
         const int rt = base + (is_short ? 5 : 3), kt = base + (is_short ? 6 : 2);
         if (rt == from || rt == to || kt == from || kt == to || has_king(rt) || has_king(kt)) return false;
-        es[0] = from ^ 56; ewo[0] = 0; ewn[0] = 1; ev[0] = 0;
-        es[1] = to ^ 56; ewo[1] = 5; ewn[1] = 1; ev[1] = 0;
-        es[2] = rt ^ 56; ewo[2] = occupied(rt) ? 5 : 1; ewn[2] = 5; ev[2] = stream_token(rook);
-        es[3] = kt ^ 56; ewo[3] = occupied(kt) ? 5 : 1; ewn[3] = 0; ev[3] = 0;
+        e0 = edit(from, 0, 1, 0);
+        e1 = edit(to, 5, 1, 0);
+        e2 = edit(rt, occupied(rt) ? 5 : 1, 5, stream_token(rook));
+        e3 = edit(kt, occupied(kt) ? 5 : 1, 0, 0);
         n = 4;
         new_king_sq = kt;
     } else {
@@ -120,19 +123,19 @@ __device__ __forceinline__ bool stream_apply_move(u32 (&W)[8], const Pos& p, con
         const int wto = occupied(to) ? 5 : 1;
         if (king_moves) {
             if (m.type != MT_NORMAL) return false;
-            es[0] = from ^ 56; ewo[0] = 0; ewn[0] = 1; ev[0] = 0;
-            es[1] = to ^ 56; ewo[1] = wto; ewn[1] = 0; ev[1] = 0;
+            e0 = edit(from, 0, 1, 0);
+            e1 = edit(to, wto, 0, 0);
             new_king_sq = to;
         } else {
             const int placed = m.type == MT_PROMOTION ? m.promo : pc;
             if (placed == NO_PIECE) return false;
-            es[0] = from ^ 56; ewo[0] = 5; ewn[0] = 1; ev[0] = 0;
-            es[1] = to ^ 56; ewo[1] = wto; ewn[1] = 5; ev[1] = stream_token(placed);
+            e0 = edit(from, 5, 1, 0);
+            e1 = edit(to, wto, 5, stream_token(placed));
             if (m.type == MT_ENPASSANT) {
                 const int cap = (to & 7) | (from & 56);
                 if ((pc >> 1) != PT_PAWN || cap == from || cap == to || has_king(cap)) return false;
                 if (occupied(cap)) {
-                    es[2] = cap ^ 56; ewo[2] = 5; ewn[2] = 1; ev[2] = 0;
+                    e2 = edit(cap, 5, 1, 0);
                     n = 3;
                 }
             }
@@ -140,23 +143,23 @@ __device__ __forceinline__ bool stream_apply_move(u32 (&W)[8], const Pos& p, con
     }
     const u64 s_all = bswap64(all);
     const int ks1 = lsb64(wkb) ^ 56, ks2 = lsb64(bkb) ^ 56;
-    int X[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        // position of stream square s in the stream of `p`: 13 + non-king squares before it
+    // one loop body for all edits (the kernels are instruction-cache sensitive); edits applied
+    // earlier at lower stream squares have moved the later ones
+    u32 done_lo = 0;  // packed (square, delta + 8) of the edits already applied, 10 bits each
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) {
+        const u32 e = j == 0 ? e0 : j == 1 ? e1 : j == 2 ? e2 : e3;
+        const int sq = (int)(e & 63u), wo = (int)((e >> 6) & 7u), wn = (int)((e >> 9) & 7u);
+        // position of stream square sq in the stream of `p`: 13 + non-king squares before it
         // + 4 bits for every non-king piece before it
-        const int s = es[j];
-        const int ab = popc64(s_all & before64(s));
-        const int kb = (s > ks1) + (s > ks2);
-        int x = 13 + s + 4 * ab - 5 * kb;
-#pragma unroll
-        for (int i = 0; i < j; ++i)  // edits already applied below this one moved it
-            if (i < n && es[i] < s) x += ewn[i] - ewo[i];
-        X[j] = x;
+        const int ab = popc64(s_all & before64(sq));
+        const int kb = (sq > ks1) + (sq > ks2);
+        int x = 13 + sq + 4 * ab - 5 * kb;
+        for (u32 d = done_lo; d; d >>= 10)
+            if ((int)(d & 63u) < sq) x += (int)((d >> 6) & 15u) - 8;
+        stream_edit(W, x, wo, wn, e >> 12);
+        done_lo = (done_lo << 10) | (u32)sq | ((u32)(wn - wo + 8) << 6);
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (j < n) stream_edit(W, X[j], ewo[j], ewn[j], ev[j]);
     u32 w0 = W[0] ^ 1u;  // side to move
     if (new_king_sq >= 0) {
         const int f = (pc & 1) ? 7 : 1;

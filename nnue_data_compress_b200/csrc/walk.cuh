@@ -1,0 +1,150 @@
+// walk.cuh -- the chain-walking form of the .bin compressor's per-record step.
+//
+// CompressedTrainingDataEntryWriter::addTrainingDataEntry (compress_file.cpp:1061-1092) asks, for
+// every record, whether it continues its predecessor: isContinuation (:587-593) compares the
+// predecessor's position after its move with the record's decoded position. Decoding every
+// PackedSfen from scratch (pos_from_packed_sfen :364-446, a loop over up to 30 Huffman tokens) is
+// what the reference spends 90 % of its compression time on. Along a chain it is not needed: the
+// expected stream of the next record is the current one with two to four tokens replaced
+// (stream.cuh), so "decode and compare positions" becomes "splice and compare bits":
+//
+//   * equal header + board bits  <=>  equal side to move, king squares and board, because the
+//     token stream of a board is unique (kings are named in the header, every other square is
+//     '0' or 1+type+colour, and type codes above Queen are rejected by the decoder);
+//   * castling rights and the (post-move nullified, Position.h:868-872) ep square are read from the
+//     record's tail right behind the board bits and compared as values;
+//   * rule50 and the full-move counter are ignored, as Position::operator== does (Position.h:977-984).
+//
+// Only anchors (the record before a run, and chain heads) are decoded from scratch.
+#pragma once
+#include "link.cuh"
+#include "stream.cuh"
+
+namespace nnp {
+
+__device__ __forceinline__ RecordFields record_fields(u32 w8, u32 w9)
+{
+    RecordFields f;
+    f.score = (int)(short)(w8 & 0xFFFF);
+    f.mv = sfmove_to_move(w8 >> 16);
+    f.ply = (int)(w9 & 0xFFFF);
+    f.result = (int)(signed char)((w9 >> 16) & 0xFF);
+    return f;
+}
+
+// the two field tests of isContinuation (:589-590), on the raw words 9 of both records
+__device__ __forceinline__ bool fields_link(u32 prev_w9, u32 cur_w9)
+{
+    const int pr = (int)(signed char)((prev_w9 >> 16) & 0xFF), cr = (int)(signed char)((cur_w9 >> 16) & 0xFF);
+    const int pp = (int)(prev_w9 & 0xFFFF), cp = (int)(cur_w9 & 0xFFFF);
+    return pr == -cr && pp + 1 == cp;
+}
+
+// From-scratch decode of record `rec` (pos_from_packed_sfen :364-446). Not inlined: the kernels that
+// walk chains keep one copy of the Huffman loop, off their hot path.
+static __device__ __noinline__ bool decode_record(const unsigned char* __restrict__ bin, u64 rec, Pos& P)
+{
+    const u32* w = reinterpret_cast<const u32*>(bin + rec * 40);
+    pos_clear(P);
+    return sfen_decode([&](int j) { return w[j]; }, P);
+}
+
+static __device__ __noinline__ void store_stem_cold(const Pos& P, u32 w8, u32 w9, u32* stem_out)
+{
+    store_stem(P, record_fields(w8, w9), stem_out);
+}
+
+// The reference's own route for one record, taken when the splice cannot decide: decode the record
+// and compare positions (isContinuation :587-593). On entry Q is the predecessor's position after
+// its move; on return it is the record's own position. Emits the stem when the record starts a chain.
+static __device__ __noinline__ bool walk_slow(const unsigned char* __restrict__ bin, u64 rec, Pos& Q, u32 c8, u32 c9,
+                                              u32* __restrict__ stems, bool& ok)
+{
+    Pos C;
+    ok = decode_record(bin, rec, C);
+    const bool cont = ok && pos_equal(Q, C);
+    if (!cont) store_stem(C, record_fields(c8, c9), stems + rec * 8);
+    Q = C;
+    return cont;
+}
+
+// One work item: decode record `a` from scratch (the anchor; when it is a chain head also emit
+// its code 0 and its stem), then produce the codes of records a+1 .. e-1 by walking. The walk
+// stops at the first record whose ply / result fields rule out a continuation: such a record is a
+// chain head whatever its position, and park(rec) hands it to a later, dense round of items.
+// on_error(rec) reports "Improperly encoded bin sfen" (:407-408, :441-442).
+template <typename ErrFn, typename ParkFn>
+__device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin, u64 a, bool a_is_head, u64 e,
+                                          u32* __restrict__ codes, u32* __restrict__ stems, ErrFn on_error, ParkFn park)
+{
+    u32 Wp[8], p8, p9;
+    {
+        const uint2* src = reinterpret_cast<const uint2*>(bin + a * 40);
+        const uint2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+        Wp[0] = v0.x; Wp[1] = v0.y; Wp[2] = v1.x; Wp[3] = v1.y; Wp[4] = v2.x; Wp[5] = v2.y; Wp[6] = v3.x; Wp[7] = v3.y;
+        p8 = v4.x; p9 = v4.y;
+    }
+    Pos P;
+    bool valid = decode_record(bin, a, P);
+    if (!valid) on_error(a);
+    if (a_is_head) {
+        codes[a] = 0u;
+        store_stem_cold(P, p8, p9, stems + a * 8);
+    }
+    for (u64 rec = a + 1; rec < e; ++rec) {
+        u32 Wc[8], c8, c9;
+        {
+            const uint2* src = reinterpret_cast<const uint2*>(bin + rec * 40);
+            const uint2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+            Wc[0] = v0.x; Wc[1] = v0.y; Wc[2] = v1.x; Wc[3] = v1.y; Wc[4] = v2.x; Wc[5] = v2.y; Wc[6] = v3.x; Wc[7] = v3.y;
+            c8 = v4.x; c9 = v4.y;
+        }
+        if (!valid || !fields_link(p9, c9)) {
+            park(rec);
+            return;
+        }
+        const Move pm = sfmove_to_move(p8 >> 16);
+        const bool spliced = stream_apply_move(Wp, P, pm);  // Wp becomes the expected stream
+        pos_do_move(P, pm);                                  // Position::afterMove
+        bool cont = false;
+        if (spliced) {
+            const int end = stream_board_end(P);
+            u32 diff = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) diff |= (Wp[k] ^ Wc[k]) & stream_low_mask(end, k);
+            if (diff == 0) {
+                // same side to move, kings and board; castling(4) and ep(1[+6]) follow the board bits
+                const u32* cw = reinterpret_cast<const u32*>(bin + rec * 40);
+                const int wi = end >> 5;  // end <= 203: wi + 1 <= 7
+                const u32 t = __funnelshift_r(cw[wi], cw[wi + 1], end & 31);
+                const int cr = (int)(t & 15u);
+                int ep = SQ_NONE;
+                if (t & 16u) {
+                    const int sq = (int)((t >> 5) & 63u);
+                    if (ep_possible(P, sq, P.stm)) ep = sq;  // setEpSquare Position.h:868-872
+                }
+                cont = cr == P.cr && ep == P.ep;
+            }
+        }
+        if (!cont) {
+            bool ok;
+            cont = walk_slow(bin, rec, P, c8, c9, stems, ok);
+            if (!ok) on_error(rec);
+            valid = ok;
+        }
+        u32 code = 0u;
+        if (cont) {
+            int nbits;
+            const u32 bits = encode_ply(P, sfmove_to_move(c8 >> 16), (int)(short)(c8 & 0xFFFF),
+                                        (int)(short)(-(int)(short)(p8 & 0xFFFF)), nbits);
+            code = bits | (1u << (31 - nbits));
+        }
+        codes[rec] = code;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) Wp[k] = Wc[k];
+        p8 = c8;
+        p9 = c9;
+    }
+}
+
+}  // namespace nnp

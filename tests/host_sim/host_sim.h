@@ -62,3 +62,13 @@ inline unsigned int __funnelshift_rc(unsigned int lo, unsigned int hi, unsigned 
     if (s == 32) return hi;
     return (unsigned int)((((unsigned long long)hi << 32) | lo) >> s);
 }
+
+struct uint2 {
+    unsigned int x, y;
+};
+struct uint4 {
+    unsigned int x, y, z, w;
+};
+inline uint2 make_uint2(unsigned int x, unsigned int y) { return uint2{x, y}; }
+inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned int w) { return uint4{x, y, z, w}; }
+#define __restrict__

@@ -8,6 +8,8 @@
 #include "host_sim.h"
 #include "../../nnue_data_compress_b200/csrc/chess.cuh"
 #include "../../nnue_data_compress_b200/csrc/stream.cuh"
+#include "../../nnue_data_compress_b200/csrc/walk.cuh"
+#include <vector>
 
 using namespace nnp;
 
@@ -114,6 +116,66 @@ uint64_t sim_stream_fuzz(const unsigned char* bin, size_t n, int moves_per_pos, 
         }
     }
     return accepted;
+}
+
+// The chain-walking compressor step (walk.cuh) against the record-parallel one (link.cuh) on a
+// whole .bin: runs of `run` records, parked heads worked off in rounds exactly as
+// k_walk_link_encode does. Returns the number of records whose code or stem differs; *parked and
+// *errors report how many heads were queued and how many decode errors were seen.
+uint64_t sim_walk_check(const unsigned char* bin, size_t n, int run, uint64_t* parked, uint64_t* first_error)
+{
+    std::vector<u32> codes_a(n, 0xDEADBEEFu), codes_b(n, 0xDEADBEEFu);
+    std::vector<u32> stems_a(n * 8 + 8, 0u), stems_b(n * 8 + 8, 0u);
+    uint64_t err_a = ~0ull, err_b = ~0ull;
+    *parked = 0;
+    // (a) record-parallel reference form
+    for (size_t i = 0; i < n; ++i) {
+        const Rec r = load(bin, i);
+        Pos cur, prev;
+        pos_clear(cur);
+        pos_clear(prev);
+        const bool ok = sfen_decode([&](int j) { return r.w[j]; }, cur);
+        if (!ok && i < err_a) err_a = i;
+        bool prev_ok = false;
+        RecordFields pf = record_fields(r.w[8], r.w[9]);
+        if (i > 0) {
+            const Rec q = load(bin, i - 1);
+            prev_ok = sfen_decode([&](int j) { return q.w[j]; }, prev);
+            pf = record_fields(q.w[8], q.w[9]);
+        }
+        const RecordFields cf = record_fields(r.w[8], r.w[9]);
+        const u32 code = link_code(i > 0 && ok && prev_ok, prev, pf, cur, cf);
+        codes_a[i] = code;
+        if (code == 0u) store_stem(cur, cf, &stems_a[i * 8]);
+    }
+    // (b) chain walk
+    std::vector<uint64_t> queue, next;
+    auto on_error = [&](u64 rec) { if (rec < err_b) err_b = rec; };
+    for (size_t r0 = 0; r0 < n; r0 += (size_t)run) {
+        const size_t e = r0 + run < n ? r0 + run : n;
+        bool head = r0 == 0;
+        if (!head) head = !fields_link(load(bin, r0 - 1).w[9], load(bin, r0).w[9]);
+        walk_item(bin, head ? r0 : r0 - 1, head, e, codes_b.data(), stems_b.data(), on_error,
+                  [&](u64 rec) { queue.push_back(rec); });
+    }
+    while (!queue.empty()) {
+        *parked += queue.size();
+        next.clear();
+        for (uint64_t rec : queue) {
+            size_t e = (rec / run + 1) * run;
+            if (e > n) e = n;
+            walk_item(bin, rec, true, e, codes_b.data(), stems_b.data(), on_error, [&](u64 r) { next.push_back(r); });
+        }
+        queue.swap(next);
+    }
+    *first_error = err_b;
+    uint64_t bad = err_a != err_b ? 1 : 0;
+    const size_t lim = err_a == ~0ull ? n : (size_t)err_a;  // records behind the first error are never used
+    for (size_t i = 0; i < lim; ++i) {
+        if (codes_a[i] != codes_b[i]) ++bad;
+        else if (codes_a[i] == 0u && std::memcmp(&stems_a[i * 8], &stems_b[i * 8], 32) != 0) ++bad;
+    }
+    return bad;
 }
 
 }  // extern "C"

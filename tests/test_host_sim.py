@@ -1,0 +1,82 @@
+"""Device functions on the CPU (tests/host_sim): chess.cuh / stream.cuh / walk.cuh are compiled with
+plain-C++ stand-ins for the CUDA intrinsics and checked against each other and against data written
+by the reference. This is test infrastructure: the product library is never built this way."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+from refutil import GOLDEN_SETS, ROOT, golden, have_ref, ref_generate
+
+SIM_DIR = os.path.join(ROOT, "tests", "host_sim")
+SIM_SO = os.path.join(SIM_DIR, "libsim.so")
+CSRC = os.path.join(ROOT, "nnue_data_compress_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def sim():
+    srcs = [os.path.join(SIM_DIR, "sim.cpp"), os.path.join(SIM_DIR, "host_sim.h")] + [
+        os.path.join(CSRC, f) for f in ("chess.cuh", "stream.cuh", "walk.cuh", "link.cuh")]
+    if not os.path.exists(SIM_SO) or any(os.path.getmtime(s) > os.path.getmtime(SIM_SO) for s in srcs):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-DNNP_HOST_SIM", "-I" + SIM_DIR,
+                        "-shared", "-fPIC", "-o", SIM_SO, srcs[0]], check=True)
+    L = ctypes.CDLL(SIM_SO)
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    L.sim_stream_check.argtypes = [ctypes.c_char_p, ctypes.c_size_t, u64p, u64p, u64p, u64p]
+    L.sim_stream_fuzz.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, u64p]
+    L.sim_stream_fuzz.restype = ctypes.c_uint64
+    L.sim_walk_check.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, u64p, u64p]
+    L.sim_walk_check.restype = ctypes.c_uint64
+    return L
+
+
+def _inputs():
+    data = [(s, golden(s + ".bin")) for s in GOLDEN_SETS] + [(s + ".rt", golden(s + ".rt.bin")) for s in GOLDEN_SETS]
+    if have_ref():
+        data += [("gen100", ref_generate(120_000, 100, 42, 0)), ("gen400", ref_generate(40_000, 400, 9, 0)),
+                 ("shuffled", ref_generate(30_000, 100, 5, 1)), ("restart", ref_generate(30_000, 60, 11, 2)),
+                 ("heads", ref_generate(20_000, 1, 3, 0)), ("gen8", ref_generate(30_000, 8, 3, 0))]
+    return data
+
+
+def test_stream_splice_equals_from_scratch_encoding(sim):
+    """stream_from_pos + stream_with_tail == SfenPacker::pack restatement, and the stream spliced by
+    the record's own move == the encoding of the position after the move."""
+    for name, b in _inputs():
+        a = [ctypes.c_uint64() for _ in range(4)]
+        sim.sim_stream_check(b, len(b) // 40, *[ctypes.byref(x) for x in a])
+        assert a[0].value == 0 and a[1].value == 0, (name, [x.value for x in a])
+        assert a[2].value == len(b) // 40, name  # every move of real data is inside the splice domain
+
+
+def test_stream_splice_fuzz(sim):
+    """Pseudo-random moves of all four types (mostly illegal): whatever the splice accepts must
+    equal pos_do_move + from-scratch encoding."""
+    b = golden("long400.bin") + golden("games100.bin")
+    mm = ctypes.c_uint64()
+    accepted = sim.sim_stream_fuzz(b, len(b) // 40, 256, 7, ctypes.byref(mm))
+    assert accepted > 50_000 and mm.value == 0
+
+
+@pytest.mark.parametrize("run", [1, 5, 16, 64])
+def test_chain_walk_equals_record_parallel_step(sim, run):
+    """walk_item (chain-walking K1) produces the codes and stems of link_code (record-parallel K1)."""
+    for name, b in _inputs():
+        parked, err = ctypes.c_uint64(), ctypes.c_uint64()
+        bad = sim.sim_walk_check(b, len(b) // 40, run, ctypes.byref(parked), ctypes.byref(err))
+        assert bad == 0 and err.value == 2**64 - 1, (name, bad, err.value)
+
+
+def test_chain_walk_reports_bad_sfen(sim):
+    good = golden("games100.bin")[:4000]
+    bits = [0] + [0] * 6 + [1, 0, 0, 0, 0, 0] + [1, 0, 0, 0, 0] * 49
+    sfen = bytearray(32)
+    for i, v in enumerate(bits[:256]):
+        sfen[i // 8] |= v << (i & 7)
+    bad_rec = bytes(sfen) + bytes(8)
+    for cut, run in ((100, 16), (37, 5), (16, 16), (15, 16), (1, 3)):
+        data = good[: 40 * cut] + bad_rec + good
+        parked, err = ctypes.c_uint64(), ctypes.c_uint64()
+        bad = sim.sim_walk_check(data, len(data) // 40, run, ctypes.byref(parked), ctypes.byref(err))
+        assert bad == 0 and err.value == cut
