@@ -33,12 +33,12 @@ struct Context {
     cudaStream_t stream = nullptr;      // stream all kernels and copies are issued on
     cudaStream_t own_stream = nullptr;  // the library's default stream
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     Workspace ws[WS_COUNT];
     void* pinned = nullptr;  // small pinned scratch for read-backs
     uint64_t launches = 0;
     std::string last_cuda_error;
-    float last_total_ms = 0.f, last_dominant_ms = 0.f;
+    float last_total_ms = 0.f, last_dominant_ms = 0.f, last_stage_ms = 0.f;
     uint32_t debug_reject_mod = 0;
     bool debug_k1_per_record = false;  // "k1_per_record": the record-parallel K1 instead of the chain walk
     bool debug_exhaustive = false;     // NNP_DEBUG_EXHAUSTIVE: skip the optimistic decode strategy
@@ -194,6 +194,7 @@ int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_ca
     if (C.debug_k1_per_record) {
         launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, s);
         LAUNCHED(1, "k_decode_link_encode");
+        CK(cudaEventRecord(C.ev[3], s));
         CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     } else {
@@ -203,6 +204,7 @@ int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_ca
         u32* lists[2] = {park_a, park_b};
         launch_walk_runs(d_bin, n_all, codes, stems, d_tot, lists[0], &d_tot->parked[0], s);
         LAUNCHED(1, "k_walk_runs");
+        CK(cudaEventRecord(C.ev[3], s));
         for (int cur = 0;; cur ^= 1) {
             CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
@@ -228,7 +230,8 @@ int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_ca
     CK(cudaEventRecord(C.ev[2], s));
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
-    CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[0], C.ev[1]));
+    CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[0], C.ev[3]));  // k_walk_runs alone
+    CK(cudaEventElapsedTime(&C.last_stage_ms, C.ev[0], C.ev[1]));     // + the rounds of k_walk_items
     return rc;
 }
 

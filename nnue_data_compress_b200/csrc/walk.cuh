@@ -71,79 +71,88 @@ static __device__ __noinline__ bool walk_slow(const unsigned char* __restrict__ 
 // One work item: decode record `a` from scratch (the anchor; when it is a chain head also emit
 // its code 0 and its stem), then produce the codes of records a+1 .. e-1 by walking. The walk
 // stops at the first record whose ply / result fields rule out a continuation: such a record is a
-// chain head whatever its position, and park(rec) hands it to a later, dense round of items.
+// chain head whatever its position, and park(rec) hands it to a later, dense round of items --
+// unless it directly follows the anchor: back-to-back heads (files of single positions) are
+// decoded on the spot, where all lanes of the warp do the same thing anyway.
 // on_error(rec) reports "Improperly encoded bin sfen" (:407-408, :441-442).
 template <typename ErrFn, typename ParkFn>
 __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin, u64 a, bool a_is_head, u64 e,
                                           u32* __restrict__ codes, u32* __restrict__ stems, ErrFn on_error, ParkFn park)
 {
-    u32 Wp[8], p8, p9;
-    {
-        const uint2* src = reinterpret_cast<const uint2*>(bin + a * 40);
-        const uint2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
-        Wp[0] = v0.x; Wp[1] = v0.y; Wp[2] = v1.x; Wp[3] = v1.y; Wp[4] = v2.x; Wp[5] = v2.y; Wp[6] = v3.x; Wp[7] = v3.y;
-        p8 = v4.x; p9 = v4.y;
-    }
-    Pos P;
-    bool valid = decode_record(bin, a, P);
-    if (!valid) on_error(a);
-    if (a_is_head) {
-        codes[a] = 0u;
-        store_stem_cold(P, p8, p9, stems + a * 8);
-    }
-    for (u64 rec = a + 1; rec < e; ++rec) {
-        u32 Wc[8], c8, c9;
+    for (;;) {
+        u32 Wp[8], p8, p9;
         {
-            const uint2* src = reinterpret_cast<const uint2*>(bin + rec * 40);
+            const uint2* src = reinterpret_cast<const uint2*>(bin + a * 40);
             const uint2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
-            Wc[0] = v0.x; Wc[1] = v0.y; Wc[2] = v1.x; Wc[3] = v1.y; Wc[4] = v2.x; Wc[5] = v2.y; Wc[6] = v3.x; Wc[7] = v3.y;
-            c8 = v4.x; c9 = v4.y;
+            Wp[0] = v0.x; Wp[1] = v0.y; Wp[2] = v1.x; Wp[3] = v1.y; Wp[4] = v2.x; Wp[5] = v2.y; Wp[6] = v3.x; Wp[7] = v3.y;
+            p8 = v4.x; p9 = v4.y;
         }
-        if (!valid || !fields_link(p9, c9)) {
+        Pos P;
+        bool valid = decode_record(bin, a, P);
+        if (!valid) on_error(a);
+        if (a_is_head) {
+            codes[a] = 0u;
+            store_stem_cold(P, p8, p9, stems + a * 8);
+        }
+        u64 rec = a + 1;
+        for (; rec < e; ++rec) {
+            u32 Wc[8], c8, c9;
+            {
+                const uint2* src = reinterpret_cast<const uint2*>(bin + rec * 40);
+                const uint2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+                Wc[0] = v0.x; Wc[1] = v0.y; Wc[2] = v1.x; Wc[3] = v1.y; Wc[4] = v2.x; Wc[5] = v2.y; Wc[6] = v3.x; Wc[7] = v3.y;
+                c8 = v4.x; c9 = v4.y;
+            }
+            if (!valid || !fields_link(p9, c9)) break;  // rec starts a chain
+            const Move pm = sfmove_to_move(p8 >> 16);
+            const bool spliced = stream_apply_move(Wp, P, pm);  // Wp becomes the expected stream
+            pos_do_move(P, pm);                                  // Position::afterMove
+            bool cont = false;
+            if (spliced) {
+                const int end = stream_board_end(P);
+                u32 diff = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) diff |= (Wp[k] ^ Wc[k]) & stream_low_mask(end, k);
+                if (diff == 0) {
+                    // same side to move, kings and board; castling(4) and ep(1[+6]) follow the board bits
+                    const u32* cw = reinterpret_cast<const u32*>(bin + rec * 40);
+                    const int wi = end >> 5;  // end <= 203: wi + 1 <= 7
+                    const u32 t = __funnelshift_r(cw[wi], cw[wi + 1], end & 31);
+                    const int cr = (int)(t & 15u);
+                    int ep = SQ_NONE;
+                    if (t & 16u) {
+                        const int sq = (int)((t >> 5) & 63u);
+                        if (ep_possible(P, sq, P.stm)) ep = sq;  // setEpSquare Position.h:868-872
+                    }
+                    cont = cr == P.cr && ep == P.ep;
+                }
+            }
+            if (!cont) {
+                bool ok;
+                cont = walk_slow(bin, rec, P, c8, c9, stems, ok);
+                if (!ok) on_error(rec);
+                valid = ok;
+            }
+            u32 code = 0u;
+            if (cont) {
+                int nbits;
+                const u32 bits = encode_ply(P, sfmove_to_move(c8 >> 16), (int)(short)(c8 & 0xFFFF),
+                                            (int)(short)(-(int)(short)(p8 & 0xFFFF)), nbits);
+                code = bits | (1u << (31 - nbits));
+            }
+            codes[rec] = code;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) Wp[k] = Wc[k];
+            p8 = c8;
+            p9 = c9;
+        }
+        if (rec >= e) return;
+        if (rec != a + 1) {
             park(rec);
             return;
         }
-        const Move pm = sfmove_to_move(p8 >> 16);
-        const bool spliced = stream_apply_move(Wp, P, pm);  // Wp becomes the expected stream
-        pos_do_move(P, pm);                                  // Position::afterMove
-        bool cont = false;
-        if (spliced) {
-            const int end = stream_board_end(P);
-            u32 diff = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) diff |= (Wp[k] ^ Wc[k]) & stream_low_mask(end, k);
-            if (diff == 0) {
-                // same side to move, kings and board; castling(4) and ep(1[+6]) follow the board bits
-                const u32* cw = reinterpret_cast<const u32*>(bin + rec * 40);
-                const int wi = end >> 5;  // end <= 203: wi + 1 <= 7
-                const u32 t = __funnelshift_r(cw[wi], cw[wi + 1], end & 31);
-                const int cr = (int)(t & 15u);
-                int ep = SQ_NONE;
-                if (t & 16u) {
-                    const int sq = (int)((t >> 5) & 63u);
-                    if (ep_possible(P, sq, P.stm)) ep = sq;  // setEpSquare Position.h:868-872
-                }
-                cont = cr == P.cr && ep == P.ep;
-            }
-        }
-        if (!cont) {
-            bool ok;
-            cont = walk_slow(bin, rec, P, c8, c9, stems, ok);
-            if (!ok) on_error(rec);
-            valid = ok;
-        }
-        u32 code = 0u;
-        if (cont) {
-            int nbits;
-            const u32 bits = encode_ply(P, sfmove_to_move(c8 >> 16), (int)(short)(c8 & 0xFFFF),
-                                        (int)(short)(-(int)(short)(p8 & 0xFFFF)), nbits);
-            code = bits | (1u << (31 - nbits));
-        }
-        codes[rec] = code;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) Wp[k] = Wc[k];
-        p8 = c8;
-        p9 = c9;
+        a = rec;
+        a_is_head = true;
     }
 }
 
