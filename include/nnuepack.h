@@ -48,7 +48,8 @@ typedef enum nnp_status {
     NNP_ERR_CAPACITY = -8,        /* output buffer too small; *out_bytes = bytes required */
     NNP_ERR_NO_DEVICE = -9,       /* no CUDA device / extension cannot run: there is no CPU path */
     NNP_ERR_NOT_INITIALISED = -10,
-    NNP_ERR_CUDA = -11            /* a CUDA runtime call failed; see nnp_last_cuda_error() */
+    NNP_ERR_CUDA = -11,           /* a CUDA runtime call failed; see nnp_last_cuda_error() */
+    NNP_ERR_WINDOW = -12          /* sharded compression: the overlap window does not reach the next chain head */
 } nnp_status;
 
 /* ---- lifecycle ------------------------------------------------------------------ */
@@ -96,6 +97,50 @@ int nnp_plain_to_binpack_dev(const void* d_plain, size_t plain_bytes, void* d_ou
 int nnp_binpack_to_plain_dev(const void* d_binpack, size_t binpack_bytes, void* d_out, size_t out_cap, size_t* out_bytes);
 int nnp_bin_to_plain_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_cap, size_t* out_bytes);
 int nnp_plain_to_bin_dev(const void* d_plain, size_t plain_bytes, void* d_out, size_t out_cap, size_t* out_bytes);
+
+/* ---- .bin -> .binpack over several GPUs, byte-identical to one reference run ------------------
+ *
+ * compressBin is sequential in two places: chains (a record joins the chain of its predecessor,
+ * compress_file.cpp:587-593, :1061-1092) and chunks (a chunk is flushed when a chain head arrives and
+ * at least 1 MiB has gathered since the last flush, :1076-1080). Both are kept exact when the records
+ * are split over ranks (one process per GPU):
+ *
+ *   1. every rank calls nnp_shard_compress_begin_dev() on the records it owns plus one halo record
+ *      before them and an overlap window behind them. A chain belongs to the rank its head lies in.
+ *   2. the ranks all-gather `payload_bytes` (8 bytes each): the exclusive prefix sum is each rank's
+ *      `payload_base`, the offset of its chains in the header-less payload of the whole file.
+ *   3. in rank order, nnp_shard_compress_orbit(payload_base, carry_in, ...) replays the flush rule
+ *      over the rank's chain heads; `carry_out` (the global offset of the last chunk start so far)
+ *      and the running number of chunks are handed to the next rank (16 bytes, NO payload).
+ *   4. the ranks all-gather `first_start`; nnp_shard_compress_emit_dev(next_start, ...) writes the
+ *      rank's slice of the .binpack: its payload with a BINP header in front of every chunk start.
+ *      `next_start` = the first chunk start of any later rank, or the total payload size: it closes
+ *      the rank's last chunk. The slice belongs at file offset payload_base + 8 * chunks_before.
+ *
+ * nnue_data_compress_b200/sharding.py drives these calls over torch.distributed (NCCL / gloo).
+ * A malformed record (NNP_ERR_BAD_SFEN) is reported with its index and ends the sharded run: the
+ * partial-output rule of the single-GPU entry point is not replayed across ranks. */
+typedef struct nnp_shard_info {
+    uint64_t first_owned_record; /* index (in the buffer) of the first chain head >= own_lo */
+    uint64_t end_owned_record;   /* index of the first chain head >= own_hi (records before it are owned) */
+    uint64_t payload_bytes;      /* bytes of the owned chains: sum of 34 + ceil(movetext bits / 8) */
+    uint64_t chains;
+    uint64_t first_bad_record;   /* NNP_ERR_BAD_SFEN: index of the first malformed record, else ~0 */
+} nnp_shard_info;
+#define NNP_NO_CARRY (~(uint64_t)0)
+
+/* d_bin: records [g0, g1) of the file, device memory; own_lo / own_hi: the rank's nominal range as
+ * indices into that buffer (own_lo = 1 when a halo record is present, 0 for the first rank);
+ * reaches_eof: the buffer ends with the file, so a chain that crosses own_hi may run to its end
+ * (otherwise NNP_ERR_WINDOW asks for a larger overlap window). */
+int nnp_shard_compress_begin_dev(const void* d_bin, size_t n_records, size_t own_lo, size_t own_hi, int reaches_eof,
+                                 nnp_shard_info* info);
+/* carry_in: NNP_NO_CARRY for the first rank that has any payload. first_start = NNP_NO_CARRY when
+ * no chunk starts inside this rank's payload. */
+int nnp_shard_compress_orbit(uint64_t payload_base, uint64_t carry_in, uint64_t* n_chunk_starts, uint64_t* first_start,
+                             uint64_t* carry_out);
+/* d_out == NULL: *out_bytes = size of the slice (payload_bytes + 8 * n_chunk_starts). */
+int nnp_shard_compress_emit_dev(uint64_t next_start, void* d_out, size_t out_cap, size_t* out_bytes);
 
 /* ---- helpers around the path --------------------------------------------------------- */
 

@@ -45,6 +45,7 @@ STATUS = {
     -9: "NNP_ERR_NO_DEVICE",
     -10: "NNP_ERR_NOT_INITIALISED",
     -11: "NNP_ERR_CUDA",
+    -12: "NNP_ERR_WINDOW",
 }
 # statuses after which the reference prints a message and still leaves partial output behind
 REFERENCE_ERRORS = (-1, -2, -3)
@@ -58,7 +59,17 @@ EXPORTS = [
     "nnp_binpack_to_plain_dev", "nnp_bin_to_plain_dev", "nnp_plain_to_bin_dev",
     "nnp_binpack_count_dev", "nnp_generate_bin_dev", "nnp_last_timing", "nnp_decode_stats",
     "nnp_debug_config",
+    "nnp_shard_compress_begin_dev", "nnp_shard_compress_orbit", "nnp_shard_compress_emit_dev",
 ]
+
+
+class ShardInfo(ctypes.Structure):
+    """nnp_shard_info (include/nnuepack.h)."""
+    _fields_ = [("first_owned_record", ctypes.c_uint64), ("end_owned_record", ctypes.c_uint64),
+                ("payload_bytes", ctypes.c_uint64), ("chains", ctypes.c_uint64), ("first_bad_record", ctypes.c_uint64)]
+
+
+NO_CARRY = (1 << 64) - 1
 
 
 class NnpError(RuntimeError):
@@ -88,6 +99,8 @@ def lib() -> ctypes.CDLL:
             if name.endswith(("_to_binpack", "_to_bin", "_to_plain", "_dev")) and name not in (
                 "nnp_binpack_count_dev",
                 "nnp_generate_bin_dev",
+                "nnp_shard_compress_begin_dev",
+                "nnp_shard_compress_emit_dev",
             ):
                 fn.argtypes = conv
                 fn.restype = ctypes.c_int
@@ -108,6 +121,15 @@ def lib() -> ctypes.CDLL:
         L.nnp_binpack_count_dev.restype = ctypes.c_int
         L.nnp_generate_bin_dev.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint64]
         L.nnp_generate_bin_dev.restype = ctypes.c_int
+        u64p = ctypes.POINTER(ctypes.c_uint64)
+        L.nnp_shard_compress_begin_dev.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t,
+                                                   ctypes.c_int, ctypes.POINTER(ShardInfo)]
+        L.nnp_shard_compress_begin_dev.restype = ctypes.c_int
+        L.nnp_shard_compress_orbit.argtypes = [ctypes.c_uint64, ctypes.c_uint64, u64p, u64p, u64p]
+        L.nnp_shard_compress_orbit.restype = ctypes.c_int
+        L.nnp_shard_compress_emit_dev.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t,
+                                                  ctypes.POINTER(ctypes.c_size_t)]
+        L.nnp_shard_compress_emit_dev.restype = ctypes.c_int
         L.nnp_debug_config.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
         L.nnp_debug_config.restype = ctypes.c_int
         L.nnp_decode_stats.argtypes = [ctypes.POINTER(ctypes.c_uint64)]

@@ -120,8 +120,17 @@ size_t binpack_capacity_for_records(size_t n)
 
 // ---------------------------------------------------------------- shared tail of both compressors
 
-// codes/stems of n records -> payload scan, payload write, chunk orbit, chunk emission
-int compress_tail(const u32* codes, const u32* stems, u64 n, int status, void* d_out, size_t out_cap, size_t* out_bytes)
+// codes/stems of n records -> payload scan and payload write; leaves the headerless payload stream
+// and the head offsets in the workspaces
+struct PayloadPlan {
+    u64 payload_bytes = 0, heads = 0, max_chunks = 0;
+    u32* payload = nullptr;
+    u64* head_off = nullptr;
+    u64* seg_off = nullptr;
+    CompressTotals* d_tot = nullptr;
+};
+
+int build_payload(const u32* codes, const u32* stems, u64 n, PayloadPlan& P)
 {
     Context& C = g_ctx;
     cudaStream_t s = C.stream;
@@ -133,22 +142,50 @@ int compress_tail(const u32* codes, const u32* stems, u64 n, int status, void* d
     LAUNCHED(2, "payload scan");
     CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    const u64 payload_bytes = h_tot->payload_bytes, heads = h_tot->heads;
-    const u64 max_chunks = payload_bytes / CHUNK_THRESHOLD + 2;
-    WS(WS_PAYLOAD, payload_bytes + 64, u32, payload);
-    WS(WS_HEAD_OFF, (heads + 1) * 8, u64, head_off);
-    WS(WS_CHUNK_OFF, (max_chunks + 2) * 8, u64, chunk_off);
-    CK(cudaMemsetAsync(payload, 0, payload_bytes + 64, s));
+    P.payload_bytes = h_tot->payload_bytes;
+    P.heads = h_tot->heads;
+    P.max_chunks = P.payload_bytes / CHUNK_THRESHOLD + 2;
+    P.d_tot = d_tot;
+    WS(WS_PAYLOAD, P.payload_bytes + 64, u32, payload);
+    WS(WS_HEAD_OFF, (P.heads + 1) * 8, u64, head_off);
+    WS(WS_CHUNK_OFF, (P.max_chunks + 3) * 8, u64, seg_off);
+    P.payload = payload;
+    P.head_off = head_off;
+    P.seg_off = seg_off;
+    CK(cudaMemsetAsync(payload, 0, P.payload_bytes + 64, s));
     launch_write_payload(codes, stems, n, tile_agg, payload, head_off, s);
-    launch_chunk_orbit(head_off, d_tot, chunk_off, max_chunks, s);
-    LAUNCHED(2, "k_write_payload/k_chunk_orbit");
-    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
+    LAUNCHED(1, "k_write_payload");
+    return NNP_OK;
+}
+
+// chunk orbit over the payload's heads; returns the number of chunks opened in it
+int run_orbit(const PayloadPlan& P, u64 base, u64 carry, u64* chunks)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
+    launch_chunk_orbit(P.head_off, P.d_tot, P.seg_off, P.max_chunks, base, carry, s);
+    LAUNCHED(1, "k_chunk_orbit");
+    CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    const u64 chunks = h_tot->chunks;
-    const u64 total = payload_bytes + 8 * chunks;
+    *chunks = h_tot->chunks;
+    return NNP_OK;
+}
+
+// codes/stems of n records -> payload scan, payload write, chunk orbit, chunk emission
+int compress_tail(const u32* codes, const u32* stems, u64 n, int status, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    Context& C = g_ctx;
+    PayloadPlan P;
+    int rc = build_payload(codes, stems, n, P);
+    if (rc != NNP_OK) return rc;
+    u64 chunks = 0;
+    rc = run_orbit(P, 0, NO_CARRY, &chunks);
+    if (rc != NNP_OK) return rc;
+    const u64 total = P.payload_bytes + 8 * chunks;
     *out_bytes = total;
     if (total > out_cap) return NNP_ERR_CAPACITY;
-    launch_emit_chunks(payload, chunk_off, chunks, d_out, s);
+    launch_emit_chunks(P.payload, P.seg_off, chunks, d_out, NATURAL_SIZE, C.stream);
     LAUNCHED(1, "k_emit_chunks");
     return status;
 }
@@ -170,26 +207,20 @@ int reset_compress_totals(CompressTotals** d_tot_out)
 
 // ---------------------------------------------------------------- .bin -> .binpack
 
-int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+// K1: codes and stems of all n records (the chain walk, or the record-parallel kernel under the
+// "k1_per_record" switch); *error_index = first malformed record or NO_ERROR_IDX
+int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** stems_out, u64* error_index)
 {
     Context& C = g_ctx;
-    const u64 n_all = bin_bytes / 40;  // a short trailing record is dropped (compress_file.cpp:1360)
-    if (!d_out) {
-        *out_bytes = binpack_capacity_for_records(n_all);
-        return NNP_OK;
-    }
-    *out_bytes = 0;
-    if (n_all == 0) return NNP_OK;  // empty input -> empty file
-    if (((uintptr_t)d_bin & 7) || ((uintptr_t)d_out & 7)) return NNP_ERR_BAD_ARG;
-
     cudaStream_t s = C.stream;
     WS(WS_CODES, n_all * 4, u32, codes);
     WS(WS_STEMS, n_all * 32, u32, stems);
+    *codes_out = codes;
+    *stems_out = stems;
     CompressTotals* d_tot = nullptr;
     int rc = reset_compress_totals(&d_tot);
     if (rc != NNP_OK) return rc;
     CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
-
     CK(cudaEventRecord(C.ev[0], s));
     if (C.debug_k1_per_record) {
         launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, s);
@@ -216,13 +247,34 @@ int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_ca
         }
     }
     CK(cudaEventRecord(C.ev[1], s));
+    *error_index = h_tot->error_index;
+    return NNP_OK;
+}
+
+int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    Context& C = g_ctx;
+    const u64 n_all = bin_bytes / 40;  // a short trailing record is dropped (compress_file.cpp:1360)
+    if (!d_out) {
+        *out_bytes = binpack_capacity_for_records(n_all);
+        return NNP_OK;
+    }
+    *out_bytes = 0;
+    if (n_all == 0) return NNP_OK;  // empty input -> empty file
+    if (((uintptr_t)d_bin & 7) || ((uintptr_t)d_out & 7)) return NNP_ERR_BAD_ARG;
+
+    cudaStream_t s = C.stream;
+    u32 *codes = nullptr, *stems = nullptr;
+    u64 error_index = NO_ERROR_IDX;
+    int rc = link_encode_records(d_bin, n_all, &codes, &stems, &error_index);
+    if (rc != NNP_OK) return rc;
     int status = NNP_OK;
     u64 n = n_all;
-    if (h_tot->error_index != NO_ERROR_IDX) {
+    if (error_index != NO_ERROR_IDX) {
         // "Improperly encoded bin sfen": the reference stops at the first malformed record and its
         // writer still flushes everything gathered before it (compress_file.cpp:407-408, :1094-1106)
         status = NNP_ERR_BAD_SFEN;
-        n = h_tot->error_index;
+        n = error_index;
         if (n == 0) return status;
     }
     rc = compress_tail(codes, stems, n, status, d_out, out_cap, out_bytes);
@@ -233,6 +285,118 @@ int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_ca
     CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[0], C.ev[3]));  // k_walk_runs alone
     CK(cudaEventElapsedTime(&C.last_stage_ms, C.ev[0], C.ev[1]));     // + the rounds of k_walk_items
     return rc;
+}
+
+// ---------------------------------------------------------------- sharded .bin -> .binpack
+//
+// One shard = the records a rank owns plus one halo record before them and an overlap window
+// behind them. A chain belongs to the shard its head lies in, so the shard's payload is made of the
+// chains whose heads fall into [own_lo, own_hi); the records in front of the first such head end a
+// chain of the previous shard, which is why that shard looks at them through its overlap window.
+
+struct ShardState {
+    bool active = false;
+    PayloadPlan plan;
+    u64 base = 0, chunks = 0;
+    bool orbit_done = false;
+};
+ShardState g_shard;
+
+int shard_begin_dev(const void* d_bin, u64 n_records, u64 own_lo, u64 own_hi, int reaches_eof, nnp_shard_info* info)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    g_shard = ShardState();
+    std::memset(info, 0, sizeof(*info));
+    info->first_bad_record = NO_ERROR_IDX;
+    if (own_lo > own_hi || own_hi > n_records) return NNP_ERR_BAD_ARG;
+    if ((uintptr_t)d_bin & 7) return NNP_ERR_BAD_ARG;
+    if (n_records == 0) {
+        g_shard.active = true;
+        return NNP_OK;
+    }
+    u32 *codes = nullptr, *stems = nullptr;
+    u64 error_index = NO_ERROR_IDX;
+    int rc = link_encode_records(d_bin, n_records, &codes, &stems, &error_index);
+    if (rc != NNP_OK) return rc;
+    if (error_index != NO_ERROR_IDX) {
+        info->first_bad_record = error_index;
+        return NNP_ERR_BAD_SFEN;
+    }
+    // first owned head and first head of the next shard
+    u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+    WS(WS_TEXT_D, 64, u64, d_found);
+    launch_find_head(codes, n_records, own_lo, d_found, s);
+    launch_find_head(codes, n_records, own_hi, d_found + 1, s);
+    LAUNCHED(2, "k_find_head");
+    CK(cudaMemcpyAsync(h_u64, d_found, 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    u64 first = h_u64[0];
+    const u64 end = h_u64[1];
+    // no head behind own_hi: fine when the buffer ends with the file (the chain runs to the end),
+    // otherwise the chain crossing own_hi does not end inside the window
+    if (end >= n_records && !reaches_eof) return NNP_ERR_WINDOW;
+    if (first > end) first = end;  // no head of its own: the whole range continues an earlier shard's chain
+    info->first_owned_record = first;
+    info->end_owned_record = end;
+    g_shard.active = true;
+    if (first == end) return NNP_OK;
+    rc = build_payload(codes + first, stems + first * 8, end - first, g_shard.plan);
+    if (rc != NNP_OK) return rc;
+    info->payload_bytes = g_shard.plan.payload_bytes;
+    info->chains = g_shard.plan.heads;
+    return NNP_OK;
+}
+
+int shard_orbit(u64 payload_base, u64 carry_in, u64* n_starts, u64* first_start, u64* carry_out)
+{
+    if (!g_shard.active) return NNP_ERR_BAD_ARG;
+    g_shard.base = payload_base;
+    g_shard.chunks = 0;
+    g_shard.orbit_done = true;
+    *n_starts = 0;
+    *first_start = NO_CARRY;
+    *carry_out = carry_in;
+    if (g_shard.plan.payload_bytes == 0) return NNP_OK;
+    Context& C = g_ctx;
+    int rc = run_orbit(g_shard.plan, payload_base, carry_in, &g_shard.chunks);
+    if (rc != NNP_OK) return rc;
+    *n_starts = g_shard.chunks;
+    if (g_shard.chunks > 0) {
+        u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+        CK(cudaMemcpyAsync(h_u64, g_shard.plan.seg_off + 1, 8, cudaMemcpyDeviceToHost, C.stream));
+        CK(cudaMemcpyAsync(h_u64 + 1, g_shard.plan.seg_off + g_shard.chunks, 8, cudaMemcpyDeviceToHost, C.stream));
+        CK(cudaStreamSynchronize(C.stream));
+        *first_start = payload_base + h_u64[0];
+        *carry_out = payload_base + h_u64[1];
+    }
+    return NNP_OK;
+}
+
+int shard_emit_dev(u64 next_start, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    if (!g_shard.active || !g_shard.orbit_done) return NNP_ERR_BAD_ARG;
+    Context& C = g_ctx;
+    const PayloadPlan& P = g_shard.plan;
+    const u64 total = P.payload_bytes + 8 * g_shard.chunks;
+    *out_bytes = total;
+    if (!d_out) return NNP_OK;
+    if (total > out_cap) return NNP_ERR_CAPACITY;
+    if ((uintptr_t)d_out & 7) return NNP_ERR_BAD_ARG;
+    if (P.payload_bytes == 0) return NNP_OK;
+    u64 last_size = NATURAL_SIZE;
+    if (g_shard.chunks > 0) {
+        u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+        CK(cudaMemcpyAsync(h_u64, P.seg_off + g_shard.chunks, 8, cudaMemcpyDeviceToHost, C.stream));
+        CK(cudaStreamSynchronize(C.stream));
+        const u64 last_start = g_shard.base + h_u64[0];
+        if (next_start <= last_start) return NNP_ERR_BAD_ARG;
+        last_size = next_start - last_start;
+    }
+    launch_emit_chunks(P.payload, P.seg_off, g_shard.chunks, d_out, last_size, C.stream);
+    LAUNCHED(1, "k_emit_chunks");
+    CK(cudaStreamSynchronize(C.stream));
+    return NNP_OK;
 }
 
 // ---------------------------------------------------------------- .plain -> entries
@@ -756,6 +920,7 @@ const char* nnp_strerror(int status)
     case NNP_ERR_NO_DEVICE: return "no usable sm_100a CUDA device (libnnuepack has no CPU path)";
     case NNP_ERR_NOT_INITIALISED: return "nnp_init() has not been called";
     case NNP_ERR_CUDA: return "CUDA runtime error";
+    case NNP_ERR_WINDOW: return "the overlap window behind the shard does not reach the next chain head";
     default: return "unknown status";
     }
 }
@@ -892,6 +1057,33 @@ int nnp_generate_bin_dev(void* d_out, size_t n_positions, uint32_t max_plies, ui
         n_games = n_games * 2 + 64;
     }
     return NNP_ERR_BAD_ARG;
+}
+
+int nnp_shard_compress_begin_dev(const void* d_bin, size_t n_records, size_t own_lo, size_t own_hi, int reaches_eof,
+                                 nnp_shard_info* info)
+{
+    std::lock_guard<std::mutex> lock_(g_mutex);
+    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    if (!info) return NNP_ERR_BAD_ARG;
+    return shard_begin_dev(d_bin, n_records, own_lo, own_hi, reaches_eof, info);
+}
+int nnp_shard_compress_orbit(uint64_t payload_base, uint64_t carry_in, uint64_t* n_chunk_starts, uint64_t* first_start,
+                             uint64_t* carry_out)
+{
+    std::lock_guard<std::mutex> lock_(g_mutex);
+    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    if (!n_chunk_starts || !first_start || !carry_out) return NNP_ERR_BAD_ARG;
+    u64 a = 0, b = 0, c = 0;
+    const int rc = shard_orbit(payload_base, carry_in, &a, &b, &c);
+    *n_chunk_starts = a;
+    *first_start = b;
+    *carry_out = c;
+    return rc;
+}
+int nnp_shard_compress_emit_dev(uint64_t next_start, void* d_out, size_t out_cap, size_t* out_bytes)
+{
+    REQUIRE_READY();
+    return shard_emit_dev(next_start, d_out, out_cap, out_bytes);
 }
 
 int nnp_debug_config(const char* key, uint64_t value)

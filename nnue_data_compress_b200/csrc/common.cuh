@@ -11,6 +11,8 @@ namespace nnp {
 constexpr u32 CHUNK_THRESHOLD = 1u << 20;          // suggestedChunkSize compress_file.cpp:20
 constexpr u32 MAX_CHUNK_SIZE = 100u * (1u << 20);  // maxChunkSize compress_file.cpp:22
 constexpr u64 NO_ERROR_IDX = ~0ull;
+constexpr u64 NO_CARRY = ~0ull;      // chunk orbit: no chunk was opened before this shard
+constexpr u64 NATURAL_SIZE = ~0ull;  // chunk emission: the last chunk ends with the payload
 
 // Summary of a run of records for the segmented payload scan ("payload scan").
 // A run is described by what happens before its first chain head (bits/plies that still

@@ -396,66 +396,92 @@ k_write_payload(const u32* __restrict__ codes, const u32* __restrict__ stems, u6
 // The writer flushes a chunk when a new chain head arrives and the bytes gathered since the
 // last flush reached 1 MiB (:1076-1080). With P[h] the payload offset of head h that is the
 // orbit b0 = 0, b(k+1) = min{h : P[h] - P[b(k)] >= 2^20}; one warp follows it with a 32-ary
-// search per hop. chunk_off[k] = P[b(k)], chunk_off[K] = payload size.
+// search per hop.
+//
+// Sharded compression runs the same orbit over one shard's heads: `base` is the
+// shard's offset in the global payload and `carry` the global offset of the last chunk start
+// before it (NO_CARRY for the first shard, whose first head opens chunk 0).
+//
+// Output: seg_off[0] = 0, seg_off[1 + k] = local payload offset of the k-th chunk start,
+// seg_off[1 + K] = payload size; segment 0 = [0, first chunk start) belongs to a chunk opened by an
+// earlier shard (empty for a whole file) and gets no header.
+
+// first h in [lo, H) with head_off[h] >= target, H if none (whole warp)
+__device__ __forceinline__ u64 orbit_search(const u64* __restrict__ head_off, u64 lo, u64 H, u64 target, int lane)
+{
+    u64 hi = H;  // answer in [lo, hi]; hi == H means none
+    while (lo < hi) {
+        const u64 span = hi - lo;
+        const u64 step = (span + 31) / 32;  // 32 probes; the last one reaches hi - 1 or beyond
+        const u64 probe = lo + (u64)(lane + 1) * step - 1;
+        const bool ge = probe < hi ? (head_off[probe] >= target) : true;
+        const u32 m = __ballot_sync(0xffffffffu, ge);
+        if (m == 0) { lo = hi; break; }  // every head below hi is too small
+        const int f = __ffs((int)m) - 1;  // first lane whose probe is >= target
+        const u64 new_hi = lo + (u64)(f + 1) * step - 1;
+        lo = lo + (u64)f * step;
+        hi = new_hi < hi ? new_hi : hi;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(32)
-k_chunk_orbit(const u64* __restrict__ head_off, CompressTotals* tot, u64* __restrict__ chunk_off, u64 max_chunks)
+k_chunk_orbit(const u64* __restrict__ head_off, CompressTotals* tot, u64* __restrict__ seg_off, u64 max_chunks, u64 base,
+              u64 carry)
 {
     const int lane = threadIdx.x;
     const u64 H = tot->heads;
     const u64 total = tot->payload_bytes;
     u64 k = 0;
+    if (lane == 0) seg_off[0] = 0;
+    u64 cur = H;  // head index of the current chunk start; H = none
     if (H > 0) {
-        u64 cur = 0;  // head index of the current chunk start
-        for (;;) {
-            if (lane == 0 && k < max_chunks) chunk_off[k] = head_off[cur];
-            ++k;
-            const u64 target = head_off[cur] + CHUNK_THRESHOLD;
-            if (target > total) break;  // no head can reach it (P[h] < total)
-            // first h in (cur, H) with head_off[h] >= target
-            u64 lo = cur + 1, hi = H;  // answer in [lo, hi]; hi == H means none
-            while (lo < hi) {
-                const u64 span = hi - lo;
-                const u64 step = (span + 31) / 32;  // 32 probes; the last one reaches hi - 1 or beyond
-                const u64 probe = lo + (u64)(lane + 1) * step - 1;
-                const bool ge = probe < hi ? (head_off[probe] >= target) : true;
-                const u32 m = __ballot_sync(0xffffffffu, ge);
-                if (m == 0) { lo = hi; break; }  // every head below hi is too small
-                const int f = __ffs((int)m) - 1;  // first lane whose probe is >= target
-                const u64 new_hi = lo + (u64)(f + 1) * step - 1;
-                lo = lo + (u64)f * step;
-                hi = new_hi < hi ? new_hi : hi;
-            }
-            if (lo >= H) break;
-            cur = lo;
+        if (carry == NO_CARRY) {
+            cur = 0;
+        } else {
+            const u64 target_global = carry + CHUNK_THRESHOLD;
+            const u64 target = target_global > base ? target_global - base : 0;
+            if (target <= total) cur = orbit_search(head_off, 0, H, target, lane);
         }
     }
+    while (cur < H) {
+        if (lane == 0 && k < max_chunks) seg_off[1 + k] = head_off[cur];
+        ++k;
+        const u64 target = head_off[cur] + CHUNK_THRESHOLD;
+        if (target > total) break;  // no head can reach it (P[h] < total)
+        cur = orbit_search(head_off, cur + 1, H, target, lane);
+    }
     if (lane == 0) {
-        if (k <= max_chunks) chunk_off[k < max_chunks ? k : max_chunks] = total;
+        seg_off[1 + (k < max_chunks ? k : max_chunks)] = total;
         tot->chunks = k;
     }
 }
 
 // ------------------------------------------------------------------ chunk emission
-// grid = (EMIT_BLOCKS_PER_CHUNK, chunks): copies payload [chunk_off[k], chunk_off[k+1]) behind
-// its 8-byte header 'B','I','N','P',LE32(size) (:486-498). Source and destination differ by
-// 8(k+1) bytes, so they share their alignment and the body moves as aligned 16-byte vectors.
+// grid = (EMIT_BLOCKS_PER_CHUNK, 1 + chunks): segment 0 is copied as it is, segment 1 + k behind its
+// 8-byte header 'B','I','N','P',LE32(size) (:486-498). Source and destination of a segment differ by
+// a multiple of 8 bytes, so they share their alignment and the body moves as aligned vectors.
+// `last_size`: size field of the last chunk when it continues in the next shard (else NATURAL_SIZE).
 constexpr int EMIT_THREADS = 256;
 __global__ void __launch_bounds__(EMIT_THREADS)
-k_emit_chunks(const unsigned char* __restrict__ payload, const u64* __restrict__ chunk_off,
-              unsigned char* __restrict__ out)
+k_emit_chunks(const unsigned char* __restrict__ payload, const u64* __restrict__ seg_off, unsigned char* __restrict__ out,
+              u64 last_size)
 {
-    const u64 k = blockIdx.y;
-    const u64 s0 = chunk_off[k], s1 = chunk_off[k + 1];
-    const u64 size = s1 - s0;
-    unsigned char* dst = out + s0 + 8 * k;
-    if (blockIdx.x == 0 && threadIdx.x < 8) {
-        const unsigned char hdr[8] = {'B', 'I', 'N', 'P', (unsigned char)size, (unsigned char)(size >> 8),
-                                      (unsigned char)(size >> 16), (unsigned char)(size >> 24)};
-        dst[threadIdx.x] = hdr[threadIdx.x];
+    const u64 seg = blockIdx.y;
+    const u64 s0 = seg_off[seg], s1 = seg_off[seg + 1];
+    u64 size = s1 - s0;
+    unsigned char* dst = out + s0;
+    if (seg > 0) {
+        dst += 8 * (seg - 1);
+        const u64 field = (seg == gridDim.y - 1 && last_size != NATURAL_SIZE) ? last_size : size;
+        if (blockIdx.x == 0 && threadIdx.x < 8) {
+            const unsigned char hdr[8] = {'B', 'I', 'N', 'P', (unsigned char)field, (unsigned char)(field >> 8),
+                                          (unsigned char)(field >> 16), (unsigned char)(field >> 24)};
+            dst[threadIdx.x] = hdr[threadIdx.x];
+        }
+        dst += 8;
     }
-    dst += 8;
     const unsigned char* src = payload + s0;
-    // head bytes up to 16-byte alignment of src (dst - src = 8(k+1): same alignment mod 8)
     const u64 tid = (u64)blockIdx.x * EMIT_THREADS + threadIdx.x;
     const u64 nthreads = (u64)gridDim.x * EMIT_THREADS;
     u64 head = (8 - ((uintptr_t)src & 7)) & 7;
@@ -467,6 +493,20 @@ k_emit_chunks(const unsigned char* __restrict__ payload, const u64* __restrict__
     for (u64 i = tid; i < nvec; i += nthreads) d8[i] = s8[i];
     const u64 tail0 = head + (nvec << 3);
     for (u64 i = tail0 + tid; i < size; i += nthreads) dst[i] = src[i];
+}
+
+// first index i in [start, n) with codes[i] == 0 (a chain head), n if none; one warp
+__global__ void __launch_bounds__(32) k_find_head(const u32* __restrict__ codes, u64 n, u64 start, u64* __restrict__ out)
+{
+    const int lane = threadIdx.x;
+    u64 found = n;
+    for (u64 i = start; i < n; i += 32) {
+        const u64 j = i + lane;
+        const bool head = j < n && codes[j] == 0u;
+        const u32 m = __ballot_sync(0xffffffffu, head);
+        if (m) { found = i + (u64)(__ffs((int)m) - 1); break; }
+    }
+    if (lane == 0) *out = found;
 }
 
 // ------------------------------------------------------------------ host launchers
@@ -509,15 +549,19 @@ void launch_write_payload(const u32* codes, const u32* stems, u64 n, const Agg* 
     if (n == 0) return;
     k_write_payload<<<(unsigned)scan_tiles(n), SCAN_THREADS, 0, s>>>(codes, stems, n, tile_prefix, payload, head_off);
 }
-void launch_chunk_orbit(const u64* head_off, CompressTotals* tot, u64* chunk_off, u64 max_chunks, cudaStream_t s)
+void launch_chunk_orbit(const u64* head_off, CompressTotals* tot, u64* seg_off, u64 max_chunks, u64 base, u64 carry,
+                        cudaStream_t s)
 {
-    k_chunk_orbit<<<1, 32, 0, s>>>(head_off, tot, chunk_off, max_chunks);
+    k_chunk_orbit<<<1, 32, 0, s>>>(head_off, tot, seg_off, max_chunks, base, carry);
 }
-void launch_emit_chunks(const void* payload, const u64* chunk_off, u64 chunks, void* out, cudaStream_t s)
+void launch_emit_chunks(const void* payload, const u64* seg_off, u64 chunks, void* out, u64 last_size, cudaStream_t s)
 {
-    if (chunks == 0) return;
-    dim3 grid(8, (unsigned)chunks);
-    k_emit_chunks<<<grid, EMIT_THREADS, 0, s>>>((const unsigned char*)payload, chunk_off, (unsigned char*)out);
+    dim3 grid(8, (unsigned)(chunks + 1));
+    k_emit_chunks<<<grid, EMIT_THREADS, 0, s>>>((const unsigned char*)payload, seg_off, (unsigned char*)out, last_size);
+}
+void launch_find_head(const u32* codes, u64 n, u64 start, u64* out, cudaStream_t s)
+{
+    k_find_head<<<1, 32, 0, s>>>(codes, n, start, out);
 }
 
 }  // namespace nnp

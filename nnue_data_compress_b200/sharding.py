@@ -1,12 +1,19 @@
 """Multi-GPU plumbing of the conversion path: one process per GPU, every rank converts its own
-contiguous shard, and the only exchange is an all-gather of the per-shard output byte counts,
-which gives each shard its offset in the concatenated output. The payload never
+contiguous shard and only a few integers per rank are exchanged. The payload never
 crosses NVLink.
 
-Sharded output semantics: shard outputs are concatenated. For .binpack that is exactly what the
-reference produces when it is run once per shard file with ``-a`` (BINP chunks are
-self-delimiting, compress_file.cpp:449-522, :1663-1666); for .bin and .plain outputs the
-concatenation equals the single-run output byte for byte because records are independent.
+Two ways to shard .bin -> .binpack:
+
+* independent shards (``exchange_offsets``): every rank compresses its records as a file of its own
+  and the outputs are concatenated. That is what the reference produces when it is run once per
+  shard file with ``-a`` (BINP chunks are self-delimiting, compress_file.cpp:449-522, :1663-1666);
+  chains that cross a shard boundary are cut and chunks restart per shard.
+* one file (``compress_sharded``): byte-identical to ONE reference run over all records. Chains
+  belong to the rank that holds their head (the rank before sees the rest of the chain through an
+  overlap window), and the chunk-flush rule is replayed in rank order with a 16-byte carry.
+
+.binpack -> .bin / .plain shards by chunk ranges; the concatenation of the shard outputs equals the
+single-run output byte for byte because chunks are independent.
 """
 from __future__ import annotations
 
@@ -60,3 +67,67 @@ def chunk_bounds_binpack(data: bytes) -> List[Tuple[int, int]]:
         out.append((pos, 8 + size))
         pos += 8 + size
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# one .binpack from record ranges spread over ranks (include/nnuepack.h, "sharded" entry points)
+
+NO_CARRY = (1 << 64) - 1
+
+
+def shard_window(n_records: int, world: int, rank: int, overlap: int):
+    """Record range a rank must hold for ``compress_sharded``: its balanced share plus one halo record
+    in front and ``overlap`` records behind. Returns (g0, g1, own_lo, own_hi, reaches_eof): [g0, g1)
+    are file record indices, own_lo / own_hi index into that buffer."""
+    lo, hi = shard_bounds(n_records, world, rank)
+    g0 = lo - 1 if lo > 0 else 0
+    g1 = min(n_records, hi + overlap)
+    return g0, g1, lo - g0, hi - g0, g1 == n_records
+
+
+def compress_sharded(payload_bytes: int, orbit, emit, device=None, group=None):
+    """The exchange steps 2-4 of the sharded compressor around a rank's local calls.
+
+    ``payload_bytes``: from nnp_shard_compress_begin_dev (step 1, done by the caller).
+    ``orbit(payload_base, carry_in) -> (n_chunk_starts, first_start, carry_out)`` and
+    ``emit(next_start) -> result`` wrap nnp_shard_compress_orbit / nnp_shard_compress_emit_dev.
+    Returns (emit's result, file offset of this rank's slice, total file bytes)."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized():
+        world, rank = 1, 0
+    else:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def gather(value: int):
+        if world == 1:
+            return [int(value)]
+        mine = torch.tensor([int(value)], dtype=torch.int64, device=device)
+        out = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(out, mine, group=group)
+        return [int(t.item()) for t in out]
+
+    sizes = gather(payload_bytes)
+    bases = offsets_from_sizes(sizes)
+    total_payload = sum(sizes)
+
+    # the chunk-flush rule in rank order: (offset of the last chunk start or -1, chunks so far)
+    carry, chunks_before = -1, 0
+    if rank > 0:
+        buf = torch.zeros(2, dtype=torch.int64, device=device)
+        dist.recv(buf, src=rank - 1, group=group)
+        carry, chunks_before = int(buf[0].item()), int(buf[1].item())
+    n_starts, first_start, carry_out = orbit(bases[rank], NO_CARRY if carry < 0 else carry)
+    if rank < world - 1:
+        buf = torch.tensor([-1 if carry_out == NO_CARRY else carry_out, chunks_before + n_starts], dtype=torch.int64,
+                           device=device)
+        dist.send(buf, dst=rank + 1, group=group)
+
+    firsts = gather(-1 if first_start == NO_CARRY else first_start)
+    later = [f for f in firsts[rank + 1:] if f >= 0]
+    next_start = later[0] if later else total_payload
+    result = emit(next_start)
+    all_chunks = gather(n_starts)
+    total_file = total_payload + 8 * sum(all_chunks)
+    return result, bases[rank] + 8 * chunks_before, total_file

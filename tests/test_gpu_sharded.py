@@ -1,0 +1,92 @@
+"""GPU suite: sharded .bin -> .binpack through the C ABI (nnp_shard_compress_*). One process plays
+all ranks in turn (the library holds one shard at a time, so the orbit pass and the emit pass each
+redo `begin`); the slices written at their offsets must be the single-run .binpack byte for byte."""
+import ctypes
+
+import pytest
+
+from refutil import BIN_TO_BINPACK, golden, oracle_convert
+
+pytestmark = pytest.mark.gpu
+
+NO_CARRY = (1 << 64) - 1
+
+
+def _sharded(nnp, b, world, overlap):
+    import numpy as np
+    import torch
+
+    from nnue_data_compress_b200.sharding import offsets_from_sizes, shard_window
+
+    L = nnp.lib()
+    n = len(b) // 40
+    d_all = torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()).cuda()
+
+    def begin(r):
+        g0, g1, lo, hi, eof = shard_window(n, world, r, overlap)
+        info = nnp.ShardInfo()
+        rc = L.nnp_shard_compress_begin_dev(ctypes.c_void_p(d_all.data_ptr() + g0 * 40), g1 - g0, lo, hi, int(eof),
+                                            ctypes.byref(info))
+        assert rc == 0, (r, rc)
+        return info
+
+    def orbit(base, carry):
+        a, f, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        assert L.nnp_shard_compress_orbit(base, carry, ctypes.byref(a), ctypes.byref(f), ctypes.byref(c)) == 0
+        return a.value, f.value, c.value
+
+    sizes = [begin(r).payload_bytes for r in range(world)]
+    bases = offsets_from_sizes(sizes)
+    total_payload = sum(sizes)
+    carry, chunks = NO_CARRY, 0
+    carry_in, chunks_before, firsts = [], [], []
+    for r in range(world):
+        begin(r)
+        carry_in.append(carry)
+        chunks_before.append(chunks)
+        ns, first, carry = orbit(bases[r], carry)
+        chunks += ns
+        firsts.append(first)
+    out = bytearray(total_payload + 8 * chunks)
+    for r in range(world):
+        begin(r)
+        ns, _, _ = orbit(bases[r], carry_in[r])
+        later = [f for f in firsts[r + 1:] if f != NO_CARRY]
+        next_start = later[0] if later else total_payload
+        need = ctypes.c_size_t(0)
+        assert L.nnp_shard_compress_emit_dev(next_start, None, 0, ctypes.byref(need)) == 0
+        assert need.value == sizes[r] + 8 * ns
+        d_out = torch.empty(max(need.value, 8), dtype=torch.uint8, device="cuda")
+        got = ctypes.c_size_t(0)
+        assert L.nnp_shard_compress_emit_dev(next_start, ctypes.c_void_p(d_out.data_ptr()), need.value, ctypes.byref(got)) == 0
+        off = bases[r] + 8 * chunks_before[r]
+        out[off:off + got.value] = d_out[: got.value].cpu().numpy().tobytes()
+    return bytes(out)
+
+
+@pytest.mark.parametrize("name,world,overlap", [("twochunks", 2, 64), ("twochunks", 5, 8), ("games100", 3, 128),
+                                               ("long400", 4, 500), ("restart", 2, 200), ("heads", 3, 4),
+                                               ("shuffled", 7, 4)])
+def test_sharded_golden(nnp, name, world, overlap):
+    assert _sharded(nnp, golden(name + ".bin"), world, overlap) == golden(name + ".binpack")
+
+
+@pytest.mark.parametrize("n,plies,world,overlap", [(600_000, 100, 4, 1024), (2_000_000, 3, 8, 16), (300_000, 400, 8, 4096),
+                                                  (500_000, 100, 1, 0)])
+def test_sharded_synthetic(nnp, n, plies, world, overlap):
+    b = nnp.generate_bin(n, plies, 17)
+    rc, want = oracle_convert(BIN_TO_BINPACK, b)
+    assert rc == 0
+    assert _sharded(nnp, b, world, overlap) == want
+    assert nnp.bin_to_binpack(b) == want
+
+
+def test_sharded_window_too_small(nnp):
+    import numpy as np
+    import torch
+
+    b = golden("long400.bin")
+    d = torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()).cuda()
+    info = nnp.ShardInfo()
+    rc = nnp.lib().nnp_shard_compress_begin_dev(ctypes.c_void_p(d.data_ptr()), 60, 0, 50, 0, ctypes.byref(info))
+    assert rc == -12  # NNP_ERR_WINDOW: the 400-ply chain does not end within 10 records of the boundary

@@ -99,3 +99,57 @@ def test_shard_bounds_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
     assert offsets_from_sizes([3, 0, 5]) == [0, 3, 3]
+
+
+# ---------------------------------------------------------------------------------------------
+# one .binpack from several ranks, byte-identical to a single run
+
+
+def _worker_one_file(rank, world, port, tmpdir, name, overlap, small_threshold):
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import shardsim
+    from nnue_data_compress_b200.sharding import compress_sharded, shard_window
+    from refutil import golden
+
+    if small_threshold:
+        shardsim.THRESHOLD = small_threshold
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b = golden(name)
+        n = len(b) // 40
+        g0, g1, lo, hi, eof = shard_window(n, world, rank, overlap)
+        sh = shardsim.OracleShard(b[g0 * 40:g1 * 40], lo, hi, eof)
+        data, off, total = compress_sharded(sh.payload_bytes, sh.orbit, sh.emit)
+        with open(os.path.join(tmpdir, f"slice{rank}"), "wb") as f:
+            f.write(off.to_bytes(8, "little") + total.to_bytes(8, "little") + data)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,world,overlap", [("twochunks.bin", 2, 64), ("twochunks.bin", 3, 8), ("games100.bin", 3, 128),
+                                               ("long400.bin", 3, 500), ("restart.bin", 2, 200)])
+def test_ranks_write_one_file(tmp_path, name, world, overlap):
+    """The rank orchestration (all-gather of payload sizes, carry of the chunk-flush rule in rank
+    order, all-gather of first chunk starts) with the oracle standing in for the CUDA entry points:
+    the slices assembled at their offsets are the single-run .binpack of the whole input."""
+    import torch.multiprocessing as mp
+
+    from refutil import BIN_TO_BINPACK, golden, oracle_convert
+
+    port = _free_port()
+    mp.spawn(_worker_one_file, args=(world, port, str(tmp_path), name, overlap, 0), nprocs=world, join=True)
+    rc, expect = oracle_convert(BIN_TO_BINPACK, golden(name))
+    assert rc == 0
+    out = bytearray(len(expect))
+    for r in range(world):
+        raw = (tmp_path / f"slice{r}").read_bytes()
+        off, total = int.from_bytes(raw[:8], "little"), int.from_bytes(raw[8:16], "little")
+        assert total == len(expect)
+        out[off:off + len(raw) - 16] = raw[16:]
+    assert bytes(out) == expect
