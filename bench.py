@@ -278,7 +278,7 @@ def main():
     nnp.init(local_rank)
     L = nnp.lib()
     stream = torch.cuda.current_stream()
-    L.nnp_set_stream(ctypes.c_void_p(stream.cuda_stream))
+    nnp.use_torch_stream()  # kernels on torch's current stream: ordered with torch ops, bracketed by torch events
 
     def check(rc, what):
         if rc != 0:
@@ -310,18 +310,69 @@ def main():
     t_total = ctypes.c_float(0)
     t_dom = ctypes.c_float(0)
 
+    # N > 1: the ranks write ONE .binpack, byte-identical to a single reference run over all records
+    # (SURVEY.md 8e). Setup, untimed: every rank gets the last record of the rank before it (halo) and
+    # the first records of the rank behind it (overlap window) -- what a file reader would read
+    # directly -- so that every chain is owned by exactly one rank.
+    one_file = None
+    if world > 1:
+        from nnue_data_compress_b200.sharding import compress_sharded
+
+        window = min(65536, n_pos)
+        heads = [torch.empty(window * 40, dtype=torch.uint8, device=dev) for _ in range(world)]
+        tails = [torch.empty(40, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(heads, d_bin[: window * 40].contiguous())
+        dist.all_gather(tails, d_bin[-40:].contiguous())
+        parts = ([tails[rank - 1]] if rank > 0 else []) + [d_bin] + ([heads[rank + 1]] if rank < world - 1 else [])
+        d_buf = torch.cat(parts)
+        del heads, tails, parts
+        own_lo = 1 if rank > 0 else 0
+        d_slice = torch.empty(cap_guess, dtype=torch.uint8, device=dev)
+        slice_info = {}
+
+        def orbit(base, carry):
+            a, f, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+            check(L.nnp_shard_compress_orbit(base, carry, ctypes.byref(a), ctypes.byref(f), ctypes.byref(c)), "orbit")
+            return a.value, f.value, c.value
+
+        def emit(next_start):
+            got = ctypes.c_size_t(0)
+            check(L.nnp_shard_compress_emit_dev(next_start, ctypes.c_void_p(d_slice.data_ptr()), cap_guess, ctypes.byref(got)),
+                  "emit")
+            return got.value
+
+        def one_file():
+            info = nnp.ShardInfo()
+            check(L.nnp_shard_compress_begin_dev(ctypes.c_void_p(d_buf.data_ptr()), d_buf.numel() // 40, own_lo, own_lo + n_pos,
+                                                 int(rank == world - 1), ctypes.byref(info)), "shard begin")
+            L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
+            dom = t_dom.value
+            got, off, total = compress_sharded(info.payload_bytes, orbit, emit, device=dev)
+            slice_info.update(bytes=got, offset=off, file_bytes=total)
+            return dom
+
     def step_device():
         n1 = ctypes.c_size_t(0)
-        check(L.nnp_bin_to_binpack_dev(ctypes.c_void_p(d_bin.data_ptr()), bin_bytes, ctypes.c_void_p(d_pack.data_ptr()),
-                                       cap_guess, ctypes.byref(n1)), "bin->binpack")
-        L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
-        c_ms, c_dom = t_total.value, t_dom.value
+        if one_file is None:
+            check(L.nnp_bin_to_binpack_dev(ctypes.c_void_p(d_bin.data_ptr()), bin_bytes, ctypes.c_void_p(d_pack.data_ptr()),
+                                           cap_guess, ctypes.byref(n1)), "bin->binpack")
+            L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
+            c_ms, c_dom = t_total.value, t_dom.value
+            pack_in = n1.value
+        else:
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(stream)
+            c_dom = one_file()
+            eb.record(stream)
+            pack_in = pack_bytes  # the rank's own chunk-aligned .binpack (made by the sizing pass)
         n2 = ctypes.c_size_t(0)
-        check(L.nnp_binpack_to_bin_dev(ctypes.c_void_p(d_pack.data_ptr()), n1.value, ctypes.c_void_p(d_out.data_ptr()),
+        check(L.nnp_binpack_to_bin_dev(ctypes.c_void_p(d_pack.data_ptr()), pack_in, ctypes.c_void_p(d_out.data_ptr()),
                                        bin_bytes, ctypes.byref(n2)), "binpack->bin")
         L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
         assert n2.value == bin_bytes, (n2.value, bin_bytes)
-        return c_ms, c_dom, t_total.value, t_dom.value, n1.value
+        if one_file is not None:
+            c_ms = ea.elapsed_time(eb)
+        return c_ms, c_dom, t_total.value, t_dom.value, pack_in
 
     def barrier():
         if world > 1:
@@ -406,12 +457,11 @@ def main():
 
     shard_offsets = None
     if world > 1:
-        # the one exchange step of the multi-GPU path: byte counts -> each shard's output offset
-        mine = torch.tensor([pack_bytes], dtype=torch.int64, device=dev)
+        # where every rank's slice of the one .binpack belongs (from the exchange inside the timed steps)
+        mine = torch.tensor([slice_info["offset"], slice_info["bytes"], slice_info["file_bytes"]], dtype=torch.int64, device=dev)
         allc = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allc, mine)
-        sizes = [int(t.item()) for t in allc]
-        shard_offsets = [sum(sizes[:i]) for i in range(world)]
+        shard_offsets = [[int(v) for v in t.tolist()] for t in allc]
 
     elapsed_ms = allmax(elapsed_ms)
     ms_per_step = elapsed_ms / K
@@ -509,7 +559,9 @@ def main():
             "bin_bytes_per_gpu": bin_bytes,
             "binpack_bytes_per_gpu": pack_bytes,
             "l2": "inputs (4.0 GB .bin, 0.2 GB .binpack per GPU) are far larger than the 126 MB L2",
-            "sharding": "independent shards per GPU, all-gather of byte counts only" if world > 1 else "single GPU",
+            "sharding": ("compress: ONE .binpack over all ranks, byte-identical to a single run (chains owned by the rank of "
+                         "their head via halo + overlap window; chunk-flush carry in rank order, 16 B per rank; two 8-byte "
+                         "all-gathers; no payload crosses NVLink); decompress: per-rank chunk ranges") if world > 1 else "single GPU",
         },
         "compress_mpos_s": total_pos / (c_ms_m * 1e-3) / 1e6,
         "decompress_mpos_s": total_pos / (d_ms_m * 1e-3) / 1e6,
@@ -530,7 +582,7 @@ def main():
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
     if shard_offsets is not None:
-        line["config"]["shard_output_offsets"] = shard_offsets
+        line["config"]["slices_offset_bytes_filebytes"] = shard_offsets
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

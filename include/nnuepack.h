@@ -62,7 +62,10 @@ void nnp_shutdown(void);
 const char* nnp_strerror(int status);
 /* Runs all further work on the caller's CUDA stream (a cudaStream_t of the bound device, e.g.
  * torch's current stream) so that the caller's events bracket it; NULL restores the library's own
- * stream. Calls still return only after their result size is known. */
+ * stream. Calls still return only after their result size is known. The library's own stream is
+ * non-blocking: device buffers written by work on another stream must be complete (or that stream
+ * must be the one given here) before a *_dev entry point reads them. To name the legacy default
+ * stream pass cudaStreamLegacy ((cudaStream_t)0x1), since NULL selects the library's stream. */
 int nnp_set_stream(void* cuda_stream);
 const char* nnp_last_cuda_error(void);
 /* number of kernel launches issued by this library since nnp_init (for bench accounting) */

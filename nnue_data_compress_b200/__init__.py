@@ -154,6 +154,20 @@ def init(device: int | None = None) -> None:
     _initialised = True
 
 
+def use_torch_stream() -> None:
+    """Runs the library's kernels on torch's current CUDA stream, so that device tensors produced by
+    torch ops are ordered before the library reads them (the library's own stream is non-blocking
+    and does not wait for torch's). torch's default stream has the handle 0, which nnp_set_stream
+    takes as "back to the library's stream"; it is passed as cudaStreamLegacy (0x1) instead."""
+    import torch
+
+    _ensure_init()
+    handle = torch.cuda.current_stream().cuda_stream or 1
+    rc = lib().nnp_set_stream(ctypes.c_void_p(handle))
+    if rc != 0:
+        raise NnpError(rc, _strerror(rc))
+
+
 def shutdown() -> None:
     global _initialised
     if _lib is not None:

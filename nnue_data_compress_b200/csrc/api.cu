@@ -319,6 +319,10 @@ int shard_begin_dev(const void* d_bin, u64 n_records, u64 own_lo, u64 own_hi, in
     u64 error_index = NO_ERROR_IDX;
     int rc = link_encode_records(d_bin, n_records, &codes, &stems, &error_index);
     if (rc != NNP_OK) return rc;
+    CK(cudaEventSynchronize(C.ev[1]));
+    CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[0], C.ev[3]));  // k_walk_runs alone
+    CK(cudaEventElapsedTime(&C.last_stage_ms, C.ev[0], C.ev[1]));
+    C.last_total_ms = C.last_stage_ms;
     if (error_index != NO_ERROR_IDX) {
         info->first_bad_record = error_index;
         return NNP_ERR_BAD_SFEN;

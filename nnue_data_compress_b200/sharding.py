@@ -113,16 +113,20 @@ def compress_sharded(payload_bytes: int, orbit, emit, device=None, group=None):
     total_payload = sum(sizes)
 
     # the chunk-flush rule in rank order: (offset of the last chunk start or -1, chunks so far)
+    def p2p(op, tensor, peer):
+        for req in dist.batch_isend_irecv([dist.P2POp(op, tensor, peer, group=group)]):
+            req.wait()
+
     carry, chunks_before = -1, 0
     if rank > 0:
         buf = torch.zeros(2, dtype=torch.int64, device=device)
-        dist.recv(buf, src=rank - 1, group=group)
+        p2p(dist.irecv, buf, rank - 1)
         carry, chunks_before = int(buf[0].item()), int(buf[1].item())
     n_starts, first_start, carry_out = orbit(bases[rank], NO_CARRY if carry < 0 else carry)
     if rank < world - 1:
         buf = torch.tensor([-1 if carry_out == NO_CARRY else carry_out, chunks_before + n_starts], dtype=torch.int64,
                            device=device)
-        dist.send(buf, dst=rank + 1, group=group)
+        p2p(dist.isend, buf, rank + 1)
 
     firsts = gather(-1 if first_start == NO_CARRY else first_start)
     later = [f for f in firsts[rank + 1:] if f >= 0]

@@ -18,5 +18,6 @@ def nnp():
     import nnue_data_compress_b200 as pkg
 
     pkg.init(int(os.environ.get("LOCAL_RANK", "0")))
+    pkg.use_torch_stream()  # tests hand torch device tensors to the *_dev entry points
     yield pkg
     pkg.shutdown()
