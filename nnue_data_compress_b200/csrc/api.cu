@@ -24,7 +24,7 @@ enum WsSlot {
     WS_CODES = 0, WS_STEMS, WS_TILE_AGG, WS_PAYLOAD, WS_HEAD_OFF, WS_CHUNK_OFF, WS_TOTALS,
     WS_CHUNK_START, WS_CHUNK_LEN, WS_CHUNK_TILE_BASE, WS_CHUNK_INFO, WS_TILE_COUNT, WS_TILE_PREFIX,
     WS_CAND_CHUNK, WS_CAND_OFF, WS_CAND_NEXT, WS_CAND_BASE, WS_CAND_CNT, WS_CHUNK_COUNT, WS_CHUNK_SLOW, WS_CHUNK_BASE,
-    WS_DTOTALS, WS_PARK_A, WS_PARK_B, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
+    WS_DTOTALS, WS_HEAD_NEXT, WS_PARK_A, WS_PARK_B, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
 };
 
 struct Context {
@@ -127,6 +127,7 @@ struct PayloadPlan {
     u32* payload = nullptr;
     u64* head_off = nullptr;
     u64* seg_off = nullptr;
+    u32* head_next = nullptr;
     CompressTotals* d_tot = nullptr;
 };
 
@@ -149,6 +150,8 @@ int build_payload(const u32* codes, const u32* stems, u64 n, PayloadPlan& P)
     WS(WS_PAYLOAD, P.payload_bytes + 64, u32, payload);
     WS(WS_HEAD_OFF, (P.heads + 1) * 8, u64, head_off);
     WS(WS_CHUNK_OFF, (P.max_chunks + 3) * 8, u64, seg_off);
+    WS(WS_HEAD_NEXT, (P.heads + 1) * 4, u32, head_next);
+    P.head_next = head_next;
     P.payload = payload;
     P.head_off = head_off;
     P.seg_off = seg_off;
@@ -164,8 +167,8 @@ int run_orbit(const PayloadPlan& P, u64 base, u64 carry, u64* chunks)
     Context& C = g_ctx;
     cudaStream_t s = C.stream;
     CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
-    launch_chunk_orbit(P.head_off, P.d_tot, P.seg_off, P.max_chunks, base, carry, s);
-    LAUNCHED(1, "k_chunk_orbit");
+    launch_chunk_orbit(P.head_off, P.heads, P.head_next, P.d_tot, P.seg_off, P.max_chunks, base, carry, s);
+    LAUNCHED(2, "k_chunk_orbit");
     CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     *chunks = h_tot->chunks;

@@ -244,12 +244,41 @@ __device__ __forceinline__ Agg block_exclusive_scan(const Agg& local, Agg& total
     }
     if (lane == 31) warp_tot[wid] = inc;
     __syncthreads();
-    Agg wprefix = agg_identity();
-    Agg all = agg_identity();
+    Agg wprefix, all;
+    if (THREADS / 32 == 32) {
+        // a full warp of warp totals: scan them with shuffles instead of a 32-step loop per thread
+        Agg w = warp_tot[lane];
+        Agg winc = w;
 #pragma unroll
-    for (int i = 0; i < THREADS / 32; ++i) {
-        if (i == wid) wprefix = all;
-        all = agg_combine(all, warp_tot[i]);
+        for (int d = 1; d < 32; d <<= 1) {
+            Agg o = agg_shfl_up(winc, d);
+            if (lane >= d) winc = agg_combine(o, winc);
+        }
+        Agg wexc = agg_shfl_up(winc, 1);
+        if (lane == 0) wexc = agg_identity();
+        // every warp computed the same scan; pick this warp's entries
+        wprefix.bytes = __shfl_sync(0xffffffffu, wexc.bytes, wid);
+        wprefix.pre_bits = __shfl_sync(0xffffffffu, wexc.pre_bits, wid);
+        wprefix.pre_plies = __shfl_sync(0xffffffffu, wexc.pre_plies, wid);
+        wprefix.post_bits = __shfl_sync(0xffffffffu, wexc.post_bits, wid);
+        wprefix.post_plies = __shfl_sync(0xffffffffu, wexc.post_plies, wid);
+        wprefix.heads = __shfl_sync(0xffffffffu, wexc.heads, wid);
+        wprefix.pad = 0;
+        all.bytes = __shfl_sync(0xffffffffu, winc.bytes, 31);
+        all.pre_bits = __shfl_sync(0xffffffffu, winc.pre_bits, 31);
+        all.pre_plies = __shfl_sync(0xffffffffu, winc.pre_plies, 31);
+        all.post_bits = __shfl_sync(0xffffffffu, winc.post_bits, 31);
+        all.post_plies = __shfl_sync(0xffffffffu, winc.post_plies, 31);
+        all.heads = __shfl_sync(0xffffffffu, winc.heads, 31);
+        all.pad = 0;
+    } else {
+        wprefix = agg_identity();
+        all = agg_identity();
+#pragma unroll
+        for (int i = 0; i < THREADS / 32; ++i) {
+            if (i == wid) wprefix = all;
+            all = agg_combine(all, warp_tot[i]);
+        }
     }
     total = all;
     Agg exc = agg_shfl_up(inc, 1);
@@ -273,28 +302,37 @@ k_tile_aggregate(const u32* __restrict__ codes, u64 n, Agg* __restrict__ tile_ag
     if (threadIdx.x == 0) tile_agg[blockIdx.x] = total;
 }
 
-// single block: exclusive scan of the tile aggregates in place + totals
+// single block: exclusive scan of the tile aggregates in place + totals. The aggregates are taken in
+// batches of AGGSCAN_ITEMS consecutive ones per thread, each batch scanned across the block and
+// chained to the next through a running carry.
 constexpr int AGGSCAN_THREADS = 1024;
+constexpr int AGGSCAN_ITEMS = 4;
 __global__ void __launch_bounds__(AGGSCAN_THREADS)
 k_scan_aggregates(Agg* __restrict__ tile_agg, u64 ntiles, CompressTotals* tot)
 {
     __shared__ Agg warp_tot[AGGSCAN_THREADS / 32];
-    const u64 per = (ntiles + AGGSCAN_THREADS - 1) / AGGSCAN_THREADS;
-    const u64 lo = (u64)threadIdx.x * per;
-    u64 hi = lo + per;
-    if (hi > ntiles) hi = ntiles;
-    Agg local = agg_identity();
-    for (u64 i = lo; i < hi; ++i) local = agg_combine(local, tile_agg[i]);
-    Agg total;
-    Agg run = block_exclusive_scan<AGGSCAN_THREADS>(local, total, warp_tot);
-    for (u64 i = lo; i < hi; ++i) {
-        Agg v = tile_agg[i];
-        tile_agg[i] = run;
-        run = agg_combine(run, v);
+    Agg carry = agg_identity();
+    for (u64 base = 0; base < ntiles; base += (u64)AGGSCAN_THREADS * AGGSCAN_ITEMS) {
+        const u64 i0 = base + (u64)threadIdx.x * AGGSCAN_ITEMS;
+        Agg v[AGGSCAN_ITEMS];
+        Agg local = agg_identity();
+#pragma unroll
+        for (int j = 0; j < AGGSCAN_ITEMS; ++j) {
+            v[j] = i0 + j < ntiles ? tile_agg[i0 + j] : agg_identity();
+            local = agg_combine(local, v[j]);
+        }
+        Agg total;
+        Agg run = agg_combine(carry, block_exclusive_scan<AGGSCAN_THREADS>(local, total, warp_tot));
+#pragma unroll
+        for (int j = 0; j < AGGSCAN_ITEMS; ++j) {
+            if (i0 + j < ntiles) tile_agg[i0 + j] = run;
+            run = agg_combine(run, v[j]);
+        }
+        carry = agg_combine(carry, total);
     }
     if (threadIdx.x == 0) {
-        tot->payload_bytes = total.heads ? total.bytes + ceil8(total.post_bits) : 0;
-        tot->heads = total.heads;
+        tot->payload_bytes = carry.heads ? carry.bytes + ceil8(carry.post_bits) : 0;
+        tot->heads = carry.heads;
     }
 }
 
@@ -425,9 +463,28 @@ __device__ __forceinline__ u64 orbit_search(const u64* __restrict__ head_off, u6
     return lo;
 }
 
+// next[h] = first head h' > h with P[h'] - P[h] >= 2^20 (H if none): the successor of h on the orbit
+// if h opens a chunk. One thread per head, binary search; neighbouring threads probe the same lines.
+__global__ void __launch_bounds__(256)
+k_head_next(const u64* __restrict__ head_off, const CompressTotals* __restrict__ tot, u32* __restrict__ next)
+{
+    const u64 H = tot->heads;
+    const u64 h = (u64)blockIdx.x * 256 + threadIdx.x;
+    if (h >= H) return;
+    const u64 target = head_off[h] + CHUNK_THRESHOLD;
+    u64 lo = h + 1, hi = H;  // first index in [lo, hi) with head_off >= target, hi if none
+    if (target > tot->payload_bytes) lo = hi;
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if (head_off[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    next[h] = (u32)lo;
+}
+
+// follows the orbit through next[]: one dependent load per chunk
 __global__ void __launch_bounds__(32)
-k_chunk_orbit(const u64* __restrict__ head_off, CompressTotals* tot, u64* __restrict__ seg_off, u64 max_chunks, u64 base,
-              u64 carry)
+k_chunk_orbit(const u64* __restrict__ head_off, const u32* __restrict__ next, CompressTotals* tot, u64* __restrict__ seg_off,
+              u64 max_chunks, u64 base, u64 carry)
 {
     const int lane = threadIdx.x;
     const u64 H = tot->heads;
@@ -444,14 +501,14 @@ k_chunk_orbit(const u64* __restrict__ head_off, CompressTotals* tot, u64* __rest
             if (target <= total) cur = orbit_search(head_off, 0, H, target, lane);
         }
     }
-    while (cur < H) {
-        if (lane == 0 && k < max_chunks) seg_off[1 + k] = head_off[cur];
-        ++k;
-        const u64 target = head_off[cur] + CHUNK_THRESHOLD;
-        if (target > total) break;  // no head can reach it (P[h] < total)
-        cur = orbit_search(head_off, cur + 1, H, target, lane);
-    }
     if (lane == 0) {
+        while (cur < H) {
+            const u64 off = head_off[cur];
+            const u64 nx = next[cur];
+            if (k < max_chunks) seg_off[1 + k] = off;
+            ++k;
+            cur = nx;
+        }
         seg_off[1 + (k < max_chunks ? k : max_chunks)] = total;
         tot->chunks = k;
     }
@@ -549,10 +606,11 @@ void launch_write_payload(const u32* codes, const u32* stems, u64 n, const Agg* 
     if (n == 0) return;
     k_write_payload<<<(unsigned)scan_tiles(n), SCAN_THREADS, 0, s>>>(codes, stems, n, tile_prefix, payload, head_off);
 }
-void launch_chunk_orbit(const u64* head_off, CompressTotals* tot, u64* seg_off, u64 max_chunks, u64 base, u64 carry,
-                        cudaStream_t s)
+void launch_chunk_orbit(const u64* head_off, u64 heads, u32* next, CompressTotals* tot, u64* seg_off, u64 max_chunks, u64 base,
+                        u64 carry, cudaStream_t s)
 {
-    k_chunk_orbit<<<1, 32, 0, s>>>(head_off, tot, seg_off, max_chunks, base, carry);
+    if (heads > 0) k_head_next<<<(unsigned)((heads + 255) / 256), 256, 0, s>>>(head_off, tot, next);
+    k_chunk_orbit<<<1, 32, 0, s>>>(head_off, next, tot, seg_off, max_chunks, base, carry);
 }
 void launch_emit_chunks(const void* payload, const u64* seg_off, u64 chunks, void* out, u64 last_size, cudaStream_t s)
 {

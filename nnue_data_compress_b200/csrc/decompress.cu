@@ -162,20 +162,42 @@ static_assert(CAND_TILE == CAND_THREADS * 16, "stage 1 of k_candidates_scan test
 __device__ __forceinline__ bool plausible_stem(const unsigned char* s)
 {
     if (s[30] != 0) return false;
-    u64 occ = 0;
+    // bytes 0..27 as seven little-endian words, from aligned shared-memory loads
+    u32 v[7];
+    {
+        const u32* wp = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
+        const int sh = (int)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
+        u32 prev = wp[0];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) occ = (occ << 8) | s[i];
+        for (int j = 0; j < 7; ++j) {
+            const u32 next = wp[j + 1];
+            v[j] = __funnelshift_r(prev, next, sh);
+            prev = next;
+        }
+    }
+    const u64 occ = ((u64)__byte_perm(v[0], 0, 0x0123) << 32) | __byte_perm(v[1], 0, 0x0123);  // big-endian (:1245-1257)
     const int n = popc64(occ);
     if (n < 2 || n > 32) return false;
-    int wk = 0, bk = 0, stm = WHITE;
+    // nibble k of the 16 nibble bytes is bits 4(k%8).. of word 2 + k/8; nibbles n.. must be zero, and
+    // among the first n there is exactly one white king (10) and one black king (11, or 15 = black to move)
+    int wk = 0, bk = 0, k15 = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const u32 b = s[8 + i];
-        const int lo = b & 15, hi = b >> 4;
-        if (2 * i < n) { wk += (lo == 10); bk += (lo == 11 || lo == 15); stm |= (lo == 15); } else if (lo) return false;
-        if (2 * i + 1 < n) { wk += (hi == 10); bk += (hi == 11 || hi == 15); stm |= (hi == 15); } else if (hi) return false;
+    for (int j = 0; j < 4; ++j) {
+        const u32 x = v[2 + j];
+        const u32 used = stream_low_mask(4 * n, j);
+        if (x & ~used) return false;
+        const u32 flags = 0x11111111u & used;
+        auto count_eq = [&](u32 pattern) {
+            const u32 t = x ^ pattern;
+            const u32 nz = (t | (t >> 1) | (t >> 2) | (t >> 3));
+            return __popc(~nz & flags);
+        };
+        wk += count_eq(0xAAAAAAAAu);
+        bk += count_eq(0xBBBBBBBBu);
+        k15 += count_eq(0xFFFFFFFFu);
     }
-    if (wk != 1 || bk != 1) return false;
+    if (wk != 1 || bk + k15 != 1) return false;
+    const int stm = k15 ? BLACK : WHITE;
     // per-square checks (reached by about one offset in 10^5)
     const u32 cm = ((u32)s[24] << 8) | s[25];
     const int mtype = (int)(cm >> 14), from = (int)((cm >> 8) & 63), to = (int)((cm >> 2) & 63);
@@ -269,8 +291,9 @@ k_candidates_scan(const unsigned char* __restrict__ in, u64 n_in, ChunkTable tab
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const u32 y = __funnelshift_r(x[i], x[i + 1], sh);
-            const u32 z = __vcmpeq4(y, 0u);  // 0xFF in every zero byte
-            mask |= (((z & 0x08040201u) * 0x01010101u) >> 24) << (4 * i);
+            // bit 7 of every zero byte (a 0x01 byte above a zero byte is flagged too: stage 2 re-tests)
+            const u32 z = (y - 0x01010101u) & ~y & 0x80808080u;
+            mask |= ((((z >> 7) * 0x00204081u) >> 21) & 15u) << (4 * i);
         }
         // offsets with a whole stem + numPlies inside the chunk
         const long long last = (long long)avail - 34 - 16 * t;  // last valid local bit index
