@@ -415,9 +415,13 @@ def main():
     e2e = None
     if not args.no_e2e:
         # pinned host buffers (cudaHostAlloc through torch); nnp_host_alloc() hands out the same kind
-        t_bin = torch.empty(bin_bytes, dtype=torch.uint8, pin_memory=True)
-        t_pack = torch.empty(cap_guess, dtype=torch.uint8, pin_memory=True)
-        t_out = torch.empty(bin_bytes, dtype=torch.uint8, pin_memory=True)
+        try:
+            t_bin = torch.empty(bin_bytes, dtype=torch.uint8, pin_memory=True)
+            t_pack = torch.empty(cap_guess, dtype=torch.uint8, pin_memory=True)
+            t_out = torch.empty(bin_bytes, dtype=torch.uint8, pin_memory=True)
+        except RuntimeError as exc:  # not enough lockable host memory for N ranks x 8.5 GB
+            raise SystemExit(f"bench.py: cannot pin {2 * bin_bytes + cap_guess} bytes of host memory for the e2e leg "
+                             f"(rerun with --no-e2e): {exc}")
         t_bin.copy_(d_bin)  # untimed setup: the step's input starts in host memory
         torch.cuda.synchronize()
         h_bin, h_pack, h_out = t_bin.data_ptr(), t_pack.data_ptr(), t_out.data_ptr()

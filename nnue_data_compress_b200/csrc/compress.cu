@@ -143,7 +143,7 @@ k_decode_link_encode(const unsigned char* __restrict__ bin, u64 n, u32* __restri
 #define KW_RUN_N 16
 #endif
 #ifndef KW_MIN_BLOCKS
-#define KW_MIN_BLOCKS 6
+#define KW_MIN_BLOCKS 5
 #endif
 constexpr int KW_THREADS = KW_THREADS_N;
 constexpr int KW_RUN = KW_RUN_N;

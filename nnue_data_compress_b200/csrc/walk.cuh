@@ -95,13 +95,20 @@ __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin,
             store_stem_cold(P, p8, p9, stems + a * 8);
         }
         u64 rec = a + 1;
+        // software pipeline: the loads of record rec + 1 are in flight while record rec is processed
+        uint2 n0, n1, n2, n3, n4;
+        n0 = n1 = n2 = n3 = n4 = make_uint2(0u, 0u);
+        if (rec < e) {
+            const uint2* src = reinterpret_cast<const uint2*>(bin + rec * 40);
+            n0 = src[0]; n1 = src[1]; n2 = src[2]; n3 = src[3]; n4 = src[4];
+        }
         for (; rec < e; ++rec) {
             u32 Wc[8], c8, c9;
-            {
-                const uint2* src = reinterpret_cast<const uint2*>(bin + rec * 40);
-                const uint2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
-                Wc[0] = v0.x; Wc[1] = v0.y; Wc[2] = v1.x; Wc[3] = v1.y; Wc[4] = v2.x; Wc[5] = v2.y; Wc[6] = v3.x; Wc[7] = v3.y;
-                c8 = v4.x; c9 = v4.y;
+            Wc[0] = n0.x; Wc[1] = n0.y; Wc[2] = n1.x; Wc[3] = n1.y; Wc[4] = n2.x; Wc[5] = n2.y; Wc[6] = n3.x; Wc[7] = n3.y;
+            c8 = n4.x; c9 = n4.y;
+            if (rec + 1 < e) {
+                const uint2* src = reinterpret_cast<const uint2*>(bin + (rec + 1) * 40);
+                n0 = src[0]; n1 = src[1]; n2 = src[2]; n3 = src[3]; n4 = src[4];
             }
             if (!valid || !fields_link(p9, c9)) break;  // rec starts a chain
             const Move pm = sfmove_to_move(p8 >> 16);
