@@ -419,9 +419,15 @@ def main():
             t_bin = torch.empty(bin_bytes, dtype=torch.uint8, pin_memory=True)
             t_pack = torch.empty(cap_guess, dtype=torch.uint8, pin_memory=True)
             t_out = torch.empty(bin_bytes, dtype=torch.uint8, pin_memory=True)
+            pinned_ok = 1
         except RuntimeError as exc:  # not enough lockable host memory for N ranks x 8.5 GB
-            raise SystemExit(f"bench.py: cannot pin {2 * bin_bytes + cap_guess} bytes of host memory for the e2e leg "
-                             f"(rerun with --no-e2e): {exc}")
+            log(f"cannot pin host memory for the e2e leg: {exc}")
+            pinned_ok = 0
+        if world > 1:
+            flag = torch.tensor([pinned_ok], dtype=torch.int64, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            pinned_ok = int(flag.item())
+    if not args.no_e2e and pinned_ok:
         t_bin.copy_(d_bin)  # untimed setup: the step's input starts in host memory
         torch.cuda.synchronize()
         h_bin, h_pack, h_out = t_bin.data_ptr(), t_pack.data_ptr(), t_out.data_ptr()

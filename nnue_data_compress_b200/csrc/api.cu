@@ -39,6 +39,12 @@ struct Context {
     uint64_t launches = 0;
     std::string last_cuda_error;
     float last_total_ms = 0.f, last_dominant_ms = 0.f, last_stage_ms = 0.f;
+    // host-buffer entry points: the copies are pipelined with the dominant kernel of the direction
+    const void* pipe_src = nullptr;  // compress: host source of the records (d_bin is the staging buffer)
+    void* pipe_dst = nullptr;        // decompress: host destination of the records
+    size_t pipe_dst_cap = 0;
+    bool pipe_dst_done = false;      // the pipelined D2H delivered the output
+    cudaEvent_t pipe_ev[16] = {};
     uint32_t debug_reject_mod = 0;
     bool debug_k1_per_record = false;  // "k1_per_record": the record-parallel K1 instead of the chain walk
     bool debug_exhaustive = false;     // NNP_DEBUG_EXHAUSTIVE: skip the optimistic decode strategy
@@ -226,6 +232,7 @@ int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** ste
     CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
     CK(cudaEventRecord(C.ev[0], s));
     if (C.debug_k1_per_record) {
+        if (C.pipe_src) CK(cudaMemcpyAsync(const_cast<void*>(d_bin), C.pipe_src, n_all * 40, cudaMemcpyHostToDevice, s));
         launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, s);
         LAUNCHED(1, "k_decode_link_encode");
         CK(cudaEventRecord(C.ev[3], s));
@@ -236,8 +243,30 @@ int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** ste
         WS(WS_PARK_A, (walk_runs(n_all) + 1) * 4, u32, park_a);
         WS(WS_PARK_B, (walk_runs(n_all) + 1) * 4, u32, park_b);
         u32* lists[2] = {park_a, park_b};
-        launch_walk_runs(d_bin, n_all, codes, stems, d_tot, lists[0], &d_tot->parked[0], s);
-        LAUNCHED(1, "k_walk_runs");
+        const u64 runs = walk_runs(n_all);
+        if (C.pipe_src) {
+            // host input: copy it in PIPE_PIECES pieces on the copy stream and walk every piece as soon
+            // as it has landed (a piece is a whole number of runs; its halo record is in the piece before)
+            constexpr u64 PIPE_PIECES = 16;
+            const u64 runs_per = (runs + PIPE_PIECES - 1) / PIPE_PIECES;
+            const u64 run_bytes = (u64)walk_run_records() * 40;
+            CK(cudaEventRecord(C.pipe_ev[0], s));
+            CK(cudaStreamWaitEvent(C.copy_stream, C.pipe_ev[0], 0));  // the staging buffer is free
+            for (u64 k = 0; k < PIPE_PIECES; ++k) {
+                const u64 lo = k * runs_per, hi = lo + runs_per < runs ? lo + runs_per : runs;
+                if (lo >= hi) break;
+                const u64 b0 = lo * run_bytes, b1 = hi * run_bytes < n_all * 40 ? hi * run_bytes : n_all * 40;
+                CK(cudaMemcpyAsync((char*)const_cast<void*>(d_bin) + b0, (const char*)C.pipe_src + b0, b1 - b0,
+                                   cudaMemcpyHostToDevice, C.copy_stream));
+                CK(cudaEventRecord(C.pipe_ev[k % 16], C.copy_stream));
+                CK(cudaStreamWaitEvent(s, C.pipe_ev[k % 16], 0));
+                launch_walk_runs(d_bin, n_all, lo, hi, codes, stems, d_tot, lists[0], &d_tot->parked[0], s);
+                LAUNCHED(1, "k_walk_runs");
+            }
+        } else {
+            launch_walk_runs(d_bin, n_all, 0, runs, codes, stems, d_tot, lists[0], &d_tot->parked[0], s);
+            LAUNCHED(1, "k_walk_runs");
+        }
         CK(cudaEventRecord(C.ev[3], s));
         for (int cur = 0;; cur ^= 1) {
             CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
@@ -719,9 +748,39 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
         C.last_violations = ~0ull;
         if (positions * 40 <= out_cap) {
             CK(cudaEventRecord(C.ev[1], s));
-            launch_emit_chains_verify(d_in, P.tab, P.chunks, P.tile_prefix, P.cand_chunk, P.cand_off, P.cand_cnt, cand_rec, P.ncand, d_out,
-                                      &P.d_tot->violations, s);
-            LAUNCHED(2, "k_emit_chains_verify");
+            launch_check_chunks(P.tab, P.chunks, P.tile_prefix, &P.d_tot->violations, s);
+            LAUNCHED(1, "k_check_chunks");
+            if (C.pipe_dst && positions * 40 <= C.pipe_dst_cap) {
+                // host output: emit in groups of chains and copy every group's records out while the
+                // next group is decoded (the record index of a chain is the prefix sum cand_rec)
+                constexpr u64 PIPE_GROUPS = 16;
+                const u64 per = (P.ncand + PIPE_GROUPS - 1) / PIPE_GROUPS;
+                u64* h_edges = reinterpret_cast<u64*>((char*)C.pinned + 2048);
+                u64 n_groups = 0;
+                for (u64 g = 0; g < PIPE_GROUPS && g * per < P.ncand; ++g, ++n_groups)
+                    CK(cudaMemcpyAsync(h_edges + g, cand_rec + g * per, 8, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                h_edges[n_groups] = positions;
+                for (u64 g = 0; g < n_groups; ++g) {
+                    const u64 lo = g * per, hi = lo + per < P.ncand ? lo + per : P.ncand;
+                    launch_emit_chains_verify(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_cnt, cand_rec, P.ncand, lo, hi, d_out,
+                                              &P.d_tot->violations, s);
+                    LAUNCHED(1, "k_emit_chains_verify");
+                    CK(cudaEventRecord(C.pipe_ev[g % 16], s));
+                    CK(cudaStreamWaitEvent(C.copy_stream, C.pipe_ev[g % 16], 0));
+                    const u64 b0 = h_edges[g] * 40, b1 = h_edges[g + 1] * 40;
+                    if (b1 > b0)
+                        CK(cudaMemcpyAsync((char*)C.pipe_dst + b0, (const char*)d_out + b0, b1 - b0, cudaMemcpyDeviceToHost,
+                                           C.copy_stream));
+                }
+                CK(cudaEventRecord(C.pipe_ev[0], C.copy_stream));
+                CK(cudaStreamWaitEvent(s, C.pipe_ev[0], 0));  // the call's final sync on `s` covers the copies
+                C.pipe_dst_done = true;
+            } else {
+                launch_emit_chains_verify(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_cnt, cand_rec, P.ncand, 0, P.ncand, d_out,
+                                          &P.d_tot->violations, s);
+                LAUNCHED(1, "k_emit_chains_verify");
+            }
             CK(cudaEventRecord(C.ev[2], s));
             CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(DecompressTotals), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
@@ -739,6 +798,7 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
             }
         }
         ++C.optimistic_misses;
+        C.pipe_dst_done = false;  // whatever was copied out is overwritten by the exhaustive result
     }
 
     rc = decode_plan(d_in, in_bytes, false, P, true);
@@ -823,7 +883,10 @@ int run_host(dev_fn fn, const void* in, size_t in_bytes, void* out, size_t out_c
 {
     Context& C = g_ctx;
     WS(WS_STAGE_IN, in_bytes + 64, unsigned char, d_in);
-    if (in_bytes) CK(cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, C.stream));
+    // .bin -> .binpack overlaps its H2D with K1, .binpack -> .bin its D2H with the chain decoder
+    const bool pipe_in = out && fn == compress_dev && in_bytes >= (64u << 20);
+    const bool pipe_out = out && fn == decompress_dev;
+    if (in_bytes && !pipe_in) CK(cudaMemcpyAsync(d_in, in, in_bytes, cudaMemcpyHostToDevice, C.stream));
     if (!out) {
         int rc = fn(d_in, in_bytes, nullptr, 0, out_bytes);
         return is_reference_error(rc) ? NNP_OK : rc;  // the status is reported by the real call
@@ -831,11 +894,19 @@ int run_host(dev_fn fn, const void* in, size_t in_bytes, void* out, size_t out_c
     const size_t need = dev_out_cap ? dev_out_cap : out_cap;
     WS(WS_STAGE_OUT, need + 64, unsigned char, d_out);
     size_t produced = 0;
+    C.pipe_src = pipe_in ? in : nullptr;
+    C.pipe_dst = pipe_out ? out : nullptr;
+    C.pipe_dst_cap = out_cap;
+    C.pipe_dst_done = false;
     int rc = fn(d_in, in_bytes, d_out, need, &produced);
+    const bool delivered = C.pipe_dst_done;
+    C.pipe_src = nullptr;
+    C.pipe_dst = nullptr;
+    C.pipe_dst_done = false;
     *out_bytes = produced;
     if (rc != NNP_OK && !is_reference_error(rc)) return rc;
     if (produced > out_cap) return NNP_ERR_CAPACITY;
-    if (produced) {
+    if (produced && !delivered) {
         CK(cudaMemcpyAsync(out, d_out, produced, cudaMemcpyDeviceToHost, C.stream));
         CK(cudaStreamSynchronize(C.stream));
     }
@@ -879,6 +950,8 @@ int nnp_init(int device)
     if (cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking) != cudaSuccess) return NNP_ERR_CUDA;
     for (auto& ev : g_ctx.ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return NNP_ERR_CUDA;
+    for (auto& ev : g_ctx.pipe_ev)
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return NNP_ERR_CUDA;
     if (cudaMallocHost(&g_ctx.pinned, 4096) != cudaSuccess) return NNP_ERR_NOMEM;
     const char* dbg = std::getenv("NNP_DEBUG_REJECT_MOD");
     g_ctx.debug_reject_mod = dbg ? (uint32_t)std::strtoul(dbg, nullptr, 10) : 0u;
@@ -902,6 +975,10 @@ void nnp_shutdown(void)
     if (g_ctx.pinned) cudaFreeHost(g_ctx.pinned);
     g_ctx.pinned = nullptr;
     for (auto& ev : g_ctx.ev) {
+        if (ev) cudaEventDestroy(ev);
+        ev = nullptr;
+    }
+    for (auto& ev : g_ctx.pipe_ev) {
         if (ev) cudaEventDestroy(ev);
         ev = nullptr;
     }

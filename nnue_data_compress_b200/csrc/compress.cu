@@ -162,12 +162,13 @@ __device__ __forceinline__ void park_append(u32 parked, u32* __restrict__ list, 
 }
 
 __global__ void __launch_bounds__(KW_THREADS, KW_MIN_BLOCKS)
-k_walk_runs(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ codes, u32* __restrict__ stems,
-            CompressTotals* tot, u32* __restrict__ park_list, u64* park_count)
+k_walk_runs(const unsigned char* __restrict__ bin, u64 n, u64 run_lo, u64 run_hi, u32* __restrict__ codes,
+            u32* __restrict__ stems, CompressTotals* tot, u32* __restrict__ park_list, u64* park_count)
 {
-    const u64 r0 = ((u64)blockIdx.x * KW_THREADS + threadIdx.x) * KW_RUN;
+    const u64 run = run_lo + (u64)blockIdx.x * KW_THREADS + threadIdx.x;
+    const u64 r0 = run * KW_RUN;
     u32 parked = KW_NONE;
-    if (r0 < n) {
+    if (run < run_hi && r0 < n) {
         const u64 e = r0 + KW_RUN < n ? r0 + KW_RUN : n;
         bool head = r0 == 0;
         if (!head) {
@@ -575,12 +576,15 @@ void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems,
     k_decode_link_encode<<<(unsigned)blocks, K1_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems, tot);
 }
 u64 walk_runs(u64 n) { return (n + KW_RUN - 1) / KW_RUN; }
-void launch_walk_runs(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u32* park_list, u64* park_count,
-                      cudaStream_t s)
+int walk_run_records() { return KW_RUN; }
+// runs [run_lo, run_hi) of the n records at d_bin (the records before run_lo * KW_RUN must be there too)
+void launch_walk_runs(const void* d_bin, u64 n, u64 run_lo, u64 run_hi, u32* codes, u32* stems, CompressTotals* tot,
+                      u32* park_list, u64* park_count, cudaStream_t s)
 {
-    if (n == 0) return;
-    const u64 blocks = (walk_runs(n) + KW_THREADS - 1) / KW_THREADS;
-    k_walk_runs<<<(unsigned)blocks, KW_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems, tot, park_list, park_count);
+    if (run_hi <= run_lo) return;
+    const u64 blocks = (run_hi - run_lo + KW_THREADS - 1) / KW_THREADS;
+    k_walk_runs<<<(unsigned)blocks, KW_THREADS, 0, s>>>((const unsigned char*)d_bin, n, run_lo, run_hi, codes, stems, tot,
+                                                       park_list, park_count);
 }
 void launch_walk_items(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, const u32* items, u64 n_items,
                        u32* park_list, u64* park_count, cudaStream_t s)

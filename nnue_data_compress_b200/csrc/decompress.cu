@@ -660,11 +660,11 @@ k_mark_conflicts(const unsigned char* __restrict__ in, ChunkTable tab, const u32
 __global__ void __launch_bounds__(EMITC_THREADS, EMIT_MIN_BLOCKS)
 k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
                      const u32* __restrict__ cand_off, const u32* __restrict__ cand_cnt, const u64* __restrict__ cand_rec,
-                     u64 ncand, unsigned char* __restrict__ out, u64* __restrict__ violations)
+                     u64 ncand, u64 cand_lo, u64 cand_hi, unsigned char* __restrict__ out, u64* __restrict__ violations)
 {
     __shared__ u32 scratch[8 * EMITC_THREADS];
-    const u64 i = (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
-    if (i >= ncand) return;
+    const u64 i = cand_lo + (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
+    if (i >= cand_hi) return;
     if (cand_cnt[i] == 0) return;  // marked by k_mark_conflicts
     const u32 c = cand_chunk[i], off = cand_off[i];
     const u32 clen = tab.len[c];
@@ -802,15 +802,19 @@ void launch_candidates_list(const void* d_in, ChunkTable tab, u64 tiles, const u
     k_candidates_list<<<(unsigned)tiles, LIST_THREADS, 0, s>>>((const unsigned char*)d_in, tab, tile_flags, tile_prefix,
                                                              cand_chunk, cand_off, cand_cnt);
 }
-void launch_emit_chains_verify(const void* d_in, ChunkTable tab, u64 chunks, const u64* tile_prefix, const u32* cand_chunk,
-                               const u32* cand_off, const u32* cand_cnt, const u64* cand_rec, u64 ncand, void* out,
-                               u64* violations, cudaStream_t s)
+void launch_check_chunks(ChunkTable tab, u64 chunks, const u64* tile_prefix, u64* violations, cudaStream_t s)
 {
     if (chunks == 0) return;
     k_check_chunks<<<(unsigned)((chunks + 127) / 128), 128, 0, s>>>(tab, tile_prefix, violations);
-    if (ncand == 0) return;
-    k_emit_chains_verify<<<(unsigned)((ncand + EMITC_THREADS - 1) / EMITC_THREADS), EMITC_THREADS, 0, s>>>(
-        (const unsigned char*)d_in, tab, cand_chunk, cand_off, cand_cnt, cand_rec, ncand, (unsigned char*)out, violations);
+}
+void launch_emit_chains_verify(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off,
+                               const u32* cand_cnt, const u64* cand_rec, u64 ncand, u64 cand_lo, u64 cand_hi, void* out,
+                               u64* violations, cudaStream_t s)
+{
+    if (cand_hi <= cand_lo) return;
+    k_emit_chains_verify<<<(unsigned)((cand_hi - cand_lo + EMITC_THREADS - 1) / EMITC_THREADS), EMITC_THREADS, 0, s>>>(
+        (const unsigned char*)d_in, tab, cand_chunk, cand_off, cand_cnt, cand_rec, ncand, cand_lo, cand_hi, (unsigned char*)out,
+        violations);
 }
 void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s)
 {

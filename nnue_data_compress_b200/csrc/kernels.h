@@ -7,8 +7,9 @@ namespace nnp {
 // ---- compress (.bin -> .binpack), compress.cu
 void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, cudaStream_t s);
 u64 walk_runs(u64 n);  // number of runs = upper bound of the parked heads of any round
-void launch_walk_runs(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u32* park_list, u64* park_count,
-                      cudaStream_t s);
+int walk_run_records();
+void launch_walk_runs(const void* d_bin, u64 n, u64 run_lo, u64 run_hi, u32* codes, u32* stems, CompressTotals* tot,
+                      u32* park_list, u64* park_count, cudaStream_t s);
 void launch_walk_items(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, const u32* items, u64 n_items,
                        u32* park_list, u64* park_count, cudaStream_t s);
 u64 scan_tiles(u64 n);
@@ -44,8 +45,10 @@ void launch_mark_conflicts(const void* d_in, ChunkTable tab, const u32* cand_chu
                            u64 ncand, cudaStream_t s);
 void launch_candidates_list(const void* d_in, ChunkTable tab, u64 tiles, const u32* tile_flags, const u64* tile_prefix,
                             u32* cand_chunk, u32* cand_off, u32* cand_cnt, cudaStream_t s);
-void launch_emit_chains_verify(const void* d_in, ChunkTable tab, u64 chunks, const u64* tile_prefix, const u32* cand_chunk,
-                               const u32* cand_off, const u32* cand_cnt, const u64* cand_rec, u64 ncand, void* out,
+void launch_check_chunks(ChunkTable tab, u64 chunks, const u64* tile_prefix, u64* violations, cudaStream_t s);
+// candidates [cand_lo, cand_hi)
+void launch_emit_chains_verify(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off,
+                               const u32* cand_cnt, const u64* cand_rec, u64 ncand, u64 cand_lo, u64 cand_hi, void* out,
                                u64* violations, cudaStream_t s);
 void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s);
 void launch_exclusive_sum64(const u64* in, u64 n, u64* out, cudaStream_t s);
