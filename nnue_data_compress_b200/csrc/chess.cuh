@@ -275,16 +275,30 @@ __device__ __forceinline__ int preserved_cr(int sq)
     return m;
 }
 
+// Board::doMove for MoveType::Normal / Promotion (Position.h:300-350): `placed` lands on `to`, whatever
+// stood there disappears, `from` is vacated -- place(piece, to) then place(none, from), so a move
+// with from == to leaves the square empty. One masked update per plane instead of three generic
+// square operations.
+__device__ __forceinline__ void pos_move_piece(Pos& p, int from, int to, int placed)
+{
+    const u64 bf = bit64(from), bt = bit64(to);
+    const u64 keep = ~(bf | bt);
+    const u64 set = (from == to || placed == NO_PIECE) ? 0ull : bt;
+    const int t = placed >> 1;
+    p.occ[0] = (p.occ[0] & keep) | ((placed & 1) ? 0ull : set);
+    p.occ[1] = (p.occ[1] & keep) | ((placed & 1) ? set : 0ull);
+    p.t0 = (p.t0 & keep) | ((t & 1) ? set : 0ull);
+    p.t1 = (p.t1 & keep) | ((t & 2) ? set : 0ull);
+    p.t2 = (p.t2 & keep) | ((t & 4) ? set : 0ull);
+}
+
 // Board::doMove + doMoveColdPath (Position.h:300-439), mailbox semantics on the planes
 __device__ __forceinline__ void board_do_move(Pos& p, const Move& m)
 {
     if (m.type == MT_NORMAL) {
-        int pc = pos_piece_at(p, m.from);
-        pos_put(p, m.to, pc);
-        pos_remove(p, m.from);
+        pos_move_piece(p, m.from, m.to, pos_piece_at(p, m.from));
     } else if (m.type == MT_PROMOTION) {
-        pos_put(p, m.to, m.promo);
-        pos_remove(p, m.from);
+        pos_move_piece(p, m.from, m.to, m.promo);
     } else if (m.type == MT_ENPASSANT) {
         int pc = pos_piece_at(p, m.from);
         pos_put(p, m.to, pc);
@@ -690,13 +704,24 @@ __device__ __forceinline__ u32 encode_ply(const Pos& p, const Move& mv, int scor
     return (u32)(acc << (32 - n));
 }
 
-// MSB-first bit reader over a byte span (PackedMoveScoreListReader::extractBitsLE8 :623-648)
+// MSB-first bit reader over a byte span (PackedMoveScoreListReader::extractBitsLE8 :623-648).
+// Reads the one or two bytes a field touches straight from memory (L1 hits): a 64-bit register
+// window with 32-bit refills was measured slower in the chain decoder (more registers and 64-bit
+// shifts than the byte loads cost). `pos` counts the bits consumed (numReadBytes :815-818).
 struct BitReader {
     const unsigned char* p;
     u32 nbits;   // bits available
     u32 pos;
     bool overrun;
-    __device__ __forceinline__ u32 get(int n)
+    __device__ __forceinline__ void init(const unsigned char* p0, u64 bytes)
+    {
+        p = p0;
+        const u64 bits = bytes * 8;
+        nbits = bits > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)bits;
+        pos = 0;
+        overrun = false;
+    }
+    __device__ __forceinline__ u32 get(int n)  // n <= 8
     {
         if (n == 0) return 0;
         if (pos + (u32)n > nbits) { overrun = true; pos += n; return 0; }
@@ -704,7 +729,7 @@ struct BitReader {
         u32 v = ((u32)p[byte] << 16);
         if (((pos + n - 1) >> 3) > byte) v |= ((u32)p[byte + 1] << 8);
         pos += n;
-        return (v >> (24 - sh - n)) & ((1u << n) - 1u);  // n <= 8
+        return (v >> (24 - sh - n)) & ((1u << n) - 1u);
     }
 };
 

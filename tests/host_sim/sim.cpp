@@ -9,6 +9,7 @@
 #include "../../nnue_data_compress_b200/csrc/chess.cuh"
 #include "../../nnue_data_compress_b200/csrc/stream.cuh"
 #include "../../nnue_data_compress_b200/csrc/walk.cuh"
+#include "../../nnue_data_compress_b200/csrc/chain.cuh"
 #include <vector>
 
 using namespace nnp;
@@ -176,6 +177,33 @@ uint64_t sim_walk_check(const unsigned char* bin, size_t n, int run, uint64_t* p
         else if (codes_a[i] == 0u && std::memcmp(&stems_a[i * 8], &stems_b[i * 8], 32) != 0) ++bad;
     }
     return bad;
+}
+
+// .binpack -> .bin with the device-side chain walker (chain.cuh: BitReader, decode_ply, pos_do_move,
+// spliced stream): chunks and chains are followed sequentially as the reference reader does.
+// Returns the number of records written, or -1 on a malformed chunk / chain.
+long long sim_decode_binpack(const unsigned char* in, size_t n, unsigned char* out, size_t out_cap_records)
+{
+    size_t pos = 0;
+    unsigned long long rec = 0;
+    u32 col[8];
+    while (pos < n) {
+        if (n - pos < 8 || std::memcmp(in + pos, "BINP", 4) != 0) return -1;
+        u32 size;
+        std::memcpy(&size, in + pos + 4, 4);
+        if (n - pos - 8 < size) return -1;
+        const unsigned char* chunk = in + pos + 8;
+        u32 cur = 0;
+        while ((unsigned long long)cur + 34 <= size) {
+            const u32 plies = ((u32)chunk[cur + 32] << 8) | chunk[cur + 33];
+            u32 consumed = 0;
+            if (!emit_chain_bin(chunk + cur, size - cur - 34, out, rec, out_cap_records, col, 1, consumed)) return -1;
+            rec += 1ull + plies;
+            cur += consumed;
+        }
+        pos += 8 + (size_t)size;
+    }
+    return (long long)rec;
 }
 
 }  // extern "C"

@@ -17,7 +17,7 @@ CSRC = os.path.join(ROOT, "nnue_data_compress_b200", "csrc")
 @pytest.fixture(scope="module")
 def sim():
     srcs = [os.path.join(SIM_DIR, "sim.cpp"), os.path.join(SIM_DIR, "host_sim.h")] + [
-        os.path.join(CSRC, f) for f in ("chess.cuh", "stream.cuh", "walk.cuh", "link.cuh")]
+        os.path.join(CSRC, f) for f in ("chess.cuh", "stream.cuh", "walk.cuh", "link.cuh", "chain.cuh")]
     if not os.path.exists(SIM_SO) or any(os.path.getmtime(s) > os.path.getmtime(SIM_SO) for s in srcs):
         subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-DNNP_HOST_SIM", "-I" + SIM_DIR,
                         "-shared", "-fPIC", "-o", SIM_SO, srcs[0]], check=True)
@@ -28,6 +28,8 @@ def sim():
     L.sim_stream_fuzz.restype = ctypes.c_uint64
     L.sim_walk_check.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, u64p, u64p]
     L.sim_walk_check.restype = ctypes.c_uint64
+    L.sim_decode_binpack.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    L.sim_decode_binpack.restype = ctypes.c_longlong
     return L
 
 
@@ -80,3 +82,24 @@ def test_chain_walk_reports_bad_sfen(sim):
         parked, err = ctypes.c_uint64(), ctypes.c_uint64()
         bad = sim.sim_walk_check(data, len(data) // 40, run, ctypes.byref(parked), ctypes.byref(err))
         assert bad == 0 and err.value == cut
+
+
+def test_chain_decoder_reproduces_reference_bin(sim):
+    """chain.cuh (bit reader window, decode_ply, doMove, spliced stream) over whole .binpack files:
+    the records must be the reference's own decompression output."""
+    from refutil import BIN_TO_BINPACK, BINPACK_TO_BIN, oracle_convert
+
+    cases = [(golden(s + ".binpack"), golden(s + ".rt.bin")) for s in GOLDEN_SETS]
+    if have_ref():
+        for args in ((150_000, 100, 42, 0), (40_000, 400, 9, 0), (30_000, 8, 3, 0)):
+            b = ref_generate(*args)
+            rc, bp = oracle_convert(BIN_TO_BINPACK, b)
+            assert rc == 0
+            rc, rt = oracle_convert(BINPACK_TO_BIN, bp)
+            assert rc == 0
+            cases.append((bp, rt))
+    for bp, want in cases:
+        out = ctypes.create_string_buffer(len(want) + 40)
+        n = sim.sim_decode_binpack(bp, len(bp), out, len(want) // 40)
+        assert n == len(want) // 40
+        assert out.raw[: len(want)] == want
