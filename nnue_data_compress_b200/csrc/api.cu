@@ -46,7 +46,8 @@ struct Context {
     bool pipe_dst_done = false;      // the pipelined D2H delivered the output
     cudaEvent_t pipe_ev[16] = {};
     uint32_t debug_reject_mod = 0;
-    bool debug_k1_per_record = false;  // "k1_per_record": the record-parallel K1 instead of the chain walk
+    bool debug_k1_per_record = false;  // "k1_per_record": always the record-parallel K1
+    bool debug_k1_walk = false;        // "k1_walk": always the chain walk (no density sample)
     bool debug_exhaustive = false;     // NNP_DEBUG_EXHAUSTIVE: skip the optimistic decode strategy
     uint64_t optimistic_misses = 0;    // optimistic decodes that had to be redone exhaustively
     uint64_t optimistic_hits = 0;
@@ -231,7 +232,21 @@ int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** ste
     if (rc != NNP_OK) return rc;
     CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
     CK(cudaEventRecord(C.ev[0], s));
-    if (C.debug_k1_per_record) {
+    // device-resident input: pick K1 from a sample of the chain-head density (host input is walked
+    // piece by piece while it arrives, so there is nothing to sample yet)
+    bool per_record = C.debug_k1_per_record;
+    if (!per_record && !C.debug_k1_walk && !C.pipe_src && n_all >= 4096) {
+        const u64 samples = n_all / 2 < 65536 ? n_all / 2 : 65536;
+        const u64 stride = (n_all - 1) / samples;
+        CK(cudaMemsetAsync(&d_tot->parked[1], 0, 8, s));
+        launch_sample_heads(d_bin, n_all, stride, samples, &d_tot->parked[1], s);
+        LAUNCHED(1, "k_sample_heads");
+        CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        per_record = h_tot->parked[1] * 3 > samples;  // more than one record in three starts a chain
+        CK(cudaMemsetAsync(&d_tot->parked[1], 0, 8, s));
+    }
+    if (per_record) {
         if (C.pipe_src) CK(cudaMemcpyAsync(const_cast<void*>(d_bin), C.pipe_src, n_all * 40, cudaMemcpyHostToDevice, s));
         launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, s);
         LAUNCHED(1, "k_decode_link_encode");
@@ -1176,6 +1191,7 @@ int nnp_debug_config(const char* key, uint64_t value)
     if (!key) return NNP_ERR_BAD_ARG;
     if (!std::strcmp(key, "exhaustive")) g_ctx.debug_exhaustive = value != 0;
     else if (!std::strcmp(key, "k1_per_record")) g_ctx.debug_k1_per_record = value != 0;
+    else if (!std::strcmp(key, "k1_walk")) g_ctx.debug_k1_walk = value != 0;
     else if (!std::strcmp(key, "reject_mod")) g_ctx.debug_reject_mod = (uint32_t)value;
     else return NNP_ERR_BAD_ARG;
     return NNP_OK;

@@ -149,6 +149,25 @@ constexpr int KW_THREADS = KW_THREADS_N;
 constexpr int KW_RUN = KW_RUN_N;
 constexpr u32 KW_NONE = 0xFFFFFFFFu;
 
+// Fraction of chain heads, estimated from evenly spaced record pairs with the field tests of
+// isContinuation alone: files of (nearly) single positions are better served by the record-parallel
+// kernel, which does not pay for walking state it never uses.
+__global__ void __launch_bounds__(256)
+k_sample_heads(const unsigned char* __restrict__ bin, u64 n, u64 stride, u64 samples, u64* __restrict__ heads)
+{
+    const u64 i = (u64)blockIdx.x * 256 + threadIdx.x;
+    bool head = false;
+    if (i < samples) {
+        const u64 rec = 1 + i * stride;
+        if (rec < n) {
+            const u32* w = reinterpret_cast<const u32*>(bin + (rec - 1) * 40);
+            head = !fields_link(w[9], w[19]);
+        }
+    }
+    const u32 m = __ballot_sync(0xffffffffu, head);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(heads, (u64)__popc(m));
+}
+
 // appends the parked records of a warp with one atomic
 __device__ __forceinline__ void park_append(u32 parked, u32* __restrict__ list, u64* count)
 {
@@ -574,6 +593,11 @@ void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems,
     if (n == 0) return;
     const u64 blocks = (n + K1_TILE - 1) / K1_TILE;
     k_decode_link_encode<<<(unsigned)blocks, K1_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems, tot);
+}
+void launch_sample_heads(const void* d_bin, u64 n, u64 stride, u64 samples, u64* heads, cudaStream_t s)
+{
+    if (samples == 0) return;
+    k_sample_heads<<<(unsigned)((samples + 255) / 256), 256, 0, s>>>((const unsigned char*)d_bin, n, stride, samples, heads);
 }
 u64 walk_runs(u64 n) { return (n + KW_RUN - 1) / KW_RUN; }
 int walk_run_records() { return KW_RUN; }

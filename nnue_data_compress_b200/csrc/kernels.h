@@ -7,6 +7,7 @@ namespace nnp {
 // ---- compress (.bin -> .binpack), compress.cu
 void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, cudaStream_t s);
 u64 walk_runs(u64 n);  // number of runs = upper bound of the parked heads of any round
+void launch_sample_heads(const void* d_bin, u64 n, u64 stride, u64 samples, u64* heads, cudaStream_t s);
 int walk_run_records();
 void launch_walk_runs(const void* d_bin, u64 n, u64 run_lo, u64 run_hi, u32* codes, u32* stems, CompressTotals* tot,
                       u32* park_list, u64* park_count, cudaStream_t s);

@@ -81,6 +81,22 @@ def test_many_chunks(nnp, n, plies):
     assert nnp.binpack_to_bin(got) == oracle_convert(BINPACK_TO_BIN, want)[1]
 
 
+@pytest.mark.parametrize("force", ["k1_walk", "k1_per_record"])
+@pytest.mark.parametrize("n,plies", [(400_000, 100), (400_000, 1), (300_000, 5)])
+def test_both_forms_of_k1(nnp, force, n, plies):
+    """The compressor's first kernel exists in a chain-walking and a record-parallel form (a sample
+    of the chain-head density picks one); both must give the oracle's bytes on long and short chains."""
+    b = nnp.generate_bin(n, plies, 31)
+    rc, want = oracle_convert(BIN_TO_BINPACK, b)
+    assert rc == 0
+    nnp.lib().nnp_debug_config(force.encode(), 1)
+    try:
+        assert nnp.bin_to_binpack(b) == want
+    finally:
+        nnp.lib().nnp_debug_config(force.encode(), 0)
+    assert nnp.bin_to_binpack(b) == want
+
+
 def test_reference_parity_1m(nnp):
     """BASELINE config 1: 1M positions, ~100 plies per chain, against the reference binary."""
     b = _synthetic(1_000_000, 100, 42)
