@@ -584,29 +584,38 @@ __device__ __forceinline__ void stem_unpack(ByteFn B, Pos& p, Move& mv, int& sco
     u64 occ = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) occ = (occ << 8) | (u64)B(i);
+    // the occupied squares are distinct, so the planes are built by OR-ing one bit per piece
+    // (Board::place on an empty board) instead of generic square updates
+    u64 o0 = 0, o1 = 0, t0 = 0, t1 = 0, t2 = 0;
     int k = 0;
     u64 b = occ;
     while (b) {
-        int sq = lsb64(b);
+        const int sq = lsb64(b);
+        const u64 bit = b & (0ull - b);
         b &= b - 1;
-        int nib = (B(8 + (k >> 1)) >> ((k & 1) * 4)) & 15;
+        const int nib = (B(8 + (k >> 1)) >> ((k & 1) * 4)) & 15;
         ++k;
-        if (nib < 12) {
-            pos_put(p, sq, nib);
-        } else if (nib == 12) {
-            if ((sq >> 3) == 3) { pos_put(p, sq, (PT_PAWN << 1) | WHITE); p.ep = (sq - 8) & 0xFF; }
-            else { pos_put(p, sq, (PT_PAWN << 1) | BLACK); p.ep = (sq + 8) & 0xFF; }
+        int piece = nib;  // 0..11: Piece ordinal (type << 1 | colour)
+        if (nib == 12) {  // pawn that just made a double push: rank 4 = white, else black (Position.h:1440-1456)
+            if ((sq >> 3) == 3) { piece = (PT_PAWN << 1) | WHITE; p.ep = (sq - 8) & 0xFF; }
+            else { piece = (PT_PAWN << 1) | BLACK; p.ep = (sq + 8) & 0xFF; }
         } else if (nib == 13) {
-            pos_put(p, sq, (PT_ROOK << 1) | WHITE);
+            piece = (PT_ROOK << 1) | WHITE;
             p.cr |= (sq == 0) ? CR_WQ : CR_WK;
         } else if (nib == 14) {
-            pos_put(p, sq, (PT_ROOK << 1) | BLACK);
+            piece = (PT_ROOK << 1) | BLACK;
             p.cr |= (sq == 56) ? CR_BQ : CR_BK;
-        } else {
-            pos_put(p, sq, (PT_KING << 1) | BLACK);
+        } else if (nib == 15) {
+            piece = (PT_KING << 1) | BLACK;
             p.stm = BLACK;
         }
+        const int t = piece >> 1;
+        if (piece & 1) o1 |= bit; else o0 |= bit;
+        if (t & 1) t0 |= bit;
+        if (t & 2) t1 |= bit;
+        if (t & 4) t2 |= bit;
     }
+    p.occ[0] = o0; p.occ[1] = o1; p.t0 = t0; p.t1 = t1; p.t2 = t2;
     u32 cm = ((u32)B(24) << 8) | (u32)B(25);
     if (cm == 0) {
         mv.from = mv.to = SQ_NONE;  // Move::null()

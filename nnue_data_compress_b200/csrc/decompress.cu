@@ -160,7 +160,7 @@ static_assert(CAND_TILE == CAND_THREADS * 16, "stage 1 of k_candidates_scan test
 // one king per side, at most 32 pieces, no pawn on rank 1/8, the stored move starts on a piece of
 // the side to move and does not land on an own piece. A real stem that fails group (2) (possible
 // only for inputs outside that domain) merely sends the file through the exhaustive path.
-__device__ __forceinline__ bool plausible_stem(const unsigned char* s)
+__device__ __forceinline__ bool plausible_stem_quick(const unsigned char* s)
 {
     if (s[30] != 0) return false;
     // bytes 0..27 as seven little-endian words, from aligned shared-memory loads
@@ -181,12 +181,15 @@ __device__ __forceinline__ bool plausible_stem(const unsigned char* s)
     if (n < 2 || n > 32) return false;
     // nibble k of the 16 nibble bytes is bits 4(k%8).. of word 2 + k/8; nibbles n.. must be zero, and
     // among the first n there is exactly one white king (10) and one black king (11, or 15 = black to move)
+    u32 stray = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) stray |= v[2 + j] & ~stream_low_mask(4 * n, j);
+    if (stray) return false;  // the cheapest of the strong tests first: most non-stems fail here
     int wk = 0, bk = 0, k15 = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const u32 x = v[2 + j];
         const u32 used = stream_low_mask(4 * n, j);
-        if (x & ~used) return false;
         const u32 flags = 0x11111111u & used;
         auto count_eq = [&](u32 pattern) {
             const u32 t = x ^ pattern;
@@ -197,9 +200,17 @@ __device__ __forceinline__ bool plausible_stem(const unsigned char* s)
         bk += count_eq(0xBBBBBBBBu);
         k15 += count_eq(0xFFFFFFFFu);
     }
-    if (wk != 1 || bk + k15 != 1) return false;
-    const int stm = k15 ? BLACK : WHITE;
-    // per-square checks (reached by about one offset in 10^5)
+    return wk == 1 && bk + k15 == 1;
+}
+
+// the per-square half of the test, for offsets that passed plausible_stem_quick
+__device__ __forceinline__ bool plausible_stem_squares(const unsigned char* s)
+{
+    u64 occ = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) occ = (occ << 8) | s[i];
+    int stm = WHITE;
+    for (int i = 0; i < 16; ++i) stm |= ((s[8 + i] & 15) == 15) | ((s[8 + i] >> 4) == 15);
     const u32 cm = ((u32)s[24] << 8) | s[25];
     const int mtype = (int)(cm >> 14), from = (int)((cm >> 8) & 63), to = (int)((cm >> 2) & 63);
     if (cm != 0 && (from == to || ((cm & 3u) && mtype != MT_PROMOTION))) return false;
@@ -259,9 +270,9 @@ k_candidates_scan(const unsigned char* __restrict__ in, u64 n_in, ChunkTable tab
 {
     __shared__ __align__(16) unsigned char sm[CAND_TILE + 96];  // the tile from its 16-byte aligned base
     __shared__ u32 flags[CAND_TILE / 32];
-    __shared__ unsigned short queue[CAND_TILE];
+    __shared__ unsigned short queue[CAND_TILE], queue2[CAND_TILE];
     __shared__ u32 warp_tot[CAND_THREADS / 32];
-    __shared__ u32 nq;
+    __shared__ u32 nq, nq2;
     const int t = threadIdx.x, lane = t & 31;
     const u64 tile = blockIdx.x;
     const u64 c = find_chunk(tab.tile_base, tab.info->chunks, tile);
@@ -276,7 +287,7 @@ k_candidates_scan(const unsigned char* __restrict__ in, u64 n_in, ChunkTable tab
     for (int i = t; i < nvec; i += CAND_THREADS)
         reinterpret_cast<uint4*>(sm)[i] = load16_clipped(base + 16 * i, in, in + n_in);
     if (t < CAND_TILE / 32) flags[t] = 0;
-    if (t == 0) nq = 0;
+    if (t == 0) nq = nq2 = 0;
     __syncthreads();
     const unsigned char* s0 = sm + delta;  // s0[o] = byte at chunk offset off0 + o
 
@@ -317,11 +328,18 @@ k_candidates_scan(const unsigned char* __restrict__ in, u64 n_in, ChunkTable tab
         }
     }
     __syncthreads();
-    // stage 2: the full test on the survivors
+    // stage 2: the word-parallel tests on the survivors; stage 3: the per-square tests on what is
+    // left (in files of single positions that is every 34th offset: it has to run dense, too)
     const u32 n_queued = nq;
     for (u32 q = t; q < n_queued; q += CAND_THREADS) {
         const int o = queue[q];
-        bool ok = plausible_stem(s0 + o);
+        if (plausible_stem_quick(s0 + o)) queue2[atomicAdd(&nq2, 1u)] = (unsigned short)o;
+    }
+    __syncthreads();
+    const u32 n_queued2 = nq2;
+    for (u32 q = t; q < n_queued2; q += CAND_THREADS) {
+        const int o = queue2[q];
+        bool ok = plausible_stem_squares(s0 + o);
         // test hook: drop a pseudo-random subset of candidates to exercise the fallbacks
         if (debug_reject_mod && (u32)(((off0 + (u64)o) * 2654435761ull) >> 11) % debug_reject_mod == 0) ok = false;
         if (ok) atomicOr(&flags[o >> 5], 1u << (o & 31));
