@@ -24,7 +24,7 @@ enum WsSlot {
     WS_CODES = 0, WS_STEMS, WS_TILE_AGG, WS_PAYLOAD, WS_HEAD_OFF, WS_CHUNK_OFF, WS_TOTALS,
     WS_CHUNK_START, WS_CHUNK_LEN, WS_CHUNK_TILE_BASE, WS_CHUNK_INFO, WS_TILE_COUNT, WS_TILE_PREFIX,
     WS_CAND_CHUNK, WS_CAND_OFF, WS_CAND_NEXT, WS_CAND_BASE, WS_CAND_CNT, WS_CHUNK_COUNT, WS_CHUNK_SLOW, WS_CHUNK_BASE,
-    WS_DTOTALS, WS_HEAD_NEXT, WS_PARK_A, WS_PARK_B, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
+    WS_DTOTALS, WS_AGG_TOP, WS_HEAD_NEXT, WS_PARK_A, WS_PARK_B, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
 };
 
 struct Context {
@@ -145,9 +145,10 @@ int build_payload(const u32* codes, const u32* stems, u64 n, PayloadPlan& P)
     WS(WS_TILE_AGG, scan_tiles(n) * sizeof(Agg), Agg, tile_agg);
     WS(WS_TOTALS, sizeof(CompressTotals), CompressTotals, d_tot);
     CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
+    WS(WS_AGG_TOP, (scan_blocks(scan_tiles(n)) + 1) * sizeof(Agg), Agg, agg_top);
     launch_tile_aggregate(codes, n, tile_agg, s);
-    launch_scan_aggregates(tile_agg, scan_tiles(n), d_tot, s);
-    LAUNCHED(2, "payload scan");
+    launch_scan_aggregates(tile_agg, scan_tiles(n), agg_top, d_tot, s);
+    LAUNCHED(4, "payload scan");
     CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     P.payload_bytes = h_tot->payload_bytes;

@@ -307,53 +307,91 @@ __device__ __forceinline__ Agg block_exclusive_scan(const Agg& local, Agg& total
     return agg_combine(wprefix, exc);
 }
 
+// appends one record to a run summary: agg_combine(a, agg_of_code(code)) without the generic case analysis
+__device__ __forceinline__ void agg_push(Agg& a, u32 code)
+{
+    if (code == 0u) {
+        a.bytes += (a.heads ? ceil8(a.post_bits) : 0ull) + 34;
+        a.post_bits = 0;
+        a.post_plies = 0;
+        a.heads += 1;
+    } else {
+        const u32 nb = (u32)code_bits(code);
+        if (a.heads) { a.post_bits += nb; a.post_plies += 1; }
+        else { a.pre_bits += nb; a.pre_plies += 1; }
+    }
+}
+
+// the SCAN_ITEMS codes of one thread (two 16-byte loads; a zero-bit continuation fills the tail)
+static_assert(SCAN_ITEMS == 8, "load_codes reads two uint4");
+__device__ __forceinline__ void load_codes(const u32* __restrict__ codes, u64 base, u64 n, u32 (&c)[SCAN_ITEMS])
+{
+    // base is a multiple of 8; the array itself starts mid-way for a shard's owned range
+    if (base + SCAN_ITEMS <= n && (reinterpret_cast<uintptr_t>(codes + base) & 15) == 0) {
+        const uint4* v = reinterpret_cast<const uint4*>(codes + base);
+        const uint4 a = v[0], b = v[1];
+        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) c[i] = base + i < n ? codes[base + i] : (1u << 31);
+    }
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_tile_aggregate(const u32* __restrict__ codes, u64 n, Agg* __restrict__ tile_agg)
 {
     __shared__ Agg warp_tot[SCAN_THREADS / 32];
     const u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    u32 c[SCAN_ITEMS];
+    load_codes(codes, base, n, c);
     Agg local = agg_identity();
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        if (base + i < n) local = agg_combine(local, agg_of_code(codes[base + i]));
+        if (base + i < n) agg_push(local, c[i]);
     }
     Agg total;
     block_exclusive_scan<SCAN_THREADS>(local, total, warp_tot);
     if (threadIdx.x == 0) tile_agg[blockIdx.x] = total;
 }
 
-// single block: exclusive scan of the tile aggregates in place + totals. The aggregates are taken in
-// batches of AGGSCAN_ITEMS consecutive ones per thread, each batch scanned across the block and
-// chained to the next through a running carry.
+// Exclusive scan of the tile aggregates in place + totals, in three small launches: every block
+// scans AGGSCAN_THREADS aggregates and leaves its total; one block scans the block totals; every
+// block adds its prefix.
 constexpr int AGGSCAN_THREADS = 1024;
-constexpr int AGGSCAN_ITEMS = 4;
 __global__ void __launch_bounds__(AGGSCAN_THREADS)
-k_scan_aggregates(Agg* __restrict__ tile_agg, u64 ntiles, CompressTotals* tot)
+k_scan_aggregates_local(Agg* __restrict__ tile_agg, u64 ntiles, Agg* __restrict__ block_tot)
+{
+    __shared__ Agg warp_tot[AGGSCAN_THREADS / 32];
+    const u64 i = (u64)blockIdx.x * AGGSCAN_THREADS + threadIdx.x;
+    const Agg mine = i < ntiles ? tile_agg[i] : agg_identity();
+    Agg total;
+    const Agg exc = block_exclusive_scan<AGGSCAN_THREADS>(mine, total, warp_tot);
+    if (i < ntiles) tile_agg[i] = exc;
+    if (threadIdx.x == 0) block_tot[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(AGGSCAN_THREADS)
+k_scan_aggregates_top(Agg* __restrict__ block_tot, u64 nblocks, CompressTotals* tot)
 {
     __shared__ Agg warp_tot[AGGSCAN_THREADS / 32];
     Agg carry = agg_identity();
-    for (u64 base = 0; base < ntiles; base += (u64)AGGSCAN_THREADS * AGGSCAN_ITEMS) {
-        const u64 i0 = base + (u64)threadIdx.x * AGGSCAN_ITEMS;
-        Agg v[AGGSCAN_ITEMS];
-        Agg local = agg_identity();
-#pragma unroll
-        for (int j = 0; j < AGGSCAN_ITEMS; ++j) {
-            v[j] = i0 + j < ntiles ? tile_agg[i0 + j] : agg_identity();
-            local = agg_combine(local, v[j]);
-        }
+    for (u64 base = 0; base < nblocks; base += AGGSCAN_THREADS) {
+        const u64 i = base + threadIdx.x;
+        const Agg mine = i < nblocks ? block_tot[i] : agg_identity();
         Agg total;
-        Agg run = agg_combine(carry, block_exclusive_scan<AGGSCAN_THREADS>(local, total, warp_tot));
-#pragma unroll
-        for (int j = 0; j < AGGSCAN_ITEMS; ++j) {
-            if (i0 + j < ntiles) tile_agg[i0 + j] = run;
-            run = agg_combine(run, v[j]);
-        }
+        const Agg exc = block_exclusive_scan<AGGSCAN_THREADS>(mine, total, warp_tot);
+        if (i < nblocks) block_tot[i] = agg_combine(carry, exc);
         carry = agg_combine(carry, total);
     }
     if (threadIdx.x == 0) {
         tot->payload_bytes = carry.heads ? carry.bytes + ceil8(carry.post_bits) : 0;
         tot->heads = carry.heads;
     }
+}
+__global__ void __launch_bounds__(AGGSCAN_THREADS)
+k_scan_aggregates_apply(Agg* __restrict__ tile_agg, u64 ntiles, const Agg* __restrict__ block_tot)
+{
+    const u64 i = (u64)blockIdx.x * AGGSCAN_THREADS + threadIdx.x;
+    if (i < ntiles) tile_agg[i] = agg_combine(block_tot[blockIdx.x], tile_agg[i]);
 }
 
 // ---- byte/bit writers into the zero-initialised payload (all writes are ORs, so ragged
@@ -400,14 +438,11 @@ k_write_payload(const u32* __restrict__ codes, const u32* __restrict__ stems, u6
     __shared__ Agg warp_tot[SCAN_THREADS / 32];
     const u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
     u32 c[SCAN_ITEMS];
+    load_codes(codes, base, n, c);
     Agg local = agg_identity();
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        c[i] = 1u << 31;  // harmless zero-bit continuation for out-of-range slots
-        if (base + i < n) {
-            c[i] = codes[base + i];
-            local = agg_combine(local, agg_of_code(c[i]));
-        }
+        if (base + i < n) agg_push(local, c[i]);
     }
     Agg total;
     const Agg exc = block_exclusive_scan<SCAN_THREADS>(local, total, warp_tot);
@@ -624,9 +659,13 @@ void launch_tile_aggregate(const u32* codes, u64 n, Agg* tile_agg, cudaStream_t 
     if (n == 0) return;
     k_tile_aggregate<<<(unsigned)scan_tiles(n), SCAN_THREADS, 0, s>>>(codes, n, tile_agg);
 }
-void launch_scan_aggregates(Agg* tile_agg, u64 ntiles, CompressTotals* tot, cudaStream_t s)
+u64 scan_blocks(u64 ntiles) { return (ntiles + AGGSCAN_THREADS - 1) / AGGSCAN_THREADS; }
+void launch_scan_aggregates(Agg* tile_agg, u64 ntiles, Agg* block_tot, CompressTotals* tot, cudaStream_t s)
 {
-    k_scan_aggregates<<<1, AGGSCAN_THREADS, 0, s>>>(tile_agg, ntiles, tot);
+    const u64 nb = scan_blocks(ntiles);
+    if (nb > 0) k_scan_aggregates_local<<<(unsigned)nb, AGGSCAN_THREADS, 0, s>>>(tile_agg, ntiles, block_tot);
+    k_scan_aggregates_top<<<1, AGGSCAN_THREADS, 0, s>>>(block_tot, nb, tot);
+    if (nb > 0) k_scan_aggregates_apply<<<(unsigned)nb, AGGSCAN_THREADS, 0, s>>>(tile_agg, ntiles, block_tot);
 }
 void launch_write_payload(const u32* codes, const u32* stems, u64 n, const Agg* tile_prefix, u32* payload,
                           u64* head_off, cudaStream_t s)

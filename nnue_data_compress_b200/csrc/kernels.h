@@ -15,7 +15,8 @@ void launch_walk_items(const void* d_bin, u64 n, u32* codes, u32* stems, Compres
                        u32* park_list, u64* park_count, cudaStream_t s);
 u64 scan_tiles(u64 n);
 void launch_tile_aggregate(const u32* codes, u64 n, Agg* tile_agg, cudaStream_t s);
-void launch_scan_aggregates(Agg* tile_agg, u64 ntiles, CompressTotals* tot, cudaStream_t s);
+u64 scan_blocks(u64 ntiles);  // entries of the block_tot scratch
+void launch_scan_aggregates(Agg* tile_agg, u64 ntiles, Agg* block_tot, CompressTotals* tot, cudaStream_t s);
 void launch_write_payload(const u32* codes, const u32* stems, u64 n, const Agg* tile_prefix, u32* payload,
                           u64* head_off, cudaStream_t s);
 void launch_chunk_orbit(const u64* head_off, u64 heads, u32* next, CompressTotals* tot, u64* seg_off, u64 max_chunks, u64 base,
