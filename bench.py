@@ -330,24 +330,15 @@ def main():
         d_slice = torch.empty(cap_guess, dtype=torch.uint8, device=dev)
         slice_info = {}
 
-        def orbit(base, carry):
-            a, f, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
-            check(L.nnp_shard_compress_orbit(base, carry, ctypes.byref(a), ctypes.byref(f), ctypes.byref(c)), "orbit")
-            return a.value, f.value, c.value
-
-        def emit(next_start):
-            got = ctypes.c_size_t(0)
-            check(L.nnp_shard_compress_emit_dev(next_start, ctypes.c_void_p(d_slice.data_ptr()), cap_guess, ctypes.byref(got)),
-                  "emit")
-            return got.value
+        calls = nnp.ShardCalls(d_slice, dev)
 
         def one_file():
-            info = nnp.ShardInfo()
-            check(L.nnp_shard_compress_begin_dev(ctypes.c_void_p(d_buf.data_ptr()), d_buf.numel() // 40, own_lo, own_lo + n_pos,
-                                                 int(rank == world - 1), ctypes.byref(info)), "shard begin")
+            calls.begin(d_buf, d_buf.numel() // 40, own_lo, own_lo + n_pos, rank == world - 1)
+            info_bytes = calls.last_payload_bytes
             L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
             dom = t_dom.value
-            got, off, total = compress_sharded(info.payload_bytes, orbit, emit, device=dev)
+            got, off, total = compress_sharded(info_bytes, calls.orbit, calls.emit, device=dev, table=calls.table,
+                                               resolve=calls.resolve)
             slice_info.update(bytes=got, offset=off, file_bytes=total)
             return dom
 

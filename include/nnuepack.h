@@ -145,6 +145,20 @@ int nnp_shard_compress_orbit(uint64_t payload_base, uint64_t carry_in, uint64_t*
 /* d_out == NULL: *out_bytes = size of the slice (payload_bytes + 8 * n_chunk_starts). */
 int nnp_shard_compress_emit_dev(uint64_t next_start, void* d_out, size_t out_cap, size_t* out_bytes);
 
+/* Step 3 without the rank-order wait. The carry into a rank lies before its payload, so a chunk can
+ * only be entered at one of the chain heads of the rank's first MiB (at most 2^20 / 34 of them, the
+ * size of a chain being at least 34 bytes). nnp_shard_compress_table_dev() follows the flush rule from
+ * every such head to the end of the rank's payload and writes NNP_ORBIT_TABLE_ENTRIES entries of
+ * three uint64 {offset of the entry head in the rank's payload (~0 = unused), offset of the last chunk
+ * start, number of chunk starts} into d_table (device memory). The ranks all-gather their tables
+ * (0.7 MB each); nnp_shard_compress_resolve_dev() then replays the whole chain locally by table lookup
+ * and returns what nnp_shard_compress_orbit() and _emit_dev() need for this rank, plus the number of
+ * chunks of the whole file. */
+#define NNP_ORBIT_TABLE_ENTRIES 30848
+int nnp_shard_compress_table_dev(void* d_table);
+int nnp_shard_compress_resolve_dev(const void* d_tables, const uint64_t* payload_bytes, int world, int rank, uint64_t* carry_in,
+                                   uint64_t* chunks_before, uint64_t* next_start, uint64_t* total_chunks);
+
 /* ---- helpers around the path --------------------------------------------------------- */
 
 /* Number of positions a binpack holds = sum over chains of (1 + numPlies)

@@ -60,6 +60,7 @@ EXPORTS = [
     "nnp_binpack_count_dev", "nnp_generate_bin_dev", "nnp_last_timing", "nnp_decode_stats",
     "nnp_debug_config",
     "nnp_shard_compress_begin_dev", "nnp_shard_compress_orbit", "nnp_shard_compress_emit_dev",
+    "nnp_shard_compress_table_dev", "nnp_shard_compress_resolve_dev",
 ]
 
 
@@ -101,6 +102,8 @@ def lib() -> ctypes.CDLL:
                 "nnp_generate_bin_dev",
                 "nnp_shard_compress_begin_dev",
                 "nnp_shard_compress_emit_dev",
+                "nnp_shard_compress_table_dev",
+                "nnp_shard_compress_resolve_dev",
             ):
                 fn.argtypes = conv
                 fn.restype = ctypes.c_int
@@ -130,6 +133,10 @@ def lib() -> ctypes.CDLL:
         L.nnp_shard_compress_emit_dev.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t,
                                                   ctypes.POINTER(ctypes.c_size_t)]
         L.nnp_shard_compress_emit_dev.restype = ctypes.c_int
+        L.nnp_shard_compress_table_dev.argtypes = [ctypes.c_void_p]
+        L.nnp_shard_compress_table_dev.restype = ctypes.c_int
+        L.nnp_shard_compress_resolve_dev.argtypes = [ctypes.c_void_p, u64p, ctypes.c_int, ctypes.c_int, u64p, u64p, u64p, u64p]
+        L.nnp_shard_compress_resolve_dev.restype = ctypes.c_int
         L.nnp_debug_config.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
         L.nnp_debug_config.restype = ctypes.c_int
         L.nnp_decode_stats.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
@@ -152,6 +159,55 @@ def init(device: int | None = None) -> None:
     if rc != 0:
         raise NnpError(rc, lib().nnp_strerror(rc).decode() + " / " + lib().nnp_last_cuda_error().decode())
     _initialised = True
+
+
+class ShardCalls:
+    """The local calls of the sharded compressor (include/nnuepack.h) in the shape
+    sharding.compress_sharded() expects: orbit / emit / table / resolve as bound methods. `d_out` is the
+    device tensor the rank's slice is written to."""
+
+    def __init__(self, d_out, device=None):
+        self.d_out = d_out
+        self.device = device
+
+    @staticmethod
+    def _check(rc):
+        if rc != 0:
+            raise NnpError(rc, _strerror(rc))
+
+    def begin(self, d_records, n_records: int, own_lo: int, own_hi: int, reaches_eof: bool) -> ShardInfo:
+        info = ShardInfo()
+        self._check(lib().nnp_shard_compress_begin_dev(ctypes.c_void_p(d_records.data_ptr()), n_records, own_lo, own_hi,
+                                                      int(reaches_eof), ctypes.byref(info)))
+        self.last_payload_bytes = int(info.payload_bytes)
+        return info
+
+    def orbit(self, base: int, carry: int):
+        a, f, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(lib().nnp_shard_compress_orbit(base, carry, ctypes.byref(a), ctypes.byref(f), ctypes.byref(c)))
+        return a.value, f.value, c.value
+
+    def emit(self, next_start: int) -> int:
+        got = ctypes.c_size_t(0)
+        self._check(lib().nnp_shard_compress_emit_dev(next_start, ctypes.c_void_p(self.d_out.data_ptr()), self.d_out.numel(),
+                                                     ctypes.byref(got)))
+        return got.value
+
+    def table(self):
+        import torch
+
+        from .sharding import ORBIT_TABLE_ENTRIES
+
+        t = torch.empty(3 * ORBIT_TABLE_ENTRIES, dtype=torch.int64, device=self.device or self.d_out.device)
+        self._check(lib().nnp_shard_compress_table_dev(ctypes.c_void_p(t.data_ptr())))
+        return t
+
+    def resolve(self, tables, sizes, world: int, rank: int):
+        arr = (ctypes.c_uint64 * world)(*[int(v) for v in sizes])
+        c, b, nx, tot = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(lib().nnp_shard_compress_resolve_dev(ctypes.c_void_p(tables.data_ptr()), arr, world, rank, ctypes.byref(c),
+                                                        ctypes.byref(b), ctypes.byref(nx), ctypes.byref(tot)))
+        return c.value, b.value, nx.value, tot.value
 
 
 def use_torch_stream() -> None:

@@ -165,7 +165,8 @@ int build_payload(const u32* codes, const u32* stems, u64 n, PayloadPlan& P)
     P.seg_off = seg_off;
     CK(cudaMemsetAsync(payload, 0, P.payload_bytes + 64, s));
     launch_write_payload(codes, stems, n, tile_agg, payload, head_off, s);
-    LAUNCHED(1, "k_write_payload");
+    launch_head_next(head_off, P.heads, head_next, d_tot, s);
+    LAUNCHED(2, "k_write_payload");
     return NNP_OK;
 }
 
@@ -175,8 +176,8 @@ int run_orbit(const PayloadPlan& P, u64 base, u64 carry, u64* chunks)
     Context& C = g_ctx;
     cudaStream_t s = C.stream;
     CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
-    launch_chunk_orbit(P.head_off, P.heads, P.head_next, P.d_tot, P.seg_off, P.max_chunks, base, carry, s);
-    LAUNCHED(2, "k_chunk_orbit");
+    launch_chunk_orbit(P.head_off, P.head_next, P.d_tot, P.seg_off, P.max_chunks, base, carry, s);
+    LAUNCHED(1, "k_chunk_orbit");
     CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     *chunks = h_tot->chunks;
@@ -422,6 +423,40 @@ int shard_orbit(u64 payload_base, u64 carry_in, u64* n_starts, u64* first_start,
         *first_start = payload_base + h_u64[0];
         *carry_out = payload_base + h_u64[1];
     }
+    return NNP_OK;
+}
+
+int shard_table_dev(void* d_table)
+{
+    if (!g_shard.active) return NNP_ERR_BAD_ARG;
+    Context& C = g_ctx;
+    if ((uintptr_t)d_table & 7) return NNP_ERR_BAD_ARG;
+    if (g_shard.plan.payload_bytes == 0) {
+        CK(cudaMemsetAsync(d_table, 0xFF, (size_t)NNP_ORBIT_TABLE_ENTRIES * 24, C.stream));
+    } else {
+        launch_orbit_table(g_shard.plan.head_off, g_shard.plan.head_next, g_shard.plan.d_tot, (u64*)d_table,
+                           NNP_ORBIT_TABLE_ENTRIES, C.stream);
+        LAUNCHED(1, "k_orbit_table");
+    }
+    CK(cudaStreamSynchronize(C.stream));
+    return NNP_OK;
+}
+
+int shard_resolve_dev(const void* d_tables, const uint64_t* payload_bytes, int world, int rank, uint64_t* out5)
+{
+    Context& C = g_ctx;
+    if (world <= 0 || rank < 0 || rank >= world) return NNP_ERR_BAD_ARG;
+    WS(WS_TEXT_C, (size_t)world * 8 + 128, u64, d_sizes);
+    if (world > 128) return NNP_ERR_BAD_ARG;  // the pinned scratch holds 128 sizes
+    u64* h_sizes = reinterpret_cast<u64*>((char*)C.pinned + 2560);
+    for (int r = 0; r < world; ++r) h_sizes[r] = payload_bytes[r];
+    CK(cudaMemcpyAsync(d_sizes, h_sizes, (size_t)world * 8, cudaMemcpyHostToDevice, C.stream));
+    launch_orbit_resolve((const u64*)d_tables, NNP_ORBIT_TABLE_ENTRIES, d_sizes, world, rank, d_sizes + world, C.stream);
+    LAUNCHED(1, "k_orbit_resolve");
+    u64* h_out = reinterpret_cast<u64*>((char*)C.pinned + 768);
+    CK(cudaMemcpyAsync(h_out, d_sizes + world, 40, cudaMemcpyDeviceToHost, C.stream));
+    CK(cudaStreamSynchronize(C.stream));
+    for (int i = 0; i < 5; ++i) out5[i] = h_out[i];
     return NNP_OK;
 }
 
@@ -1184,6 +1219,27 @@ int nnp_shard_compress_emit_dev(uint64_t next_start, void* d_out, size_t out_cap
 {
     REQUIRE_READY();
     return shard_emit_dev(next_start, d_out, out_cap, out_bytes);
+}
+int nnp_shard_compress_table_dev(void* d_table)
+{
+    std::lock_guard<std::mutex> lock_(g_mutex);
+    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    if (!d_table) return NNP_ERR_BAD_ARG;
+    return shard_table_dev(d_table);
+}
+int nnp_shard_compress_resolve_dev(const void* d_tables, const uint64_t* payload_bytes, int world, int rank, uint64_t* carry_in,
+                                   uint64_t* chunks_before, uint64_t* next_start, uint64_t* total_chunks)
+{
+    std::lock_guard<std::mutex> lock_(g_mutex);
+    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    if (!d_tables || !payload_bytes || !carry_in || !chunks_before || !next_start || !total_chunks) return NNP_ERR_BAD_ARG;
+    uint64_t out5[5] = {0, 0, 0, 0, 0};
+    const int rc = shard_resolve_dev(d_tables, payload_bytes, world, rank, out5);
+    *carry_in = out5[0];
+    *chunks_before = out5[1];
+    *next_start = out5[2];
+    *total_chunks = out5[3];
+    return rc;
 }
 
 int nnp_debug_config(const char* key, uint64_t value)

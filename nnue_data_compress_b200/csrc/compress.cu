@@ -569,6 +569,71 @@ k_chunk_orbit(const u64* __restrict__ head_off, const u32* __restrict__ next, Co
     }
 }
 
+// Orbit table of a shard (sharded compression): a chunk can only be entered within the first MiB of a
+// shard's payload (the carry lies before the shard), i.e. at a head whose predecessor starts below
+// 2^20. For every such entry head the orbit is followed to the end of the shard, which turns the
+// rank-order carry chain into table lookups: entry e -> (offset of e, offset of the last chunk start,
+// number of chunk starts). Unused entries hold first_local = ~0.
+__global__ void __launch_bounds__(128)
+k_orbit_table(const u64* __restrict__ head_off, const u32* __restrict__ next, const CompressTotals* __restrict__ tot,
+              u64* __restrict__ table, u64 entries)
+{
+    const u64 e = (u64)blockIdx.x * 128 + threadIdx.x;
+    if (e >= entries) return;
+    const u64 H = tot->heads;
+    u64 first = ~0ull, last = 0, count = 0;
+    if (e < H && (e == 0 || head_off[e - 1] < CHUNK_THRESHOLD)) {
+        first = head_off[e];
+        for (u64 cur = e; cur < H; cur = next[cur]) {
+            last = head_off[cur];
+            ++count;
+        }
+    }
+    table[3 * e] = first;
+    table[3 * e + 1] = last;
+    table[3 * e + 2] = count;
+}
+
+// The carry chain over the gathered tables of all ranks, for rank `rank`: out[0] = carry into the
+// rank (NO_CARRY if no chunk was opened before it), out[1] = chunks opened before it, out[2] = offset
+// of the first chunk start behind the rank's own last one (the total payload size if none),
+// out[3] = chunks of the whole file, out[4] = 1 if a chunk starts inside the rank's payload.
+__global__ void k_orbit_resolve(const u64* __restrict__ tables, u64 entries, const u64* __restrict__ sizes, int world, int rank,
+                                u64* __restrict__ out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    u64 base = 0, carry = NO_CARRY, chunks = 0, next_start = ~0ull;
+    u64 my_carry = NO_CARRY, my_before = 0, my_has = 0;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { my_carry = carry; my_before = chunks; }
+        const u64* t = tables + (u64)r * entries * 3;
+        if (sizes[r] != 0) {
+            u64 target = 0;
+            if (carry != NO_CARRY) {
+                const u64 g = carry + CHUNK_THRESHOLD;
+                target = g > base ? g - base : 0;
+            }
+            u64 lo = 0, hi = entries;  // first entry with first_local >= target (padding is ~0)
+            while (lo < hi) {
+                const u64 mid = (lo + hi) >> 1;
+                if (t[3 * mid] >= target) hi = mid; else lo = mid + 1;
+            }
+            if (lo < entries && t[3 * lo] != ~0ull) {
+                if (r > rank && next_start == ~0ull) next_start = base + t[3 * lo];
+                if (r == rank) my_has = 1;
+                carry = base + t[3 * lo + 1];
+                chunks += t[3 * lo + 2];
+            }
+        }
+        base += sizes[r];
+    }
+    out[0] = my_carry;
+    out[1] = my_before;
+    out[2] = next_start == ~0ull ? base : next_start;
+    out[3] = chunks;
+    out[4] = my_has;
+}
+
 // ------------------------------------------------------------------ chunk emission
 // grid = (EMIT_BLOCKS_PER_CHUNK, 1 + chunks): segment 0 is copied as it is, segment 1 + k behind its
 // 8-byte header 'B','I','N','P',LE32(size) (:486-498). Source and destination of a segment differ by
@@ -673,11 +738,22 @@ void launch_write_payload(const u32* codes, const u32* stems, u64 n, const Agg* 
     if (n == 0) return;
     k_write_payload<<<(unsigned)scan_tiles(n), SCAN_THREADS, 0, s>>>(codes, stems, n, tile_prefix, payload, head_off);
 }
-void launch_chunk_orbit(const u64* head_off, u64 heads, u32* next, CompressTotals* tot, u64* seg_off, u64 max_chunks, u64 base,
-                        u64 carry, cudaStream_t s)
+void launch_head_next(const u64* head_off, u64 heads, u32* next, CompressTotals* tot, cudaStream_t s)
 {
     if (heads > 0) k_head_next<<<(unsigned)((heads + 255) / 256), 256, 0, s>>>(head_off, tot, next);
+}
+void launch_chunk_orbit(const u64* head_off, const u32* next, CompressTotals* tot, u64* seg_off, u64 max_chunks, u64 base,
+                        u64 carry, cudaStream_t s)
+{
     k_chunk_orbit<<<1, 32, 0, s>>>(head_off, next, tot, seg_off, max_chunks, base, carry);
+}
+void launch_orbit_table(const u64* head_off, const u32* next, const CompressTotals* tot, u64* table, u64 entries, cudaStream_t s)
+{
+    k_orbit_table<<<(unsigned)((entries + 127) / 128), 128, 0, s>>>(head_off, next, tot, table, entries);
+}
+void launch_orbit_resolve(const u64* tables, u64 entries, const u64* sizes, int world, int rank, u64* out, cudaStream_t s)
+{
+    k_orbit_resolve<<<1, 32, 0, s>>>(tables, entries, sizes, world, rank, out);
 }
 void launch_emit_chunks(const void* payload, const u64* seg_off, u64 chunks, void* out, u64 last_size, cudaStream_t s)
 {

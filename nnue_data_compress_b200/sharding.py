@@ -85,12 +85,19 @@ def shard_window(n_records: int, world: int, rank: int, overlap: int):
     return g0, g1, lo - g0, hi - g0, g1 == n_records
 
 
-def compress_sharded(payload_bytes: int, orbit, emit, device=None, group=None):
+ORBIT_TABLE_ENTRIES = 30848  # NNP_ORBIT_TABLE_ENTRIES (include/nnuepack.h)
+
+
+def compress_sharded(payload_bytes: int, orbit, emit, device=None, group=None, table=None, resolve=None):
     """The exchange steps 2-4 of the sharded compressor around a rank's local calls.
 
     ``payload_bytes``: from nnp_shard_compress_begin_dev (step 1, done by the caller).
     ``orbit(payload_base, carry_in) -> (n_chunk_starts, first_start, carry_out)`` and
     ``emit(next_start) -> result`` wrap nnp_shard_compress_orbit / nnp_shard_compress_emit_dev.
+    With ``table() -> int64 tensor of 3 * ORBIT_TABLE_ENTRIES`` and ``resolve(tables, sizes, world, rank) ->
+    (carry_in, chunks_before, next_start, total_chunks)`` (nnp_shard_compress_table_dev / _resolve_dev) the
+    rank-order carry is replaced by one all-gather of the ranks' orbit tables; without them the carry
+    travels from rank to rank (16 bytes per hop).
     Returns (emit's result, file offset of this rank's slice, total file bytes)."""
     import torch
     import torch.distributed as dist
@@ -112,11 +119,24 @@ def compress_sharded(payload_bytes: int, orbit, emit, device=None, group=None):
     bases = offsets_from_sizes(sizes)
     total_payload = sum(sizes)
 
-    # the chunk-flush rule in rank order: (offset of the last chunk start or -1, chunks so far)
+    if table is not None and resolve is not None:
+        mine = table()
+        if world == 1:
+            tables = mine
+        else:
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine, group=group)
+            tables = torch.cat(parts)
+        carry_in, chunks_before, next_start, total_chunks = resolve(tables, sizes, world, rank)
+        orbit(bases[rank], carry_in)
+        result = emit(next_start)
+        return result, bases[rank] + 8 * chunks_before, total_payload + 8 * total_chunks
+
     def p2p(op, tensor, peer):
         for req in dist.batch_isend_irecv([dist.P2POp(op, tensor, peer, group=group)]):
             req.wait()
 
+    # the chunk-flush rule in rank order: (offset of the last chunk start or -1, chunks so far)
     carry, chunks_before = -1, 0
     if rank > 0:
         buf = torch.zeros(2, dtype=torch.int64, device=device)

@@ -64,3 +64,55 @@ class OracleShard:
                 size = next_start - (self.base + cuts[k])
             out += b"BINP" + size.to_bytes(4, "little") + self.payload[cuts[k]:cuts[k + 1]]
         return bytes(out)
+
+    # -- the table form of the carry chain (nnp_shard_compress_table_dev / _resolve_dev) ----------
+
+    def table(self):
+        import torch
+
+        from nnue_data_compress_b200.sharding import ORBIT_TABLE_ENTRIES
+
+        nxt = []
+        for h, off in enumerate(self.head_off):
+            j = h + 1
+            while j < len(self.head_off) and self.head_off[j] - off < THRESHOLD:
+                j += 1
+            nxt.append(j)
+        rows = []
+        for e in range(ORBIT_TABLE_ENTRIES):
+            if e < len(self.head_off) and (e == 0 or self.head_off[e - 1] < THRESHOLD):
+                cur, last, count = e, 0, 0
+                while cur < len(self.head_off):
+                    last = self.head_off[cur]
+                    count += 1
+                    cur = nxt[cur]
+                rows += [self.head_off[e], last, count]
+            else:
+                rows += [-1, 0, 0]
+        return torch.tensor(rows, dtype=torch.int64)
+
+    @staticmethod
+    def resolve(tables, sizes, world, rank):
+        from nnue_data_compress_b200.sharding import ORBIT_TABLE_ENTRIES
+
+        t = tables.tolist()
+        base, carry, chunks, next_start = 0, None, 0, None
+        mine = None
+        for r in range(world):
+            if r == rank:
+                mine = (NO_CARRY if carry is None else carry, chunks)
+            if sizes[r]:
+                target = 0 if carry is None else max(carry + THRESHOLD - base, 0)
+                rows = t[r * ORBIT_TABLE_ENTRIES * 3:(r + 1) * ORBIT_TABLE_ENTRIES * 3]
+                for e in range(ORBIT_TABLE_ENTRIES):
+                    first = rows[3 * e]
+                    if first < 0:
+                        break
+                    if first >= target:
+                        if r > rank and next_start is None:
+                            next_start = base + first
+                        carry = base + rows[3 * e + 1]
+                        chunks += rows[3 * e + 2]
+                        break
+            base += sizes[r]
+        return mine[0], mine[1], base if next_start is None else next_start, chunks

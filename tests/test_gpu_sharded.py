@@ -47,6 +47,26 @@ def _sharded(nnp, b, world, overlap):
         ns, first, carry = orbit(bases[r], carry)
         chunks += ns
         firsts.append(first)
+    # the table form of the carry chain must agree with the rank-order chain for every rank
+    import torch as _torch
+
+    from nnue_data_compress_b200.sharding import ORBIT_TABLE_ENTRIES
+
+    tables = []
+    for r in range(world):
+        begin(r)
+        t = _torch.empty(3 * ORBIT_TABLE_ENTRIES, dtype=_torch.int64, device="cuda")
+        assert L.nnp_shard_compress_table_dev(ctypes.c_void_p(t.data_ptr())) == 0
+        tables.append(t)
+    all_tables = _torch.cat(tables)
+    arr = (ctypes.c_uint64 * world)(*sizes)
+    for r in range(world):
+        c, b2, nx, tot = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        assert L.nnp_shard_compress_resolve_dev(ctypes.c_void_p(all_tables.data_ptr()), arr, world, r, ctypes.byref(c),
+                                                ctypes.byref(b2), ctypes.byref(nx), ctypes.byref(tot)) == 0
+        later = [f for f in firsts[r + 1:] if f != NO_CARRY]
+        assert (c.value, b2.value, tot.value) == (carry_in[r], chunks_before[r], chunks), r
+        assert nx.value == (later[0] if later else total_payload), r
     out = bytearray(total_payload + 8 * chunks)
     for r in range(world):
         begin(r)

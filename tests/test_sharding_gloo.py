@@ -105,7 +105,7 @@ def test_shard_bounds_cover_everything():
 # one .binpack from several ranks, byte-identical to a single run
 
 
-def _worker_one_file(rank, world, port, tmpdir, name, overlap, small_threshold):
+def _worker_one_file(rank, world, port, tmpdir, name, overlap, small_threshold, use_table):
     import torch.distributed as dist
 
     sys.path.insert(0, ROOT)
@@ -124,7 +124,8 @@ def _worker_one_file(rank, world, port, tmpdir, name, overlap, small_threshold):
         n = len(b) // 40
         g0, g1, lo, hi, eof = shard_window(n, world, rank, overlap)
         sh = shardsim.OracleShard(b[g0 * 40:g1 * 40], lo, hi, eof)
-        data, off, total = compress_sharded(sh.payload_bytes, sh.orbit, sh.emit)
+        extra = dict(table=sh.table, resolve=sh.resolve) if use_table else {}
+        data, off, total = compress_sharded(sh.payload_bytes, sh.orbit, sh.emit, **extra)
         with open(os.path.join(tmpdir, f"slice{rank}"), "wb") as f:
             f.write(off.to_bytes(8, "little") + total.to_bytes(8, "little") + data)
         dist.barrier()
@@ -132,9 +133,10 @@ def _worker_one_file(rank, world, port, tmpdir, name, overlap, small_threshold):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("use_table", [False, True])
 @pytest.mark.parametrize("name,world,overlap", [("twochunks.bin", 2, 64), ("twochunks.bin", 3, 8), ("games100.bin", 3, 128),
                                                ("long400.bin", 3, 500), ("restart.bin", 2, 200)])
-def test_ranks_write_one_file(tmp_path, name, world, overlap):
+def test_ranks_write_one_file(tmp_path, name, world, overlap, use_table):
     """The rank orchestration (all-gather of payload sizes, carry of the chunk-flush rule in rank
     order, all-gather of first chunk starts) with the oracle standing in for the CUDA entry points:
     the slices assembled at their offsets are the single-run .binpack of the whole input."""
@@ -143,7 +145,7 @@ def test_ranks_write_one_file(tmp_path, name, world, overlap):
     from refutil import BIN_TO_BINPACK, golden, oracle_convert
 
     port = _free_port()
-    mp.spawn(_worker_one_file, args=(world, port, str(tmp_path), name, overlap, 0), nprocs=world, join=True)
+    mp.spawn(_worker_one_file, args=(world, port, str(tmp_path), name, overlap, 0, use_table), nprocs=world, join=True)
     rc, expect = oracle_convert(BIN_TO_BINPACK, golden(name))
     assert rc == 0
     out = bytearray(len(expect))

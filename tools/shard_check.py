@@ -38,25 +38,13 @@ def main():
     parts = ([tails[rank - 1]] if rank > 0 else []) + [own] + ([heads[rank + 1]] if rank < world - 1 else [])
     buf = torch.cat(parts)
     lo = 1 if rank > 0 else 0
-    info = nnp.ShardInfo()
-    rc = L.nnp_shard_compress_begin_dev(ctypes.c_void_p(buf.data_ptr()), buf.numel() // 40, lo, lo + n, int(rank == world - 1),
-                                        ctypes.byref(info))
-    assert rc == 0, rc
-
-    def orbit(base, carry):
-        a, f, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
-        assert L.nnp_shard_compress_orbit(base, carry, ctypes.byref(a), ctypes.byref(f), ctypes.byref(c)) == 0
-        return a.value, f.value, c.value
-
-    def emit(next_start):
-        need = ctypes.c_size_t(0)
-        assert L.nnp_shard_compress_emit_dev(next_start, None, 0, ctypes.byref(need)) == 0
-        out = torch.empty(max(need.value, 8), dtype=torch.uint8, device=dev)
-        got = ctypes.c_size_t(0)
-        assert L.nnp_shard_compress_emit_dev(next_start, ctypes.c_void_p(out.data_ptr()), need.value, ctypes.byref(got)) == 0
-        return out[: got.value]
-
-    piece, off, total = compress_sharded(info.payload_bytes, orbit, emit, device=dev)
+    use_table = os.environ.get("SHARD_TABLE", "1") == "1"
+    d_slice = torch.empty(max(buf.numel() // 8 + (1 << 20) if plies > 20 else buf.numel() + (1 << 20), 8), dtype=torch.uint8, device=dev)
+    calls = nnp.ShardCalls(d_slice, dev)
+    info = calls.begin(buf, buf.numel() // 40, lo, lo + n, rank == world - 1)
+    extra = dict(table=calls.table, resolve=calls.resolve) if use_table else {}
+    got, off, total = compress_sharded(info.payload_bytes, calls.orbit, calls.emit, device=dev, **extra)
+    piece = d_slice[:got]
     # assemble on rank 0 and compare with one single-GPU run over all records
     sizes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([piece.numel(), off], dtype=torch.int64, device=dev))
@@ -81,7 +69,7 @@ def main():
             ln, o = int(sizes[r][0]), int(sizes[r][1])
             asm[o:o + ln] = pieces[r][:ln]
         ok = sz.value == total and torch.equal(asm, ref[: sz.value])
-        print(f"SHARD_CHECK world={world} positions={n * world} plies={plies} file_bytes={total} "
+        print(f"SHARD_CHECK world={world} positions={n * world} plies={plies} table={use_table} file_bytes={total} "
               f"{'IDENTICAL' if ok else 'MISMATCH'} to the single-GPU run", flush=True)
     dist.barrier()
     dist.destroy_process_group()
