@@ -806,7 +806,7 @@ __device__ __forceinline__ bool decode_ply(BitReader& r, const Pos& p, int& last
         v |= (block & 15u) << off;
         if (!(block >> 4) || r.overrun) break;
         off += 4;
-        if (off > 28) { if (strict) return false; off = 28; }
+        if (off > 28) return false;  // a ninth block: the reference shifts a 16-bit value by 32 (undefined); no encoder emits it
     }
     score = (int)(short)(last_score + zz_dec(v & 0xFFFFu));
     last_score = (int)(short)(-score);
