@@ -625,16 +625,19 @@ k_emit_chains_text(const unsigned char* __restrict__ in, ChunkTable tab, const u
                    const u32* __restrict__ cand_off, const u32* __restrict__ cand_base, const u64* __restrict__ cand_tbase,
                    u64 ncand, const u64* __restrict__ chunk_tbase, unsigned char* __restrict__ out, DecompressTotals* tot)
 {
+    __shared__ uint4 windows[4 * EMITC_THREADS];
     const u64 i = (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
     if (i >= ncand) return;
     if (cand_base[i] == 0xFFFFFFFFu) return;
     const u32 c = cand_chunk[i], off = cand_off[i];
     const unsigned char* s = in + tab.start[c] + off;
-    WriteSink sink{out + chunk_tbase[c] + cand_tbase[i]};
+    BufferedSink sink;
+    sink.init(out + chunk_tbase[c] + cand_tbase[i], windows + threadIdx.x, EMITC_THREADS);
     u32 consumed = 0;
     const bool ok = walk_chain(s, tab.len[c] - off - 34,
                                [&](const ChainCursor& cc, u32) { put_plain_entry(sink, cc.pos, cc.mv, cc.score, cc.ply, cc.result); },
                                consumed);
+    sink.finish();
     if (!ok) atomicMin(&tot->error_chunk, (u64)c);
 }
 

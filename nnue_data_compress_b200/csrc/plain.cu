@@ -292,11 +292,13 @@ k_entries_to_bin(const Entry* __restrict__ entries, u64 n, unsigned char* __rest
 
 // ------------------------------------------------------------------ text out: .bin -> .plain
 
+constexpr int BIN_TEXT_THREADS = 128;
 template <bool WRITE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(BIN_TEXT_THREADS)
 k_bin_text(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ lens, const u64* __restrict__ offs,
            unsigned char* __restrict__ out, CompressTotals* tot)
 {
+    __shared__ uint4 windows[WRITE ? 4 * BIN_TEXT_THREADS : 1];
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u32* w = reinterpret_cast<const u32*>(bin + i * 40);
@@ -310,8 +312,10 @@ k_bin_text(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ lens,
     const Move mv = sfmove_to_move(w8 >> 16);
     const int score = (int)(short)(w8 & 0xFFFF), ply = (int)(w9 & 0xFFFF), result = (int)(signed char)((w9 >> 16) & 0xFF);
     if (WRITE) {
-        WriteSink s{out + offs[i]};
+        BufferedSink s;
+        s.init(out + offs[i], windows + threadIdx.x, BIN_TEXT_THREADS);
         put_plain_entry(s, p, mv, score, ply, result);
+        s.finish();
     } else {
         CountSink s;
         put_plain_entry(s, p, mv, score, ply, result);
