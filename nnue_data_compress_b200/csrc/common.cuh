@@ -98,4 +98,17 @@ struct PlainTotals {
     u64 committed;  // scratch for the flush-boundary orbit
 };
 
+#ifdef __CUDACC__
+// 16 bytes at p, zero-filled outside [lo, hi)
+__device__ __forceinline__ uint4 load16_clipped(const unsigned char* p, const unsigned char* lo, const unsigned char* hi)
+{
+    if (p >= lo && p + 16 <= hi) return *reinterpret_cast<const uint4*>(p);  // p is 16-byte aligned by construction
+    u32 w[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 16; ++i)
+        if (p + i >= lo && p + i < hi) w[i >> 2] |= (u32)p[i] << ((i & 3) * 8);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+#endif
+
 }  // namespace nnp

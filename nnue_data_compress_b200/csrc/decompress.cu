@@ -248,16 +248,6 @@ __device__ __forceinline__ u64 find_chunk(const u64* base, u64 chunks, u64 tile)
     return lo;
 }
 
-// 16 bytes at p, zero-filled outside [lo, hi)
-__device__ __forceinline__ uint4 load16_clipped(const unsigned char* p, const unsigned char* lo, const unsigned char* hi)
-{
-    if (p >= lo && p + 16 <= hi) return *reinterpret_cast<const uint4*>(p);  // p is 16-byte aligned by construction
-    u32 w[4] = {0, 0, 0, 0};
-    for (int i = 0; i < 16; ++i)
-        if (p + i >= lo && p + i < hi) w[i >> 2] |= (u32)p[i] << ((i & 3) * 8);
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
 // pass 0: tests every offset of the tile, stores the tile's flag bitmap (CAND_TILE / 32 words) and
 //         tile_count[tile].
 // Stage 1 looks at one byte per offset -- the high byte of the stem's rule50 field, which packEntry

@@ -193,11 +193,41 @@ __device__ __forceinline__ bool key_is(const Span& k, const char* lit, int n)
     return true;
 }
 
-__global__ void __launch_bounds__(128)
+// The block's records are contiguous text (about 105 bytes each): it is staged in shared memory with
+// 16-byte loads and parsed there, because byte-wise walking of global memory costs one sector
+// request per character and lane. Lines in front of the staged region (a record that inherits a
+// field from far back) and blocks whose text does not fit are read from global memory.
+constexpr int PARSE_THREADS = 128;
+constexpr int PARSE_STAGE = 32768;
+__global__ void __launch_bounds__(PARSE_THREADS)
 k_parse_records(const unsigned char* __restrict__ text, u64 n, const u64* __restrict__ rec_pos, u64 nrec,
                 Entry* __restrict__ entries, PlainTotals* tot)
 {
-    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(16) unsigned char stage[PARSE_STAGE + 32];
+    __shared__ u64 reg_lo_s, reg_hi_s;
+    const u64 r0 = (u64)blockIdx.x * PARSE_THREADS;
+    if (threadIdx.x == 0) {
+        const u64 r_last = r0 + PARSE_THREADS <= nrec ? r0 + PARSE_THREADS - 1 : nrec - 1;
+        u64 lo = r0 > 0 ? rec_pos[r0 - 1] : 0;
+        while (lo > 0 && text[lo - 1] != '\n') --lo;  // start of the previous terminator's line
+        u64 hi = rec_pos[r_last] + 1;
+        if (hi - lo > PARSE_STAGE) hi = lo;  // does not fit: everything from global memory
+        reg_lo_s = lo;
+        reg_hi_s = hi;
+    }
+    __syncthreads();
+    const u64 reg_lo = reg_lo_s, reg_hi = reg_hi_s;
+    const unsigned char* gbase = reinterpret_cast<const unsigned char*>(reinterpret_cast<uintptr_t>(text + reg_lo) & ~(uintptr_t)15);
+    const int delta = (int)((text + reg_lo) - gbase);
+    const int nvec = reg_hi > reg_lo ? (int)((delta + (reg_hi - reg_lo) + 15) >> 4) : 0;
+    for (int i = threadIdx.x; i < nvec; i += PARSE_THREADS)
+        reinterpret_cast<uint4*>(stage)[i] = load16_clipped(gbase + 16 * i, text, text + n);
+    __syncthreads();
+    // byte i of the text: staged copy if inside the region
+    const unsigned char* sbase = stage + delta - reg_lo;  // sbase + i is valid for reg_lo <= i < reg_hi
+    auto at = [&](u64 i) -> const unsigned char* { return (i >= reg_lo && i < reg_hi) ? sbase + i : text + i; };
+
+    const u64 r = r0 + threadIdx.x;
     if (r >= nrec) return;
     const u64 epos = rec_pos[r];
     const u64 stop_validate = r > 0 ? rec_pos[r - 1] : 0;  // every line down to here is checked
@@ -206,13 +236,15 @@ k_parse_records(const unsigned char* __restrict__ text, u64 n, const u64* __rest
     bool bad = false;
     // start of the terminator's line
     u64 cur = epos;
-    while (cur > 0 && text[cur - 1] != '\n') --cur;
+    while (cur > 0 && *at(cur - 1) != '\n') --cur;
     while (cur > 0 && (found != 31 || cur > stop_validate)) {
         const u64 le = cur - 1;  // the '\n' that ends the previous line
         u64 ls = le;
-        while (ls > 0 && text[ls - 1] != '\n') --ls;
+        while (ls > 0 && *at(ls - 1) != '\n') --ls;
         Span key, val;
-        const int kind = split_line(text + ls, text + le, key, val);
+        // a line lies entirely inside or entirely in front of the staged region (it starts at a line start)
+        const unsigned char* lp = at(ls);
+        const int kind = split_line(lp, lp + (le - ls), key, val);
         if (kind == 1 && !key_is(key, "e", 1)) bad = true;  // "key\nvalue": stream and line semantics differ
         if (kind == 2) {
             if (key_is(key, "fen", 3)) { if (!(found & 1)) { fen = val; found |= 1; } }
@@ -363,7 +395,7 @@ void launch_parse_records(const void* text, u64 n, const u64* rec_pos, u64 nrec,
                           cudaStream_t s)
 {
     if (nrec == 0) return;
-    k_parse_records<<<(unsigned)((nrec + 127) / 128), 128, 0, s>>>((const unsigned char*)text, n, rec_pos, nrec, entries, tot);
+    k_parse_records<<<(unsigned)((nrec + PARSE_THREADS - 1) / PARSE_THREADS), PARSE_THREADS, 0, s>>>((const unsigned char*)text, n, rec_pos, nrec, entries, tot);
 }
 void launch_entries_link_encode(const Entry* entries, u64 n, u32* codes, u32* stems, cudaStream_t s)
 {
