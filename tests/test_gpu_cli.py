@@ -1,0 +1,60 @@
+"""GPU suite: the native command line (nnue_data_compress_b200/nnue_data_compression, csrc/cli.cpp)
+run as a process on files, as a user of the reference tool would: same dispatch by extension, same
+bytes, `-a` appends, reference errors print their message and `Exiting...` with exit code 0."""
+import os
+import subprocess
+
+import pytest
+
+from refutil import BIN_TO_BINPACK, ROOT, golden, have_ref, ref_convert
+
+pytestmark = pytest.mark.gpu
+
+CLI = os.path.join(ROOT, "nnue_data_compress_b200", "nnue_data_compression")
+
+
+def _run(*args):
+    return subprocess.run([CLI, *args], capture_output=True, text=True, timeout=300)
+
+
+def test_cli_all_six_directions(tmp_path):
+    d = tmp_path
+    (d / "g.bin").write_bytes(golden("games100.bin"))
+    r = _run(str(d / "g.bin"), str(d / "g"))  # implied .binpack extension
+    assert r.returncode == 0 and "Compressing" in r.stdout
+    assert (d / "g.binpack").read_bytes() == golden("games100.binpack")
+    assert _run(str(d / "g.binpack"), str(d / "rt.bin")).returncode == 0
+    assert (d / "rt.bin").read_bytes() == golden("games100.rt.bin")
+    assert _run(str(d / "g.binpack"), str(d / "g.plain")).returncode == 0
+    assert (d / "g.plain").read_bytes() == golden("games100.plain")
+    assert _run(str(d / "g.plain"), str(d / "p.binpack")).returncode == 0
+    assert (d / "p.binpack").read_bytes() == golden("games100.p.binpack")
+    assert _run(str(d / "g.bin"), str(d / "b.plain")).returncode == 0
+    assert (d / "b.plain").read_bytes() == golden("games100.b.plain")
+    assert _run(str(d / "b.plain"), str(d / "p.bin")).returncode == 0
+    assert (d / "p.bin").read_bytes() == golden("games100.p.bin")
+
+
+def test_cli_append_and_errors(tmp_path):
+    d = tmp_path
+    (d / "a.bin").write_bytes(golden("heads.bin"))
+    (d / "b.bin").write_bytes(golden("long400.bin"))
+    assert _run(str(d / "a.bin"), str(d / "out.binpack")).returncode == 0
+    assert _run("-a", str(d / "b.bin"), str(d / "out.binpack")).returncode == 0
+    assert (d / "out.binpack").read_bytes() == golden("heads.binpack") + golden("long400.binpack")
+    # "--append" is stored as "-append" by the reference's readArgs and ignored: the file is replaced
+    assert _run("--append", str(d / "a.bin"), str(d / "out.binpack")).returncode == 0
+    assert (d / "out.binpack").read_bytes() == golden("heads.binpack")
+    bp = bytearray(golden("twochunks.binpack"))
+    second = 8 + int.from_bytes(bp[4:8], "little")
+    bp[second:second + 4] = b"BINX"
+    (d / "bad.binpack").write_bytes(bytes(bp))
+    r = _run(str(d / "bad.binpack"), str(d / "bad.bin"))
+    assert r.returncode == 0 and "Invalid binpack file or chunk." in r.stderr and "Exiting..." in r.stderr
+    if have_ref():
+        from refutil import BINPACK_TO_BIN
+
+        assert (d / "bad.bin").read_bytes() == ref_convert(BINPACK_TO_BIN, bytes(bp))
+    r = _run(str(d / "missing.bin"), str(d / "x"))
+    assert "Input file doesn't exist." in r.stderr and r.returncode == 0
+    assert _run("only_one_argument").returncode == 1
