@@ -159,6 +159,17 @@ int nnp_shard_compress_table_dev(void* d_table);
 int nnp_shard_compress_resolve_dev(const void* d_tables, const uint64_t* payload_bytes, int world, int rank, uint64_t* carry_in,
                                    uint64_t* chunks_before, uint64_t* next_start, uint64_t* total_chunks);
 
+/* ---- whole files of any size -----------------------------------------------------
+ * File-to-file forms of the two headline drivers for inputs that do not fit the device: the input is
+ * processed in slabs of about `slab_bytes` (0 = default: 2 GiB of records / 256 MiB of chunks).
+ * .bin -> .binpack visits the slabs with the sharded compressor above, one slab after the other, and
+ * writes exactly the file one reference run writes, whatever the slab size; .binpack -> .bin decodes
+ * groups of whole chunks. `append` != 0 appends to the output file (the tool's -a). *positions (may be
+ * NULL) receives the number of positions converted. The reference errors return their status after
+ * leaving in the file what the reference tool would have left. */
+int nnp_bin_to_binpack_file(const char* in_path, const char* out_path, int append, size_t slab_bytes, uint64_t* positions);
+int nnp_binpack_to_bin_file(const char* in_path, const char* out_path, int append, size_t slab_bytes, uint64_t* positions);
+
 /* ---- helpers around the path --------------------------------------------------------- */
 
 /* Number of positions a binpack holds = sum over chains of (1 + numPlies)

@@ -61,6 +61,7 @@ EXPORTS = [
     "nnp_debug_config",
     "nnp_shard_compress_begin_dev", "nnp_shard_compress_orbit", "nnp_shard_compress_emit_dev",
     "nnp_shard_compress_table_dev", "nnp_shard_compress_resolve_dev",
+    "nnp_bin_to_binpack_file", "nnp_binpack_to_bin_file",
 ]
 
 
@@ -97,7 +98,7 @@ def lib() -> ctypes.CDLL:
         conv = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         for name in EXPORTS:
             fn = getattr(L, name)
-            if name.endswith(("_to_binpack", "_to_bin", "_to_plain", "_dev")) and name not in (
+            if name.endswith(("_to_binpack", "_to_bin", "_to_plain", "_dev")) and not name.endswith("_file") and name not in (
                 "nnp_binpack_count_dev",
                 "nnp_generate_bin_dev",
                 "nnp_shard_compress_begin_dev",
@@ -133,6 +134,9 @@ def lib() -> ctypes.CDLL:
         L.nnp_shard_compress_emit_dev.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t,
                                                   ctypes.POINTER(ctypes.c_size_t)]
         L.nnp_shard_compress_emit_dev.restype = ctypes.c_int
+        for name in ("nnp_bin_to_binpack_file", "nnp_binpack_to_bin_file"):
+            getattr(L, name).argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_size_t, u64p]
+            getattr(L, name).restype = ctypes.c_int
         L.nnp_shard_compress_table_dev.argtypes = [ctypes.c_void_p]
         L.nnp_shard_compress_table_dev.restype = ctypes.c_int
         L.nnp_shard_compress_resolve_dev.argtypes = [ctypes.c_void_p, u64p, ctypes.c_int, ctypes.c_int, u64p, u64p, u64p, u64p]
@@ -159,6 +163,19 @@ def init(device: int | None = None) -> None:
     if rc != 0:
         raise NnpError(rc, lib().nnp_strerror(rc).decode() + " / " + lib().nnp_last_cuda_error().decode())
     _initialised = True
+
+
+def convert_file(direction: str, input_path: str, output_path: str, append: bool = False, slab_bytes: int = 0) -> int:
+    """File-to-file conversion in slabs (nnp_bin_to_binpack_file / nnp_binpack_to_bin_file): inputs of
+    any size. `direction` is "bin_to_binpack" or "binpack_to_bin". Returns the number of positions; a
+    reference error raises NnpError after the file holds what the reference would have left."""
+    _ensure_init()
+    fn = getattr(lib(), f"nnp_{direction}_file")
+    n = ctypes.c_uint64(0)
+    rc = fn(os.fsencode(input_path), os.fsencode(output_path), int(append), slab_bytes, ctypes.byref(n))
+    if rc != 0:
+        raise NnpError(rc, _strerror(rc))
+    return int(n.value)
 
 
 class ShardCalls:

@@ -70,6 +70,31 @@ void runDriver(driver_fn fn, const char* verb, const std::string& inputPath, con
     std::cout << "Processed " << n << " bytes into " << produced << " bytes.\n";
 }
 
+// Inputs above NNP_STREAM_THRESHOLD bytes (default 8 GiB) go through the slab-wise file drivers
+// (nnp_*_file): neither host nor device memory has to hold the whole file. NNP_SLAB_BYTES sets the
+// slab size (0 = the library's default).
+typedef int (*file_fn)(const char*, const char*, int, size_t, uint64_t*);
+
+bool runFileDriver(file_fn fn, const char* verb, const std::string& inputPath, const std::string& outputPath, bool append)
+{
+    std::ifstream in(inputPath, std::ios_base::binary | std::ios_base::ate);
+    const unsigned long long size = in ? static_cast<unsigned long long>(in.tellg()) : 0ull;
+    const char* t = std::getenv("NNP_STREAM_THRESHOLD");
+    const unsigned long long threshold = t ? std::strtoull(t, nullptr, 10) : (8ull << 30);
+    if (size <= threshold) return false;
+    const char* sl = std::getenv("NNP_SLAB_BYTES");
+    std::cout << verb << " " << inputPath << " to " << outputPath << '\n';
+    uint64_t positions = 0;
+    const int rc = fn(inputPath.c_str(), outputPath.c_str(), append ? 1 : 0, sl ? std::strtoull(sl, nullptr, 10) : 0, &positions);
+    if (rc == NNP_ERR_BAD_MAGIC || rc == NNP_ERR_CHUNK_TOO_LARGE || rc == NNP_ERR_BAD_SFEN) throw std::runtime_error(nnp_strerror(rc));
+    if (rc != NNP_OK) {
+        std::cerr << nnp_strerror(rc) << " " << nnp_last_cuda_error() << "\n";
+        std::exit(2);
+    }
+    std::cout << "Processed " << size << " bytes and " << positions << " positions.\n";
+    return true;
+}
+
 void convert(const std::string& inputPath, std::string outputPath, bool append)
 {
     if (!fileExists(inputPath)) {
@@ -82,10 +107,13 @@ void convert(const std::string& inputPath, std::string outputPath, bool append)
         runDriver(nnp_plain_to_bin, "Compressing", inputPath, outputPath, append);
     } else if (endsWith(inputPath, plainExtension) || endsWith(inputPath, binExtension)) {
         if (!endsWith(outputPath, binpackExtension)) outputPath += binpackExtension;
+        if (endsWith(inputPath, binExtension) && runFileDriver(nnp_bin_to_binpack_file, "Compressing", inputPath, outputPath, append))
+            return;
         runDriver(endsWith(inputPath, binExtension) ? nnp_bin_to_binpack : nnp_plain_to_binpack, "Compressing", inputPath,
                   outputPath, append);
     } else if (endsWith(inputPath, binpackExtension)) {
         if (endsWith(outputPath, binExtension)) {
+            if (runFileDriver(nnp_binpack_to_bin_file, "Decompressing", inputPath, outputPath, append)) return;
             runDriver(nnp_binpack_to_bin, "Decompressing", inputPath, outputPath, append);
         } else if (endsWith(outputPath, plainExtension)) {
             runDriver(nnp_binpack_to_plain, "Decompressing", inputPath, outputPath, append);

@@ -58,3 +58,17 @@ def test_cli_append_and_errors(tmp_path):
     r = _run(str(d / "missing.bin"), str(d / "x"))
     assert "Input file doesn't exist." in r.stderr and r.returncode == 0
     assert _run("only_one_argument").returncode == 1
+
+
+def test_cli_streams_large_files(tmp_path, monkeypatch):
+    """Above NNP_STREAM_THRESHOLD the CLI converts slab by slab (nnp_*_file); same bytes."""
+    d = tmp_path
+    (d / "g.bin").write_bytes(golden("twochunks.bin"))
+    env = dict(os.environ, NNP_STREAM_THRESHOLD="1000", NNP_SLAB_BYTES=str(40 * 7000))
+    r = subprocess.run([CLI, str(d / "g.bin"), str(d / "g.binpack")], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "positions" in r.stdout
+    assert (d / "g.binpack").read_bytes() == golden("twochunks.binpack")
+    env["NNP_SLAB_BYTES"] = str(700_000)
+    r = subprocess.run([CLI, str(d / "g.binpack"), str(d / "rt.bin")], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0
+    assert (d / "rt.bin").read_bytes() == golden("twochunks.rt.bin")
