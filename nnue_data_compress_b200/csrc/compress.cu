@@ -1,16 +1,24 @@
 // compress.cu -- .bin -> .binpack kernels (compressBin, compress_file.cpp:1338-1374, and the
 // CompressedTrainingDataEntryWriter it drives, :1045-1126), restructured for a B200:
 //
-//   k_decode_link_encode  one thread per 40-byte record: Huffman sfen decode (:364-446),
-//                         continuation test against the previous record (:587-593) and, for
-//                         continuation plies, the move/score bit string (:877-989); chain
-//                         heads get their 32-byte stem (:997-1020).
+//   k_walk_runs, k_walk_items
+//                         K1, chain-walking form (walk.cuh): every thread walks a run of records,
+//                         splicing the predecessor's Huffman stream by its move and comparing it
+//                         with the record's own bits instead of decoding every sfen (:364-446);
+//                         continuation plies get their move/score bit string (:877-989), chain
+//                         heads their 32-byte stem (:997-1020). Heads met inside a run are parked
+//                         and worked off in dense rounds.
+//   k_decode_link_encode  K1, record-parallel form: one thread per record decodes it and tests it
+//                         against its predecessor (:587-593). Chosen for files of (nearly) single
+//                         positions (k_sample_heads) and kept as a cross-check of the walk.
 //   k_tile_aggregate      per-tile summary of the segmented payload scan
-//   k_scan_aggregates     exclusive scan of the tile summaries (+ totals)
+//   k_scan_aggregates_*   exclusive scan of the tile summaries (+ totals), three small launches
 //   k_write_payload       re-scans each tile with its carry-in and writes stems, numPlies
 //                         fields and movetext bits at their final *payload* offsets
-//   k_chunk_orbit         replays the writer's greedy chunk-flush rule (:1076-1080) over the
-//                         chain-head offsets
+//   k_head_next, k_chunk_orbit
+//                         replays the writer's greedy chunk-flush rule (:1076-1080) over the
+//                         chain-head offsets; k_orbit_table / k_orbit_resolve do the same across
+//                         the ranks of the sharded compressor
 //   k_emit_chunks         inserts the 8-byte BINP headers (:486-498)
 //
 // Each record's bit string depends only on its own position/move/score and the previous

@@ -4,22 +4,28 @@
 // The reference walks a chunk strictly sequentially: chain k+1 starts where chain k's
 // movetext ends, and that length is only known after decoding it (:815-818). Chunk-level
 // parallelism (a few hundred chunks) cannot feed 148 SMs, so the chains are found
-// speculatively instead:
+// speculatively and the reader's walk is verified instead of followed:
 //
-//   k_walk_chunks      one thread follows the 8-byte BINP headers (:500-521)
-//   k_candidates<0/1>  every byte offset of every chunk is tested for "could be a stem the
-//                      reference writer emits"; pass 0 counts per tile, pass 1 lists the
-//                      survivors in file order
-//   k_probe_chains     one thread per candidate decodes its chain far enough to learn where it
-//                      ends (strict mode: ids the encoder cannot produce kill a false candidate)
-//   k_resolve_chunks   per chunk, follows offset 0 -> next -> next ... through the candidate
-//                      list, marks the real chains and counts their positions; a chunk whose
-//                      walk leaves the candidate set is flagged for the sequential fallback
-//   k_slow_count       sequential per-chunk walk for flagged chunks (correctness net; never
-//                      taken for files the reference itself wrote from legal-move data)
-//   k_emit_chains      one thread per real chain: doMove / nextMoveScore per ply (:669-813) and
-//                      SfenPacker::pack (:266-312) into the final 40-byte records
-//   k_slow_emit        the same, sequentially, for flagged chunks
+//   k_walk_chunks         one thread follows the 8-byte BINP headers (:500-521)
+//   k_candidates_scan     every byte offset of every chunk is tested for "could be a stem the
+//                         reference writer emits", in three stages of increasing cost, each run
+//                         on the compacted survivors of the one before; result: a bitmap per tile
+//   k_candidates_list     the flagged offsets in file order, with the position count of their header
+//   k_mark_conflicts      two candidates closer than a stem cannot both be chain starts
+//   k_emit_chains_verify  the optimistic strategy: one thread per candidate decodes its chain
+//                         (doMove / nextMoveScore per ply, :669-813), writes the 40-byte records
+//                         (SfenPacker::pack :266-312 through the spliced stream) at the index the
+//                         prefix sum of the header counts gives it, and checks its link of the
+//                         reader's walk; no violation anywhere = the output is the reader's
+//   k_probe_chains, k_resolve_chunks, k_emit_chains
+//                         the exhaustive strategy, taken when a link does not hold: decode every
+//                         candidate to learn where it ends, follow offset 0 -> next -> next per
+//                         chunk skipping false candidates, emit the real chains
+//   k_slow_count, k_slow_emit
+//                         sequential per-chunk walk for chunks even that cannot resolve
+//                         (correctness net; exercised through the test hooks only)
+//   k_emit_chains_text, k_slow_emit_text
+//                         the same walks writing emitPlainEntry text (decompressPlain :1299-1335)
 #include "common.cuh"
 #include "kernels.h"
 #include "chain.cuh"
