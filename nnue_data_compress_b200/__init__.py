@@ -339,8 +339,17 @@ Example usage:
 """
 
 
+_FILE_DRIVERS = {"bin_to_binpack", "binpack_to_bin"}
+
+
 def _run_driver(driver, label: str, input_path: str, output_path: str, append: bool, out=sys.stdout) -> None:
     out.write(f"{label} {input_path} to {output_path}\n")
+    # like the native CLI: inputs above NNP_STREAM_THRESHOLD bytes (default 8 GiB) are converted slab
+    # by slab, so that neither host nor device memory has to hold the whole file
+    threshold = int(os.environ.get("NNP_STREAM_THRESHOLD", str(8 << 30)))
+    if driver.__name__ in _FILE_DRIVERS and os.path.getsize(input_path) > threshold:
+        convert_file(driver.__name__, input_path, output_path, append, int(os.environ.get("NNP_SLAB_BYTES", "0")))
+        return
     with open(input_path, "rb") as f:
         data = f.read()
     err = None
