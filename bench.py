@@ -140,6 +140,7 @@ class ClockSampler:
             "sm_max_mhz": self.smax,
             "samples": len(sm),
             "source": self.source,
+            "window": "warm-up + timed steps (same workload)",
             "reasons": sorted(self.reasons),
         }
 
@@ -383,9 +384,8 @@ def main():
         torch.cuda.synchronize()
 
     log(f"binpack is {pack_bytes} bytes; warm-up")
-    for _ in range(args.warmup):
-        step_device()
-    log("timed region")
+    # the clock sampler runs from the first warm-up step to the end of the timed region: the same
+    # workload throughout, and the timed region alone (tens of ms) is too short for NVML's latency
     visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
     phys = local_rank
     if visible:
@@ -393,9 +393,12 @@ def main():
         if local_rank < len(ids) and ids[local_rank].strip().isdigit():
             phys = int(ids[local_rank])
     sampler = ClockSampler(phys)
+    sampler.start()
+    for _ in range(args.warmup):
+        step_device()
+    log("timed region")
     launches0 = L.nnp_kernel_launches()
     barrier()
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     c_ms = c_dom = d_ms = d_dom = 0.0
