@@ -78,6 +78,13 @@ uint64_t file_size(FILE* f)
 
 constexpr uint64_t NO_CARRY = ~(uint64_t)0;
 
+// there is no CPU path: refuse before touching any file unless the library is bound to a device
+bool library_ready()
+{
+    size_t bound = 0;
+    return nnp_bin_to_binpack_dev(nullptr, 0, nullptr, 0, &bound) == NNP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -86,6 +93,7 @@ int nnp_bin_to_binpack_file(const char* in_path, const char* out_path, int appen
 {
     if (!in_path || !out_path) return NNP_ERR_BAD_ARG;
     if (positions) *positions = 0;
+    if (!library_ready()) return NNP_ERR_NOT_INITIALISED;
     File in, out;
     in.f = std::fopen(in_path, "rb");
     if (!in.f) return NNP_ERR_BAD_ARG;
@@ -180,6 +188,7 @@ int nnp_binpack_to_bin_file(const char* in_path, const char* out_path, int appen
 {
     if (!in_path || !out_path) return NNP_ERR_BAD_ARG;
     if (positions) *positions = 0;
+    if (!library_ready()) return NNP_ERR_NOT_INITIALISED;
     File in, out;
     in.f = std::fopen(in_path, "rb");
     if (!in.f) return NNP_ERR_BAD_ARG;

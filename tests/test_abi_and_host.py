@@ -59,6 +59,10 @@ def test_no_cpu_fallback():
     for name in ("nnp_bin_to_binpack", "nnp_binpack_to_bin", "nnp_plain_to_binpack", "nnp_binpack_to_plain",
                  "nnp_bin_to_plain", "nnp_plain_to_bin"):
         assert getattr(lib, name)(buf, 40, buf, 64, ctypes.byref(n)) == -10
+    for name in ("nnp_bin_to_binpack_file", "nnp_binpack_to_bin_file"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+        assert fn(b"/nonexistent/in", b"/nonexistent/out", 0, 0, None) == -10
     assert lib.nnp_init(0) == -9  # NNP_ERR_NO_DEVICE
     import nnue_data_compress_b200 as pkg
 
