@@ -555,7 +555,8 @@ __device__ __forceinline__ void stem_pack(const Pos& p, const Move& mv, int scor
         u32 n = (u32)stem_nibble(p, sq, pos_piece_at(p, sq));
         u32 v = n << ((k & 7) * 4);
         int w = k >> 3;
-        if (w == 0) nib[0] |= v; else if (w == 1) nib[1] |= v; else if (w == 2) nib[2] |= v; else nib[3] |= v;
+        // a 33rd piece has no nibble (the reference writes past m_packedState[16], Position.h:1374-1406): dropped
+        if (w == 0) nib[0] |= v; else if (w == 1) nib[1] |= v; else if (w == 2) nib[2] |= v; else if (w == 3) nib[3] |= v;
         ++k;
     }
     out[2] = nib[0]; out[3] = nib[1]; out[4] = nib[2]; out[5] = nib[3];
