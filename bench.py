@@ -574,7 +574,7 @@ def main():
             "positions_per_gpu": n_pos,
             "bin_bytes_per_gpu": bin_bytes,
             "binpack_bytes_per_gpu": pack_bytes,
-            "l2": "inputs (4.0 GB .bin, 0.2 GB .binpack per GPU) are far larger than the 126 MB L2",
+            "l2": f"inputs ({bin_bytes / 1e9:.1f} GB .bin, {pack_bytes / 1e9:.2f} GB .binpack per GPU) are larger than the 126 MB L2",
             "sharding": ("compress: ONE .binpack over all ranks, byte-identical to a single run (chains owned by the rank of "
                          "their head via halo + overlap window; chunk-flush carry in rank order, 16 B per rank; two 8-byte "
                          "all-gathers; no payload crosses NVLink); decompress: per-rank chunk ranges") if world > 1 else "single GPU",
