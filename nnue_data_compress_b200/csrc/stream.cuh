@@ -23,7 +23,11 @@ __device__ __forceinline__ u32 stream_low_mask(int p, int k)
 }
 
 // Replaces the `wo` bits at stream position X by the `wn` low bits of `val` (wo, wn <= 5); all bits
-// above move by wn - wo. Bits pushed beyond position 255 are dropped.
+// above move by wn - wo. Header + board tokens of a position with at most 32 non-king pieces end
+// below bit 13 + 62 + 4 * 32 = 203, so only words 0..6 are edited: word 7 (bits 224..255) never
+// holds a token, it only ever receives tail bits (stream_with_tail) or, in the compressor, the
+// junk behind the compared range.
+constexpr int STREAM_BOARD_WORDS = 7;
 __device__ __forceinline__ void stream_edit(u32 (&W)[8], int X, int wo, int wn, u32 val)
 {
     const u32 up = (u32)(wn - wo + 8);  // 3 .. 13: shift up, applied to the stream moved down one byte
@@ -31,11 +35,11 @@ __device__ __forceinline__ void stream_edit(u32 (&W)[8], int X, int wo, int wn, 
     const u32 field = (1u << wn) - 1u;  // the inserted bits: cleared in the shifted stream, then set
     const u32 clo = field << sb, chi = __funnelshift_l(field, 0u, sb);
     const u32 vlo = val << sb, vhi = __funnelshift_l(val, 0u, sb);
-    u32 N[8];
+    u32 N[STREAM_BOARD_WORDS];
     u32 below = W[0] << 24;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const u32 next = k < 7 ? W[k + 1] : 0u;
+    for (int k = 0; k < STREAM_BOARD_WORDS; ++k) {
+        const u32 next = W[k + 1];
         const u32 b8 = __byte_perm(W[k], next, 0x4321);   // stream bits 32k+8 .. 32k+39
         const u32 sh = __funnelshift_l(below, b8, up);     // bit i of the result = old bit i - (wn - wo)
         below = b8;
@@ -46,7 +50,7 @@ __device__ __forceinline__ void stream_edit(u32 (&W)[8], int X, int wo, int wn, 
         N[k] = v;
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) W[k] = N[k];
+    for (int k = 0; k < STREAM_BOARD_WORDS; ++k) W[k] = N[k];
 }
 
 __device__ __forceinline__ u32 stream_token(int piece) { return 1u | ((u32)(piece >> 1) << 1) | ((u32)(piece & 1) << 4); }

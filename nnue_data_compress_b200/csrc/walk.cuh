@@ -94,6 +94,7 @@ __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin,
             codes[a] = 0u;
             store_stem_cold(P, p8, p9, stems + a * 8);
         }
+        Move pmv = sfmove_to_move(p8 >> 16);  // the move of the record in front, decoded once
         u64 rec = a + 1;
         // software pipeline: the loads of record rec + 1 are in flight while record rec is processed
         uint2 n0, n1, n2, n3, n4;
@@ -111,7 +112,8 @@ __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin,
                 n0 = src[0]; n1 = src[1]; n2 = src[2]; n3 = src[3]; n4 = src[4];
             }
             if (!valid || !fields_link(p9, c9)) break;  // rec starts a chain
-            const Move pm = sfmove_to_move(p8 >> 16);
+            const Move pm = pmv;
+            const Move cm = sfmove_to_move(c8 >> 16);
             const bool spliced = stream_apply_move(Wp, P, pm);  // Wp becomes the expected stream
             pos_do_move(P, pm);                                  // Position::afterMove
             bool cont = false;
@@ -119,7 +121,7 @@ __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin,
                 const int end = stream_board_end(P);
                 u32 diff = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) diff |= (Wp[k] ^ Wc[k]) & stream_low_mask(end, k);
+                for (int k = 0; k < STREAM_BOARD_WORDS; ++k) diff |= (Wp[k] ^ Wc[k]) & stream_low_mask(end, k);
                 if (diff == 0) {
                     // same side to move, kings and board; castling(4) and ep(1[+6]) follow the board bits
                     const u32* cw = reinterpret_cast<const u32*>(bin + rec * 40);
@@ -143,7 +145,7 @@ __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin,
             u32 code = 0u;
             if (cont) {
                 int nbits;
-                const u32 bits = encode_ply(P, sfmove_to_move(c8 >> 16), (int)(short)(c8 & 0xFFFF),
+                const u32 bits = encode_ply(P, cm, (int)(short)(c8 & 0xFFFF),
                                             (int)(short)(-(int)(short)(p8 & 0xFFFF)), nbits);
                 code = bits | (1u << (31 - nbits));
             }
@@ -152,6 +154,7 @@ __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin,
             for (int k = 0; k < 8; ++k) Wp[k] = Wc[k];
             p8 = c8;
             p9 = c9;
+            pmv = cm;
         }
         if (rec >= e) return;
         if (rec != a + 1) {
