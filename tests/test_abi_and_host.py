@@ -42,6 +42,18 @@ def test_library_exports_every_declared_symbol():
     assert sorted(pkg.EXPORTS) == names
 
 
+def test_header_is_plain_c_and_library_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header compiles as C99 with -pedantic and a C program links
+    against the library (and is refused without a device)."""
+    exe = str(tmp_path / "abi_c_check")
+    libdir = os.path.dirname(LIB)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_c_check.c"), "-o", exe, "-L", libdir, "-lnnuepack",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ABI_C_OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_error_strings_are_the_reference_messages():
     lib = ctypes.CDLL(LIB)
     lib.nnp_strerror.restype = ctypes.c_char_p
