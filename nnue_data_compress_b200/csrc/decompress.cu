@@ -166,37 +166,53 @@ static_assert(CAND_TILE == CAND_THREADS * 16, "stage 1 of k_candidates_scan test
 // one king per side, at most 32 pieces, no pawn on rank 1/8, the stored move starts on a piece of
 // the side to move and does not land on an own piece. A real stem that fails group (2) (possible
 // only for inputs outside that domain) merely sends the file through the exhaustive path.
-__device__ __forceinline__ bool plausible_stem_quick(const unsigned char* s)
+// bytes 0..27 of a would-be stem as seven little-endian words, from aligned shared-memory loads
+__device__ __forceinline__ void stem_words(const unsigned char* s, u32 (&v)[7])
+{
+    const u32* wp = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
+    const int sh = (int)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
+    u32 prev = wp[0];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const u32 next = wp[j + 1];
+        v[j] = __funnelshift_r(prev, next, sh);
+        prev = next;
+    }
+}
+__device__ __forceinline__ int stem_piece_count(const u32 (&v)[7])
+{
+    const u64 occ = ((u64)__byte_perm(v[0], 0, 0x0123) << 32) | __byte_perm(v[1], 0, 0x0123);  // big-endian (:1245-1257)
+    return popc64(occ);
+}
+
+// stage 2a: 2..32 occupied squares and nothing but zeros behind their nibbles. The cheapest of the
+// strong tests: in files of short chains it is what most zero-byte survivors fail.
+__device__ __forceinline__ bool plausible_stem_count(const unsigned char* s)
 {
     if (s[30] != 0) return false;
-    // bytes 0..27 as seven little-endian words, from aligned shared-memory loads
     u32 v[7];
-    {
-        const u32* wp = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
-        const int sh = (int)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
-        u32 prev = wp[0];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            const u32 next = wp[j + 1];
-            v[j] = __funnelshift_r(prev, next, sh);
-            prev = next;
-        }
-    }
-    const u64 occ = ((u64)__byte_perm(v[0], 0, 0x0123) << 32) | __byte_perm(v[1], 0, 0x0123);  // big-endian (:1245-1257)
-    const int n = popc64(occ);
+    stem_words(s, v);
+    const int n = stem_piece_count(v);
     if (n < 2 || n > 32) return false;
-    // nibble k of the 16 nibble bytes is bits 4(k%8).. of word 2 + k/8; nibbles n.. must be zero, and
-    // among the first n there is exactly one white king (10) and one black king (11, or 15 = black to move)
+    // nibble k of the 16 nibble bytes is bits 4(k%8).. of word 2 + k/8; nibbles n.. must be zero
     u32 stray = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) stray |= v[2 + j] & ~stream_low_mask(4 * n, j);
-    if (stray) return false;  // the cheapest of the strong tests first: most non-stems fail here
+    return stray == 0;
+}
+
+// stage 2b: among the first n nibbles there is exactly one white king (10) and one black king
+// (11, or 15 = black to move), counted nibble-parallel on the four words
+__device__ __forceinline__ bool plausible_stem_kings(const unsigned char* s)
+{
+    u32 v[7];
+    stem_words(s, v);
+    const int n = stem_piece_count(v);
     int wk = 0, bk = 0, k15 = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const u32 x = v[2 + j];
-        const u32 used = stream_low_mask(4 * n, j);
-        const u32 flags = 0x11111111u & used;
+        const u32 flags = 0x11111111u & stream_low_mask(4 * n, j);
         auto count_eq = [&](u32 pattern) {
             const u32 t = x ^ pattern;
             const u32 nz = (t | (t >> 1) | (t >> 2) | (t >> 3));
@@ -209,7 +225,7 @@ __device__ __forceinline__ bool plausible_stem_quick(const unsigned char* s)
     return wk == 1 && bk + k15 == 1;
 }
 
-// the per-square half of the test, for offsets that passed plausible_stem_quick
+// stage 3: the per-square tests, for offsets that passed plausible_stem_count and plausible_stem_kings
 __device__ __forceinline__ bool plausible_stem_squares(const unsigned char* s)
 {
     u64 occ = 0;
@@ -324,17 +340,26 @@ k_candidates_scan(const unsigned char* __restrict__ in, u64 n_in, ChunkTable tab
         }
     }
     __syncthreads();
-    // stage 2: the word-parallel tests on the survivors; stage 3: the per-square tests on what is
-    // left (in files of single positions that is every 34th offset: it has to run dense, too)
+    // stages 2a / 2b: the word-parallel tests on the survivors; stage 3: the per-square tests on what
+    // is left (in files of single positions that is every 34th offset: it has to run dense, too).
+    // The queues alternate: queue -> queue2 -> queue -> flags.
     const u32 n_queued = nq;
     for (u32 q = t; q < n_queued; q += CAND_THREADS) {
         const int o = queue[q];
-        if (plausible_stem_quick(s0 + o)) queue2[atomicAdd(&nq2, 1u)] = (unsigned short)o;
+        if (plausible_stem_count(s0 + o)) queue2[atomicAdd(&nq2, 1u)] = (unsigned short)o;
     }
     __syncthreads();
-    const u32 n_queued2 = nq2;
-    for (u32 q = t; q < n_queued2; q += CAND_THREADS) {
+    const u32 n_counted = nq2;
+    if (t == 0) nq = 0;
+    __syncthreads();
+    for (u32 q = t; q < n_counted; q += CAND_THREADS) {
         const int o = queue2[q];
+        if (plausible_stem_kings(s0 + o)) queue[atomicAdd(&nq, 1u)] = (unsigned short)o;
+    }
+    __syncthreads();
+    const u32 n_kings = nq;
+    for (u32 q = t; q < n_kings; q += CAND_THREADS) {
+        const int o = queue[q];
         bool ok = plausible_stem_squares(s0 + o);
         // test hook: drop a pseudo-random subset of candidates to exercise the fallbacks
         if (debug_reject_mod && (u32)(((off0 + (u64)o) * 2654435761ull) >> 11) % debug_reject_mod == 0) ok = false;
