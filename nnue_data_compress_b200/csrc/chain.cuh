@@ -23,10 +23,10 @@ __device__ __forceinline__ void chain_open(const unsigned char* s, ChainCursor& 
 }
 
 // PackedMoveScoreListReader::nextEntry (:669-678)
-__device__ __forceinline__ bool chain_step(ChainCursor& c, BitReader& r, bool strict)
+__device__ __forceinline__ bool chain_step(ChainCursor& c, BitReader& r, bool strict, int moved = -1)
 {
     if (strict && (c.mv.from > 63 || c.mv.to > 63)) return false;  // null move followed by plies
-    pos_do_move(c.pos, c.mv);
+    pos_do_move(c.pos, c.mv, moved);
     Move m;
     int sc;
     if (!decode_ply(r, c.pos, c.last_score, m, sc, strict)) return false;
@@ -50,8 +50,8 @@ __device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_aft
     r.init(s + 34, (u64)bytes_after_stem);
     for (u32 k = 0; k < cc.num_plies; ++k) {
         if (cc.mv.from > 63 || cc.mv.to > 63) return false;
-        before_move(cc);
-        if (!chain_step(cc, r, false)) return false;
+        const int moved = before_move(cc);  // the piece on cc.mv.from if the hook looked it up, else -1
+        if (!chain_step(cc, r, false, moved)) return false;
         emit(cc, k + 1);
     }
     consumed = 34 + ((r.pos + 7) >> 3);
@@ -60,7 +60,7 @@ __device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_aft
 template <typename EmitFn>
 __device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_after_stem, EmitFn emit, u32& consumed)
 {
-    return walk_chain(s, bytes_after_stem, [](const ChainCursor&) {}, emit, consumed);
+    return walk_chain(s, bytes_after_stem, [](const ChainCursor&) { return -1; }, emit, consumed);
 }
 
 // walk_chain writing 40-byte .bin records rec0, rec0 + 1, ... (below rec_limit). The Huffman stream
@@ -72,7 +72,12 @@ __device__ __forceinline__ bool emit_chain_bin(const unsigned char* s, u32 bytes
     u32 W[8];
     bool spliced = false;
     return walk_chain(
-        s, bytes_after_stem, [&](const ChainCursor& cc) { spliced = stream_apply_move(W, cc.pos, cc.mv); },
+        s, bytes_after_stem,
+        [&](const ChainCursor& cc) {
+            const int moved = pos_piece_at(cc.pos, cc.mv.from);
+            spliced = stream_apply_move(W, cc.pos, cc.mv, moved);
+            return moved;
+        },
         [&](const ChainCursor& cc, u32 k) {
             const int end = (k == 0 || !spliced) ? stream_from_pos(cc.pos, col, stride, W) : stream_board_end(cc.pos);
             if (rec0 + k >= rec_limit) return;

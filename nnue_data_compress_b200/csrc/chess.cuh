@@ -293,19 +293,20 @@ __device__ __forceinline__ void pos_move_piece(Pos& p, int from, int to, int pla
 }
 
 // Board::doMove + doMoveColdPath (Position.h:300-439), mailbox semantics on the planes
-__device__ __forceinline__ void board_do_move(Pos& p, const Move& m)
+// `moved` = pos_piece_at(p, m.from), which the callers have at hand
+__device__ __forceinline__ void board_do_move(Pos& p, const Move& m, int moved)
 {
     if (m.type == MT_NORMAL) {
-        pos_move_piece(p, m.from, m.to, pos_piece_at(p, m.from));
+        pos_move_piece(p, m.from, m.to, moved);
     } else if (m.type == MT_PROMOTION) {
         pos_move_piece(p, m.from, m.to, m.promo);
     } else if (m.type == MT_ENPASSANT) {
-        int pc = pos_piece_at(p, m.from);
+        int pc = moved;
         pos_put(p, m.to, pc);
         pos_remove(p, m.from);
         pos_remove(p, (m.to & 7) | (m.from & 56));
     } else {
-        int rook = pos_piece_at(p, m.to), king = pos_piece_at(p, m.from);
+        int rook = pos_piece_at(p, m.to), king = moved;
         int base = (king & 1) ? 56 : 0;  // king.color(); Piece::none() counts as white
         bool is_short = (m.to & 7) == 7;  // CastlingTraits::moveCastlingType CastlingTraits.h:37-40
         pos_remove(p, m.to);
@@ -316,9 +317,10 @@ __device__ __forceinline__ void board_do_move(Pos& p, const Move& m)
 }
 
 // Position::doMove (Position.cpp:626-662)
-__device__ __forceinline__ void pos_do_move(Pos& p, const Move& m)
+// `moved` (optional) = pos_piece_at(p, m.from) when the caller has already looked it up
+__device__ __forceinline__ void pos_do_move(Pos& p, const Move& m, int moved = -1)
 {
-    int moved = pos_piece_at(p, m.from);
+    if (moved < 0) moved = pos_piece_at(p, m.from);
     int moved_type = moved >> 1;
     p.ply = (p.ply + 1) & 0xFFFF;
     p.rule50 = (p.rule50 + 1) & 0xFF;
@@ -329,7 +331,7 @@ __device__ __forceinline__ void pos_do_move(Pos& p, const Move& m)
         int cand = (m.to + m.from) >> 1;
         if (ep_possible(p, cand, p.stm ^ 1)) p.ep = cand;  // on the PRE-move board
     }
-    board_do_move(p, m);
+    board_do_move(p, m, moved);
     p.stm ^= 1;
 }
 
@@ -760,44 +762,42 @@ __device__ __forceinline__ bool decode_ply(BitReader& r, const Pos& p, int& last
     mv.type = MT_NORMAL;
     mv.promo = NO_PIECE;
     mv.to = 0;
+    // Every mover type yields a destination set and a move count; the id is then read and the
+    // destination selected at ONE place, so that a warp whose lanes move different piece types
+    // goes through the bit reader and the n-th-bit selection once, not once per type.
+    u64 dest;
+    u32 n, att_n = 0;
+    bool promotes = false;
     if (pt == PT_PAWN) {
-        u64 dest = pawn_destinations(p, from, ours, theirs);
-        u32 n = (u32)popc64(dest);
-        int promotion_rank = stm == WHITE ? 6 : 1;
-        if ((from >> 3) == promotion_rank) {
-            u32 id = r.get(used_bits(n * 4));
-            if (strict && id >= n * 4) return false;
-            mv.promo = ((PT_KNIGHT + (int)(id & 3)) << 1) | stm;
-            mv.to = nth_set_bit(dest, id >> 2);
-            mv.type = MT_PROMOTION;
-        } else {
-            u32 id = r.get(used_bits(n));
-            if (strict && id >= n) return false;
-            mv.to = nth_set_bit(dest, id);
-            if (mv.to == p.ep) mv.type = MT_ENPASSANT;
-        }
+        dest = pawn_destinations(p, from, ours, theirs);
+        n = (u32)popc64(dest);
+        promotes = (from >> 3) == (stm == WHITE ? 6 : 1);
+        if (promotes) n *= 4;
     } else if (pt == PT_KING) {
-        int our_mask = stm == WHITE ? (CR_WK | CR_WQ) : (CR_BK | CR_BQ);
-        u64 att = king_attacks(from) & ~ours;
-        u32 att_n = (u32)popc64(att);
-        u32 n_cr = (u32)__popc((u32)(p.cr & our_mask));
-        u32 id = r.get(used_bits(att_n + n_cr));
-        if (strict && id >= att_n + n_cr) return false;
-        if (id >= att_n) {
-            int long_right = stm == WHITE ? CR_WQ : CR_BQ;
-            bool is_long = (id - att_n == 0) && (p.cr & long_right);
-            mv.from = stm == WHITE ? 4 : 60;  // Move::castle Chess.h:1029-1040
-            mv.to = (stm == WHITE ? 0 : 56) + (is_long ? 0 : 7);
-            mv.type = MT_CASTLE;
-        } else {
-            mv.to = nth_set_bit(att, id);
-        }
+        const int our_mask = stm == WHITE ? (CR_WK | CR_WQ) : (CR_BK | CR_BQ);
+        dest = king_attacks(from) & ~ours;
+        att_n = (u32)popc64(dest);
+        n = att_n + (u32)__popc((u32)(p.cr & our_mask));
     } else {
-        u64 att = piece_attacks(pt, from, occ) & ~ours;
-        u32 n = (u32)popc64(att);
-        u32 id = r.get(used_bits(n));
-        if (strict && id >= n) return false;
-        mv.to = nth_set_bit(att, id);
+        dest = piece_attacks(pt, from, occ) & ~ours;
+        n = (u32)popc64(dest);
+    }
+    const u32 id = r.get(used_bits(n));
+    if (strict && id >= n) return false;
+    if (pt == PT_KING && id >= att_n) {
+        const int long_right = stm == WHITE ? CR_WQ : CR_BQ;
+        const bool is_long = (id - att_n == 0) && (p.cr & long_right);
+        mv.from = stm == WHITE ? 4 : 60;  // Move::castle Chess.h:1029-1040
+        mv.to = (stm == WHITE ? 0 : 56) + (is_long ? 0 : 7);
+        mv.type = MT_CASTLE;
+    } else {
+        mv.to = nth_set_bit(dest, promotes ? id >> 2 : id);
+        if (promotes) {
+            mv.promo = ((PT_KNIGHT + (int)(id & 3)) << 1) | stm;
+            mv.type = MT_PROMOTION;
+        } else if (pt == PT_PAWN && mv.to == p.ep) {
+            mv.type = MT_ENPASSANT;
+        }
     }
     // extractVle16 (:650-667)
     u32 v = 0;

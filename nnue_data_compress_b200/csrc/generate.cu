@@ -58,7 +58,7 @@ __device__ __forceinline__ int castle_moves(const Pos& p, Move* out /* [2] */)
 __device__ __forceinline__ bool leaves_king_safe(const Pos& p, const Move& m)
 {
     Pos q = p;
-    board_do_move(q, m);
+    board_do_move(q, m, pos_piece_at(q, m.from));
     const u64 kings = pos_type_bb(q, PT_KING) & pos_occ(q, p.stm);
     if (!kings) return false;
     return !square_attacked(q, lsb64(kings), p.stm ^ 1, pos_all(q));

@@ -90,7 +90,7 @@ __device__ __forceinline__ int stream_from_pos(const Pos& p, u32* col, int strid
 
 // Applies move `m`, made in position `p` (the position BEFORE the move), to the stream of `p`.
 // The token changes mirror Board::doMove (Position.h:300-439) as restated in board_do_move.
-__device__ __forceinline__ bool stream_apply_move(u32 (&W)[8], const Pos& p, const Move& m)
+__device__ __forceinline__ bool stream_apply_move(u32 (&W)[8], const Pos& p, const Move& m, int moved = -1)
 {
     const u64 all = pos_all(p);
     const u64 kings = pos_type_bb(p, PT_KING);
@@ -98,7 +98,7 @@ __device__ __forceinline__ bool stream_apply_move(u32 (&W)[8], const Pos& p, con
     if (popc64(wkb) != 1 || popc64(bkb) != 1 || popc64(all) > 34) return false;
     const int from = m.from, to = m.to;
     if (from > 63 || to > 63 || from == to) return false;
-    const int pc = pos_piece_at(p, from);
+    const int pc = moved >= 0 ? moved : pos_piece_at(p, from);  // the caller may have looked it up already
     if (pc == NO_PIECE) return false;
     const bool king_moves = (pc >> 1) == PT_KING;
     auto occupied = [&](int sq) { return (int)((all >> sq) & 1); };

@@ -114,8 +114,9 @@ __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin,
             if (!valid || !fields_link(p9, c9)) break;  // rec starts a chain
             const Move pm = pmv;
             const Move cm = sfmove_to_move(c8 >> 16);
-            const bool spliced = stream_apply_move(Wp, P, pm);  // Wp becomes the expected stream
-            pos_do_move(P, pm);                                  // Position::afterMove
+            const int moved = pm.from < 64 ? pos_piece_at(P, pm.from) : NO_PIECE;
+            const bool spliced = stream_apply_move(Wp, P, pm, moved);  // Wp becomes the expected stream
+            pos_do_move(P, pm, moved);                                  // Position::afterMove
             bool cont = false;
             if (spliced) {
                 const int end = stream_board_end(P);
