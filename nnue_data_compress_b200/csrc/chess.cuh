@@ -668,35 +668,35 @@ __device__ __forceinline__ u32 encode_ply(const Pos& p, const Move& mv, int scor
     u64 ours = pos_occ(p, stm), theirs = pos_occ(p, stm ^ 1);
     u64 occ = ours | theirs;
     u32 piece_id = (u32)popc64(ours & before64(mv.from));
-    u32 num_moves = 0, move_id = 0;
     int pc = pos_piece_at(p, mv.from);
     int pt = pc >> 1;
+    // every mover type yields a destination set; counting it and ranking the destination happen
+    // once behind the branches (a warp usually holds movers of all types)
+    u64 dest;
+    u32 extra_moves = 0;
+    bool promotes = false;
     if (pt == PT_PAWN) {
-        u64 dest = pawn_destinations(p, mv.from, ours, theirs);
-        move_id = (u32)popc64(dest & before64(mv.to));
-        num_moves = (u32)popc64(dest);
-        int second_to_last = stm == WHITE ? 6 : 1;
-        if ((mv.from >> 3) == second_to_last) {
-            move_id = move_id * 4 + (u32)((mv.promo >> 1) - PT_KNIGHT);
-            num_moves *= 4;
-        }
+        dest = pawn_destinations(p, mv.from, ours, theirs);
+        promotes = (mv.from >> 3) == (stm == WHITE ? 6 : 1);
     } else if (pt == PT_KING) {
-        int our_mask = stm == WHITE ? (CR_WK | CR_WQ) : (CR_BK | CR_BQ);
-        u64 att = king_attacks(mv.from) & ~ours;
-        u32 att_n = (u32)popc64(att);
-        num_moves = att_n + (u32)__popc((u32)(p.cr & our_mask));
-        if (mv.type == MT_CASTLE) {
-            int long_right = stm == WHITE ? CR_WQ : CR_BQ;
-            move_id = att_n - 1;
-            if (p.cr & long_right) move_id += 1;
-            if ((mv.to & 7) == 7) move_id += 1;
-        } else {
-            move_id = (u32)popc64(att & before64(mv.to));
-        }
+        const int our_mask = stm == WHITE ? (CR_WK | CR_WQ) : (CR_BK | CR_BQ);
+        dest = king_attacks(mv.from) & ~ours;
+        extra_moves = (u32)__popc((u32)(p.cr & our_mask));
     } else {
-        u64 att = piece_attacks(pt, mv.from, occ) & ~ours;
-        move_id = (u32)popc64(att & before64(mv.to));
-        num_moves = (u32)popc64(att);
+        dest = piece_attacks(pt, mv.from, occ) & ~ours;
+    }
+    const u32 dest_n = (u32)popc64(dest);
+    u32 num_moves = dest_n + extra_moves;
+    u32 move_id = (u32)popc64(dest & before64(mv.to));
+    if (promotes) {
+        move_id = move_id * 4 + (u32)((mv.promo >> 1) - PT_KNIGHT);
+        num_moves *= 4;
+    }
+    if (pt == PT_KING && mv.type == MT_CASTLE) {
+        const int long_right = stm == WHITE ? CR_WQ : CR_BQ;
+        move_id = dest_n - 1;
+        if (p.cr & long_right) move_id += 1;
+        if ((mv.to & 7) == 7) move_id += 1;
     }
     int w1 = used_bits((u32)popc64(ours)), w2 = used_bits(num_moves);
     u64 acc = 0;  // bits accumulate at the low end, MSB-first order == append order
