@@ -23,13 +23,14 @@ __device__ __forceinline__ void chain_open(const unsigned char* s, ChainCursor& 
 }
 
 // PackedMoveScoreListReader::nextEntry (:669-678)
-__device__ __forceinline__ bool chain_step(ChainCursor& c, BitReader& r, bool strict, int moved = -1)
+__device__ __forceinline__ bool chain_step(ChainCursor& c, BitReader& r, bool strict, int moved = -1,
+                                           const StepTables* T = nullptr)
 {
     if (strict && (c.mv.from > 63 || c.mv.to > 63)) return false;  // null move followed by plies
     pos_do_move(c.pos, c.mv, moved);
     Move m;
     int sc;
-    if (!decode_ply(r, c.pos, c.last_score, m, sc, strict)) return false;
+    if (!decode_ply(r, c.pos, c.last_score, m, sc, strict, T)) return false;
     c.mv = m;
     c.score = sc;
     c.ply = (c.ply + 1) & 0xFFFF;
@@ -41,7 +42,7 @@ __device__ __forceinline__ bool chain_step(ChainCursor& c, BitReader& r, bool st
 // just before the cursor's move is made; returns false when the movetext runs off the chunk
 template <typename MoveFn, typename EmitFn>
 __device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_after_stem, MoveFn before_move, EmitFn emit,
-                                           u32& consumed)
+                                           u32& consumed, const StepTables* T = nullptr)
 {
     ChainCursor cc;
     chain_open(s, cc);
@@ -51,7 +52,7 @@ __device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_aft
     for (u32 k = 0; k < cc.num_plies; ++k) {
         if (cc.mv.from > 63 || cc.mv.to > 63) return false;
         const int moved = before_move(cc);  // the piece on cc.mv.from if the hook looked it up, else -1
-        if (!chain_step(cc, r, false, moved)) return false;
+        if (!chain_step(cc, r, false, moved, T)) return false;
         emit(cc, k + 1);
     }
     consumed = 34 + ((r.pos + 7) >> 3);
@@ -67,7 +68,8 @@ __device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_aft
 // of the position is carried along the chain (stream.cuh): built once for the chain head, then
 // spliced per move. `col` is the thread's 8-word scratch column in shared memory.
 __device__ __forceinline__ bool emit_chain_bin(const unsigned char* s, u32 bytes_after_stem, unsigned char* out, u64 rec0,
-                                               u64 rec_limit, u32* col, int stride, u32& consumed)
+                                               u64 rec_limit, u32* col, int stride, u32& consumed,
+                                               const StepTables* T = nullptr)
 {
     u32 W[8];
     bool spliced = false;
@@ -93,7 +95,7 @@ __device__ __forceinline__ bool emit_chain_bin(const unsigned char* s, u32 bytes
             d[3] = make_uint2(w[6], w[7]);
             d[4] = make_uint2(w8, w9);
         },
-        consumed);
+        consumed, T);
 }
 
 }  // namespace nnp

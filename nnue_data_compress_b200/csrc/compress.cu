@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(KW_THREADS, KW_MIN_BLOCKS)
 k_walk_runs(const unsigned char* __restrict__ bin, u64 n, u64 run_lo, u64 run_hi, u32* __restrict__ codes,
             u32* __restrict__ stems, CompressTotals* tot, u32* __restrict__ park_list, u64* park_count)
 {
+    __shared__ StepTables T;
+    step_tables_fill(T);
     const u64 run = run_lo + (u64)blockIdx.x * KW_THREADS + threadIdx.x;
     const u64 r0 = run * KW_RUN;
     u32 parked = KW_NONE;
@@ -203,7 +205,7 @@ k_walk_runs(const unsigned char* __restrict__ bin, u64 n, u64 run_lo, u64 run_hi
             head = !fields_link(w[9], w[19]);
         }
         walk_item(bin, head ? r0 : r0 - 1, head, e, codes, stems, [&](u64 rec) { atomicMin(&tot->error_index, rec); },
-                  [&](u64 rec) { parked = (u32)rec; });
+                  [&](u64 rec) { parked = (u32)rec; }, &T);
     }
     park_append(parked, park_list, park_count);
 }
@@ -212,6 +214,8 @@ __global__ void __launch_bounds__(KW_THREADS, KW_MIN_BLOCKS)
 k_walk_items(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ codes, u32* __restrict__ stems,
              CompressTotals* tot, const u32* __restrict__ items, u64 n_items, u32* __restrict__ park_list, u64* park_count)
 {
+    __shared__ StepTables T;
+    step_tables_fill(T);
     const u64 i = (u64)blockIdx.x * KW_THREADS + threadIdx.x;
     u32 parked = KW_NONE;
     if (i < n_items) {
@@ -219,7 +223,7 @@ k_walk_items(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ cod
         u64 e = (rec / KW_RUN + 1) * KW_RUN;
         if (e > n) e = n;
         walk_item(bin, rec, true, e, codes, stems, [&](u64 r) { atomicMin(&tot->error_index, r); },
-                  [&](u64 r) { parked = (u32)r; });
+                  [&](u64 r) { parked = (u32)r; }, &T);
     }
     park_append(parked, park_list, park_count);
 }

@@ -611,6 +611,8 @@ k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const
                      u64 ncand, u64 cand_lo, u64 cand_hi, unsigned char* __restrict__ out, u64* __restrict__ violations)
 {
     __shared__ u32 scratch[8 * EMITC_THREADS];
+    __shared__ StepTables T;
+    step_tables_fill(T);
     const u64 i = cand_lo + (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
     if (i >= cand_hi) return;
     if (cand_cnt[i] == 0) return;  // marked by k_mark_conflicts
@@ -619,7 +621,7 @@ k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const
     const u64 rec0 = cand_rec[i];
     const unsigned char* s = in + tab.start[c] + off;
     u32 consumed = 0;
-    bool ok = emit_chain_bin(s, clen - off - 34, out, rec0, ~0ull, scratch + threadIdx.x, EMITC_THREADS, consumed);
+    bool ok = emit_chain_bin(s, clen - off - 34, out, rec0, ~0ull, scratch + threadIdx.x, EMITC_THREADS, consumed, &T);
     const u32 end = off + consumed;
     u64 prev = i, next = i + 1;  // neighbours in the chunk, skipping marked candidates
     while (prev > 0 && cand_chunk[prev - 1] == c && cand_cnt[prev - 1] == 0) --prev;

@@ -77,7 +77,8 @@ static __device__ __noinline__ bool walk_slow(const unsigned char* __restrict__ 
 // on_error(rec) reports "Improperly encoded bin sfen" (:407-408, :441-442).
 template <typename ErrFn, typename ParkFn>
 __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin, u64 a, bool a_is_head, u64 e,
-                                          u32* __restrict__ codes, u32* __restrict__ stems, ErrFn on_error, ParkFn park)
+                                          u32* __restrict__ codes, u32* __restrict__ stems, ErrFn on_error, ParkFn park,
+                                          const StepTables* T = nullptr)
 {
     for (;;) {
         u32 Wp[8], p8, p9;
@@ -147,7 +148,7 @@ __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin,
             if (cont) {
                 int nbits;
                 const u32 bits = encode_ply(P, cm, (int)(short)(c8 & 0xFFFF),
-                                            (int)(short)(-(int)(short)(p8 & 0xFFFF)), nbits);
+                                            (int)(short)(-(int)(short)(p8 & 0xFFFF)), nbits, T);
                 code = bits | (1u << (31 - nbits));
             }
             codes[rec] = code;
