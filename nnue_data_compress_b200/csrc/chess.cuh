@@ -785,7 +785,9 @@ __device__ __forceinline__ bool decode_ply(BitReader& r, const Pos& p, int& last
     u32 n_ours = (u32)popc64(ours);
     u32 piece_id = r.get(used_bits(n_ours));
     if (strict && piece_id >= n_ours) return false;
-    int from = nth_set_bit(ours, piece_id);
+    // an id beyond the count (corrupted movetext; the reference indexes its lookup table out of range,
+    // ArithmeticUtility.h:186-209) selects square 0, as the oracle does
+    int from = piece_id < n_ours ? nth_set_bit(ours, piece_id) : 0;
     int pt = pos_piece_at(p, from) >> 1;
     mv.from = from;
     mv.type = MT_NORMAL;
@@ -820,7 +822,7 @@ __device__ __forceinline__ bool decode_ply(BitReader& r, const Pos& p, int& last
         mv.to = (stm == WHITE ? 0 : 56) + (is_long ? 0 : 7);
         mv.type = MT_CASTLE;
     } else {
-        mv.to = nth_set_bit(dest, promotes ? id >> 2 : id);
+        mv.to = id < n ? nth_set_bit(dest, promotes ? id >> 2 : id) : 0;
         if (promotes) {
             mv.promo = ((PT_KNIGHT + (int)(id & 3)) << 1) | stm;
             mv.type = MT_PROMOTION;
