@@ -210,6 +210,32 @@ def test_decode_fallbacks_are_exact(nnp, env):
     assert "FALLBACK_OK" in out.stdout, out.stdout + out.stderr
 
 
+def test_corrupted_binpack_follows_the_oracle(nnp):
+    """Random bit flips in valid .binpack files: whenever both the oracle (= the reference's reading of
+    malformed movetext) and the CUDA path decode the file, the records are identical; the CUDA path may
+    instead refuse movetext that runs off its chunk (NNP_ERR_TRUNCATED), never anything else."""
+    import random
+
+    rng = random.Random(20260)
+    packs = [golden(n + ".binpack") for n in ("games100", "long400", "restart", "heads", "shuffled")]
+    compared = 0
+    for _ in range(250):
+        b = bytearray(rng.choice(packs))
+        for _ in range(rng.randrange(1, 5)):
+            b[rng.randrange(8, len(b))] ^= 1 << rng.randrange(8)
+        rc, want = oracle_convert(BINPACK_TO_BIN, bytes(b))
+        if rc != 0:
+            continue
+        try:
+            got = nnp.binpack_to_bin(bytes(b))
+        except nnp.NnpError as e:
+            assert e.status == -4, e.status
+            continue
+        assert got == want
+        compared += 1
+    assert compared > 100
+
+
 # ---------------------------------------------------------------------------------------------
 # .plain path (compressPlain / decompressPlain / convertBinToPlain / convertPlainToBin)
 
