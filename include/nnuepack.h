@@ -170,6 +170,39 @@ int nnp_shard_compress_resolve_dev(const void* d_tables, const uint64_t* payload
 int nnp_bin_to_binpack_file(const char* in_path, const char* out_path, int append, size_t slab_bytes, uint64_t* positions);
 int nnp_binpack_to_bin_file(const char* in_path, const char* out_path, int append, size_t slab_bytes, uint64_t* positions);
 
+/* ---- decode fused into its consumer: HalfKP feature rows ------------ */
+
+/* What the NNUE trainer's data loader (README.md:3 of the reference points at it) computes from every
+ * decoded position, produced on the device straight from the chain walk, without the .bin record in
+ * between. The reference itself has no feature code: the index is the published HalfKP definition
+ * (nodchip learner / nnue-pytorch halfkp_idx), restated in csrc/halfkp.cuh and oracle/oracle.c:
+ *   index = 1 + orient(P, sq) + 64 * (2 * type + (colour != P)) + 641 * orient(P, king square of P),
+ *   orient(white, sq) = sq, orient(black, sq) = sq ^ 63, type pawn..queen = 0..4, kings excluded.
+ * Row r belongs to record r of the .bin file nnp_binpack_to_bin writes for the same input (for the
+ * .bin entry point: to record r of the input). d_white / d_black: [positions][NNP_HALFKP_ROW] int32,
+ * the non-king pieces, the same piece at the same slot of both rows, padded with -1 at the end. Rows
+ * made from .bin records and from chain heads are ordered by (2 * type + colour, square), i.e. the
+ * white row ascends; along a chain the row is updated in place (a piece keeps its slot while it stands,
+ * the row's last entry takes over the slot of a captured piece), so the order is deterministic but
+ * follows the chain's history -- a sparse feature transformer sums over the row and does not care; d_meta: [positions] nnp_halfkp_meta. All three 16-byte aligned. d_white == NULL: count
+ * only (*positions is set). NNP_ERR_CAPACITY when cap_positions is too small (*positions = needed).
+ * Malformed input: same status codes as nnp_binpack_to_bin_dev / nnp_bin_to_plain_dev; *positions
+ * then is the number of leading rows that are valid. */
+#define NNP_HALFKP_ROW 32
+#define NNP_HALFKP_FEATURES 41024 /* 64 * 641 */
+typedef struct nnp_halfkp_meta {
+    int16_t score;    /* as stored: from the side to move's point of view */
+    uint16_t ply;
+    int8_t result;    /* as stored in the .bin record (int8 narrowing, compress_file.cpp:570-585) */
+    uint8_t stm;      /* 0 white, 1 black */
+    uint8_t n_active; /* entries of each row that are not padding */
+    uint8_t reserved; /* 0 */
+} nnp_halfkp_meta;
+int nnp_binpack_to_halfkp_dev(const void* d_binpack, size_t binpack_bytes, int32_t* d_white, int32_t* d_black,
+                              nnp_halfkp_meta* d_meta, size_t cap_positions, size_t* positions);
+int nnp_bin_to_halfkp_dev(const void* d_bin, size_t bin_bytes, int32_t* d_white, int32_t* d_black, nnp_halfkp_meta* d_meta,
+                          size_t cap_positions, size_t* positions);
+
 /* ---- helpers around the path --------------------------------------------------------- */
 
 /* Number of positions a binpack holds = sum over chains of (1 + numPlies)

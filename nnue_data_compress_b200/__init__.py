@@ -62,6 +62,7 @@ EXPORTS = [
     "nnp_shard_compress_begin_dev", "nnp_shard_compress_orbit", "nnp_shard_compress_emit_dev",
     "nnp_shard_compress_table_dev", "nnp_shard_compress_resolve_dev",
     "nnp_bin_to_binpack_file", "nnp_binpack_to_bin_file",
+    "nnp_binpack_to_halfkp_dev", "nnp_bin_to_halfkp_dev",
 ]
 
 
@@ -105,6 +106,8 @@ def lib() -> ctypes.CDLL:
                 "nnp_shard_compress_emit_dev",
                 "nnp_shard_compress_table_dev",
                 "nnp_shard_compress_resolve_dev",
+                "nnp_binpack_to_halfkp_dev",
+                "nnp_bin_to_halfkp_dev",
             ):
                 fn.argtypes = conv
                 fn.restype = ctypes.c_int
@@ -141,6 +144,10 @@ def lib() -> ctypes.CDLL:
         L.nnp_shard_compress_table_dev.restype = ctypes.c_int
         L.nnp_shard_compress_resolve_dev.argtypes = [ctypes.c_void_p, u64p, ctypes.c_int, ctypes.c_int, u64p, u64p, u64p, u64p]
         L.nnp_shard_compress_resolve_dev.restype = ctypes.c_int
+        for name in ("nnp_binpack_to_halfkp_dev", "nnp_bin_to_halfkp_dev"):
+            getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+            getattr(L, name).restype = ctypes.c_int
         L.nnp_debug_config.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
         L.nnp_debug_config.restype = ctypes.c_int
         L.nnp_decode_stats.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
@@ -421,6 +428,38 @@ def decode_stats() -> dict:
     lib().nnp_decode_stats(a)
     return {"optimistic_hits": a[0], "optimistic_misses": a[1], "candidates": a[2], "tentative_positions": a[3],
             "violations": a[4], "false_candidates": a[5], "false_sample": [(v >> 32, v & 0xFFFFFFFF) for v in a[6:14]]}
+
+
+HALFKP_ROW = 32
+HALFKP_FEATURES = 41024
+
+
+def halfkp_rows(d_data, kind: str = "binpack", positions: int | None = None):
+    """HalfKP feature rows of a .binpack (or .bin) held in a CUDA uint8 tensor, produced on the device
+    (nnp_binpack_to_halfkp_dev / nnp_bin_to_halfkp_dev). Returns
+    (white [n, 32] int32, black [n, 32] int32, meta [n, 8] uint8 = nnp_halfkp_meta); torch only provides
+    the device buffers. The library's stream must be ordered with the producer of `d_data`
+    (use_torch_stream())."""
+    import torch
+
+    _ensure_init()
+    fn = {"binpack": lib().nnp_binpack_to_halfkp_dev, "bin": lib().nnp_bin_to_halfkp_dev}[kind]
+    src = ctypes.c_void_p(d_data.data_ptr() if d_data.numel() else 0)
+    n = ctypes.c_size_t(0)
+    if positions is None:
+        rc = fn(src, d_data.numel(), None, None, None, 0, ctypes.byref(n))
+        if rc != 0:
+            raise NnpError(rc, _strerror(rc))
+        positions = n.value
+    rows = max(positions, 1)
+    white = torch.empty((rows, HALFKP_ROW), dtype=torch.int32, device=d_data.device)
+    black = torch.empty((rows, HALFKP_ROW), dtype=torch.int32, device=d_data.device)
+    meta = torch.empty((rows, 8), dtype=torch.uint8, device=d_data.device)
+    rc = fn(src, d_data.numel(), ctypes.c_void_p(white.data_ptr()), ctypes.c_void_p(black.data_ptr()),
+            ctypes.c_void_p(meta.data_ptr()), positions, ctypes.byref(n))
+    if rc != 0:
+        raise NnpError(rc, _strerror(rc))
+    return white[: n.value], black[: n.value], meta[: n.value]
 
 
 def generate_bin(n_positions: int, max_plies: int = 100, seed: int = 42) -> bytes:

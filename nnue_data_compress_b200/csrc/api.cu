@@ -922,6 +922,111 @@ int binpack_to_plain_dev(const void* d_in, size_t in_bytes, void* d_out, size_t 
     return NNP_OK;
 }
 
+// ---------------------------------------------------------------- .binpack / .bin -> HalfKP rows
+
+// decompress_dev with the record writer replaced by the feature-row writer (halfkp.cu)
+int binpack_to_halfkp_dev(const void* d_in, size_t in_bytes, int* white, int* black, void* meta, size_t cap, size_t* positions)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    *positions = 0;
+    if (white && (!black || !meta)) return NNP_ERR_BAD_ARG;
+    if (white && (((uintptr_t)white | (uintptr_t)black | (uintptr_t)meta) & 15)) return NNP_ERR_BAD_ARG;
+    if (in_bytes == 0) return NNP_OK;
+    CK(cudaEventRecord(C.ev[0], s));
+    DecodePlan P;
+    int rc = decode_front(d_in, in_bytes, P);
+    if (rc != NNP_OK) return rc;
+    DecompressTotals* h_tot = reinterpret_cast<DecompressTotals*>((char*)C.pinned + 512);
+    u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+
+    if (white && P.chunks > 0 && P.ncand > 0 && !C.debug_exhaustive) {  // optimistic strategy, see decompress_dev
+        WS(WS_CAND_REC, (P.ncand + 2) * 8, u64, cand_rec);
+        WS(WS_LSUM_A, (large_sum_tiles(P.ncand) + 1) * 4, u32, lsum_a);
+        WS(WS_LSUM_B, (large_sum_tiles(P.ncand) + 2) * 8, u64, lsum_b);
+        launch_mark_conflicts(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_cnt, P.ncand, s);
+        launch_exclusive_sum_large(P.cand_cnt, P.ncand, cand_rec, lsum_a, lsum_b, s);
+        LAUNCHED(4, "candidate record offsets");
+        CK(cudaMemcpyAsync(h_u64, cand_rec + P.ncand, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        const u64 n = h_u64[0];
+        C.last_candidates = P.ncand;
+        C.last_tentative_positions = n;
+        C.last_violations = ~0ull;
+        if (n <= cap) {
+            CK(cudaEventRecord(C.ev[1], s));
+            launch_check_chunks(P.tab, P.chunks, P.tile_prefix, &P.d_tot->violations, s);
+            launch_emit_chains_halfkp_verify(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_cnt, cand_rec, P.ncand, white, black,
+                                             meta, &P.d_tot->violations, s);
+            LAUNCHED(2, "k_emit_chains_halfkp_verify");
+            CK(cudaEventRecord(C.ev[2], s));
+            CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(DecompressTotals), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            C.last_violations = h_tot->violations;
+            if (h_tot->violations == 0) {
+                ++C.optimistic_hits;
+                CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
+                CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[1], C.ev[2]));
+                *positions = n;
+                return P.walk_status;
+            }
+        }
+        ++C.optimistic_misses;
+    }
+
+    rc = decode_plan(d_in, in_bytes, false, P, true);
+    if (rc != NNP_OK) return rc;
+    *positions = P.positions;
+    if (!white) return P.walk_status;
+    if (P.positions > cap) return NNP_ERR_CAPACITY;
+    CK(cudaEventRecord(C.ev[1], s));
+    if (P.chunks > 0) {
+        launch_emit_chains_halfkp(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_base, P.ncand, P.chunk_base, white, black, meta,
+                                  P.d_tot, s);
+        launch_slow_emit_halfkp(d_in, P.tab, P.chunks, P.chunk_slow, P.chunk_base, white, black, meta, s);
+        LAUNCHED(2, "k_emit_chains_halfkp");
+    }
+    CK(cudaEventRecord(C.ev[2], s));
+    CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(DecompressTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
+    CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[1], C.ev[2]));
+    if (h_tot->error_chunk != NO_ERROR_IDX) {
+        *positions = 0;
+        return NNP_ERR_TRUNCATED;
+    }
+    return P.walk_status;
+}
+
+int bin_to_halfkp_dev(const void* d_bin, size_t bin_bytes, int* white, int* black, void* meta, size_t cap, size_t* positions)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    const u64 n = bin_bytes / 40;  // a short trailing record is dropped (:1360)
+    *positions = n;
+    if (!white || n == 0) return NNP_OK;
+    if (!black || !meta) return NNP_ERR_BAD_ARG;
+    if ((((uintptr_t)white | (uintptr_t)black | (uintptr_t)meta) & 15) || ((uintptr_t)d_bin & 7)) return NNP_ERR_BAD_ARG;
+    if (n > cap) return NNP_ERR_CAPACITY;
+    CompressTotals* d_tot = nullptr;
+    int rc = reset_compress_totals(&d_tot);
+    if (rc != NNP_OK) return rc;
+    CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
+    CK(cudaEventRecord(C.ev[0], s));
+    launch_bin_halfkp(d_bin, n, white, black, meta, d_tot, s);
+    LAUNCHED(1, "k_bin_halfkp");
+    CK(cudaEventRecord(C.ev[2], s));
+    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
+    C.last_dominant_ms = C.last_total_ms;
+    if (h_tot->error_index != NO_ERROR_IDX) {
+        *positions = h_tot->error_index;
+        return NNP_ERR_BAD_SFEN;
+    }
+    return NNP_OK;
+}
+
 // ---------------------------------------------------------------- host-buffer wrappers
 
 typedef int (*dev_fn)(const void*, size_t, void*, size_t, size_t*);
@@ -1153,6 +1258,23 @@ int nnp_binpack_to_plain(const void* binpack, size_t binpack_bytes, void* out, s
 {
     REQUIRE_READY();
     return run_host(binpack_to_plain_dev, binpack, binpack_bytes, out, out_cap, out_bytes, 0);
+}
+
+int nnp_binpack_to_halfkp_dev(const void* d_binpack, size_t binpack_bytes, int32_t* d_white, int32_t* d_black,
+                              nnp_halfkp_meta* d_meta, size_t cap_positions, size_t* positions)
+{
+    std::lock_guard<std::mutex> lock_(g_mutex);
+    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    if (!positions || (binpack_bytes && !d_binpack)) return NNP_ERR_BAD_ARG;
+    return binpack_to_halfkp_dev(d_binpack, binpack_bytes, d_white, d_black, d_meta, cap_positions, positions);
+}
+int nnp_bin_to_halfkp_dev(const void* d_bin, size_t bin_bytes, int32_t* d_white, int32_t* d_black, nnp_halfkp_meta* d_meta,
+                          size_t cap_positions, size_t* positions)
+{
+    std::lock_guard<std::mutex> lock_(g_mutex);
+    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    if (!positions || (bin_bytes >= 40 && !d_bin)) return NNP_ERR_BAD_ARG;
+    return bin_to_halfkp_dev(d_bin, bin_bytes, d_white, d_black, d_meta, cap_positions, positions);
 }
 
 int nnp_binpack_count_dev(const void* d_binpack, size_t binpack_bytes, uint64_t* n_positions)

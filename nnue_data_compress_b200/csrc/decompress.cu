@@ -31,6 +31,7 @@
 #include "chain.cuh"
 #include "stream.cuh"
 #include "text.cuh"
+#include "verify.cuh"
 
 namespace nnp {
 
@@ -622,15 +623,7 @@ k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const
     const unsigned char* s = in + tab.start[c] + off;
     u32 consumed = 0;
     bool ok = emit_chain_bin(s, clen - off - 34, out, rec0, ~0ull, scratch + threadIdx.x, EMITC_THREADS, consumed, &T);
-    const u32 end = off + consumed;
-    u64 prev = i, next = i + 1;  // neighbours in the chunk, skipping marked candidates
-    while (prev > 0 && cand_chunk[prev - 1] == c && cand_cnt[prev - 1] == 0) --prev;
-    while (next < ncand && cand_chunk[next] == c && cand_cnt[next] == 0) ++next;
-    const bool first = prev == 0 || cand_chunk[prev - 1] != c;
-    const bool last = next == ncand || cand_chunk[next] != c;
-    if (first && off != 0) ok = false;
-    if (last) { if ((u64)end + 34 <= clen) ok = false; }
-    else if (cand_off[next] != end) ok = false;
+    if (!reader_links_hold(cand_chunk, cand_off, cand_cnt, ncand, i, off + consumed, clen)) ok = false;
     if (!ok) atomicAdd(violations, 1ull);
 }
 

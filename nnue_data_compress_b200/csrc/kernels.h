@@ -74,6 +74,17 @@ void launch_emit_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk,
 void launch_slow_emit(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, const u64* chunk_base, void* out,
                       cudaStream_t s);
 
+// ---- HalfKP feature rows, halfkp.cu (white / black: [positions][32] int, meta: [positions] nnp_halfkp_meta)
+void launch_emit_chains_halfkp_verify(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off,
+                                      const u32* cand_cnt, const u64* cand_rec, u64 ncand, int* white, int* black, void* meta,
+                                      u64* violations, cudaStream_t s);
+void launch_emit_chains_halfkp(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off,
+                               const u32* cand_base, u64 ncand, const u64* chunk_base, int* white, int* black, void* meta,
+                               DecompressTotals* tot, cudaStream_t s);
+void launch_slow_emit_halfkp(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, const u64* chunk_base,
+                             int* white, int* black, void* meta, cudaStream_t s);
+void launch_bin_halfkp(const void* d_bin, u64 n, int* white, int* black, void* meta, CompressTotals* tot, cudaStream_t s);
+
 // ---- .plain text, plain.cu
 u64 large_sum_tiles(u64 n);
 void launch_exclusive_sum_large(const u32* in, u64 n, u64* out, u32* tile_sum, u64* tile_prefix, cudaStream_t s);

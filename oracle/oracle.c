@@ -1427,3 +1427,49 @@ int64_t orc_binpack_count(const uint8_t* in, size_t in_len)
     }
     return n;
 }
+
+/* HalfKP rows: see oracle.h (published trainer formula, not reference code) */
+int orc_bin_to_halfkp(const uint8_t* bin, size_t n, int32_t* white, int32_t* black, uint8_t* meta, size_t* bad_index)
+{
+    for (size_t r = 0; r < n; ++r) {
+        const uint8_t* rec = bin + r * 40;
+        pos_t pos;
+        int rc = sfen_unpack(rec, &pos);
+        if (rc != ORC_OK) {
+            if (bad_index) *bad_index = r;
+            return rc;
+        }
+        int ksq[2] = {0, 0}, have[2] = {0, 0};
+        for (int sq = 0; sq < 64; ++sq) {
+            uint8_t pc = pos.sq[sq];
+            if (pc != NO_PIECE && P_TYPE(pc) == PT_KING && !have[P_COLOR(pc)]) {
+                have[P_COLOR(pc)] = 1;
+                ksq[P_COLOR(pc)] = sq;
+            }
+        }
+        int32_t* w = white + r * 32;
+        int32_t* b = black + r * 32;
+        int cnt = 0;
+        /* row order: by kind as white sees it (2 * type + colour), then by square */
+        for (int kind = 0; kind < 10; ++kind) {
+            for (int sq = 0; sq < 64 && cnt < 32; ++sq) {
+                uint8_t pc = pos.sq[sq];
+                if (pc == NO_PIECE || P_TYPE(pc) == PT_KING) continue;
+                int t = P_TYPE(pc), c = P_COLOR(pc);
+                if (2 * t + c != kind) continue;
+                w[cnt] = 1 + sq + 64 * (2 * t + (c != WHITE)) + 641 * ksq[WHITE];
+                b[cnt] = 1 + (sq ^ 63) + 64 * (2 * t + (c != BLACK)) + 641 * (ksq[BLACK] ^ 63);
+                ++cnt;
+            }
+        }
+        for (int k = cnt; k < 32; ++k) w[k] = b[k] = -1;
+        uint8_t* m = meta + r * 8;
+        m[0] = rec[32]; m[1] = rec[33];           /* score */
+        m[2] = rec[36]; m[3] = rec[37];           /* gamePly */
+        m[4] = rec[38];                           /* game_result */
+        m[5] = pos.stm;
+        m[6] = (uint8_t)cnt;
+        m[7] = 0;
+    }
+    return ORC_OK;
+}

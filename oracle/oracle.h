@@ -69,6 +69,18 @@ int orc_is_continuation(const uint8_t a[40], const uint8_t b[40]);
 /* number of positions a binpack buffer holds (sum of 1 + numPlies over chains) */
 int64_t orc_binpack_count(const uint8_t* in, size_t in_len);
 
+
+/* HalfKP feature rows of n 40-byte .bin records (checker of nnp_bin_to_halfkp_dev and, composed with
+ * ORC_BINPACK_TO_BIN, of nnp_binpack_to_halfkp_dev). NOT a restatement of reference code: the
+ * reference has no feature extraction. It restates the published HalfKP index of the Stockfish NNUE
+ * trainers (nodchip learner kpp_board_index / nnue-pytorch halfkp_idx):
+ *   1 + orient(P, sq) + 64 * (2 * type + (colour != P)) + 641 * orient(P, king of P), orient(black) = sq ^ 63.
+ * PARITY UNPINNED for the index formula itself (nothing under /root/reference computes it); the
+ * positions it is applied to come from sfen_unpack, which is pinned. white / black: [n][32] int32,
+ * ordered by (2 * type + colour, square) = ascending white index, -1 padded; meta: [n][8] bytes = int16 score, uint16 ply, int8 result,
+ * uint8 stm, uint8 n_active, 0. Returns ORC_OK or ORC_ERR_BAD_SFEN (then *bad_index = the record). */
+int orc_bin_to_halfkp(const uint8_t* bin, size_t n, int32_t* white, int32_t* black, uint8_t* meta, size_t* bad_index);
+
 #ifdef __cplusplus
 }
 #endif

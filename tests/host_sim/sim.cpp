@@ -10,6 +10,8 @@
 #include "../../nnue_data_compress_b200/csrc/stream.cuh"
 #include "../../nnue_data_compress_b200/csrc/walk.cuh"
 #include "../../nnue_data_compress_b200/csrc/chain.cuh"
+#include "../../nnue_data_compress_b200/csrc/halfkp.cuh"
+#include <algorithm>
 #include <vector>
 
 using namespace nnp;
@@ -204,6 +206,114 @@ long long sim_decode_binpack(const unsigned char* in, size_t n, unsigned char* o
         pos += 8 + (size_t)size;
     }
     return (long long)rec;
+}
+
+namespace {
+// the staged row kept up to date by halfkp_apply_move must hold the same (kind, square) values as a
+// row rebuilt from the position, the map must point every listed piece at its slot
+bool row_matches(const Pos& q, const HalfKpRow& R, const int* x, const unsigned char* map)
+{
+    HalfKpRow S;
+    int y[HALFKP_STAGE];
+    halfkp_rebuild<false>(q, S, y, nullptr, 0);
+    if (S.n != R.n) return false;
+    std::vector<int> a(x, x + R.n), b(y, y + S.n);
+    std::sort(a.begin(), a.end());
+    if (a != b) return false;  // the rebuilt row is ascending
+    for (int j = 0; j < R.n; ++j)
+        if (map[x[j] & 63] != j) return false;
+    return true;
+}
+}  // namespace
+
+// Walks every chain of a .binpack with the device-side walker, keeping the HalfKP row up to date with
+// halfkp_apply_move exactly as warp_emit_chains_halfkp does, and compares it with a rebuilt row after
+// every ply. Returns the number of mismatching positions (or -1 on a malformed file); *updated counts
+// the plies handled incrementally, *rebuilt those outside halfkp_apply_move's domain.
+long long sim_halfkp_chains(const unsigned char* in, size_t n, uint64_t* updated, uint64_t* rebuilt)
+{
+    size_t pos = 0;
+    long long bad = 0;
+    *updated = *rebuilt = 0;
+    while (pos < n) {
+        if (n - pos < 8 || std::memcmp(in + pos, "BINP", 4) != 0) return -1;
+        u32 size;
+        std::memcpy(&size, in + pos + 4, 4);
+        if (n - pos - 8 < size) return -1;
+        const unsigned char* chunk = in + pos + 8;
+        u32 cur = 0;
+        while ((unsigned long long)cur + 34 <= size) {
+            ChainCursor cc;
+            chain_open(chunk + cur, cc);
+            BitReader r;
+            r.init(chunk + cur + 34, (u64)(size - cur - 34));
+            HalfKpRow R;
+            int x[HALFKP_STAGE];
+            unsigned char map[64];
+            halfkp_rebuild<true>(cc.pos, R, x, map, 1);
+            for (u32 k = 0; k < cc.num_plies; ++k) {
+                if (cc.mv.from > 63 || cc.mv.to > 63) return -1;
+                const int moved = pos_piece_at(cc.pos, cc.mv.from);
+                const bool inc = halfkp_apply_move(cc.pos, cc.mv, moved, R, x, map, 1);
+                if (!chain_step(cc, r, false, moved)) return -1;
+                const int pieces = popc64(pos_all(cc.pos) & ~pos_type_bb(cc.pos, PT_KING));
+                if (!inc || pieces != R.n) {
+                    halfkp_rebuild<true>(cc.pos, R, x, map, 1);
+                    ++*rebuilt;
+                } else {
+                    ++*updated;
+                    if (!row_matches(cc.pos, R, x, map)) ++bad;
+                }
+            }
+            cur += 34 + ((r.pos + 7) >> 3);
+        }
+        pos += 8 + (size_t)size;
+    }
+    return bad;
+}
+
+// Pseudo-random moves of all four types (mostly illegal) on the positions of a .bin: whatever
+// halfkp_apply_move accepts must give the row of the position pos_do_move produces.
+uint64_t sim_halfkp_fuzz(const unsigned char* bin, size_t n, int moves_per_pos, uint64_t seed, uint64_t* mismatch)
+{
+    uint64_t accepted = 0, xs = seed;
+    *mismatch = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const Rec r = load(bin, i);
+        Pos p;
+        pos_clear(p);
+        if (!sfen_decode([&](int j) { return r.w[j]; }, p)) continue;
+        for (int k = 0; k < moves_per_pos; ++k) {
+            xs = xs * 6364136223846793005ull + 1442695040888963407ull;
+            const u32 v = (u32)(xs >> 33);
+            Move m;
+            m.from = v & 63;
+            m.to = (v >> 6) & 63;
+            m.type = (v >> 12) & 3;
+            m.promo = NO_PIECE;
+            if ((v >> 20) & 1) {
+                u64 all = pos_all(p);
+                m.from = nth_set_bit(all, (v >> 21) % (u32)popc64(all));
+            }
+            if (m.type == MT_CASTLE && ((v >> 14) & 1)) {
+                m.from = ((v >> 15) & 1) ? 4 : 60;
+                m.to = (m.from & 56) + (((v >> 16) & 1) ? 7 : 0);
+            }
+            if (m.type == MT_PROMOTION) m.promo = ((PT_KNIGHT + (int)((v >> 17) & 3)) << 1) | (int)((v >> 19) & 1);
+            HalfKpRow R;
+            int x[HALFKP_STAGE];
+            unsigned char map[64];
+            halfkp_rebuild<true>(p, R, x, map, 1);
+            const int moved = pos_piece_at(p, m.from);
+            if (!halfkp_apply_move(p, m, moved, R, x, map, 1)) continue;
+            Pos q = p;
+            pos_do_move(q, m, moved);
+            if (popc64(pos_all(q) & ~pos_type_bb(q, PT_KING)) != R.n) continue;  // the caller rebuilds
+            ++accepted;
+            if (!row_matches(q, R, x, map)) ++*mismatch;
+        }
+    }
+    return accepted;
 }
 
 }  // extern "C"

@@ -51,8 +51,55 @@ def oracle():
         lib.orc_is_continuation.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
         lib.orc_binpack_count.restype = ctypes.c_int64
         lib.orc_binpack_count.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+        lib.orc_bin_to_halfkp.restype = ctypes.c_int
+        lib.orc_bin_to_halfkp.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
         _oracle = lib
     return _oracle
+
+
+def oracle_halfkp(bin_data):
+    """HalfKP rows of .bin records by the oracle: (rc, white [n,32] int32, black [n,32] int32, meta [n,8] uint8,
+    index of the first malformed record)."""
+    import numpy as np
+
+    n = len(bin_data) // 40
+    white = np.empty((n, 32), dtype=np.int32)
+    black = np.empty((n, 32), dtype=np.int32)
+    meta = np.empty((n, 8), dtype=np.uint8)
+    bad = ctypes.c_size_t(n)
+    rc = oracle().orc_bin_to_halfkp(bytes(bin_data), n, white.ctypes.data, black.ctypes.data, meta.ctypes.data,
+                                    ctypes.byref(bad))
+    return rc, white, black, meta, bad.value
+
+
+def halfkp_from_fen(fen):
+    """The published HalfKP index (nnue-pytorch halfkp_idx) from a FEN string, written independently
+    of the oracle's C code: returns (white row, black row) as lists ordered by (kind as white sees it, square)."""
+    board = fen.split()[0]
+    pieces = {}
+    for r, row in enumerate(board.split("/")):
+        f = 0
+        for ch in row:
+            if ch.isdigit():
+                f += int(ch)
+            else:
+                pieces[(7 - r) * 8 + f] = ch
+                f += 1
+    ksq = {True: next(s for s, c in sorted(pieces.items()) if c == "K"),
+           False: next(s for s, c in sorted(pieces.items()) if c == "k")}
+    rows = {}
+    for white_pov in (True, False):
+        def orient(sq):
+            return sq if white_pov else sq ^ 63
+        row = []
+        for sq, ch in sorted(pieces.items(), key=lambda it: ("pnbrq".find(it[1].lower()) * 2 + it[1].islower(), it[0])):
+            if ch in "Kk":
+                continue
+            p_idx = "pnbrq".index(ch.lower()) * 2 + (ch.isupper() != white_pov)
+            row.append(1 + orient(sq) + p_idx * 64 + orient(ksq[white_pov]) * 641)
+        rows[white_pov] = row
+    return rows[True], rows[False]
 
 
 def oracle_convert(mode, data):

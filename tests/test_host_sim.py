@@ -17,7 +17,7 @@ CSRC = os.path.join(ROOT, "nnue_data_compress_b200", "csrc")
 @pytest.fixture(scope="module")
 def sim():
     srcs = [os.path.join(SIM_DIR, "sim.cpp"), os.path.join(SIM_DIR, "host_sim.h")] + [
-        os.path.join(CSRC, f) for f in ("chess.cuh", "stream.cuh", "walk.cuh", "link.cuh", "chain.cuh")]
+        os.path.join(CSRC, f) for f in ("chess.cuh", "stream.cuh", "walk.cuh", "link.cuh", "chain.cuh", "halfkp.cuh")]
     if not os.path.exists(SIM_SO) or any(os.path.getmtime(s) > os.path.getmtime(SIM_SO) for s in srcs):
         subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-DNNP_HOST_SIM", "-I" + SIM_DIR,
                         "-shared", "-fPIC", "-o", SIM_SO, srcs[0]], check=True)
@@ -30,6 +30,10 @@ def sim():
     L.sim_walk_check.restype = ctypes.c_uint64
     L.sim_decode_binpack.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
     L.sim_decode_binpack.restype = ctypes.c_longlong
+    L.sim_halfkp_chains.argtypes = [ctypes.c_char_p, ctypes.c_size_t, u64p, u64p]
+    L.sim_halfkp_chains.restype = ctypes.c_longlong
+    L.sim_halfkp_fuzz.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, u64p]
+    L.sim_halfkp_fuzz.restype = ctypes.c_uint64
     return L
 
 
@@ -103,3 +107,27 @@ def test_chain_decoder_reproduces_reference_bin(sim):
         n = sim.sim_decode_binpack(bp, len(bp), out, len(want) // 40)
         assert n == len(want) // 40
         assert out.raw[: len(want)] == want
+
+
+def test_halfkp_row_updates_equal_rebuilt_rows(sim):
+    """halfkp_apply_move (the in-place row update of the HalfKP chain kernels) against rows rebuilt
+    from the position after every ply; on data written from legal games every ply is incremental."""
+    packs = [(s, golden(s + ".binpack")) for s in GOLDEN_SETS]
+    if have_ref():
+        from refutil import BIN_TO_BINPACK, oracle_convert
+        for name, b in (("gen100", ref_generate(120_000, 100, 42, 0)), ("gen400", ref_generate(40_000, 400, 9, 0))):
+            packs.append((name, oracle_convert(BIN_TO_BINPACK, b)[1]))
+    total = 0
+    for name, bp in packs:
+        upd, reb = ctypes.c_uint64(), ctypes.c_uint64()
+        bad = sim.sim_halfkp_chains(bp, len(bp), ctypes.byref(upd), ctypes.byref(reb))
+        assert bad == 0 and reb.value == 0, (name, bad, upd.value, reb.value)
+        total += upd.value
+    assert total > 100_000
+
+
+def test_halfkp_row_update_fuzz(sim):
+    b = golden("long400.bin") + golden("games100.bin")
+    mm = ctypes.c_uint64()
+    accepted = sim.sim_halfkp_fuzz(b, len(b) // 40, 256, 11, ctypes.byref(mm))
+    assert accepted > 50_000 and mm.value == 0
