@@ -77,7 +77,7 @@ k_emit_chains_halfkp_verify(const unsigned char* __restrict__ in, ChunkTable tab
                             const u32* __restrict__ cand_off, const u32* __restrict__ cand_cnt,
                             const u64* __restrict__ cand_rec, u64 ncand, HalfKpOut out, u64* __restrict__ violations)
 {
-    __shared__ int stage[HALFKP_STAGE * HKP_THREADS];
+    __shared__ __align__(16) int stage[HALFKP_STAGE * HKP_THREADS];
     __shared__ unsigned char maps[64 * HKP_THREADS];
     __shared__ StepTables T;
     step_tables_fill(T);
@@ -104,7 +104,7 @@ k_emit_chains_halfkp(const unsigned char* __restrict__ in, ChunkTable tab, const
                      const u32* __restrict__ cand_off, const u32* __restrict__ cand_base, u64 ncand,
                      const u64* __restrict__ chunk_base, HalfKpOut out, DecompressTotals* tot)
 {
-    __shared__ int stage[HALFKP_STAGE * HKP_THREADS];
+    __shared__ __align__(16) int stage[HALFKP_STAGE * HKP_THREADS];
     __shared__ unsigned char maps[64 * HKP_THREADS];
     __shared__ StepTables T;
     step_tables_fill(T);
@@ -156,7 +156,7 @@ __global__ void k_slow_emit_halfkp(const unsigned char* __restrict__ in, ChunkTa
 __global__ void __launch_bounds__(HKP_THREADS)
 k_bin_halfkp(const unsigned char* __restrict__ bin, u64 n, HalfKpOut out, CompressTotals* tot)
 {
-    __shared__ int stage[HALFKP_STAGE * HKP_THREADS];
+    __shared__ __align__(16) int stage[HALFKP_STAGE * HKP_THREADS];
     const u64 i = (u64)blockIdx.x * HKP_THREADS + threadIdx.x;
     bool wr = false;
     HalfKpRow R;

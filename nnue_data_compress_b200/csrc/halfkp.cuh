@@ -29,7 +29,7 @@ namespace nnp {
 
 constexpr int HALFKP_ROW = 32;
 constexpr int HALFKP_PLANES = 641;
-constexpr int HALFKP_STAGE = HALFKP_ROW + 1;  // words per staged row: odd, so that lanes hit different banks
+constexpr int HALFKP_STAGE = HALFKP_ROW + 4;  // words per staged row: 16-byte aligned rows, eight lanes of a row read 128 B
 
 struct HalfKpOut {
     int* white;   // [positions][HALFKP_ROW]
@@ -160,22 +160,23 @@ __device__ __forceinline__ uint2 halfkp_meta(const Pos& p, int score, int ply, i
 __device__ __forceinline__ void halfkp_store_warp(u32 mask, u64 rec, const HalfKpRow& R, const int* warp_x, const HalfKpOut& o)
 {
     const int lane = threadIdx.x & 31;
-#pragma unroll 2
+    const int sub = lane >> 3, chunk = lane & 7, j = 4 * chunk;
+    const u32 bases = (u32)R.wbase | ((u32)R.bbase << 16);  // both below 1 + 641 * 64
+#pragma unroll 4
     for (int i = 0; i < 8; ++i) {
-        const int r = 4 * i + (lane >> 3), chunk = lane & 7;
+        const int r = 4 * i + sub;
         const u64 rr = __shfl_sync(0xffffffffu, rec, r);
-        const int n = __shfl_sync(0xffffffffu, R.n, r);
-        const int wb = __shfl_sync(0xffffffffu, R.wbase, r), bb = __shfl_sync(0xffffffffu, R.bbase, r);
+        const int left = __shfl_sync(0xffffffffu, R.n, r) - j;  // entries of the row at or behind this lane's first
+        const u32 pk = __shfl_sync(0xffffffffu, bases, r);
         if (!((mask >> (4 * i)) & 15u)) continue;
         if ((mask >> r) & 1u) {
-            const int* q = warp_x + r * HALFKP_STAGE + 4 * chunk;
-            const int j = 4 * chunk;
-            const int x0 = q[0], x1 = q[1], x2 = q[2], x3 = q[3];
+            const int4 x = *reinterpret_cast<const int4*>(warp_x + r * HALFKP_STAGE + j);
+            const int wb = (int)(pk & 0xFFFFu), bb = (int)(pk >> 16);
+            const int m0 = left > 0 ? 0 : -1, m1 = left > 1 ? 0 : -1, m2 = left > 2 ? 0 : -1, m3 = left > 3 ? 0 : -1;  // padding
             reinterpret_cast<int4*>(o.white + rr * HALFKP_ROW)[chunk] =
-                make_int4(j + 0 < n ? wb + x0 : -1, j + 1 < n ? wb + x1 : -1, j + 2 < n ? wb + x2 : -1, j + 3 < n ? wb + x3 : -1);
+                make_int4((wb + x.x) | m0, (wb + x.y) | m1, (wb + x.z) | m2, (wb + x.w) | m3);
             reinterpret_cast<int4*>(o.black + rr * HALFKP_ROW)[chunk] =
-                make_int4(j + 0 < n ? bb + (x0 ^ 127) : -1, j + 1 < n ? bb + (x1 ^ 127) : -1, j + 2 < n ? bb + (x2 ^ 127) : -1,
-                          j + 3 < n ? bb + (x3 ^ 127) : -1);
+                make_int4((bb + (x.x ^ 127)) | m0, (bb + (x.y ^ 127)) | m1, (bb + (x.z ^ 127)) | m2, (bb + (x.w ^ 127)) | m3);
         }
     }
 }
