@@ -316,4 +316,41 @@ uint64_t sim_halfkp_fuzz(const unsigned char* bin, size_t n, int moves_per_pos, 
     return accepted;
 }
 
+// HalfKP rows of every position of a .binpack, each rebuilt from the chain walker's position
+// ((kind, square) order): the reference for inputs whose positions a .bin record cannot hold (corrupted
+// movetext that captures a king), where rows made from the oracle's .bin differ by construction.
+// Returns the number of rows, or -1 on a malformed file.
+long long sim_halfkp_rows(const unsigned char* in, size_t n, int* white, int* black, size_t cap_rows)
+{
+    size_t pos = 0;
+    unsigned long long rec = 0;
+    auto emit = [&](const Pos& q) {
+        if (rec < cap_rows) {
+            HalfKpRow R;
+            int x[HALFKP_STAGE];
+            halfkp_rebuild<false>(q, R, x, nullptr, 0);
+            for (int j = 0; j < HALFKP_ROW; ++j) {
+                white[rec * HALFKP_ROW + j] = j < R.n ? R.wbase + x[j] : -1;
+                black[rec * HALFKP_ROW + j] = j < R.n ? R.bbase + (x[j] ^ 127) : -1;
+            }
+        }
+        ++rec;
+    };
+    while (pos < n) {
+        if (n - pos < 8 || std::memcmp(in + pos, "BINP", 4) != 0) return -1;
+        u32 size;
+        std::memcpy(&size, in + pos + 4, 4);
+        if (n - pos - 8 < size) return -1;
+        const unsigned char* chunk = in + pos + 8;
+        u32 cur = 0;
+        while ((unsigned long long)cur + 34 <= size) {
+            u32 consumed = 0;
+            if (!walk_chain(chunk + cur, size - cur - 34, [&](const ChainCursor& cc, u32) { emit(cc.pos); }, consumed)) return -1;
+            cur += consumed;
+        }
+        pos += 8 + (size_t)size;
+    }
+    return (long long)rec;
+}
+
 }  // extern "C"

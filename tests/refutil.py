@@ -154,3 +154,37 @@ def golden(name):
 
 GOLDEN_SETS = ["games100", "heads", "long400", "shuffled", "restart", "twochunks"]
 GOLDEN_PLAIN_SETS = ["games100", "heads", "long400"]
+
+
+_sim = None
+
+
+def host_sim():
+    """tests/host_sim: the device headers compiled for the CPU (TEST INFRASTRUCTURE, see host_sim.h)."""
+    global _sim
+    if _sim is None:
+        sim_dir = os.path.join(ROOT, "tests", "host_sim")
+        so = os.path.join(sim_dir, "libsim.so")
+        csrc = os.path.join(ROOT, "nnue_data_compress_b200", "csrc")
+        srcs = [os.path.join(sim_dir, "sim.cpp"), os.path.join(sim_dir, "host_sim.h")] + [
+            os.path.join(csrc, f) for f in ("chess.cuh", "stream.cuh", "walk.cuh", "link.cuh", "chain.cuh", "halfkp.cuh")]
+        if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in srcs):
+            subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-DNNP_HOST_SIM", "-I" + sim_dir,
+                            "-shared", "-fPIC", "-o", so, srcs[0]], check=True)
+        L = ctypes.CDLL(so)
+        u64p = ctypes.POINTER(ctypes.c_uint64)
+        L.sim_stream_check.argtypes = [ctypes.c_char_p, ctypes.c_size_t, u64p, u64p, u64p, u64p]
+        L.sim_stream_fuzz.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, u64p]
+        L.sim_stream_fuzz.restype = ctypes.c_uint64
+        L.sim_walk_check.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, u64p, u64p]
+        L.sim_walk_check.restype = ctypes.c_uint64
+        L.sim_decode_binpack.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+        L.sim_decode_binpack.restype = ctypes.c_longlong
+        L.sim_halfkp_chains.argtypes = [ctypes.c_char_p, ctypes.c_size_t, u64p, u64p]
+        L.sim_halfkp_chains.restype = ctypes.c_longlong
+        L.sim_halfkp_fuzz.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, u64p]
+        L.sim_halfkp_fuzz.restype = ctypes.c_uint64
+        L.sim_halfkp_rows.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        L.sim_halfkp_rows.restype = ctypes.c_longlong
+        _sim = L
+    return _sim

@@ -113,3 +113,56 @@ def test_errors_and_empty(nnp):
     with pytest.raises(nnp.NnpError) as e:
         nnp.halfkp_rows(_dev(bytes(b)), "bin", positions=50)
     assert e.value.status == -3
+
+
+def test_sequential_fallback_rows(nnp):
+    """reject_mod drops a pseudo-random subset of chain-start candidates: the optimistic walk fails and
+    the affected chunks go through k_slow_emit_halfkp; the rows must not change."""
+    binpack = golden("twochunks.binpack")
+    rc, want_bin = oracle_convert(BINPACK_TO_BIN, binpack)
+    _, white, black, meta, _ = oracle_halfkp(want_bin)
+    nnp.use_torch_stream()
+    assert nnp.lib().nnp_debug_config(b"reject_mod", 5) == 0
+    try:
+        w, k, m = nnp.halfkp_rows(_dev(binpack))
+    finally:
+        nnp.lib().nnp_debug_config(b"reject_mod", 0)
+    # the sequential kernel rebuilds every row: (kind, square) order, no sorting needed for its chunks
+    w, k = _sorted_pairs(w.cpu().numpy(), k.cpu().numpy())
+    assert np.array_equal(w, white) and np.array_equal(k, black) and np.array_equal(m.cpu().numpy(), meta)
+
+
+def test_corrupted_movetext_rows_follow_the_walker(nnp):
+    """Bit flips in the movetext produce moves no legal game contains (pieces appearing from nothing,
+    kings captured, castling through pieces): the in-place row update must fall back to rebuilding the
+    row exactly there. The reference here is tests/host_sim (rows rebuilt per position from the same
+    chain walker on the CPU), because a position without a king has no faithful .bin record for the
+    oracle to start from; the walker itself is pinned by the .bin parity tests on the same inputs."""
+    import random
+
+    from refutil import host_sim
+
+    sim = host_sim()
+    rng = random.Random(414)
+    packs = [golden(n + ".binpack") for n in ("games100", "long400", "restart")]
+    nnp.use_torch_stream()
+    compared = 0
+    for _ in range(300):
+        b = bytearray(rng.choice(packs))
+        for _ in range(rng.randrange(1, 5)):
+            b[rng.randrange(8, len(b))] ^= 1 << rng.randrange(8)
+        b = bytes(b)
+        try:
+            w, k, m = nnp.halfkp_rows(_dev(b))
+        except nnp.NnpError as e:
+            assert e.status == -4, e.status
+            continue
+        n = w.shape[0]
+        white = np.empty((n + 1, 32), dtype=np.int32)
+        black = np.empty((n + 1, 32), dtype=np.int32)
+        assert sim.sim_halfkp_rows(b, len(b), white.ctypes.data, black.ctypes.data, n + 1) == n
+        w, k = _sorted_pairs(w.cpu().numpy(), k.cpu().numpy())
+        # the walker's rows are in (kind, square) order = ascending white index, like the sorted pairs
+        assert np.array_equal(w, white[:n]) and np.array_equal(k, black[:n])
+        compared += 1
+    assert compared > 50

@@ -7,7 +7,7 @@ import subprocess
 
 import pytest
 
-from refutil import GOLDEN_SETS, ROOT, golden, have_ref, ref_generate
+from refutil import GOLDEN_SETS, ROOT, golden, have_ref, host_sim, ref_generate
 
 SIM_DIR = os.path.join(ROOT, "tests", "host_sim")
 SIM_SO = os.path.join(SIM_DIR, "libsim.so")
@@ -16,25 +16,7 @@ CSRC = os.path.join(ROOT, "nnue_data_compress_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def sim():
-    srcs = [os.path.join(SIM_DIR, "sim.cpp"), os.path.join(SIM_DIR, "host_sim.h")] + [
-        os.path.join(CSRC, f) for f in ("chess.cuh", "stream.cuh", "walk.cuh", "link.cuh", "chain.cuh", "halfkp.cuh")]
-    if not os.path.exists(SIM_SO) or any(os.path.getmtime(s) > os.path.getmtime(SIM_SO) for s in srcs):
-        subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-DNNP_HOST_SIM", "-I" + SIM_DIR,
-                        "-shared", "-fPIC", "-o", SIM_SO, srcs[0]], check=True)
-    L = ctypes.CDLL(SIM_SO)
-    u64p = ctypes.POINTER(ctypes.c_uint64)
-    L.sim_stream_check.argtypes = [ctypes.c_char_p, ctypes.c_size_t, u64p, u64p, u64p, u64p]
-    L.sim_stream_fuzz.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, u64p]
-    L.sim_stream_fuzz.restype = ctypes.c_uint64
-    L.sim_walk_check.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, u64p, u64p]
-    L.sim_walk_check.restype = ctypes.c_uint64
-    L.sim_decode_binpack.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
-    L.sim_decode_binpack.restype = ctypes.c_longlong
-    L.sim_halfkp_chains.argtypes = [ctypes.c_char_p, ctypes.c_size_t, u64p, u64p]
-    L.sim_halfkp_chains.restype = ctypes.c_longlong
-    L.sim_halfkp_fuzz.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, u64p]
-    L.sim_halfkp_fuzz.restype = ctypes.c_uint64
-    return L
+    return host_sim()
 
 
 def _inputs():
@@ -131,3 +113,19 @@ def test_halfkp_row_update_fuzz(sim):
     mm = ctypes.c_uint64()
     accepted = sim.sim_halfkp_fuzz(b, len(b) // 40, 256, 11, ctypes.byref(mm))
     assert accepted > 50_000 and mm.value == 0
+
+
+def test_halfkp_rows_of_the_walker_equal_the_oracle(sim):
+    """sim_halfkp_rows (rows rebuilt from the chain walker's positions; the GPU suite's reference for
+    corrupted movetext) against the oracle's rows of the decoded .bin on well-formed files."""
+    import numpy as np
+    from refutil import BINPACK_TO_BIN, oracle_convert, oracle_halfkp
+    for name in GOLDEN_SETS:
+        bp = golden(name + ".binpack")
+        rc, want_bin = oracle_convert(BINPACK_TO_BIN, bp)
+        _, white, black, _meta, _ = oracle_halfkp(want_bin)
+        n = len(want_bin) // 40
+        w = np.empty((n, 32), dtype=np.int32)
+        k = np.empty((n, 32), dtype=np.int32)
+        assert sim.sim_halfkp_rows(bp, len(bp), w.ctypes.data, k.ctypes.data, n) == n
+        assert np.array_equal(w, white) and np.array_equal(k, black), name
