@@ -180,9 +180,9 @@ int nnp_binpack_to_bin_file(const char* in_path, const char* out_path, int appen
  *   orient(white, sq) = sq, orient(black, sq) = sq ^ 63, type pawn..queen = 0..4, kings excluded.
  * Row r belongs to record r of the .bin file nnp_binpack_to_bin writes for the same input (for the
  * .bin entry point: to record r of the input). d_white / d_black: [positions][NNP_HALFKP_ROW] int32,
- * the non-king pieces, the same piece at the same slot of both rows, padded with -1 at the end. Rows
- * made from .bin records and from chain heads are ordered by (2 * type + colour, square), i.e. the
- * white row ascends; along a chain the row is updated in place (a piece keeps its slot while it stands,
+ * the non-king pieces, the same piece at the same slot of both rows, padded with -1 at the end. A
+ * chain head's row is ordered by (2 * type + colour, square), i.e. the white row ascends; a .bin
+ * record's row follows its Huffman stream (rank 8 first, files a to h); along a chain the row is updated in place (a piece keeps its slot while it stands,
  * the row's last entry takes over the slot of a captured piece), so the order is deterministic but
  * follows the chain's history -- a sparse feature transformer sums over the row and does not care; d_meta: [positions] nnp_halfkp_meta. All three 16-byte aligned. d_white == NULL: count
  * only (*positions is set). NNP_ERR_CAPACITY when cap_positions is too small (*positions = needed).

@@ -401,10 +401,12 @@ __device__ __forceinline__ u32 move_to_sfmove(const Move& m)
 // count-trailing-zeros, every piece sets one bit in each of the planes it belongs to. The planes of
 // this half are 32-bit registers: stream square s (rank 8 first) is square s ^ 56, i.e. bit
 // (s ^ 24) & 31 of the other 32-bit half.
-template <typename WordFn>
+// on_piece(square, token) sees every piece token in stream order (the HalfKP row of a .bin record is
+// listed straight from it; the other callers pass nothing).
+template <typename WordFn, typename PieceFn>
 __device__ __forceinline__ void sfen_decode_half(WordFn W, u32& wlo, u32& whi, int& avail, int& nextw, int& idx,
                                                  const int idx_end, const int ka, const int kb, u32& err, u32& o0,
-                                                 u32& o1, u32& q0, u32& q1, u32& q2)
+                                                 u32& o1, u32& q0, u32& q1, u32& q2, PieceFn on_piece)
 {
     while (idx < idx_end) {
         if (avail < 32) {  // insert the next word above the valid bits
@@ -432,6 +434,7 @@ __device__ __forceinline__ void sfen_decode_half(WordFn W, u32& wlo, u32& whi, i
         if (tok & 2u) q0 |= b;
         if (tok & 4u) q1 |= b;
         if (tok & 8u) q2 |= b;
+        on_piece(s ^ 56, tok);
         idx += 1;
         wlo = __funnelshift_rc(wlo, whi, 5);
         whi >>= 5;
@@ -439,8 +442,8 @@ __device__ __forceinline__ void sfen_decode_half(WordFn W, u32& wlo, u32& whi, i
     }
 }
 
-template <typename WordFn>
-__device__ __forceinline__ bool sfen_decode(WordFn W, Pos& p)
+template <typename WordFn, typename PieceFn>
+__device__ __forceinline__ bool sfen_decode(WordFn W, Pos& p, PieceFn on_piece)
 {
     const u32 w0 = W(0), w1 = W(1);
     p.stm = w0 & 1;
@@ -457,8 +460,8 @@ __device__ __forceinline__ bool sfen_decode(WordFn W, Pos& p)
     u32 err = 0;
     u32 o0h = 0, o1h = 0, q0h = 0, q1h = 0, q2h = 0;  // squares 32..63 (ranks 5..8)
     u32 o0l = 0, o1l = 0, q0l = 0, q1l = 0, q2l = 0;  // squares 0..31  (ranks 1..4)
-    sfen_decode_half(W, wlo, whi, avail, nextw, idx, half_tok, ka, kb, err, o0h, o1h, q0h, q1h, q2h);
-    sfen_decode_half(W, wlo, whi, avail, nextw, idx, ntok, ka, kb, err, o0l, o1l, q0l, q1l, q2l);
+    sfen_decode_half(W, wlo, whi, avail, nextw, idx, half_tok, ka, kb, err, o0h, o1h, q0h, q1h, q2h, on_piece);
+    sfen_decode_half(W, wlo, whi, avail, nextw, idx, ntok, ka, kb, err, o0l, o1l, q0l, q1l, q2l, on_piece);
     p.occ[0] = ((u64)o0h << 32) | o0l;
     p.occ[1] = ((u64)o1h << 32) | o1l;
     p.t0 = ((u64)q0h << 32) | q0l;
@@ -495,6 +498,12 @@ __device__ __forceinline__ bool sfen_decode(WordFn W, Pos& p)
     // the reference checks the cursor after every piece and at the end (:407-408, :441-442); it only
     // grows, so the final value decides. Type codes 5..7 never terminate its table search (:336-352).
     return cursor <= 256 && err == 0;
+}
+
+template <typename WordFn>
+__device__ __forceinline__ bool sfen_decode(WordFn W, Pos& p)
+{
+    return sfen_decode(W, p, [](int, u32) {});
 }
 
 // SfenPacker::pack (compress_file.cpp:266-312) into eight 32-bit words out[0..7].

@@ -4,7 +4,8 @@
 //   k_emit_chains_halfkp_verify   optimistic strategy (one walk, links verified, see decompress.cu)
 //   k_emit_chains_halfkp          exhaustive strategy, after probe / resolve
 //   k_slow_emit_halfkp            sequential per-chunk net
-//   k_bin_halfkp                  one thread per 40-byte record (pos_from_packed_sfen :364-446)
+//   k_bin_halfkp                  one thread per 40-byte record (pos_from_packed_sfen :364-446), the row
+//                                 listed from the record's piece tokens as they are decoded
 //
 // Rows are written at the position's index in reader order, i.e. row r describes the record r of the
 // .bin file decompressBin (:1376-1412) writes for the same input.
@@ -164,10 +165,21 @@ k_bin_halfkp(const unsigned char* __restrict__ bin, u64 n, HalfKpOut out, Compre
     if (i < n) {
         const u32* w = reinterpret_cast<const u32*>(bin + i * 40);
         Pos p;
-        wr = sfen_decode([&](int j) { return w[j]; }, p);
+        int* x = stage + threadIdx.x * HALFKP_STAGE;
+        int listed = 0;
+        // the Huffman stream names every non-king piece in turn: the row is listed while it is decoded
+        wr = sfen_decode([&](int j) { return w[j]; }, p, [&](int sq, u32 tok) {
+            if (listed < HALFKP_ROW) x[listed] = 64 * (int)(((tok >> 1) & 7u) * 2u + ((tok >> 4) & 1u)) + sq;
+            ++listed;
+        });
         if (wr) {
             const u32 w8 = w[8], w9 = w[9];
-            halfkp_rebuild<false>(p, R, stage + threadIdx.x * HALFKP_STAGE, nullptr, 0);
+            if (listed > HALFKP_ROW) {
+                halfkp_rebuild<false>(p, R, x, nullptr, 0);  // more than 32 pieces (no writer emits that): the first 32 by (kind, square)
+            } else {
+                R.n = listed;
+                halfkp_bases(p, R);
+            }
             out.meta[i] = halfkp_meta(p, (int)(short)(w8 & 0xFFFF), (int)(w9 & 0xFFFF), (int)(signed char)((w9 >> 16) & 0xFF), R.n);
         } else {
             atomicMin(&tot->error_index, i);

@@ -14,9 +14,9 @@
 //
 // 641 = 10 * 64 + 1 planes per king square, 64 * 641 = 41024 features. Entry j of the white and
 // of the black row describe the same piece; rows are padded with -1 to HALFKP_ROW entries. Order of
-// the entries: rows made from a position alone (.bin records, chain heads) list the pieces by kind as
-// white sees it (white pawn, black pawn, white knight, ... black queen) and by ascending square within
-// a kind, so the white row ascends. Along a chain the row is UPDATED, not rebuilt (a move touches one
+// the entries: a chain head's row lists the pieces by kind as white sees it (white pawn, black pawn,
+// white knight, ... black queen) and by ascending square within a kind, so the white row ascends; a
+// .bin record's row lists them as its Huffman stream does (rank 8 first, files a to h). Along a chain the row is UPDATED, not rebuilt (a move touches one
 // or two entries; rebuilding costs more than decoding the move): a piece keeps its slot while it
 // stands, and the slot of a captured piece is taken over by the row's last entry. The order is thus
 // deterministic but depends on the chain's history; the consumer (a sparse feature transformer sums

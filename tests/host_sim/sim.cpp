@@ -353,4 +353,29 @@ long long sim_halfkp_rows(const unsigned char* in, size_t n, int* white, int* bl
     return (long long)rec;
 }
 
+// The row k_bin_halfkp lists from the piece tokens of a record while decoding it, against the row
+// rebuilt from the decoded position: same entries (the order differs). Returns the mismatches.
+uint64_t sim_halfkp_tokens(const unsigned char* bin, size_t n)
+{
+    uint64_t bad = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const Rec r = load(bin, i);
+        Pos p;
+        int x[64], listed = 0;
+        const bool ok = sfen_decode([&](int j) { return r.w[j]; }, p, [&](int sq, u32 tok) {
+            if (listed < 64) x[listed] = 64 * (int)(((tok >> 1) & 7u) * 2u + ((tok >> 4) & 1u)) + sq;
+            ++listed;
+        });
+        if (!ok) continue;
+        HalfKpRow S;
+        int y[HALFKP_STAGE];
+        halfkp_rebuild<false>(p, S, y, nullptr, 0);
+        if (listed > HALFKP_ROW) continue;  // the kernel rebuilds these
+        std::vector<int> a(x, x + listed), b(y, y + S.n);
+        std::sort(a.begin(), a.end());
+        if (a != b) ++bad;
+    }
+    return bad;
+}
+
 }  // extern "C"

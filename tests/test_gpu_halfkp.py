@@ -1,9 +1,9 @@
 """GPU suite (-m gpu): HalfKP feature rows produced on the device (nnp_binpack_to_halfkp_dev,
 nnp_bin_to_halfkp_dev) against the oracle: rows(binpack) must equal the oracle's rows
-of the .bin file the oracle decodes from the same binpack. Integer work: equality is exact. Rows made
-from .bin records are in the oracle's (kind, square) order; rows made along a chain keep pieces in their
-slots (include/nnuepack.h), so their (white, black) pairs are sorted by the white index before comparing --
-which also checks that slot j of both rows describes the same piece."""
+of the .bin file the oracle decodes from the same binpack. Integer work: equality is exact. The order
+of a row's entries follows the source (include/nnuepack.h: stream order for .bin records, slot-stable
+along a chain), the oracle's is (kind, square): the (white, black) pairs are sorted by the white index
+before comparing -- which also checks that slot j of both rows describes the same piece."""
 import numpy as np
 import pytest
 import torch
@@ -36,8 +36,7 @@ def _check(nnp, binpack):
         w, k = w.cpu().numpy(), k.cpu().numpy()
         assert ((w >= 0).sum(axis=1) == meta[:, 6]).all() and ((w >= 0) == (k >= 0)).all(), kind
         assert (np.diff((w >= 0).astype(np.int8), axis=1) <= 0).all(), kind  # padding only at the end
-        if kind == "binpack":
-            w, k = _sorted_pairs(w, k)
+        w, k = _sorted_pairs(w, k)
         assert np.array_equal(w, white), kind
         assert np.array_equal(k, black), kind
         assert np.array_equal(m.cpu().numpy(), meta), kind

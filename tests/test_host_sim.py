@@ -129,3 +129,10 @@ def test_halfkp_rows_of_the_walker_equal_the_oracle(sim):
         k = np.empty((n, 32), dtype=np.int32)
         assert sim.sim_halfkp_rows(bp, len(bp), w.ctypes.data, k.ctypes.data, n) == n
         assert np.array_equal(w, white) and np.array_equal(k, black), name
+
+
+def test_halfkp_row_listed_from_sfen_tokens(sim):
+    """k_bin_halfkp lists a record's row from the piece tokens sfen_decode hands out; it must hold the
+    entries of the row rebuilt from the decoded position."""
+    for name, b in _inputs():
+        assert sim.sim_halfkp_tokens(b, len(b) // 40) == 0, name

@@ -41,7 +41,14 @@ for it in range(3):
 print(f"two-step: binpack->bin {t1:.3f} ms + bin->halfkp {a.value:.3f} ms = {t1 + a.value:.3f} ms (fused {fused:.3f})")
 torch.cuda.synchronize()
 big = torch.iinfo(torch.int32).max
-order = torch.where(white[:2_000_000] < 0, big, white[:2_000_000]).argsort(dim=1, stable=True)
-print("same rows (first 2M, pairs sorted by white index):",
-      torch.equal(white[:2_000_000].gather(1, order), w2[:2_000_000]) and torch.equal(black[:2_000_000].gather(1, order), k2[:2_000_000])
-      and torch.equal(meta, m2))
+M = 2_000_000
+
+
+def sorted_pairs(w, k):
+    order = torch.where(w < 0, big, w).argsort(dim=1, stable=True)
+    return w.gather(1, order), k.gather(1, order)
+
+
+a_w, a_k = sorted_pairs(white[:M], black[:M])
+b_w, b_k = sorted_pairs(w2[:M], k2[:M])
+print("same rows (first 2M, pairs sorted by white index):", torch.equal(a_w, b_w) and torch.equal(a_k, b_k) and torch.equal(meta, m2))
