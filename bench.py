@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="positions of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-halfkp", action="store_true", help="skip the auxiliary .binpack -> HalfKP rows measurement")
     return ap.parse_args()
 
 
@@ -463,6 +464,35 @@ def main():
         e2e = {"ms": e_ms, "value": e2e_local, "h2d": bin_bytes + n1, "d2h": n1 + n2}
         del t_bin, t_pack, t_out
 
+    # ---- auxiliary (N = 1, outside every timed region above): .binpack -> HalfKP feature rows, SURVEY 8(f)-1
+    halfkp = None
+    if world == 1 and not args.no_halfkp:
+        try:
+            log("halfkp rows")
+            white = torch.empty((n_pos, 32), dtype=torch.int32, device=dev)
+            black = torch.empty((n_pos, 32), dtype=torch.int32, device=dev)
+            meta = torch.empty((n_pos, 8), dtype=torch.uint8, device=dev)
+            cnt = ctypes.c_size_t(0)
+            for _ in range(3):
+                check(L.nnp_binpack_to_halfkp_dev(ctypes.c_void_p(d_pack.data_ptr()), pack_bytes, ctypes.c_void_p(white.data_ptr()),
+                                                  ctypes.c_void_p(black.data_ptr()), ctypes.c_void_p(meta.data_ptr()), n_pos,
+                                                  ctypes.byref(cnt)), "binpack->halfkp")
+                L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
+            assert cnt.value == n_pos, (cnt.value, n_pos)
+            halfkp = {
+                "mpos_s": n_pos / (t_total.value * 1e-3) / 1e6,
+                "ms": t_total.value,
+                "kernel": "k_emit_chains_halfkp_verify",
+                "kernel_ms": t_dom.value,
+                "bytes_per_position": 264,
+                "output_gbs": 264 * n_pos / (t_dom.value * 1e-3) / 1e9,
+                "note": "device-resident .binpack -> two int32[32] index rows + 8 B of targets per position; third call timed "
+                        "by the library's CUDA events; not part of `value`",
+            }
+            del white, black, meta
+        except Exception as e:  # auxiliary: never fails the bench line
+            halfkp = {"error": str(e)[:200]}
+
     # ---- max over ranks
     def allmax(x):
         if world == 1:
@@ -597,6 +627,8 @@ def main():
         }
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
+    if halfkp:
+        line["halfkp"] = halfkp
     if shard_offsets is not None:
         line["config"]["slices_offset_bytes_filebytes"] = shard_offsets
     print(json.dumps(line))
