@@ -75,6 +75,11 @@ def test_no_cpu_fallback():
         fn = getattr(lib, name)
         fn.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
         assert fn(b"/nonexistent/in", b"/nonexistent/out", 0, 0, None) == -10
+    for name in ("nnp_binpack_to_halfkp_dev", "nnp_bin_to_halfkp_dev"):
+        fn = getattr(lib, name)
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                       ctypes.POINTER(ctypes.c_size_t)]
+        assert fn(None, 0, None, None, None, 0, ctypes.byref(n)) == -10
     assert lib.nnp_init(0) == -9  # NNP_ERR_NO_DEVICE
     import nnue_data_compress_b200 as pkg
 
