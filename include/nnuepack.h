@@ -23,8 +23,11 @@
  *   - there is NO CPU fallback: every conversion runs CUDA kernels; without a usable
  *     device nnp_init() fails with NNP_ERR_NO_DEVICE and every other call with
  *     NNP_ERR_NOT_INITIALISED.
- *   - one call at a time per process (the library owns one context per process, bound
- *     to one GPU: the multi-GPU model is one process per GPU).
+ *   - one context per device. A host thread works on the device it bound itself to with
+ *     nnp_init() / nnp_bind_device(); a thread that never did uses the first device the process
+ *     initialised. Calls on one device are serialised, calls on different devices run
+ *     concurrently: one process per GPU (torchrun) and one host thread per GPU (the *_multi
+ *     drivers, the CLI with NNP_DEVICES) are both supported.
  */
 #ifndef NNUEPACK_H
 #define NNUEPACK_H
@@ -58,6 +61,15 @@ typedef enum nnp_status {
  * LOCAL_RANK), creates the library's streams and uploads the attack tables (the GPU
  * counterpart of the reference's static initialisation, src/chess/Bitboard.cpp:460-464). */
 int nnp_init(int device);
+/* Initialises devices 0 .. n_devices - 1 (n_devices <= 0: every visible device) and binds the calling
+ * thread to device 0. Returns the number of devices (> 0) or a negative nnp_status. This is the
+ * "all GPUs of the box" form SURVEY.md 8b asks for; convert() of a multi-GPU CLI calls it once. */
+int nnp_init_all(int n_devices);
+/* Binds the calling host thread to an initialised device: its further calls run there. */
+int nnp_bind_device(int device);
+/* number of initialised devices */
+int nnp_device_count(void);
+/* Releases every device of the process. */
 void nnp_shutdown(void);
 const char* nnp_strerror(int status);
 /* Runs all further work on the caller's CUDA stream (a cudaStream_t of the bound device, e.g.
@@ -158,6 +170,31 @@ int nnp_shard_compress_emit_dev(uint64_t next_start, void* d_out, size_t out_cap
 int nnp_shard_compress_table_dev(void* d_table);
 int nnp_shard_compress_resolve_dev(const void* d_tables, const uint64_t* payload_bytes, int world, int rank, uint64_t* carry_in,
                                    uint64_t* chunks_before, uint64_t* next_start, uint64_t* total_chunks);
+
+/* ---- .binpack -> .bin over several GPUs: ONE file, chunk ranges per rank (BASELINE configs[2]) ------
+ *
+ * decompressBin (compress_file.cpp:1376-1412) reads chunk after chunk (hasNextChunk / readNextChunk,
+ * :468-480) and every chunk starts with a stem (:1128-1214), so chunks decode independently: rank r of
+ * `world` takes the contiguous chunk range [chunks * r / world, chunks * (r + 1) / world), decodes it
+ * into its own buffer, the ranks all-gather their position counts (8 bytes each, the only exchange)
+ * and rank r's records belong at byte 40 * (positions of the ranks before it) of the .bin file.
+ * nnp_binpack_chunk_range() is the header walk alone on host memory (the rank then only needs
+ * bytes [byte_lo, byte_hi) of the file on its device and calls nnp_binpack_to_bin_dev on them);
+ * nnp_shard_decompress_dev() does walk + decode on a file that is resident on the device.
+ * Status: a broken header (NNP_ERR_BAD_MAGIC / _CHUNK_TOO_LARGE / _TRUNCATED) is reported by every
+ * rank after the chunks in front of it have been decoded; the reference's 1 MiB flush rule for the
+ * records before an error is a property of the whole run and is not replayed per rank. */
+typedef struct nnp_chunk_range {
+    uint64_t chunks_total;       /* well-formed chunks of the whole file */
+    uint64_t chunk_lo, chunk_hi; /* the rank's chunks [lo, hi) */
+    uint64_t byte_lo, byte_hi;   /* their bytes in the file, chunk headers included */
+    uint64_t positions;          /* nnp_shard_decompress_dev: positions the rank decoded */
+} nnp_chunk_range;
+int nnp_binpack_chunk_range(const void* binpack, size_t binpack_bytes, int world, int rank, nnp_chunk_range* range);
+int nnp_binpack_chunk_range_dev(const void* d_binpack, size_t binpack_bytes, int world, int rank, nnp_chunk_range* range);
+/* d_out == NULL: count only (*out_bytes = 40 * positions of the rank's range). */
+int nnp_shard_decompress_dev(const void* d_binpack, size_t binpack_bytes, int world, int rank, void* d_out, size_t out_cap,
+                             size_t* out_bytes, nnp_chunk_range* range);
 
 /* ---- whole files of any size -----------------------------------------------------
  * File-to-file forms of the two headline drivers for inputs that do not fit the device: the input is

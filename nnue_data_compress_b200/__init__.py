@@ -63,6 +63,8 @@ EXPORTS = [
     "nnp_shard_compress_table_dev", "nnp_shard_compress_resolve_dev",
     "nnp_bin_to_binpack_file", "nnp_binpack_to_bin_file",
     "nnp_binpack_to_halfkp_dev", "nnp_bin_to_halfkp_dev",
+    "nnp_init_all", "nnp_bind_device", "nnp_device_count",
+    "nnp_binpack_chunk_range", "nnp_binpack_chunk_range_dev", "nnp_shard_decompress_dev",
 ]
 
 
@@ -70,6 +72,12 @@ class ShardInfo(ctypes.Structure):
     """nnp_shard_info (include/nnuepack.h)."""
     _fields_ = [("first_owned_record", ctypes.c_uint64), ("end_owned_record", ctypes.c_uint64),
                 ("payload_bytes", ctypes.c_uint64), ("chains", ctypes.c_uint64), ("first_bad_record", ctypes.c_uint64)]
+
+
+class ChunkRange(ctypes.Structure):
+    """nnp_chunk_range (include/nnuepack.h)."""
+    _fields_ = [("chunks_total", ctypes.c_uint64), ("chunk_lo", ctypes.c_uint64), ("chunk_hi", ctypes.c_uint64),
+                ("byte_lo", ctypes.c_uint64), ("byte_hi", ctypes.c_uint64), ("positions", ctypes.c_uint64)]
 
 
 NO_CARRY = (1 << 64) - 1
@@ -108,6 +116,8 @@ def lib() -> ctypes.CDLL:
                 "nnp_shard_compress_resolve_dev",
                 "nnp_binpack_to_halfkp_dev",
                 "nnp_bin_to_halfkp_dev",
+                "nnp_binpack_chunk_range_dev",
+                "nnp_shard_decompress_dev",
             ):
                 fn.argtypes = conv
                 fn.restype = ctypes.c_int
@@ -148,6 +158,16 @@ def lib() -> ctypes.CDLL:
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
             getattr(L, name).restype = ctypes.c_int
+        for name in ("nnp_init_all", "nnp_bind_device"):
+            getattr(L, name).argtypes = [ctypes.c_int]
+            getattr(L, name).restype = ctypes.c_int
+        L.nnp_device_count.restype = ctypes.c_int
+        for name in ("nnp_binpack_chunk_range", "nnp_binpack_chunk_range_dev"):
+            getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ChunkRange)]
+            getattr(L, name).restype = ctypes.c_int
+        L.nnp_shard_decompress_dev.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                               ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ChunkRange)]
+        L.nnp_shard_decompress_dev.restype = ctypes.c_int
         L.nnp_debug_config.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
         L.nnp_debug_config.restype = ctypes.c_int
         L.nnp_decode_stats.argtypes = [ctypes.POINTER(ctypes.c_uint64)]
@@ -200,9 +220,11 @@ class ShardCalls:
             raise NnpError(rc, _strerror(rc))
 
     def begin(self, d_records, n_records: int, own_lo: int, own_hi: int, reaches_eof: bool) -> ShardInfo:
+        """nnp_shard_compress_begin_dev. Does not raise on a rank-local failure: `last_status` goes into
+        sharding.compress_sharded(status=...), which lets all ranks fail together."""
         info = ShardInfo()
-        self._check(lib().nnp_shard_compress_begin_dev(ctypes.c_void_p(d_records.data_ptr()), n_records, own_lo, own_hi,
-                                                      int(reaches_eof), ctypes.byref(info)))
+        self.last_status = lib().nnp_shard_compress_begin_dev(ctypes.c_void_p(d_records.data_ptr()), n_records, own_lo, own_hi,
+                                                              int(reaches_eof), ctypes.byref(info))
         self.last_payload_bytes = int(info.payload_bytes)
         return info
 
@@ -232,6 +254,20 @@ class ShardCalls:
         self._check(lib().nnp_shard_compress_resolve_dev(ctypes.c_void_p(tables.data_ptr()), arr, world, rank, ctypes.byref(c),
                                                         ctypes.byref(b), ctypes.byref(nx), ctypes.byref(tot)))
         return c.value, b.value, nx.value, tot.value
+
+
+def shard_decompress(d_binpack, world: int, rank: int, d_out=None):
+    """nnp_shard_decompress_dev: decodes rank `rank`'s chunk range of the ONE .binpack held in the CUDA
+    uint8 tensor `d_binpack` into `d_out` (None: count only). Returns (bytes written, ChunkRange)."""
+    _ensure_init()
+    rng = ChunkRange()
+    got = ctypes.c_size_t(0)
+    rc = lib().nnp_shard_decompress_dev(ctypes.c_void_p(d_binpack.data_ptr() if d_binpack.numel() else 0), d_binpack.numel(),
+                                        world, rank, ctypes.c_void_p(d_out.data_ptr()) if d_out is not None else None,
+                                        d_out.numel() if d_out is not None else 0, ctypes.byref(got), ctypes.byref(rng))
+    if rc != 0:
+        raise NnpError(rc, _strerror(rc))
+    return got.value, rng
 
 
 def use_torch_stream() -> None:

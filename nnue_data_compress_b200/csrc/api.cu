@@ -27,13 +27,31 @@ enum WsSlot {
     WS_DTOTALS, WS_AGG_TOP, WS_HEAD_NEXT, WS_PARK_A, WS_PARK_B, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
 };
 
+// codes/stems of n records -> payload scan and payload write; leaves the headerless payload stream
+// and the head offsets in the workspaces
+struct PayloadPlan {
+    u64 payload_bytes = 0, heads = 0, max_chunks = 0;
+    u32* payload = nullptr;
+    u64* head_off = nullptr;
+    u64* seg_off = nullptr;
+    u32* head_next = nullptr;
+    CompressTotals* d_tot = nullptr;
+};
+
+struct ShardState {
+    bool active = false;
+    PayloadPlan plan;
+    u64 base = 0, chunks = 0;
+    bool orbit_done = false;
+};
+
 struct Context {
     bool ready = false;
     int device = -1;
     cudaStream_t stream = nullptr;      // stream all kernels and copies are issued on
     cudaStream_t own_stream = nullptr;  // the library's default stream
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [4]: start of a sharded decode
     Workspace ws[WS_COUNT];
     void* pinned = nullptr;  // small pinned scratch for read-backs
     uint64_t launches = 0;
@@ -53,10 +71,20 @@ struct Context {
     uint64_t optimistic_hits = 0;
     uint64_t last_candidates = 0, last_tentative_positions = 0, last_violations = 0, last_false = 0;
     uint64_t last_false_sample[8] = {0};
+    ShardState shard;  // the shard the sharded compressor currently holds (begin .. emit)
+    std::mutex mutex;  // one call at a time per device
 };
 
-Context g_ctx;
-std::mutex g_mutex;
+// One context per device. A host thread works on the device it bound itself to (nnp_init /
+// nnp_bind_device); threads that never did use the first device the process initialised, which is the
+// whole story for the one-process-per-GPU model.
+constexpr int MAX_DEVICES = 64;
+Context g_ctxs[MAX_DEVICES];
+Context* g_default = nullptr;
+thread_local Context* t_ctx = nullptr;
+std::mutex g_init_mutex;
+inline Context& current_context() { return *(t_ctx ? t_ctx : g_default ? g_default : &g_ctxs[0]); }
+#define g_ctx (current_context())
 
 int cuda_fail(cudaError_t e, const char* what)
 {
@@ -126,17 +154,6 @@ size_t binpack_capacity_for_records(size_t n)
 }
 
 // ---------------------------------------------------------------- shared tail of both compressors
-
-// codes/stems of n records -> payload scan and payload write; leaves the headerless payload stream
-// and the head offsets in the workspaces
-struct PayloadPlan {
-    u64 payload_bytes = 0, heads = 0, max_chunks = 0;
-    u32* payload = nullptr;
-    u64* head_off = nullptr;
-    u64* seg_off = nullptr;
-    u32* head_next = nullptr;
-    CompressTotals* d_tot = nullptr;
-};
 
 int build_payload(const u32* codes, const u32* stems, u64 n, PayloadPlan& P)
 {
@@ -343,25 +360,17 @@ int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_ca
 // chains whose heads fall into [own_lo, own_hi); the records in front of the first such head end a
 // chain of the previous shard, which is why that shard looks at them through its overlap window.
 
-struct ShardState {
-    bool active = false;
-    PayloadPlan plan;
-    u64 base = 0, chunks = 0;
-    bool orbit_done = false;
-};
-ShardState g_shard;
-
 int shard_begin_dev(const void* d_bin, u64 n_records, u64 own_lo, u64 own_hi, int reaches_eof, nnp_shard_info* info)
 {
     Context& C = g_ctx;
     cudaStream_t s = C.stream;
-    g_shard = ShardState();
+    g_ctx.shard = ShardState();
     std::memset(info, 0, sizeof(*info));
     info->first_bad_record = NO_ERROR_IDX;
     if (own_lo > own_hi || own_hi > n_records) return NNP_ERR_BAD_ARG;
     if ((uintptr_t)d_bin & 7) return NNP_ERR_BAD_ARG;
     if (n_records == 0) {
-        g_shard.active = true;
+        g_ctx.shard.active = true;
         return NNP_OK;
     }
     u32 *codes = nullptr, *stems = nullptr;
@@ -392,33 +401,33 @@ int shard_begin_dev(const void* d_bin, u64 n_records, u64 own_lo, u64 own_hi, in
     if (first > end) first = end;  // no head of its own: the whole range continues an earlier shard's chain
     info->first_owned_record = first;
     info->end_owned_record = end;
-    g_shard.active = true;
+    g_ctx.shard.active = true;
     if (first == end) return NNP_OK;
-    rc = build_payload(codes + first, stems + first * 8, end - first, g_shard.plan);
+    rc = build_payload(codes + first, stems + first * 8, end - first, g_ctx.shard.plan);
     if (rc != NNP_OK) return rc;
-    info->payload_bytes = g_shard.plan.payload_bytes;
-    info->chains = g_shard.plan.heads;
+    info->payload_bytes = g_ctx.shard.plan.payload_bytes;
+    info->chains = g_ctx.shard.plan.heads;
     return NNP_OK;
 }
 
 int shard_orbit(u64 payload_base, u64 carry_in, u64* n_starts, u64* first_start, u64* carry_out)
 {
-    if (!g_shard.active) return NNP_ERR_BAD_ARG;
-    g_shard.base = payload_base;
-    g_shard.chunks = 0;
-    g_shard.orbit_done = true;
+    if (!g_ctx.shard.active) return NNP_ERR_BAD_ARG;
+    g_ctx.shard.base = payload_base;
+    g_ctx.shard.chunks = 0;
+    g_ctx.shard.orbit_done = true;
     *n_starts = 0;
     *first_start = NO_CARRY;
     *carry_out = carry_in;
-    if (g_shard.plan.payload_bytes == 0) return NNP_OK;
+    if (g_ctx.shard.plan.payload_bytes == 0) return NNP_OK;
     Context& C = g_ctx;
-    int rc = run_orbit(g_shard.plan, payload_base, carry_in, &g_shard.chunks);
+    int rc = run_orbit(g_ctx.shard.plan, payload_base, carry_in, &g_ctx.shard.chunks);
     if (rc != NNP_OK) return rc;
-    *n_starts = g_shard.chunks;
-    if (g_shard.chunks > 0) {
+    *n_starts = g_ctx.shard.chunks;
+    if (g_ctx.shard.chunks > 0) {
         u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
-        CK(cudaMemcpyAsync(h_u64, g_shard.plan.seg_off + 1, 8, cudaMemcpyDeviceToHost, C.stream));
-        CK(cudaMemcpyAsync(h_u64 + 1, g_shard.plan.seg_off + g_shard.chunks, 8, cudaMemcpyDeviceToHost, C.stream));
+        CK(cudaMemcpyAsync(h_u64, g_ctx.shard.plan.seg_off + 1, 8, cudaMemcpyDeviceToHost, C.stream));
+        CK(cudaMemcpyAsync(h_u64 + 1, g_ctx.shard.plan.seg_off + g_ctx.shard.chunks, 8, cudaMemcpyDeviceToHost, C.stream));
         CK(cudaStreamSynchronize(C.stream));
         *first_start = payload_base + h_u64[0];
         *carry_out = payload_base + h_u64[1];
@@ -428,13 +437,13 @@ int shard_orbit(u64 payload_base, u64 carry_in, u64* n_starts, u64* first_start,
 
 int shard_table_dev(void* d_table)
 {
-    if (!g_shard.active) return NNP_ERR_BAD_ARG;
+    if (!g_ctx.shard.active) return NNP_ERR_BAD_ARG;
     Context& C = g_ctx;
     if ((uintptr_t)d_table & 7) return NNP_ERR_BAD_ARG;
-    if (g_shard.plan.payload_bytes == 0) {
+    if (g_ctx.shard.plan.payload_bytes == 0) {
         CK(cudaMemsetAsync(d_table, 0xFF, (size_t)NNP_ORBIT_TABLE_ENTRIES * 24, C.stream));
     } else {
-        launch_orbit_table(g_shard.plan.head_off, g_shard.plan.head_next, g_shard.plan.d_tot, (u64*)d_table,
+        launch_orbit_table(g_ctx.shard.plan.head_off, g_ctx.shard.plan.head_next, g_ctx.shard.plan.d_tot, (u64*)d_table,
                            NNP_ORBIT_TABLE_ENTRIES, C.stream);
         LAUNCHED(1, "k_orbit_table");
     }
@@ -462,25 +471,25 @@ int shard_resolve_dev(const void* d_tables, const uint64_t* payload_bytes, int w
 
 int shard_emit_dev(u64 next_start, void* d_out, size_t out_cap, size_t* out_bytes)
 {
-    if (!g_shard.active || !g_shard.orbit_done) return NNP_ERR_BAD_ARG;
+    if (!g_ctx.shard.active || !g_ctx.shard.orbit_done) return NNP_ERR_BAD_ARG;
     Context& C = g_ctx;
-    const PayloadPlan& P = g_shard.plan;
-    const u64 total = P.payload_bytes + 8 * g_shard.chunks;
+    const PayloadPlan& P = g_ctx.shard.plan;
+    const u64 total = P.payload_bytes + 8 * g_ctx.shard.chunks;
     *out_bytes = total;
     if (!d_out) return NNP_OK;
     if (total > out_cap) return NNP_ERR_CAPACITY;
     if ((uintptr_t)d_out & 7) return NNP_ERR_BAD_ARG;
     if (P.payload_bytes == 0) return NNP_OK;
     u64 last_size = NATURAL_SIZE;
-    if (g_shard.chunks > 0) {
+    if (g_ctx.shard.chunks > 0) {
         u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
-        CK(cudaMemcpyAsync(h_u64, P.seg_off + g_shard.chunks, 8, cudaMemcpyDeviceToHost, C.stream));
+        CK(cudaMemcpyAsync(h_u64, P.seg_off + g_ctx.shard.chunks, 8, cudaMemcpyDeviceToHost, C.stream));
         CK(cudaStreamSynchronize(C.stream));
-        const u64 last_start = g_shard.base + h_u64[0];
+        const u64 last_start = g_ctx.shard.base + h_u64[0];
         if (next_start <= last_start) return NNP_ERR_BAD_ARG;
         last_size = next_start - last_start;
     }
-    launch_emit_chunks(P.payload, P.seg_off, g_shard.chunks, d_out, last_size, C.stream);
+    launch_emit_chunks(P.payload, P.seg_off, g_ctx.shard.chunks, d_out, last_size, C.stream);
     LAUNCHED(1, "k_emit_chunks");
     CK(cudaStreamSynchronize(C.stream));
     return NNP_OK;
@@ -660,7 +669,7 @@ int decode_front(const void* d_in, size_t in_bytes, DecodePlan& P)
         P.tab.len = len;
         P.tab.tile_base = tile_base;
         P.tab.info = d_info;
-        launch_walk_chunks(d_in, in_bytes, P.tab, table_cap, s);
+        launch_walk_chunks(d_in, in_bytes, P.tab, table_cap, 1, 0, s);
         LAUNCHED(1, "k_walk_chunks");
         CK(cudaMemcpyAsync(h_info, d_info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -883,6 +892,73 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
     return NNP_OK;
 }
 
+// ---------------------------------------------------------------- sharded .binpack -> .bin
+//
+// Chunks are independent (hasNextChunk / readNextChunk, compress_file.cpp:468-480; the reader starts
+// every chunk with a stem, :1128-1214): rank r of `world` decodes the contiguous chunk range
+// [chunks * r / world, chunks * (r + 1) / world) of ONE file, and the concatenation of the ranks'
+// records in rank order is the file one decompressBin run writes (:1376-1412).
+
+// header walk of the whole file (device memory): the rank's chunk range and its bytes
+int chunk_range_dev(const void* d_in, size_t in_bytes, int world, int rank, nnp_chunk_range* range, int* walk_status)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    std::memset(range, 0, sizeof(*range));
+    *walk_status = 0;
+    if (in_bytes == 0) return NNP_OK;
+    WS(WS_CHUNK_INFO, sizeof(ChunkInfo), ChunkInfo, d_info);
+    ChunkInfo* h_info = reinterpret_cast<ChunkInfo*>((char*)C.pinned + 256);
+    u64 table_cap = in_bytes / 65536 + 1024;
+    ChunkTable tab;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        WS(WS_CHUNK_START, (table_cap + 1) * 8, u64, start);
+        WS(WS_CHUNK_LEN, (table_cap + 1) * 4, u32, len);
+        WS(WS_CHUNK_TILE_BASE, (table_cap + 2) * 8, u64, tile_base);
+        tab.start = start;
+        tab.len = len;
+        tab.tile_base = tile_base;
+        tab.info = d_info;
+        launch_walk_chunks(d_in, in_bytes, tab, table_cap, (u32)world, (u32)rank, s);
+        LAUNCHED(1, "k_walk_chunks");
+        CK(cudaMemcpyAsync(h_info, d_info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h_info->chunks <= table_cap) break;
+        table_cap = h_info->chunks + 16;
+    }
+    range->chunks_total = h_info->chunks;
+    range->chunk_lo = h_info->range_lo;
+    range->chunk_hi = h_info->range_hi;
+    range->byte_lo = h_info->byte_lo;
+    range->byte_hi = h_info->byte_hi;
+    *walk_status = h_info->status;
+    return NNP_OK;
+}
+
+int shard_decompress_dev(const void* d_in, size_t in_bytes, int world, int rank, void* d_out, size_t out_cap, size_t* out_bytes,
+                         nnp_chunk_range* range)
+{
+    Context& C = g_ctx;
+    *out_bytes = 0;
+    CK(cudaEventRecord(C.ev[4], C.stream));
+    int walk_status = 0;
+    int rc = chunk_range_dev(d_in, in_bytes, world, rank, range, &walk_status);
+    if (rc != NNP_OK) return rc;
+    if (range->byte_hi > range->byte_lo) {
+        rc = decompress_dev((const unsigned char*)d_in + range->byte_lo, range->byte_hi - range->byte_lo, d_out, out_cap, out_bytes);
+        if (rc != NNP_OK) return rc;
+        // the whole call, header walk of the file included
+        float front = 0.f;
+        CK(cudaEventElapsedTime(&front, C.ev[4], C.ev[0]));
+        C.last_total_ms += front;
+    }
+    range->positions = *out_bytes / 40;
+    // a broken header further on: every rank reports it; the chunks in front of it are decoded (the
+    // reference's flush rule for the records before an error, :1395-1402, is a property of the whole
+    // run and is not replayed per rank)
+    return walk_status;
+}
+
 int binpack_to_plain_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_cap, size_t* out_bytes)
 {
     Context& C = g_ctx;
@@ -1075,74 +1151,138 @@ int run_host(dev_fn fn, const void* in, size_t in_bytes, void* out, size_t out_c
 
 using namespace nnp;
 
+// every entry point: one call at a time per device, on the device the calling thread is bound to
+#define LOCK_DEVICE()                                                \
+    Context& ctx_ = g_ctx;                                           \
+    std::lock_guard<std::mutex> lock_(ctx_.mutex);                   \
+    if (!ctx_.ready) return NNP_ERR_NOT_INITIALISED;                 \
+    if (cudaSetDevice(ctx_.device) != cudaSuccess) return NNP_ERR_CUDA;
 #define REQUIRE_READY()                                              \
-    std::lock_guard<std::mutex> lock_(g_mutex);                      \
-    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;                \
+    LOCK_DEVICE();                                                   \
     if (!out_bytes) return NNP_ERR_BAD_ARG;
 
 extern "C" {
 
-int nnp_init(int device)
+namespace {
+
+// creates the streams, events and scratch of `device` (caller holds g_init_mutex)
+int init_device(int device)
 {
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (g_ctx.ready) return g_ctx.device == device ? NNP_OK : NNP_ERR_BAD_ARG;
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) {
-        g_ctx.last_cuda_error = e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device";
-        (void)cudaGetLastError();
-        return NNP_ERR_NO_DEVICE;
-    }
-    if (device < 0 || device >= count) return NNP_ERR_BAD_ARG;
+    Context& C = g_ctxs[device];
+    if (C.ready) return NNP_OK;
     if (cudaSetDevice(device) != cudaSuccess) return NNP_ERR_NO_DEVICE;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NNP_ERR_NO_DEVICE;
     if (prop.major < 10) {
-        g_ctx.last_cuda_error = "libnnuepack is built for sm_100a only";
+        C.last_cuda_error = "libnnuepack is built for sm_100a only";
         return NNP_ERR_NO_DEVICE;
     }
-    if (cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking) != cudaSuccess) return NNP_ERR_CUDA;
-    g_ctx.stream = g_ctx.own_stream;
-    if (cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking) != cudaSuccess) return NNP_ERR_CUDA;
-    for (auto& ev : g_ctx.ev)
+    if (cudaStreamCreateWithFlags(&C.own_stream, cudaStreamNonBlocking) != cudaSuccess) return NNP_ERR_CUDA;
+    C.stream = C.own_stream;
+    if (cudaStreamCreateWithFlags(&C.copy_stream, cudaStreamNonBlocking) != cudaSuccess) return NNP_ERR_CUDA;
+    for (auto& ev : C.ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return NNP_ERR_CUDA;
-    for (auto& ev : g_ctx.pipe_ev)
+    for (auto& ev : C.pipe_ev)
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return NNP_ERR_CUDA;
-    if (cudaMallocHost(&g_ctx.pinned, 4096) != cudaSuccess) return NNP_ERR_NOMEM;
+    if (cudaMallocHost(&C.pinned, 4096) != cudaSuccess) return NNP_ERR_NOMEM;
     const char* dbg = std::getenv("NNP_DEBUG_REJECT_MOD");
-    g_ctx.debug_reject_mod = dbg ? (uint32_t)std::strtoul(dbg, nullptr, 10) : 0u;
+    C.debug_reject_mod = dbg ? (uint32_t)std::strtoul(dbg, nullptr, 10) : 0u;
     const char* dbg2 = std::getenv("NNP_DEBUG_EXHAUSTIVE");
-    g_ctx.debug_exhaustive = dbg2 && dbg2[0] == '1';
-    g_ctx.device = device;
-    g_ctx.ready = true;
+    C.debug_exhaustive = dbg2 && dbg2[0] == '1';
+    C.device = device;
+    C.ready = true;
+    if (!g_default) g_default = &C;
     return NNP_OK;
+}
+
+int device_count()
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_ctxs[0].last_cuda_error = e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device";
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return count < MAX_DEVICES ? count : MAX_DEVICES;
+}
+
+}  // namespace
+
+int nnp_init(int device)
+{
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    const int count = device_count();
+    if (count == 0) return NNP_ERR_NO_DEVICE;
+    if (device < 0 || device >= count) return NNP_ERR_BAD_ARG;
+    const int rc = init_device(device);
+    if (rc != NNP_OK) return rc;
+    t_ctx = &g_ctxs[device];
+    return NNP_OK;
+}
+
+int nnp_init_all(int n_devices)
+{
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    const int count = device_count();
+    if (count == 0) return NNP_ERR_NO_DEVICE;
+    if (n_devices <= 0 || n_devices > count) n_devices = count;
+    for (int d = 0; d < n_devices; ++d) {
+        const int rc = init_device(d);
+        if (rc != NNP_OK) return rc;
+    }
+    t_ctx = &g_ctxs[0];
+    if (cudaSetDevice(0) != cudaSuccess) return NNP_ERR_CUDA;
+    return n_devices;
+}
+
+int nnp_bind_device(int device)
+{
+    if (device < 0 || device >= MAX_DEVICES || !g_ctxs[device].ready) return NNP_ERR_NOT_INITIALISED;
+    if (cudaSetDevice(device) != cudaSuccess) return NNP_ERR_CUDA;
+    t_ctx = &g_ctxs[device];
+    return NNP_OK;
+}
+
+int nnp_device_count(void)
+{
+    int n = 0;
+    for (const Context& C : g_ctxs) n += C.ready ? 1 : 0;
+    return n;
 }
 
 void nnp_shutdown(void)
 {
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (!g_ctx.ready) return;
-    cudaStreamSynchronize(g_ctx.stream);
-    for (auto& w : g_ctx.ws) {
-        if (w.p) cudaFree(w.p);
-        w.p = nullptr;
-        w.cap = 0;
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    for (Context& C : g_ctxs) {
+        if (!C.ready) continue;
+        std::lock_guard<std::mutex> dev_lock(C.mutex);
+        cudaSetDevice(C.device);
+        cudaStreamSynchronize(C.stream);
+        for (auto& w : C.ws) {
+            if (w.p) cudaFree(w.p);
+            w.p = nullptr;
+            w.cap = 0;
+        }
+        if (C.pinned) cudaFreeHost(C.pinned);
+        C.pinned = nullptr;
+        for (auto& ev : C.ev) {
+            if (ev) cudaEventDestroy(ev);
+            ev = nullptr;
+        }
+        for (auto& ev : C.pipe_ev) {
+            if (ev) cudaEventDestroy(ev);
+            ev = nullptr;
+        }
+        cudaStreamDestroy(C.own_stream);
+        cudaStreamDestroy(C.copy_stream);
+        C.stream = C.own_stream = C.copy_stream = nullptr;
+        C.shard = ShardState();
+        C.ready = false;
+        C.device = -1;
     }
-    if (g_ctx.pinned) cudaFreeHost(g_ctx.pinned);
-    g_ctx.pinned = nullptr;
-    for (auto& ev : g_ctx.ev) {
-        if (ev) cudaEventDestroy(ev);
-        ev = nullptr;
-    }
-    for (auto& ev : g_ctx.pipe_ev) {
-        if (ev) cudaEventDestroy(ev);
-        ev = nullptr;
-    }
-    cudaStreamDestroy(g_ctx.own_stream);
-    cudaStreamDestroy(g_ctx.copy_stream);
-    g_ctx.stream = g_ctx.own_stream = g_ctx.copy_stream = nullptr;
-    g_ctx.ready = false;
-    g_ctx.device = -1;
+    g_default = nullptr;
+    t_ctx = nullptr;  // other threads must bind again after the next nnp_init
 }
 
 const char* nnp_strerror(int status)
@@ -1167,15 +1307,19 @@ const char* nnp_strerror(int status)
 
 int nnp_set_stream(void* cuda_stream)
 {
-    std::lock_guard<std::mutex> lock(g_mutex);
-    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    LOCK_DEVICE();
     cudaStreamSynchronize(g_ctx.stream);
     g_ctx.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : g_ctx.own_stream;
     return NNP_OK;
 }
 
 const char* nnp_last_cuda_error(void) { return g_ctx.last_cuda_error.c_str(); }
-uint64_t nnp_kernel_launches(void) { return g_ctx.launches; }
+uint64_t nnp_kernel_launches(void)
+{
+    uint64_t n = 0;
+    for (const Context& C : g_ctxs) n += C.launches;  // all devices of the process
+    return n;
+}
 
 void* nnp_host_alloc(size_t bytes)
 {
@@ -1263,24 +1407,21 @@ int nnp_binpack_to_plain(const void* binpack, size_t binpack_bytes, void* out, s
 int nnp_binpack_to_halfkp_dev(const void* d_binpack, size_t binpack_bytes, int32_t* d_white, int32_t* d_black,
                               nnp_halfkp_meta* d_meta, size_t cap_positions, size_t* positions)
 {
-    std::lock_guard<std::mutex> lock_(g_mutex);
-    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    LOCK_DEVICE();
     if (!positions || (binpack_bytes && !d_binpack)) return NNP_ERR_BAD_ARG;
     return binpack_to_halfkp_dev(d_binpack, binpack_bytes, d_white, d_black, d_meta, cap_positions, positions);
 }
 int nnp_bin_to_halfkp_dev(const void* d_bin, size_t bin_bytes, int32_t* d_white, int32_t* d_black, nnp_halfkp_meta* d_meta,
                           size_t cap_positions, size_t* positions)
 {
-    std::lock_guard<std::mutex> lock_(g_mutex);
-    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    LOCK_DEVICE();
     if (!positions || (bin_bytes >= 40 && !d_bin)) return NNP_ERR_BAD_ARG;
     return bin_to_halfkp_dev(d_bin, bin_bytes, d_white, d_black, d_meta, cap_positions, positions);
 }
 
 int nnp_binpack_count_dev(const void* d_binpack, size_t binpack_bytes, uint64_t* n_positions)
 {
-    std::lock_guard<std::mutex> lock_(g_mutex);
-    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    LOCK_DEVICE();
     if (!n_positions) return NNP_ERR_BAD_ARG;
     size_t bytes = 0;
     int rc = decompress_dev(d_binpack, binpack_bytes, nullptr, 0, &bytes);
@@ -1290,8 +1431,7 @@ int nnp_binpack_count_dev(const void* d_binpack, size_t binpack_bytes, uint64_t*
 
 int nnp_generate_bin_dev(void* d_out, size_t n_positions, uint32_t max_plies, uint64_t seed)
 {
-    std::lock_guard<std::mutex> lock_(g_mutex);
-    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    LOCK_DEVICE();
     if (n_positions == 0) return NNP_OK;
     if (!d_out || max_plies == 0 || ((uintptr_t)d_out & 7)) return NNP_ERR_BAD_ARG;
     cudaStream_t s = g_ctx.stream;
@@ -1319,16 +1459,14 @@ int nnp_generate_bin_dev(void* d_out, size_t n_positions, uint32_t max_plies, ui
 int nnp_shard_compress_begin_dev(const void* d_bin, size_t n_records, size_t own_lo, size_t own_hi, int reaches_eof,
                                  nnp_shard_info* info)
 {
-    std::lock_guard<std::mutex> lock_(g_mutex);
-    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    LOCK_DEVICE();
     if (!info) return NNP_ERR_BAD_ARG;
     return shard_begin_dev(d_bin, n_records, own_lo, own_hi, reaches_eof, info);
 }
 int nnp_shard_compress_orbit(uint64_t payload_base, uint64_t carry_in, uint64_t* n_chunk_starts, uint64_t* first_start,
                              uint64_t* carry_out)
 {
-    std::lock_guard<std::mutex> lock_(g_mutex);
-    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    LOCK_DEVICE();
     if (!n_chunk_starts || !first_start || !carry_out) return NNP_ERR_BAD_ARG;
     u64 a = 0, b = 0, c = 0;
     const int rc = shard_orbit(payload_base, carry_in, &a, &b, &c);
@@ -1344,16 +1482,14 @@ int nnp_shard_compress_emit_dev(uint64_t next_start, void* d_out, size_t out_cap
 }
 int nnp_shard_compress_table_dev(void* d_table)
 {
-    std::lock_guard<std::mutex> lock_(g_mutex);
-    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    LOCK_DEVICE();
     if (!d_table) return NNP_ERR_BAD_ARG;
     return shard_table_dev(d_table);
 }
 int nnp_shard_compress_resolve_dev(const void* d_tables, const uint64_t* payload_bytes, int world, int rank, uint64_t* carry_in,
                                    uint64_t* chunks_before, uint64_t* next_start, uint64_t* total_chunks)
 {
-    std::lock_guard<std::mutex> lock_(g_mutex);
-    if (!g_ctx.ready) return NNP_ERR_NOT_INITIALISED;
+    LOCK_DEVICE();
     if (!d_tables || !payload_bytes || !carry_in || !chunks_before || !next_start || !total_chunks) return NNP_ERR_BAD_ARG;
     uint64_t out5[5] = {0, 0, 0, 0, 0};
     const int rc = shard_resolve_dev(d_tables, payload_bytes, world, rank, out5);
@@ -1364,9 +1500,54 @@ int nnp_shard_compress_resolve_dev(const void* d_tables, const uint64_t* payload
     return rc;
 }
 
+int nnp_binpack_chunk_range(const void* binpack, size_t binpack_bytes, int world, int rank, nnp_chunk_range* range)
+{
+    // host memory (or an mmapped file): the header walk of compress_file.cpp:500-521, 8 bytes per chunk
+    if (!range || world <= 0 || rank < 0 || rank >= world || (binpack_bytes && !binpack)) return NNP_ERR_BAD_ARG;
+    std::memset(range, 0, sizeof(*range));
+    const unsigned char* in = static_cast<const unsigned char*>(binpack);
+    std::vector<uint64_t> starts;
+    uint64_t pos = 0;
+    int status = NNP_OK;
+    while (pos < binpack_bytes) {
+        if (binpack_bytes - pos < 8 || std::memcmp(in + pos, "BINP", 4) != 0) { status = NNP_ERR_BAD_MAGIC; break; }
+        const uint64_t size = (uint64_t)in[pos + 4] | ((uint64_t)in[pos + 5] << 8) | ((uint64_t)in[pos + 6] << 16) |
+                              ((uint64_t)in[pos + 7] << 24);
+        if (size > MAX_CHUNK_SIZE) { status = NNP_ERR_CHUNK_TOO_LARGE; break; }
+        if (binpack_bytes - pos - 8 < size || size < 34) { status = NNP_ERR_TRUNCATED; break; }
+        starts.push_back(pos);
+        pos += 8 + size;
+    }
+    starts.push_back(pos);  // end of the last good chunk
+    const uint64_t k = starts.size() - 1, w = (uint64_t)world, r = (uint64_t)rank;
+    const uint64_t base = k / w, extra = k % w;
+    const uint64_t lo = r * base + (r < extra ? r : extra), hi = lo + base + (r < extra ? 1 : 0);
+    range->chunks_total = k;
+    range->chunk_lo = lo;
+    range->chunk_hi = hi;
+    range->byte_lo = starts[lo];
+    range->byte_hi = starts[hi];
+    return status;
+}
+int nnp_binpack_chunk_range_dev(const void* d_binpack, size_t binpack_bytes, int world, int rank, nnp_chunk_range* range)
+{
+    LOCK_DEVICE();
+    if (!range || world <= 0 || rank < 0 || rank >= world || (binpack_bytes && !d_binpack)) return NNP_ERR_BAD_ARG;
+    int walk_status = 0;
+    const int rc = chunk_range_dev(d_binpack, binpack_bytes, world, rank, range, &walk_status);
+    return rc != NNP_OK ? rc : walk_status;
+}
+int nnp_shard_decompress_dev(const void* d_binpack, size_t binpack_bytes, int world, int rank, void* d_out, size_t out_cap,
+                             size_t* out_bytes, nnp_chunk_range* range)
+{
+    REQUIRE_READY();
+    if (!range || world <= 0 || rank < 0 || rank >= world || (binpack_bytes && !d_binpack)) return NNP_ERR_BAD_ARG;
+    return shard_decompress_dev(d_binpack, binpack_bytes, world, rank, d_out, out_cap, out_bytes, range);
+}
+
 int nnp_debug_config(const char* key, uint64_t value)
 {
-    std::lock_guard<std::mutex> lock_(g_mutex);
+    std::lock_guard<std::mutex> lock_(g_ctx.mutex);
     if (!key) return NNP_ERR_BAD_ARG;
     if (!std::strcmp(key, "exhaustive")) g_ctx.debug_exhaustive = value != 0;
     else if (!std::strcmp(key, "k1_per_record")) g_ctx.debug_k1_per_record = value != 0;

@@ -124,32 +124,70 @@ k_exclusive_sum64(const u64* __restrict__ in, u64 n, u64* __restrict__ out)
 
 // ------------------------------------------------------------------ chunk table
 
-__global__ void k_walk_chunks(const unsigned char* __restrict__ in, u64 n, ChunkTable tab, u64 max_chunks)
+// One warp: lane 0 follows the headers, the other lanes pull the lines of the next few headers into L2
+// while it waits. A hop is one dependent DRAM access (~0.7 us), and the writer's flush rule
+// (:1076-1080) makes a chunk 2^20 bytes plus a part of one chain, so the header j chunks ahead lies
+// within a few hundred bytes behind j * (2^20 + 8): a wrong guess only costs the miss it would have
+// been anyway. `world` / `rank`: the chunk range [chunks * rank / world, chunks * (rank + 1) / world)
+// and its bytes are left in the info block (sharded decompression; world = 1 otherwise).
+__global__ void __launch_bounds__(32) k_walk_chunks(const unsigned char* __restrict__ in, u64 n, ChunkTable tab, u64 max_chunks,
+                                                     u32 world, u32 rank)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int lane = threadIdx.x;
     u64 pos = 0, k = 0, tiles = 0;
     int status = 0;
+    // which header this lane guesses at: lane 0 the next one (exact), then 5, 9 and 13 lines for the
+    // headers two, three and four chunks ahead
+    const int ahead = lane == 0 ? 0 : lane < 6 ? 1 : lane < 15 ? 2 : lane < 28 ? 3 : -1;
+    const int first = lane == 0 ? 0 : lane < 6 ? 1 : lane < 15 ? 6 : 15;
     while (pos < n) {  // hasNextChunk: peek() / eof (:468-472)
-        if (n - pos < 8 || in[pos] != 'B' || in[pos + 1] != 'I' || in[pos + 2] != 'N' || in[pos + 3] != 'P') {
-            status = -1;  // NNP_ERR_BAD_MAGIC (:504-507)
-            break;
+        u32 size = 0;
+        int st = 0;
+        if (lane == 0) {
+            if (n - pos < 8 || in[pos] != 'B' || in[pos + 1] != 'I' || in[pos + 2] != 'N' || in[pos + 3] != 'P') {
+                st = -1;  // NNP_ERR_BAD_MAGIC (:504-507)
+            } else {
+                size = (u32)in[pos + 4] | ((u32)in[pos + 5] << 8) | ((u32)in[pos + 6] << 16) | ((u32)in[pos + 7] << 24);
+                if (size > MAX_CHUNK_SIZE) st = -2;                    // NNP_ERR_CHUNK_TOO_LARGE (:515-518)
+                else if (n - pos - 8 < size || size < 34) st = -4;      // NNP_ERR_TRUNCATED
+            }
         }
-        const u32 size = (u32)in[pos + 4] | ((u32)in[pos + 5] << 8) | ((u32)in[pos + 6] << 16) | ((u32)in[pos + 7] << 24);
-        if (size > MAX_CHUNK_SIZE) { status = -2; break; }            // NNP_ERR_CHUNK_TOO_LARGE (:515-518)
-        if (n - pos - 8 < size || size < 34) { status = -4; break; }  // NNP_ERR_TRUNCATED
-        if (k < max_chunks) {
+        size = __shfl_sync(0xffffffffu, size, 0);
+        st = __shfl_sync(0xffffffffu, st, 0);
+        if (st != 0) { status = st; break; }
+        const u64 next = pos + 8 + (u64)size;
+        if (ahead >= 0) {
+            const u64 guess = next + (u64)ahead * (CHUNK_THRESHOLD + 8) + (u64)(lane - first) * 128;
+            if (guess < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + guess));
+        }
+        if (lane == 0 && k < max_chunks) {
             tab.start[k] = pos + 8;
             tab.len[k] = size;
             tab.tile_base[k] = tiles;
             tiles += ((u64)size + CAND_TILE - 1) / CAND_TILE;
         }
         ++k;
-        pos += 8 + (u64)size;
+        pos = next;
     }
+    if (lane != 0) return;
     if (k <= max_chunks) tab.tile_base[k] = tiles;
     tab.info->chunks = k;
     tab.info->status = status;
     tab.info->tiles = tiles;
+    // the rank's share: balanced contiguous chunk range (the same split as sharding.shard_bounds)
+    const u64 w = world ? world : 1, r = rank;
+    const u64 base = k / w, extra = k % w;
+    const u64 lo = r * base + (r < extra ? r : extra);
+    const u64 hi = lo + base + (r < extra ? 1 : 0);
+    tab.info->range_lo = lo;
+    tab.info->range_hi = hi;
+    tab.info->byte_lo = tab.info->byte_hi = 0;
+    if (k <= max_chunks && hi > lo) {
+        tab.info->byte_lo = tab.start[lo] - 8;
+        tab.info->byte_hi = tab.start[hi - 1] + tab.len[hi - 1];
+    } else if (k <= max_chunks) {
+        tab.info->byte_lo = tab.info->byte_hi = lo < k ? tab.start[lo] - 8 : pos;
+    }
 }
 
 // ------------------------------------------------------------------ candidate discovery
@@ -723,9 +761,9 @@ __global__ void k_slow_emit_text(const unsigned char* __restrict__ in, ChunkTabl
 
 // ------------------------------------------------------------------ host launchers
 
-void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks, cudaStream_t s)
+void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks, u32 world, u32 rank, cudaStream_t s)
 {
-    k_walk_chunks<<<1, 32, 0, s>>>((const unsigned char*)d_in, n, tab, max_chunks);
+    k_walk_chunks<<<1, 32, 0, s>>>((const unsigned char*)d_in, n, tab, max_chunks, world, rank);
 }
 void launch_candidates_scan(const void* d_in, u64 n_in, ChunkTable tab, u64 tiles, u32* tile_count, u32* tile_flags,
                             u32 debug_reject_mod, cudaStream_t s)

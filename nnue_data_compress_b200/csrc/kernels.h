@@ -35,6 +35,8 @@ struct ChunkInfo {
     u64 tiles;   // candidate tiles over all stored chunks
     int status;  // 0 or the nnp_status of the header that stopped the walk
     int pad;
+    u64 range_lo, range_hi;  // the chunk range of (world, rank) and its bytes in the file, headers included
+    u64 byte_lo, byte_hi;
 };
 struct ChunkTable {
     u64* start;      // file offset of the chunk payload
@@ -43,7 +45,7 @@ struct ChunkTable {
     ChunkInfo* info;
 };
 
-void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks, cudaStream_t s);
+void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks, u32 world, u32 rank, cudaStream_t s);
 void launch_candidates_scan(const void* d_in, u64 n_in, ChunkTable tab, u64 tiles, u32* tile_count, u32* tile_flags,
                             u32 debug_reject_mod, cudaStream_t s);
 void launch_mark_conflicts(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u32* cand_cnt,

@@ -12,8 +12,11 @@ Two ways to shard .bin -> .binpack:
   belong to the rank that holds their head (the rank before sees the rest of the chain through an
   overlap window), and the chunk-flush rule is replayed in rank order with a 16-byte carry.
 
-.binpack -> .bin / .plain shards by chunk ranges; the concatenation of the shard outputs equals the
-single-run output byte for byte because chunks are independent.
+.binpack -> .bin / .plain shards ONE file by chunk ranges (``decompress_sharded``): rank r decodes the
+contiguous chunk range shard_bounds(chunks, world, r) (nnp_shard_decompress_dev), the ranks all-gather
+their position counts and rank r's records belong at byte 40 * (positions before it); the
+concatenation equals the single-run output byte for byte because chunks are independent
+(compress_file.cpp:468-480, :1128-1214).
 """
 from __future__ import annotations
 
@@ -48,12 +51,52 @@ def exchange_offsets(local_bytes: int, device=None, group=None) -> Tuple[int, in
         return 0, int(local_bytes), [int(local_bytes)]
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    mine = torch.tensor([int(local_bytes)], dtype=torch.int64, device=device)
-    gathered = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine, group=group)
-    sizes = [int(t.item()) for t in gathered]
+    sizes = _gather_ints(int(local_bytes), world, device, group)
     offs = offsets_from_sizes(sizes)
     return offs[rank], sum(sizes), sizes
+
+
+def _gather_rows(values: List[int], world: int, device=None, group=None) -> List[List[int]]:
+    """One all-gather of a few int64 per rank, read back with a single device-to-host copy."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return [[int(v) for v in values]]
+    mine = torch.tensor([int(v) for v in values], dtype=torch.int64, device=device)
+    out = torch.empty(world * len(values), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    flat = [int(v) for v in out.tolist()]
+    return [flat[r * len(values):(r + 1) * len(values)] for r in range(world)]
+
+
+def _gather_ints(value: int, world: int, device=None, group=None) -> List[int]:
+    return [row[0] for row in _gather_rows([value], world, device, group)]
+
+
+class ShardStatusError(RuntimeError):
+    """A rank's local step of a sharded conversion failed; every rank raises this together, before any
+    further collective, so that no rank is left waiting in one."""
+
+    def __init__(self, statuses: List[int]):
+        super().__init__(f"sharded conversion: per-rank status {statuses}")
+        self.statuses = statuses
+
+
+def decompress_sharded(decode, device=None, group=None) -> Tuple[int, int, int]:
+    """ONE .binpack decoded by all ranks (BASELINE configs[2]): ``decode(world, rank) ->
+    bytes produced`` wraps nnp_shard_decompress_dev (the rank's contiguous chunk range into the rank's
+    own buffer); one all-gather of the byte counts gives every rank the offset of its records in the
+    .bin file. Returns (bytes produced, file offset of this rank's records, total file bytes)."""
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized():
+        world, rank = 1, 0
+    else:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    produced = int(decode(world, rank))
+    sizes = _gather_ints(produced, world, device, group)
+    return produced, offsets_from_sizes(sizes)[rank], sum(sizes)
 
 
 def chunk_bounds_binpack(data: bytes) -> List[Tuple[int, int]]:
@@ -88,7 +131,7 @@ def shard_window(n_records: int, world: int, rank: int, overlap: int):
 ORBIT_TABLE_ENTRIES = 30848  # NNP_ORBIT_TABLE_ENTRIES (include/nnuepack.h)
 
 
-def compress_sharded(payload_bytes: int, orbit, emit, device=None, group=None, table=None, resolve=None):
+def compress_sharded(payload_bytes: int, orbit, emit, device=None, group=None, table=None, resolve=None, status: int = 0):
     """The exchange steps 2-4 of the sharded compressor around a rank's local calls.
 
     ``payload_bytes``: from nnp_shard_compress_begin_dev (step 1, done by the caller).
@@ -98,6 +141,10 @@ def compress_sharded(payload_bytes: int, orbit, emit, device=None, group=None, t
     (carry_in, chunks_before, next_start, total_chunks)`` (nnp_shard_compress_table_dev / _resolve_dev) the
     rank-order carry is replaced by one all-gather of the ranks' orbit tables; without them the carry
     travels from rank to rank (16 bytes per hop).
+    ``status``: the nnp_status of the rank's nnp_shard_compress_begin_dev. NNP_ERR_WINDOW and
+    NNP_ERR_BAD_SFEN are rank-local outcomes, so the statuses travel with the payload sizes in the first
+    all-gather and every rank raises ShardStatusError together when one of them is not 0 (the caller
+    widens the overlap window on every rank, or gives up on every rank).
     Returns (emit's result, file offset of this rank's slice, total file bytes)."""
     import torch
     import torch.distributed as dist
@@ -108,14 +155,12 @@ def compress_sharded(payload_bytes: int, orbit, emit, device=None, group=None, t
         world, rank = dist.get_world_size(group), dist.get_rank(group)
 
     def gather(value: int):
-        if world == 1:
-            return [int(value)]
-        mine = torch.tensor([int(value)], dtype=torch.int64, device=device)
-        out = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(out, mine, group=group)
-        return [int(t.item()) for t in out]
+        return _gather_ints(value, world, device, group)
 
-    sizes = gather(payload_bytes)
+    rows = _gather_rows([payload_bytes, status], world, device, group)
+    if any(row[1] != 0 for row in rows):
+        raise ShardStatusError([row[1] for row in rows])
+    sizes = [row[0] for row in rows]
     bases = offsets_from_sizes(sizes)
     total_payload = sum(sizes)
 

@@ -62,6 +62,43 @@ def test_error_strings_are_the_reference_messages():
     assert lib.nnp_strerror(-3) == b"Improperly encoded bin sfen"  # :408, :442
 
 
+def test_host_header_walk_names_the_chunk_ranges():
+    """nnp_binpack_chunk_range is the header walk of compress_file.cpp:500-521 on host memory (no
+    conversion, no device): balanced contiguous chunk ranges that cover the file; bad headers end it."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import nnue_data_compress_b200 as pkg
+    from nnue_data_compress_b200.sharding import chunk_bounds_binpack, shard_bounds
+    from refutil import golden
+
+    full = golden("twochunks.binpack") * 3  # appended files are valid files (:1663-1666): six chunks
+    chunks = chunk_bounds_binpack(full)
+    assert len(chunks) == 6
+    L = pkg.lib()
+    for world in (1, 2, 4, 6, 7):
+        prev_hi = 0
+        for r in range(world):
+            rng = pkg.ChunkRange()
+            assert L.nnp_binpack_chunk_range(full, len(full), world, r, ctypes.byref(rng)) == 0
+            assert (rng.chunk_lo, rng.chunk_hi) == shard_bounds(6, world, r) and rng.chunks_total == 6
+            assert rng.byte_lo == prev_hi
+            assert rng.byte_hi == (chunks[rng.chunk_hi - 1][0] + chunks[rng.chunk_hi - 1][1] if rng.chunk_hi > rng.chunk_lo
+                                   else rng.byte_lo)
+            prev_hi = rng.byte_hi
+        assert prev_hi == len(full)
+    rng = pkg.ChunkRange()
+    bad = bytearray(full)
+    bad[chunks[2][0]] = ord("X")
+    assert L.nnp_binpack_chunk_range(bytes(bad), len(bad), 2, 1, ctypes.byref(rng)) == -1  # NNP_ERR_BAD_MAGIC
+    assert (rng.chunks_total, rng.chunk_lo, rng.chunk_hi, rng.byte_hi) == (2, 1, 2, chunks[2][0])
+    huge = bytearray(full)
+    huge[chunks[1][0] + 4:chunks[1][0] + 8] = (101 << 20).to_bytes(4, "little")
+    assert L.nnp_binpack_chunk_range(bytes(huge), len(huge), 1, 0, ctypes.byref(rng)) == -2  # NNP_ERR_CHUNK_TOO_LARGE
+    assert L.nnp_binpack_chunk_range(full[:-5], len(full) - 5, 1, 0, ctypes.byref(rng)) == -4  # NNP_ERR_TRUNCATED
+    assert L.nnp_binpack_chunk_range(None, 0, 3, 2, ctypes.byref(rng)) == 0 and rng.chunks_total == 0
+
+
 @pytest.mark.skipif(have_gpu(), reason="checks the no-GPU behaviour")
 def test_no_cpu_fallback():
     lib = ctypes.CDLL(LIB)
@@ -81,6 +118,10 @@ def test_no_cpu_fallback():
                        ctypes.POINTER(ctypes.c_size_t)]
         assert fn(None, 0, None, None, None, 0, ctypes.byref(n)) == -10
     assert lib.nnp_init(0) == -9  # NNP_ERR_NO_DEVICE
+    assert lib.nnp_init_all(0) == -9 and lib.nnp_bind_device(0) == -10 and lib.nnp_device_count() == 0
+    lib.nnp_shard_decompress_dev.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p]
+    assert lib.nnp_shard_decompress_dev(None, 0, 1, 0, None, 0, ctypes.byref(n), buf) == -10
     import nnue_data_compress_b200 as pkg
 
     with pytest.raises(pkg.NnpError) as ei:

@@ -2,6 +2,7 @@
 all ranks in turn (the library holds one shard at a time, so the orbit pass and the emit pass each
 redo `begin`); the slices written at their offsets must be the single-run .binpack byte for byte."""
 import ctypes
+import os
 
 import pytest
 
@@ -110,3 +111,98 @@ def test_sharded_window_too_small(nnp):
     info = nnp.ShardInfo()
     rc = nnp.lib().nnp_shard_compress_begin_dev(ctypes.c_void_p(d.data_ptr()), 60, 0, 50, 0, ctypes.byref(info))
     assert rc == -12  # NNP_ERR_WINDOW: the 400-ply chain does not end within 10 records of the boundary
+
+
+# ---------------------------------------------------------------------------------------------
+# ONE .binpack decoded by several ranks (nnp_shard_decompress_dev; BASELINE configs[2])
+
+
+def _shard_decompress(nnp, pack: bytes, world: int):
+    """One process plays all ranks in turn: every rank decodes its chunk range of the whole file into a
+    buffer of its own; the pieces placed at 40 * (positions of the ranks before) are the .bin file."""
+    import numpy as np
+    import torch
+
+    d_all = torch.from_numpy(np.frombuffer(pack, dtype=np.uint8).copy()).cuda() if pack else torch.empty(0, dtype=torch.uint8,
+                                                                                                       device="cuda")
+    pieces, ranges = [], []
+    for r in range(world):
+        count, rng = nnp.shard_decompress(d_all, world, r, None)
+        d_out = torch.empty(max(count, 8), dtype=torch.uint8, device="cuda")
+        got, rng2 = nnp.shard_decompress(d_all, world, r, d_out)
+        assert got == count and got == 40 * rng2.positions
+        assert (rng.chunk_lo, rng.chunk_hi, rng.byte_lo, rng.byte_hi) == (rng2.chunk_lo, rng2.chunk_hi, rng2.byte_lo, rng2.byte_hi)
+        # the host-side header walk names the same range
+        host = nnp.ChunkRange()
+        assert nnp.lib().nnp_binpack_chunk_range(pack, len(pack), world, r, ctypes.byref(host)) == 0
+        assert (host.chunks_total, host.chunk_lo, host.chunk_hi, host.byte_lo, host.byte_hi) == (
+            rng.chunks_total, rng.chunk_lo, rng.chunk_hi, rng.byte_lo, rng.byte_hi)
+        pieces.append(d_out[:got].cpu().numpy().tobytes())
+        ranges.append((rng.chunk_lo, rng.chunk_hi))
+    from nnue_data_compress_b200.sharding import shard_bounds
+
+    assert ranges == [shard_bounds(rng.chunks_total, world, r) for r in range(world)]
+    return b"".join(pieces)
+
+
+@pytest.mark.parametrize("name,world", [("twochunks", 2), ("twochunks", 3), ("games100", 2), ("long400", 4), ("heads", 1)])
+def test_shard_decompress_golden(nnp, name, world):
+    assert _shard_decompress(nnp, golden(name + ".binpack"), world) == golden(name + ".rt.bin")
+
+
+@pytest.mark.parametrize("n,plies,world", [(3_000_000, 100, 8), (2_500_000, 100, 3), (1_200_000, 2, 7), (700_000, 400, 2)])
+def test_shard_decompress_synthetic(nnp, n, plies, world):
+    from refutil import BINPACK_TO_BIN
+
+    b = nnp.generate_bin(n, plies, 23)
+    pack = nnp.bin_to_binpack(b)
+    rc, want = oracle_convert(BINPACK_TO_BIN, pack)
+    assert rc == 0
+    assert pack.count(b"BINP") >= min(world, 2)  # several chunks: the ranks really split the file
+    assert _shard_decompress(nnp, pack, world) == want
+    assert nnp.binpack_to_bin(pack) == want
+
+
+def test_shard_decompress_more_ranks_than_chunks(nnp):
+    pack = golden("games100.binpack")  # one chunk
+    out = _shard_decompress(nnp, pack, 4)
+    assert out == golden("games100.rt.bin")
+    assert _shard_decompress(nnp, b"", 2) == b""
+
+
+def test_shard_decompress_bad_header_is_reported_by_every_rank(nnp):
+    import numpy as np
+    import torch
+
+    pack = bytearray(golden("twochunks.binpack"))
+    second = pack.index(b"BINP", 8)
+    pack[second] = ord("X")
+    d_all = torch.from_numpy(np.frombuffer(bytes(pack), dtype=np.uint8).copy()).cuda()
+    for r in range(2):
+        rng = nnp.ChunkRange()
+        got = ctypes.c_size_t(0)
+        d_out = torch.empty(len(golden("twochunks.rt.bin")), dtype=torch.uint8, device="cuda")
+        rc = nnp.lib().nnp_shard_decompress_dev(ctypes.c_void_p(d_all.data_ptr()), d_all.numel(), 2, r,
+                                                ctypes.c_void_p(d_out.data_ptr()), d_out.numel(), ctypes.byref(got), ctypes.byref(rng))
+        assert rc == -1 and rng.chunks_total == 1  # NNP_ERR_BAD_MAGIC; the chunk in front of it is still decoded
+        if r == 0:
+            first = oracle_convert(1, bytes(pack[:second]))[1]
+            assert d_out[: got.value].cpu().numpy().tobytes() == first
+        else:
+            assert got.value == 0
+
+
+def test_two_devices_in_one_process_if_present(nnp):
+    """Per-device contexts: a second GPU (when the box has one) converts while the first stays bound."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU")
+    L = nnp.lib()
+    assert L.nnp_init(1) == 0 and L.nnp_device_count() >= 2
+    try:
+        b = golden("games100.bin")
+        assert nnp.bin_to_binpack(b) == golden("games100.binpack")  # host buffers, device 1
+    finally:
+        assert L.nnp_bind_device(int(os.environ.get("LOCAL_RANK", "0"))) == 0
+    assert nnp.bin_to_binpack(golden("games100.bin")) == golden("games100.binpack")

@@ -26,7 +26,10 @@ def _worker(rank, world, port, tmpdir):
 
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from nnue_data_compress_b200.sharding import chunk_bounds_binpack, exchange_offsets, shard_bounds
+    import ctypes
+
+    import nnue_data_compress_b200 as pkg
+    from nnue_data_compress_b200.sharding import chunk_bounds_binpack, decompress_sharded, exchange_offsets, shard_bounds
     from refutil import BIN_TO_BINPACK, BINPACK_TO_BIN, golden, oracle_convert
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -42,16 +45,28 @@ def _worker(rank, world, port, tmpdir):
         assert sizes[rank] == len(mine) and total == sum(sizes)
         with open(os.path.join(tmpdir, f"pack{rank}"), "wb") as f:
             f.write(off.to_bytes(8, "little") + mine)
-        # decompression shards by chunk ranges of the full file
+        # decompression: ONE file, chunk ranges per rank (sharding.decompress_sharded). The range comes
+        # from the library's host-side header walk (nnp_binpack_chunk_range, no GPU needed); the oracle
+        # stands in for nnp_binpack_to_bin_dev on the rank's bytes.
         full = golden("twochunks.binpack")
-        chunks = chunk_bounds_binpack(full)
-        clo, chi = shard_bounds(len(chunks), world, rank)
-        part = b"".join(full[o:o + l] for o, l in chunks[clo:chi])
-        rc, rec = oracle_convert(BINPACK_TO_BIN, part)
-        assert rc == 0
-        off2, total2, _ = exchange_offsets(len(rec))
+        out = {}
+
+        def decode(w, r):
+            rng = pkg.ChunkRange()
+            assert pkg.lib().nnp_binpack_chunk_range(full, len(full), w, r, ctypes.byref(rng)) == 0
+            chunks = chunk_bounds_binpack(full)
+            clo, chi = shard_bounds(len(chunks), w, r)
+            assert (rng.chunks_total, rng.chunk_lo, rng.chunk_hi) == (len(chunks), clo, chi)
+            assert rng.byte_lo == (chunks[clo][0] if clo < len(chunks) else len(full))
+            rc, rec = oracle_convert(BINPACK_TO_BIN, full[rng.byte_lo:rng.byte_hi])
+            assert rc == 0
+            out["rec"] = rec
+            return len(rec)
+
+        got, off2, total2 = decompress_sharded(decode)
+        assert got == len(out["rec"]) and total2 == len(golden("twochunks.rt.bin"))
         with open(os.path.join(tmpdir, f"bin{rank}"), "wb") as f:
-            f.write(off2.to_bytes(8, "little") + rec)
+            f.write(off2.to_bytes(8, "little") + out["rec"])
         dist.barrier()
     finally:
         dist.destroy_process_group()
