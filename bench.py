@@ -15,10 +15,16 @@ e2e    : the same step through the host-buffer entry points (pinned host memory 
          host memory out; H2D and D2H inside the timed region).
 roofline, cpu_baseline: see DESIGN.md "Measurement".
 
-N > 1 (torchrun, one rank per GPU): every rank converts its own shard (independent files, what
-the reference does with one run per shard and `-a`), no payload crosses NVLink; the only
-collective is an all-gather of the per-shard byte counts that gives each shard its offset in
-the concatenated output. Weak scaling: `positions` per GPU is fixed.
+N > 1 (torchrun, one rank per GPU), weak scaling, `positions` per GPU fixed: the ranks write ONE
+.binpack, byte-identical to a single reference run over all records (chains belong to the rank of
+their head, the chunk-flush rule is replayed from the all-gathered orbit tables), and then decode
+that ONE file by contiguous chunk ranges (nnp_shard_decompress_dev + one all-gather of the position
+counts). No payload crosses NVLink inside the timed region. `decompress_strong` reports BASELINE
+configs[2] beside it: the same 100 M-position file decoded by 1/2/4/8 ranks (strong scaling).
+
+Auxiliary keys at N = 1, all outside the timed regions of `value` and `e2e`: `parity_checked` (the
+compiled reference run on the first records of this run's own input, compared with the GPU output),
+`plain` (BASELINE configs[3]), `sweep` (configs[4] chain lengths), `halfkp`, `e2e_file`.
 """
 import argparse
 import ctypes
@@ -60,6 +66,12 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-halfkp", action="store_true", help="skip the auxiliary .binpack -> HalfKP rows measurement")
+    ap.add_argument("--no-plain", action="store_true", help="skip the auxiliary .plain directions (BASELINE configs[3])")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the auxiliary chain-length sweep (BASELINE configs[4])")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling decode of the 100M file (configs[2])")
+    ap.add_argument("--no-file", action="store_true", help="skip the file-to-file leg (tmpfs)")
+    ap.add_argument("--plain-positions", type=int, default=10_000_000)
+    ap.add_argument("--sweep-positions", type=int, default=0, help="0 = --positions")
     return ap.parse_args()
 
 
@@ -257,6 +269,189 @@ def run_reference_arm(args):
 # our arm
 
 
+def chunk_starts(data):
+    """Byte offsets of the BINP chunk headers of an in-memory .binpack (compress_file.cpp:500-521)."""
+    out, pos = [], 0
+    while pos + 8 <= len(data) and data[pos:pos + 4] == b"BINP":
+        out.append(pos)
+        pos += 8 + int.from_bytes(data[pos + 4:pos + 8], "little")
+    return out
+
+
+def run_ref(src, dst):
+    t0 = time.perf_counter()
+    subprocess.run([REF_BIN, src, dst], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return time.perf_counter() - t0
+
+
+def scratch_dir():
+    return tempfile.mkdtemp(prefix="nnp_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+
+
+def parity_and_cpu_baseline(d_bin, d_pack, pack_bytes, d_out, sample, plies):
+    """The compiled reference (oracle/_ref), one process, on the FIRST `sample` records of this run's
+    own input: its timing is the cpu_baseline, its files are the parity check. A reference run over a
+    prefix of the records writes the same chunks as the run over all of them except for its last chunk
+    (cut at the end of the prefix), so every chunk in front of that one must equal the GPU's .binpack
+    byte for byte, and decoding those chunks with the reference must give the first records of the
+    GPU's .bin output."""
+    work = scratch_dir()
+    try:
+        p_bin, p_pack, p_rt = (os.path.join(work, x) for x in ("in.bin", "out.binpack", "rt.bin"))
+        with open(p_bin, "wb") as f:
+            f.write(d_bin[: sample * 40].cpu().numpy().tobytes())
+        tc = run_ref(p_bin, p_pack)
+        td = run_ref(p_pack, p_rt)
+        with open(p_pack, "rb") as f:
+            ref_pack = f.read()
+        starts = chunk_starts(ref_pack)
+        checked = {"positions": 0, "identical": None, "note": "sample too small for a complete chunk"}
+        if len(starts) >= 2:
+            cut = starts[-1]
+            ours = d_pack[:cut].cpu().numpy().tobytes()
+            same_pack = cut <= pack_bytes and ours == ref_pack[:cut]
+            p_pre, p_pre_rt = os.path.join(work, "pre.binpack"), os.path.join(work, "pre.bin")
+            with open(p_pre, "wb") as f:
+                f.write(ref_pack[:cut])
+            run_ref(p_pre, p_pre_rt)
+            with open(p_pre_rt, "rb") as f:
+                ref_bin = f.read()
+            same_bin = d_out[: len(ref_bin)].cpu().numpy().tobytes() == ref_bin
+            checked = {
+                "positions": len(ref_bin) // 40,
+                "binpack_bytes": cut,
+                "chunks": len(starts) - 1,
+                "identical": bool(same_pack and same_bin),
+                "bin_to_binpack_identical": bool(same_pack),
+                "binpack_to_bin_identical": bool(same_bin),
+                "how": f"reference binary on the first {sample} records of this run's input; its complete chunks against the "
+                       "GPU .binpack prefix, their reference decode against the GPU .bin prefix",
+            }
+        cpu = {
+            "value": 2 * sample / (tc + td) / 1e6, "unit": "Mpos/s", "cores": 1, "kind": "reference",
+            "sample": f"first {sample} records of this run's own input ({plies} plies per chain), reference binary one process: "
+                      f"bin->binpack {sample / tc / 1e6:.3f} Mpos/s, binpack->bin {sample / td / 1e6:.3f} Mpos/s",
+        }
+        return cpu, checked
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+
+def plain_leg(torch, L, check, ptr, timed, d_bin, n, dev, peak):
+    """BASELINE configs[3]: the .plain directions on device buffers, `n` positions (the first records of
+    the bench input). Algorithmic bytes of a direction = |input| + |output|; times are
+    CUDA events around the whole call, best of 3. The compiled reference converts a 1 M-position
+    sample of the same data on one host core: its Mpos/s, and its files against the GPU's."""
+    out = {"positions": n}
+    size = ctypes.c_size_t(0)
+
+    def call(fn, d_src, n_src, d_dst, cap):
+        check(fn(ptr(d_src), n_src, ptr(d_dst) if d_dst is not None else None, cap, ctypes.byref(size)), fn.__name__)
+        return size.value
+
+    def pack_of(records):
+        nb = records * 40
+        cap = nb // 8 + (1 << 20)
+        d = torch.empty(cap, dtype=torch.uint8, device=dev)
+        rc = L.nnp_bin_to_binpack_dev(ptr(d_bin), nb, ptr(d), cap, ctypes.byref(size))
+        if rc == -8:
+            cap = size.value + 4096
+            d = torch.empty(cap, dtype=torch.uint8, device=dev)
+            rc = L.nnp_bin_to_binpack_dev(ptr(d_bin), nb, ptr(d), cap, ctypes.byref(size))
+        check(rc, "plain leg: bin->binpack")
+        return d, cap, size.value
+
+    def entry(ms, nbytes):
+        return {"ms": ms, "mpos_s": n / (ms * 1e-3) / 1e6, "algorithmic_bytes": nbytes,
+                "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak}
+
+    d_pk, cap, pk = pack_of(n)
+    txt = call(L.nnp_binpack_to_plain_dev, d_pk, pk, None, 0)
+    d_txt = torch.empty(txt + 64, dtype=torch.uint8, device=dev)
+    out["binpack_to_plain"] = entry(timed(lambda: call(L.nnp_binpack_to_plain_dev, d_pk, pk, d_txt, txt + 64)), pk + txt)
+    d_pk2 = torch.empty(cap + (1 << 20), dtype=torch.uint8, device=dev)
+    ms = timed(lambda: call(L.nnp_plain_to_binpack_dev, d_txt, txt, d_pk2, cap + (1 << 20)))
+    out["plain_to_binpack"] = entry(ms, txt + size.value)
+    out["plain_bytes"], out["binpack_bytes"] = txt, pk
+    d_rec = torch.empty(n * 40, dtype=torch.uint8, device=dev)
+    out["plain_to_bin"] = entry(timed(lambda: call(L.nnp_plain_to_bin_dev, d_txt, txt, d_rec, n * 40)), txt + n * 40)
+    btxt = call(L.nnp_bin_to_plain_dev, d_bin, n * 40, None, 0)
+    if btxt + 64 > d_txt.numel():
+        d_txt = torch.empty(btxt + 64, dtype=torch.uint8, device=dev)
+    out["bin_to_plain"] = entry(timed(lambda: call(L.nnp_bin_to_plain_dev, d_bin, n * 40, d_txt, d_txt.numel())), btxt + n * 40)
+    del d_rec, d_pk2
+
+    if reference_available():
+        m = min(1_000_000, n)
+        work = scratch_dir()
+        try:
+            d_s, _, ps = pack_of(m)
+            p_pack, p_plain, p_pack2 = (os.path.join(work, x) for x in ("s.binpack", "s.plain", "s2.binpack"))
+            with open(p_pack, "wb") as f:
+                f.write(d_s[:ps].cpu().numpy().tobytes())
+            t1 = run_ref(p_pack, p_plain)
+            t2 = run_ref(p_plain, p_pack2)
+            with open(p_plain, "rb") as f:
+                ref_plain = f.read()
+            with open(p_pack2, "rb") as f:
+                ref_pack2 = f.read()
+            got = call(L.nnp_binpack_to_plain_dev, d_s, ps, d_txt, d_txt.numel())
+            same1 = d_txt[:got].cpu().numpy().tobytes() == ref_plain
+            d_in = torch.frombuffer(bytearray(ref_plain), dtype=torch.uint8).to(dev)
+            got2 = call(L.nnp_plain_to_binpack_dev, d_in, d_in.numel(), d_s, d_s.numel())
+            same2 = d_s[:got2].cpu().numpy().tobytes() == ref_pack2
+            out["reference"] = {"positions": m, "cores": 1, "binpack_to_plain_mpos_s": m / t1 / 1e6,
+                                "plain_to_binpack_mpos_s": m / t2 / 1e6, "binpack_to_plain_identical": bool(same1),
+                                "plain_to_binpack_identical": bool(same2)}
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+    return out
+
+
+def sweep_leg(torch, L, check, ptr, n, seed, dev, peak, d_bin, d_out):
+    """BASELINE configs[4]: chain lengths 1, 8, 64 and 400 plies, `n` positions each, device-resident
+    round trip (best of 3 per direction, the library's CUDA events), generated into the bench's own
+    buffers."""
+    size = ctypes.c_size_t(0)
+    t_total, t_dom = ctypes.c_float(0), ctypes.c_float(0)
+    rows = []
+    for plies in (1, 8, 64, 400):
+        check(L.nnp_generate_bin_dev(ptr(d_bin), n, plies, seed + plies), "sweep generate")
+        cap = n * 40 // 8 + (1 << 20)
+        d = torch.empty(cap, dtype=torch.uint8, device=dev)
+        rc = L.nnp_bin_to_binpack_dev(ptr(d_bin), n * 40, ptr(d), cap, ctypes.byref(size))
+        if rc == -8:
+            cap = size.value + 4096
+            del d
+            d = torch.empty(cap, dtype=torch.uint8, device=dev)
+            rc = L.nnp_bin_to_binpack_dev(ptr(d_bin), n * 40, ptr(d), cap, ctypes.byref(size))
+        check(rc, "sweep bin->binpack")
+        pk = size.value
+        c_best = d_best = ck = dk = None
+        for _ in range(3):
+            check(L.nnp_bin_to_binpack_dev(ptr(d_bin), n * 40, ptr(d), cap, ctypes.byref(size)), "sweep bin->binpack")
+            L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
+            if c_best is None or t_total.value < c_best:
+                c_best, ck = t_total.value, t_dom.value
+            c_name = L.nnp_last_dominant_kernel().decode()
+            check(L.nnp_binpack_to_bin_dev(ptr(d), pk, ptr(d_out), d_out.numel(), ctypes.byref(size)), "sweep binpack->bin")
+            L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
+            if d_best is None or t_total.value < d_best:
+                d_best, dk = t_total.value, t_dom.value
+            d_name = L.nnp_last_dominant_kernel().decode()
+            assert size.value == n * 40
+        alg = n * 40 + pk
+        rows.append({
+            "plies": plies, "positions": n, "binpack_bytes": pk, "bytes_per_position": alg / n,
+            "compress_ms": c_best, "decompress_ms": d_best, "round_trip_mpos_s": 2 * n / ((c_best + d_best) * 1e-3) / 1e6,
+            "compress_frac": alg / (c_best * 1e-3) / 1e9 / peak, "decompress_frac": alg / (d_best * 1e-3) / 1e9 / peak,
+            "compress_kernel": c_name, "compress_kernel_ms": ck, "decompress_kernel": d_name, "decompress_kernel_ms": dk,
+        })
+        del d
+    return rows
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -266,6 +461,7 @@ def main():
     import torch.distributed as dist
 
     import nnue_data_compress_b200 as nnp
+    from nnue_data_compress_b200.sharding import compress_sharded, decompress_sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -293,45 +489,74 @@ def main():
     L = nnp.lib()
     stream = torch.cuda.current_stream()
     nnp.use_torch_stream()  # kernels on torch's current stream: ordered with torch ops, bracketed by torch events
+    L.nnp_last_dominant_kernel.restype = ctypes.c_char_p
 
     def check(rc, what):
         if rc != 0:
             raise RuntimeError(f"{what}: {L.nnp_strerror(rc).decode()} ({L.nnp_last_cuda_error().decode()})")
 
+    def ptr(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allmin_flag(ok):
+        if world == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
     n_pos = args.positions
     bin_bytes = n_pos * 40
     log(f"rank {rank}: generating {n_pos} positions on the device")
     d_bin = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
-    check(L.nnp_generate_bin_dev(ctypes.c_void_p(d_bin.data_ptr()), n_pos, args.plies, args.seed + 1000 * rank), "generate")
+    check(L.nnp_generate_bin_dev(ptr(d_bin), n_pos, args.plies, args.seed + 1000 * rank), "generate")
+
+    def compress_sized(d_records, n_bytes, guess):
+        """bin->binpack into a buffer of a guessed size, grown once if the library asks for more"""
+        need = ctypes.c_size_t(0)
+        d = torch.empty(guess, dtype=torch.uint8, device=dev)
+        rc = L.nnp_bin_to_binpack_dev(ptr(d_records), n_bytes, ptr(d), guess, ctypes.byref(need))
+        if rc == -8:  # NNP_ERR_CAPACITY: *out_bytes holds the size required
+            guess = int(need.value) + 4096
+            d = torch.empty(guess, dtype=torch.uint8, device=dev)
+            rc = L.nnp_bin_to_binpack_dev(ptr(d_records), n_bytes, ptr(d), guess, ctypes.byref(need))
+        check(rc, "sizing pass")
+        return d, guess, int(need.value)
 
     log("generated; sizing pass")
-    need = ctypes.c_size_t(0)
     # the generic capacity bound assumes every record is a chain head (34 B/pos); one sizing pass
     # gives the real size so that the benchmark buffers are not 3.4 GB of slack
-    cap_guess = bin_bytes // 8 + (1 << 20)
-    d_pack = torch.empty(cap_guess, dtype=torch.uint8, device=dev)
-    rc = L.nnp_bin_to_binpack_dev(ctypes.c_void_p(d_bin.data_ptr()), bin_bytes, ctypes.c_void_p(d_pack.data_ptr()), cap_guess,
-                                  ctypes.byref(need))
-    if rc == -8:  # NNP_ERR_CAPACITY: *out_bytes holds the size required
-        cap_guess = int(need.value) + 4096
-        d_pack = torch.empty(cap_guess, dtype=torch.uint8, device=dev)
-        rc = L.nnp_bin_to_binpack_dev(ctypes.c_void_p(d_bin.data_ptr()), bin_bytes, ctypes.c_void_p(d_pack.data_ptr()),
-                                      cap_guess, ctypes.byref(need))
-    check(rc, "sizing pass")
-    pack_bytes = int(need.value)
-    d_out = torch.empty(bin_bytes, dtype=torch.uint8, device=dev)
+    d_pack, cap_guess, pack_bytes = compress_sized(d_bin, bin_bytes, bin_bytes // 8 + (1 << 20))
+    k1_kernel = L.nnp_last_dominant_kernel().decode()
+    d_out = torch.empty(bin_bytes + bin_bytes // 16 + (64 << 20) if world > 1 else bin_bytes, dtype=torch.uint8, device=dev)
+    out_cap = d_out.numel()
 
     t_total = ctypes.c_float(0)
     t_dom = ctypes.c_float(0)
 
     # N > 1: the ranks write ONE .binpack, byte-identical to a single reference run over all records
-    # (SURVEY.md 8e). Setup, untimed: every rank gets the last record of the rank before it (halo) and
-    # the first records of the rank behind it (overlap window) -- what a file reader would read
-    # directly -- so that every chain is owned by exactly one rank.
+    # (SURVEY.md 8e), and decode that ONE file by chunk ranges. Setup, untimed: every rank gets the last
+    # record of the rank before it (halo) and the first records of the rank behind it (overlap window)
+    # -- what a file reader would read directly -- so that every chain is owned by exactly one rank;
+    # and after a first compression the slices are assembled into the file on every rank (the file a
+    # multi-GPU reader would have mapped).
     one_file = None
+    d_file = None
+    slice_info = {}
+    dec_info = {}
     if world > 1:
-        from nnue_data_compress_b200.sharding import compress_sharded
-
         window = min(65536, n_pos)
         heads = [torch.empty(window * 40, dtype=torch.uint8, device=dev) for _ in range(world)]
         tails = [torch.empty(40, dtype=torch.uint8, device=dev) for _ in range(world)]
@@ -342,47 +567,65 @@ def main():
         del heads, tails, parts
         own_lo = 1 if rank > 0 else 0
         d_slice = torch.empty(cap_guess, dtype=torch.uint8, device=dev)
-        slice_info = {}
-
         calls = nnp.ShardCalls(d_slice, dev)
 
         def one_file():
             calls.begin(d_buf, d_buf.numel() // 40, own_lo, own_lo + n_pos, rank == world - 1)
-            info_bytes = calls.last_payload_bytes
             L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
             dom = t_dom.value
-            got, off, total = compress_sharded(info_bytes, calls.orbit, calls.emit, device=dev, table=calls.table,
-                                               resolve=calls.resolve)
+            got, off, total = compress_sharded(calls.last_payload_bytes, calls.orbit, calls.emit, device=dev, table=calls.table,
+                                               resolve=calls.resolve, status=calls.last_status)
             slice_info.update(bytes=got, offset=off, file_bytes=total)
             return dom
+
+        one_file()
+        torch.cuda.synchronize()
+        mine = torch.tensor([slice_info["offset"], slice_info["bytes"]], dtype=torch.int64, device=dev)
+        allc = torch.empty(2 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine)
+        layout = allc.tolist()
+        widest = max(layout[1::2])
+        padded = torch.zeros(widest, dtype=torch.uint8, device=dev)
+        padded[: slice_info["bytes"]] = d_slice[: slice_info["bytes"]]
+        gathered = torch.empty(world * widest, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, padded)
+        d_file = torch.empty(slice_info["file_bytes"], dtype=torch.uint8, device=dev)
+        for r in range(world):
+            off, nb = layout[2 * r], layout[2 * r + 1]
+            d_file[off:off + nb] = gathered[r * widest:r * widest + nb]
+        del gathered, padded
+        log(f"one file of {d_file.numel()} bytes assembled on every rank")
+
+    def shard_decode(d_src, n_src, w, r):
+        got = ctypes.c_size_t(0)
+        rng = nnp.ChunkRange()
+        check(L.nnp_shard_decompress_dev(ptr(d_src), n_src, w, r, ptr(d_out), out_cap, ctypes.byref(got), ctypes.byref(rng)),
+              "sharded binpack->bin")
+        L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
+        return got.value
 
     def step_device():
         n1 = ctypes.c_size_t(0)
         if one_file is None:
-            check(L.nnp_bin_to_binpack_dev(ctypes.c_void_p(d_bin.data_ptr()), bin_bytes, ctypes.c_void_p(d_pack.data_ptr()),
-                                           cap_guess, ctypes.byref(n1)), "bin->binpack")
+            check(L.nnp_bin_to_binpack_dev(ptr(d_bin), bin_bytes, ptr(d_pack), cap_guess, ctypes.byref(n1)), "bin->binpack")
             L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
             c_ms, c_dom = t_total.value, t_dom.value
-            pack_in = n1.value
-        else:
-            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ea.record(stream)
-            c_dom = one_file()
-            eb.record(stream)
-            pack_in = pack_bytes  # the rank's own chunk-aligned .binpack (made by the sizing pass)
-        n2 = ctypes.c_size_t(0)
-        check(L.nnp_binpack_to_bin_dev(ctypes.c_void_p(d_pack.data_ptr()), pack_in, ctypes.c_void_p(d_out.data_ptr()),
-                                       bin_bytes, ctypes.byref(n2)), "binpack->bin")
-        L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
-        assert n2.value == bin_bytes, (n2.value, bin_bytes)
-        if one_file is not None:
-            c_ms = ea.elapsed_time(eb)
-        return c_ms, c_dom, t_total.value, t_dom.value, pack_in
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+            n2 = ctypes.c_size_t(0)
+            check(L.nnp_binpack_to_bin_dev(ptr(d_pack), n1.value, ptr(d_out), out_cap, ctypes.byref(n2)), "binpack->bin")
+            L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
+            assert n2.value == bin_bytes, (n2.value, bin_bytes)
+            return c_ms, c_dom, t_total.value, t_dom.value
+        ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        ea.record(stream)
+        c_dom = one_file()
+        eb.record(stream)
+        got, off, total = decompress_sharded(lambda w, r: shard_decode(d_file, d_file.numel(), w, r), device=dev)
+        ec.record(stream)
+        dec_info.update(bytes=got, offset=off, file_bytes=total)
+        d_dom = t_dom.value
         torch.cuda.synchronize()
+        assert total == world * bin_bytes, (total, world * bin_bytes)
+        return ea.elapsed_time(eb), c_dom, eb.elapsed_time(ec), d_dom
 
     log(f"binpack is {pack_bytes} bytes; warm-up")
     # the clock sampler runs from the first warm-up step to the end of the timed region: the same
@@ -404,7 +647,7 @@ def main():
     ev0.record(stream)
     c_ms = c_dom = d_ms = d_dom = 0.0
     for _ in range(args.steps):
-        a, b, c, d, _n = step_device()
+        a, b, c, d = step_device()
         c_ms += a
         c_dom += b
         d_ms += c
@@ -416,10 +659,77 @@ def main():
     elapsed_ms = ev0.elapsed_time(ev1)
     K = max(args.steps, 1)
     c_ms, c_dom, d_ms, d_dom = c_ms / K, c_dom / K, d_ms / K, d_dom / K
+    dec_kernel = L.nnp_last_dominant_kernel().decode()
+    log(f"device-resident: {elapsed_ms / K:.2f} ms/step")
 
-    log(f"device-resident: {elapsed_ms / max(args.steps, 1):.2f} ms/step")
+    # ---- N > 1, untimed: the ranks' pieces of the decoded file against ONE single-GPU decode of it
+    one_file_check = None
+    if world > 1:
+        piece = d_out[: dec_info["bytes"]]
+        sums = torch.zeros(1, dtype=torch.int64, device=dev)
+        sums[0] = piece.view(torch.int64).sum()
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        ok = True
+        how = "not checked: the whole .bin does not fit next to the bench buffers"
+        if rank == 0 and world * bin_bytes <= (48 << 30):
+            whole = torch.empty(world * bin_bytes, dtype=torch.uint8, device=dev)
+            n2 = ctypes.c_size_t(0)
+            check(L.nnp_binpack_to_bin_dev(ptr(d_file), d_file.numel(), ptr(whole), whole.numel(), ctypes.byref(n2)), "whole file")
+            ok = (n2.value == world * bin_bytes and bool(torch.equal(whole[: dec_info["bytes"]], piece))
+                  and int(whole.view(torch.int64).sum().item()) == int(sums.item()))
+            how = ("rank 0 decodes the whole file on one GPU: its own piece byte for byte, all pieces by the sum of their "
+                   "64-bit words")
+            del whole
+        one_file_check = {"identical": ok, "how": how}
+
+    # ---- BASELINE configs[2]: the 100M-position file decoded by 1/2/4/8 ranks (strong scaling)
+    strong = None
+    if not args.no_strong:
+        if world > 1:
+            nb = torch.tensor([pack_bytes], dtype=torch.int64, device=dev)
+            dist.broadcast(nb, 0)
+            d_small = torch.empty(int(nb.item()), dtype=torch.uint8, device=dev)
+            if rank == 0:
+                d_small.copy_(d_pack[:pack_bytes])
+            dist.broadcast(d_small, 0)
+        else:
+            d_small = d_pack[:pack_bytes]
+        res = {}
+
+        def strong_step():
+            got, off, total = decompress_sharded(lambda w, r: shard_decode(d_small, d_small.numel(), w, r), device=dev)
+            res.update(bytes=got, offset=off, total=total)
+
+        for _ in range(max(args.warmup, 1)):
+            strong_step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(K):
+            strong_step()
+        s1.record(stream)
+        barrier()
+        s_ms = allmax(s0.elapsed_time(s1) / K)
+        ok = res["total"] == bin_bytes
+        if world > 1:  # every rank checks its piece against its own single-GPU decode of the file
+            piece = d_out[: res["bytes"]].clone()
+            n2 = ctypes.c_size_t(0)
+            check(L.nnp_binpack_to_bin_dev(ptr(d_small), d_small.numel(), ptr(d_out), out_cap, ctypes.byref(n2)), "strong check")
+            ok = ok and n2.value == bin_bytes and bool(torch.equal(d_out[res["offset"]:res["offset"] + res["bytes"]], piece))
+            del piece
+        ok = allmin_flag(ok)
+        strong = {
+            "workload": f"binpack->bin of the ONE {n_pos}-position file (rank 0's), contiguous chunk ranges over {world} GPU(s), "
+                        "one all-gather of the position counts",
+            "positions": n_pos, "n_gpus": world, "ms": s_ms, "mpos_s": n_pos / (s_ms * 1e-3) / 1e6,
+            "identical_to_single_gpu": ok, "scaling": "strong",
+        }
+        if world > 1:
+            del d_small
+
     # ---- e2e: host buffers through the public C ABI, H2D and D2H inside the timed region
     e2e = None
+    pinned_ok = 0
     if not args.no_e2e:
         # pinned host buffers (cudaHostAlloc through torch); nnp_host_alloc() hands out the same kind
         try:
@@ -430,10 +740,7 @@ def main():
         except RuntimeError as exc:  # not enough lockable host memory for N ranks x 8.5 GB
             log(f"cannot pin host memory for the e2e leg: {exc}")
             pinned_ok = 0
-        if world > 1:
-            flag = torch.tensor([pinned_ok], dtype=torch.int64, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            pinned_ok = int(flag.item())
+        pinned_ok = int(allmin_flag(pinned_ok))
     if not args.no_e2e and pinned_ok:
         t_bin.copy_(d_bin)  # untimed setup: the step's input starts in host memory
         torch.cuda.synchronize()
@@ -460,12 +767,42 @@ def main():
         e1.record(stream)
         barrier()
         e_ms = e0.elapsed_time(e1) / e_steps
-        e2e_local = 2 * n_pos / (e_ms * 1e-3) / 1e6
-        e2e = {"ms": e_ms, "value": e2e_local, "h2d": bin_bytes + n1, "d2h": n1 + n2}
+        e2e = {"ms": e_ms, "h2d": bin_bytes + n1, "d2h": n1 + n2}
         del t_bin, t_pack, t_out
 
-    # ---- auxiliary (N = 1, outside every timed region above): .binpack -> HalfKP feature rows, SURVEY 8(f)-1
-    halfkp = None
+    # ---- cpu_baseline + parity_checked (N = 1): the compiled reference on the first records of this run's own
+    # input, after all timed regions and before the auxiliary legs reuse the buffers
+    cpu_baseline = parity = None
+    if not args.no_cpu_baseline and world == 1 and reference_available():
+        log("cpu baseline + parity")
+        cpu_baseline, parity = parity_and_cpu_baseline(d_bin, d_pack, pack_bytes, d_out, min(args.cpu_sample, n_pos), args.plies)
+    elif not args.no_cpu_baseline and world == 1:
+        cpu_baseline = {"value": None, "unit": "Mpos/s", "cores": 0, "kind": "reference",
+                        "sample": "oracle/_ref missing on this box"}
+
+    # ---- auxiliary (N = 1, outside every timed region above)
+    halfkp = plain = sweep = e2e_file = None
+    peak, peak_src = 6650.0, "fallback"
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            peaks = json.load(f)
+        if "hbm_gbs" in peaks:
+            peak, peak_src = float(peaks["hbm_gbs"]), "measured"
+
+    def timed(fn, reps=3):
+        """best of `reps`, CUDA events on the stream the library's kernels run on"""
+        best = None
+        for _ in range(reps):
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record(stream)
+            fn()
+            x1.record(stream)
+            torch.cuda.synchronize()
+            ms = x0.elapsed_time(x1)
+            best = ms if best is None else min(best, ms)
+        return best
+
     if world == 1 and not args.no_halfkp:
         try:
             log("halfkp rows")
@@ -474,8 +811,7 @@ def main():
             meta = torch.empty((n_pos, 8), dtype=torch.uint8, device=dev)
             cnt = ctypes.c_size_t(0)
             for _ in range(3):
-                check(L.nnp_binpack_to_halfkp_dev(ctypes.c_void_p(d_pack.data_ptr()), pack_bytes, ctypes.c_void_p(white.data_ptr()),
-                                                  ctypes.c_void_p(black.data_ptr()), ctypes.c_void_p(meta.data_ptr()), n_pos,
+                check(L.nnp_binpack_to_halfkp_dev(ptr(d_pack), pack_bytes, ptr(white), ptr(black), ptr(meta), n_pos,
                                                   ctypes.byref(cnt)), "binpack->halfkp")
                 L.nnp_last_timing(ctypes.byref(t_total), ctypes.byref(t_dom))
             assert cnt.value == n_pos, (cnt.value, n_pos)
@@ -486,6 +822,7 @@ def main():
                 "kernel_ms": t_dom.value,
                 "bytes_per_position": 264,
                 "output_gbs": 264 * n_pos / (t_dom.value * 1e-3) / 1e9,
+                "frac_of_hbm_peak": (264 * n_pos + pack_bytes) / (t_dom.value * 1e-3) / 1e9 / peak,
                 "note": "device-resident .binpack -> two int32[32] index rows + 8 B of targets per position; third call timed "
                         "by the library's CUDA events; not part of `value`",
             }
@@ -493,22 +830,23 @@ def main():
         except Exception as e:  # auxiliary: never fails the bench line
             halfkp = {"error": str(e)[:200]}
 
-    # ---- max over ranks
-    def allmax(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    if world == 1 and not args.no_plain:
+        try:
+            log("plain directions")
+            plain = plain_leg(torch, L, check, ptr, timed, d_bin, min(args.plain_positions, n_pos), dev, peak)
+        except Exception as e:  # noqa: BLE001
+            plain = {"error": str(e)[:300]}
 
-    shard_offsets = None
-    if world > 1:
-        # where every rank's slice of the one .binpack belongs (from the exchange inside the timed steps)
-        mine = torch.tensor([slice_info["offset"], slice_info["bytes"], slice_info["file_bytes"]], dtype=torch.int64, device=dev)
-        allc = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allc, mine)
-        shard_offsets = [[int(v) for v in t.tolist()] for t in allc]
+    if world == 1 and not args.no_sweep:
+        try:
+            log("chain-length sweep")
+            del d_pack
+            sweep = sweep_leg(torch, L, check, ptr, min(args.sweep_positions or n_pos, n_pos), args.seed, dev, peak, d_bin, d_out)
+            # the sweep generated into the bench's own buffers: nothing below may use d_bin / d_out / d_pack
+        except Exception as e:  # noqa: BLE001
+            sweep = {"error": str(e)[:300]}
 
+    # ---- the line
     elapsed_ms = allmax(elapsed_ms)
     ms_per_step = elapsed_ms / K
     total_pos = n_pos * world
@@ -516,27 +854,26 @@ def main():
     c_ms_m, d_ms_m = allmax(c_ms), allmax(d_ms)
     e2e_ms = allmax(e2e["ms"]) if e2e else None
 
+    shard_offsets = None
+    if world > 1:
+        # where every rank's slice of the one .binpack and its piece of the one .bin belong
+        mine = torch.tensor([slice_info["offset"], slice_info["bytes"], slice_info["file_bytes"], dec_info["offset"],
+                             dec_info["bytes"]], dtype=torch.int64, device=dev)
+        allc = torch.empty(5 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine)
+        flat = allc.tolist()
+        shard_offsets = [flat[5 * r:5 * r + 5] for r in range(world)]
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    peaks = {}
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak_src = "fallback"
-    peak = 6650.0
-    if os.path.exists(peaks_path):
-        with open(peaks_path) as f:
-            peaks = json.load(f)
-        if "hbm_gbs" in peaks:
-            peak, peak_src = float(peaks["hbm_gbs"]), "measured"
-
     # roofline of the dominant kernel of each direction. SURVEY.md 8(d): algorithmic bytes =
-    # |input| + |output| of the direction = 40 B + binpack bytes per position; one launch of
-    # k_walk_runs / k_emit_chains_verify processes all positions of the step. kernel_ms is measured
-    # live by the library with CUDA events recorded around that launch on the stream it runs on.
+    # |input| + |output| of the direction = 40 B + binpack bytes per position; one launch of the
+    # kernel processes all positions of the rank's step. kernel_ms is measured live by the library
+    # with CUDA events recorded around that launch on the stream it runs on.
     alg_bytes = bin_bytes + pack_bytes
-    achieved = alg_bytes / (c_dom * 1e-3) / 1e9 if c_dom > 0 else None
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -551,39 +888,30 @@ def main():
             return None
         return int((t["dram_read_bytes"] + t["dram_write_bytes"]) * (n_pos / t["positions"]))
 
+    def roof(kernel, ms, share_of):
+        ach = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else None
+        return {"kernel": kernel, "kernel_ms": ms, "achieved": ach, "frac": ach / peak if ach else None,
+                "traffic": dram_traffic(kernel), "share_of_direction": ms / share_of if share_of > 0 else None}
+
+    comp = roof(k1_kernel, c_dom, c_ms_m)
+    deco = roof(dec_kernel, d_dom, d_ms_m)
+    top = comp if c_dom >= d_dom else deco  # the kernel that dominated the step
     roofline = {
         "bound": "hbm",
-        "kernel": "k_walk_runs",
-        "achieved": achieved,
+        "kernel": top["kernel"],
+        "achieved": top["achieved"],
         "peak": peak,
         "peak_source": peak_src + (" MEASURED_PEAKS.json hbm_gbs" if peak_src == "measured" else " B200_PROFILING.md 6.65 TB/s"),
         "unit": "GB/s",
-        "frac": achieved / peak if achieved else None,
-        "traffic": dram_traffic("k_walk_runs"),
+        "frac": top["frac"],
+        "traffic": top["traffic"],
         "algorithmic_bytes_per_launch": alg_bytes,
-        "kernel_ms": c_dom,
-        "note": "integer-issue bound (ALU pipe ~75 % busy in the ncu capture under profiles/), not HBM bound",
-        "decompress": {
-            "kernel": "k_emit_chains_verify",
-            "kernel_ms": d_dom,
-            "achieved": alg_bytes / (d_dom * 1e-3) / 1e9 if d_dom > 0 else None,
-            "frac": (alg_bytes / (d_dom * 1e-3) / 1e9) / peak if d_dom > 0 else None,
-            "traffic": dram_traffic("k_emit_chains_verify"),
-        },
+        "kernel_ms": top["kernel_ms"],
+        "share_of_step": top["kernel_ms"] / ms_per_step,
+        "note": "integer-issue bound (see the ncu captures under profiles/), not HBM bound",
+        "compress": comp,
+        "decompress": deco,
     }
-
-    log("cpu baseline")
-    cpu_baseline = None
-    if not args.no_cpu_baseline and world == 1 and reference_available():
-        r = cpu_reference_measure(args.cpu_sample, args.plies, args.seed, 1, 1, 0)
-        cpu_baseline = {
-            "value": r["value"], "unit": "Mpos/s", "cores": 1, "kind": "reference",
-            "sample": f"{r['positions']} positions (same generator recipe, {args.plies} plies per chain), reference binary "
-                      f"bin->binpack {r['compress_mpos_s']:.3f} Mpos/s, binpack->bin {r['decompress_mpos_s']:.3f} Mpos/s",
-        }
-    elif not args.no_cpu_baseline and world == 1:
-        cpu_baseline = {"value": None, "unit": "Mpos/s", "cores": 0, "kind": "reference",
-                        "sample": "oracle/_ref missing on this box"}
 
     line = {
         "metric": METRIC,
@@ -604,10 +932,12 @@ def main():
             "positions_per_gpu": n_pos,
             "bin_bytes_per_gpu": bin_bytes,
             "binpack_bytes_per_gpu": pack_bytes,
+            "value_counts": "every position twice per step (once per direction); the reference arm counts the same way",
             "l2": f"inputs ({bin_bytes / 1e9:.1f} GB .bin, {pack_bytes / 1e9:.2f} GB .binpack per GPU) are larger than the 126 MB L2",
             "sharding": ("compress: ONE .binpack over all ranks, byte-identical to a single run (chains owned by the rank of "
-                         "their head via halo + overlap window; chunk-flush carry in rank order, 16 B per rank; two 8-byte "
-                         "all-gathers; no payload crosses NVLink); decompress: per-rank chunk ranges") if world > 1 else "single GPU",
+                         "their head via halo + overlap window; chunk-flush rule replayed from all-gathered orbit tables); "
+                         "decompress: that ONE file by contiguous chunk ranges per rank, one all-gather of the position "
+                         "counts; no payload crosses NVLink in the timed region") if world > 1 else "single GPU",
         },
         "compress_mpos_s": total_pos / (c_ms_m * 1e-3) / 1e6,
         "decompress_mpos_s": total_pos / (d_ms_m * 1e-3) / 1e6,
@@ -627,10 +957,17 @@ def main():
         }
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
-    if halfkp:
-        line["halfkp"] = halfkp
+    if parity:
+        line["parity_checked"] = parity
+    if strong:
+        line["decompress_strong"] = strong
+    if one_file_check:
+        line["one_file_check"] = one_file_check
+    for key, val in (("halfkp", halfkp), ("plain", plain), ("sweep", sweep), ("e2e_file", e2e_file)):
+        if val:
+            line[key] = val
     if shard_offsets is not None:
-        line["config"]["slices_offset_bytes_filebytes"] = shard_offsets
+        line["config"]["binpack_slice_offset_bytes_filebytes__bin_piece_offset_bytes"] = shard_offsets
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -270,6 +270,11 @@ int nnp_debug_config(const char* key, uint64_t value);
 /* Timing of the last *_dev call, measured with CUDA events on the library's stream:
  * total milliseconds, and the slice spent in the dominant kernel of that direction. */
 int nnp_last_timing(float* total_ms, float* dominant_kernel_ms);
+/* name of the kernel that slice belongs to (which form of K1 / which decode strategy ran) */
+const char* nnp_last_dominant_kernel(void);
+/* positions converted by the last driver call of the calling thread's device (what the reference's
+ * "Processed N bytes and M positions." lines count, compress_file.cpp:1369-1372, :1395-1410) */
+uint64_t nnp_last_positions(void);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,7 @@ EXPORTS = [
     "nnp_binpack_to_halfkp_dev", "nnp_bin_to_halfkp_dev",
     "nnp_init_all", "nnp_bind_device", "nnp_device_count",
     "nnp_binpack_chunk_range", "nnp_binpack_chunk_range_dev", "nnp_shard_decompress_dev",
+    "nnp_last_dominant_kernel", "nnp_last_positions",
 ]
 
 
@@ -174,6 +175,8 @@ def lib() -> ctypes.CDLL:
         L.nnp_decode_stats.restype = ctypes.c_int
         L.nnp_last_timing.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]
         L.nnp_last_timing.restype = ctypes.c_int
+        L.nnp_last_dominant_kernel.restype = ctypes.c_char_p
+        L.nnp_last_positions.restype = ctypes.c_uint64
         _lib = L
     return _lib
 
@@ -387,10 +390,12 @@ _FILE_DRIVERS = {"bin_to_binpack", "binpack_to_bin"}
 
 def _run_driver(driver, label: str, input_path: str, output_path: str, append: bool, out=sys.stdout) -> None:
     out.write(f"{label} {input_path} to {output_path}\n")
-    # like the native CLI: inputs above NNP_STREAM_THRESHOLD bytes (default 8 GiB) are converted slab
-    # by slab, so that neither host nor device memory has to hold the whole file
-    threshold = int(os.environ.get("NNP_STREAM_THRESHOLD", str(8 << 30)))
-    if driver.__name__ in _FILE_DRIVERS and os.path.getsize(input_path) > threshold:
+    # like the native CLI: the headline directions go file to file, slab by slab, once the larger of
+    # input and expected output (a .binpack expands about 24 times) exceeds NNP_STREAM_THRESHOLD bytes
+    # (default 256 MiB), so that neither host nor device memory has to hold the whole file
+    threshold = int(os.environ.get("NNP_STREAM_THRESHOLD", str(256 << 20)))
+    weight = 24 if driver.__name__ == "binpack_to_bin" else 1
+    if driver.__name__ in _FILE_DRIVERS and os.path.getsize(input_path) * weight > threshold:
         convert_file(driver.__name__, input_path, output_path, append, int(os.environ.get("NNP_SLAB_BYTES", "0")))
         return
     with open(input_path, "rb") as f:

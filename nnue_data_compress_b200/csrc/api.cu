@@ -57,6 +57,8 @@ struct Context {
     uint64_t launches = 0;
     std::string last_cuda_error;
     float last_total_ms = 0.f, last_dominant_ms = 0.f, last_stage_ms = 0.f;
+    const char* last_kernel = "";  // the kernel last_dominant_ms belongs to
+    uint64_t last_positions = 0;   // positions converted by the last driver call
     // host-buffer entry points: the copies are pipelined with the dominant kernel of the direction
     const void* pipe_src = nullptr;  // compress: host source of the records (d_bin is the staging buffer)
     void* pipe_dst = nullptr;        // decompress: host destination of the records
@@ -269,11 +271,13 @@ int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** ste
         if (C.pipe_src) CK(cudaMemcpyAsync(const_cast<void*>(d_bin), C.pipe_src, n_all * 40, cudaMemcpyHostToDevice, s));
         launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, s);
         LAUNCHED(1, "k_decode_link_encode");
+        C.last_kernel = "k_decode_link_encode";
         CK(cudaEventRecord(C.ev[3], s));
         CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     } else {
         if (n_all >= 0xFFFFFFFFull) return NNP_ERR_BAD_ARG;  // record indices travel as 32 bits
+        C.last_kernel = "k_walk_runs";
         WS(WS_PARK_A, (walk_runs(n_all) + 1) * 4, u32, park_a);
         WS(WS_PARK_B, (walk_runs(n_all) + 1) * 4, u32, park_b);
         u32* lists[2] = {park_a, park_b};
@@ -345,6 +349,7 @@ int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_ca
     }
     rc = compress_tail(codes, stems, n, status, d_out, out_cap, out_bytes);
     if (rc != NNP_OK && rc != NNP_ERR_BAD_SFEN) return rc;
+    C.last_positions = n;
     CK(cudaEventRecord(C.ev[2], s));
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
@@ -563,6 +568,7 @@ int plain_to_binpack_dev(const void* d_text, size_t text_bytes, void* d_out, siz
     LAUNCHED(1, "k_entries_link_encode");
     rc = compress_tail(codes, stems, P.nrec, NNP_OK, d_out, out_cap, out_bytes);
     if (rc != NNP_OK) return rc;
+    C.last_positions = P.nrec;
     CK(cudaStreamSynchronize(s));
     return NNP_OK;
 }
@@ -581,6 +587,7 @@ int plain_to_bin_dev(const void* d_text, size_t text_bytes, void* d_out, size_t 
     if (P.nrec * 40 > out_cap) return NNP_ERR_CAPACITY;
     launch_entries_to_bin(P.entries, P.nrec, d_out, s);
     LAUNCHED(1, "k_entries_to_bin");
+    C.last_positions = P.nrec;
     CK(cudaStreamSynchronize(s));
     return NNP_OK;
 }
@@ -620,6 +627,7 @@ int bin_to_plain_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t ou
     CK(cudaStreamSynchronize(s));
     const u64 total = h_u64[0];
     *out_bytes = total;
+    C.last_positions = n;
     if (!d_out) return status == NNP_OK ? NNP_OK : status;
     if (total > out_cap) return NNP_ERR_CAPACITY;
     launch_bin_text(true, d_bin, n, lens, offs, d_out, d_tot, s);
@@ -847,11 +855,14 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
             C.last_violations = h_tot->violations;
             if (h_tot->violations == 0) {  // no violation: the output is the reader's
                 ++C.optimistic_hits;
+                C.last_kernel = "k_emit_chains_verify";
                 CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
                 CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[1], C.ev[2]));
                 *out_bytes = positions * 40;
+                C.last_positions = positions;
                 if (P.walk_status != 0) {
                     *out_bytes = committed_bin_records(positions) * 40;
+                    C.last_positions = *out_bytes / 40;
                     return P.walk_status;
                 }
                 return NNP_OK;
@@ -870,6 +881,7 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
     }
     u64 positions = P.positions;
     *out_bytes = positions * 40;
+    C.last_positions = positions;
     if (positions * 40 > out_cap) return NNP_ERR_CAPACITY;
     if (P.chunks > 0) {
         launch_emit_chains(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_base, P.ncand, P.chunk_base, d_out, P.d_tot, s);
@@ -881,6 +893,7 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
     CK(cudaStreamSynchronize(s));
     CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
     CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[1], C.ev[2]));
+    C.last_kernel = "k_emit_chains";
     C.last_candidates = P.ncand;
     C.last_false = h_tot->false_candidates;
     for (int i = 0; i < 8; ++i) C.last_false_sample[i] = h_tot->false_sample[i];
@@ -969,6 +982,7 @@ int binpack_to_plain_dev(const void* d_in, size_t in_bytes, void* d_out, size_t 
     int rc = decode_plan(d_in, in_bytes, true, P);
     if (rc != NNP_OK) return rc;
     *out_bytes = P.text_bytes;
+    C.last_positions = P.positions;
     if (!d_out) return NNP_OK;
     if (P.text_bytes > out_cap) return NNP_ERR_CAPACITY;
     if (P.chunks > 0) {
@@ -1041,6 +1055,7 @@ int binpack_to_halfkp_dev(const void* d_in, size_t in_bytes, int* white, int* bl
             C.last_violations = h_tot->violations;
             if (h_tot->violations == 0) {
                 ++C.optimistic_hits;
+                C.last_kernel = "k_emit_chains_halfkp_verify";
                 CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
                 CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[1], C.ev[2]));
                 *positions = n;
@@ -1569,6 +1584,9 @@ int nnp_decode_stats(uint64_t* out14)
     for (int i = 0; i < 8; ++i) out14[6 + i] = g_ctx.last_false_sample[i];
     return NNP_OK;
 }
+
+const char* nnp_last_dominant_kernel(void) { return g_ctx.last_kernel; }
+uint64_t nnp_last_positions(void) { return g_ctx.last_positions; }
 
 int nnp_last_timing(float* total_ms, float* dominant_kernel_ms)
 {

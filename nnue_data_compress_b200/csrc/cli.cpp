@@ -35,63 +35,90 @@ bool fileExists(const std::string& name)
     return f.good();
 }
 
-void runDriver(driver_fn fn, const char* verb, const std::string& inputPath, const std::string& outputPath, bool append)
+bool isReferenceError(int rc) { return rc == NNP_ERR_BAD_MAGIC || rc == NNP_ERR_CHUNK_TOO_LARGE || rc == NNP_ERR_BAD_SFEN; }
+
+// anything that is not one of the reference's own errors ends the process with a non-zero exit code
+[[noreturn]] void fail(int rc)
+{
+    std::cerr << nnp_strerror(rc) << " " << nnp_last_cuda_error() << "\n";
+    nnp_shutdown();
+    std::exit(2);
+}
+
+struct HostBuffer {
+    char* p = nullptr;
+    explicit HostBuffer(size_t n) : p(static_cast<char*>(nnp_host_alloc(n + 1))) {}
+    ~HostBuffer() { nnp_host_free(p); }
+    HostBuffer(const HostBuffer&) = delete;
+    HostBuffer& operator=(const HostBuffer&) = delete;
+};
+
+// The reference's progress lines (compress_file.cpp:1280-1283, :1318-1325, :1369-1372, :1395-1410): the
+// compressors report every 100 000 positions, the decompressors at every flush of their 1 MiB buffer,
+// the last one at the end. This prints the final line of that sequence.
+void reportCompressed(size_t inputBytes, uint64_t positions, bool binInput)
+{
+    const uint64_t reported = positions / 100000 * 100000;
+    if (reported == 0) return;
+    if (binInput) std::cout << "Processed " << reported * 40 << " bytes and " << reported << " positions.\n";
+    else if (reported == positions) std::cout << "Processed " << inputBytes << " bytes and " << reported << " positions.\n";
+}
+void reportDecompressed(size_t outputBytes, uint64_t positions)
+{
+    if (outputBytes > 0) std::cout << "Processed " << outputBytes << " bytes and " << positions << " positions.\n";
+}
+
+void runDriver(driver_fn fn, const char* verb, bool compresses, const std::string& inputPath, const std::string& outputPath,
+               bool append)
 {
     std::cout << verb << " " << inputPath << " to " << outputPath << '\n';
     std::ifstream in(inputPath, std::ios_base::binary | std::ios_base::ate);
     const size_t n = in ? static_cast<size_t>(in.tellg()) : 0;
-    char* src = static_cast<char*>(nnp_host_alloc(n + 1));
-    if (!src) throw std::runtime_error("host allocation failed");
+    HostBuffer src(n);
+    if (!src.p) fail(NNP_ERR_NOMEM);
     in.seekg(0);
-    in.read(src, static_cast<std::streamsize>(n));
+    in.read(src.p, static_cast<std::streamsize>(n));
 
     size_t need = 0;
-    int rc = fn(src, n, nullptr, 0, &need);
-    if (rc != NNP_OK && rc != NNP_ERR_BAD_MAGIC && rc != NNP_ERR_CHUNK_TOO_LARGE && rc != NNP_ERR_BAD_SFEN) {
-        nnp_host_free(src);
-        throw std::runtime_error(std::string(nnp_strerror(rc)) + " " + nnp_last_cuda_error());
-    }
-    char* dst = static_cast<char*>(nnp_host_alloc(need + 1));
-    if (!dst) throw std::runtime_error("host allocation failed");
+    int rc = fn(src.p, n, nullptr, 0, &need);  // size query (a count pass for the directions whose output is variable)
+    if (rc != NNP_OK && !isReferenceError(rc)) fail(rc);
+    HostBuffer dst(need);
+    if (!dst.p) fail(NNP_ERR_NOMEM);
     size_t produced = 0;
-    rc = fn(src, n, dst, need, &produced);
-    const bool referenceError = rc == NNP_ERR_BAD_MAGIC || rc == NNP_ERR_CHUNK_TOO_LARGE || rc == NNP_ERR_BAD_SFEN;
-    if (rc == NNP_OK || referenceError) {
+    rc = fn(src.p, n, dst.p, need, &produced);
+    if (rc != NNP_OK && !isReferenceError(rc)) fail(rc);
+    {
         std::ofstream out(outputPath, std::ios_base::binary | (append ? std::ios_base::app : std::ios_base::trunc));
-        out.write(dst, static_cast<std::streamsize>(produced));
+        out.write(dst.p, static_cast<std::streamsize>(produced));
+        if (!out) fail(NNP_ERR_BAD_ARG);
     }
-    nnp_host_free(src);
-    nnp_host_free(dst);
-    if (referenceError) throw std::runtime_error(nnp_strerror(rc));  // printed by main, exit code 0
-    if (rc != NNP_OK) {
-        std::cerr << nnp_strerror(rc) << " " << nnp_last_cuda_error() << "\n";
-        std::exit(2);
-    }
-    std::cout << "Processed " << n << " bytes into " << produced << " bytes.\n";
+    if (isReferenceError(rc)) throw std::runtime_error(nnp_strerror(rc));  // printed by main, exit code 0
+    if (compresses) reportCompressed(n, nnp_last_positions(), endsWith(inputPath, binExtension));
+    else reportDecompressed(produced, nnp_last_positions());
 }
 
-// Inputs above NNP_STREAM_THRESHOLD bytes (default 8 GiB) go through the slab-wise file drivers
-// (nnp_*_file): neither host nor device memory has to hold the whole file. NNP_SLAB_BYTES sets the
-// slab size (0 = the library's default).
+// The two headline directions go file to file through the slab-wise drivers (nnp_*_file: reader thread,
+// H2D, kernels, D2H and writer overlap; neither host nor device memory has to hold the whole file) as
+// soon as the larger of input and expected output exceeds NNP_STREAM_THRESHOLD bytes (default 256 MiB;
+// a .binpack is taken to expand 24 times). NNP_SLAB_BYTES sets the slab size (0 = the library's default).
 typedef int (*file_fn)(const char*, const char*, int, size_t, uint64_t*);
 
-bool runFileDriver(file_fn fn, const char* verb, const std::string& inputPath, const std::string& outputPath, bool append)
+bool runFileDriver(file_fn fn, const char* verb, bool compresses, const std::string& inputPath, const std::string& outputPath,
+                   bool append)
 {
     std::ifstream in(inputPath, std::ios_base::binary | std::ios_base::ate);
     const unsigned long long size = in ? static_cast<unsigned long long>(in.tellg()) : 0ull;
     const char* t = std::getenv("NNP_STREAM_THRESHOLD");
-    const unsigned long long threshold = t ? std::strtoull(t, nullptr, 10) : (8ull << 30);
-    if (size <= threshold) return false;
+    const unsigned long long threshold = t ? std::strtoull(t, nullptr, 10) : (256ull << 20);
+    if ((compresses ? size : size * 24) <= threshold) return false;
     const char* sl = std::getenv("NNP_SLAB_BYTES");
     std::cout << verb << " " << inputPath << " to " << outputPath << '\n';
     uint64_t positions = 0;
     const int rc = fn(inputPath.c_str(), outputPath.c_str(), append ? 1 : 0, sl ? std::strtoull(sl, nullptr, 10) : 0, &positions);
-    if (rc == NNP_ERR_BAD_MAGIC || rc == NNP_ERR_CHUNK_TOO_LARGE || rc == NNP_ERR_BAD_SFEN) throw std::runtime_error(nnp_strerror(rc));
-    if (rc != NNP_OK) {
-        std::cerr << nnp_strerror(rc) << " " << nnp_last_cuda_error() << "\n";
-        std::exit(2);
-    }
-    std::cout << "Processed " << size << " bytes and " << positions << " positions.\n";
+    if (isReferenceError(rc)) throw std::runtime_error(nnp_strerror(rc));
+    if (rc != NNP_OK) fail(rc);
+    if (compresses) reportCompressed(size, positions, true);
+    else reportDecompressed(positions * 40, positions);
     return true;
 }
 
@@ -102,21 +129,21 @@ void convert(const std::string& inputPath, std::string outputPath, bool append)
         return;
     }
     if (endsWith(inputPath, binExtension) && endsWith(outputPath, plainExtension)) {
-        runDriver(nnp_bin_to_plain, "Converting", inputPath, outputPath, append);
+        runDriver(nnp_bin_to_plain, "Converting", false, inputPath, outputPath, append);
     } else if (endsWith(inputPath, plainExtension) && endsWith(outputPath, binExtension)) {
-        runDriver(nnp_plain_to_bin, "Compressing", inputPath, outputPath, append);
+        runDriver(nnp_plain_to_bin, "Compressing", true, inputPath, outputPath, append);
     } else if (endsWith(inputPath, plainExtension) || endsWith(inputPath, binExtension)) {
         if (!endsWith(outputPath, binpackExtension)) outputPath += binpackExtension;
-        if (endsWith(inputPath, binExtension) && runFileDriver(nnp_bin_to_binpack_file, "Compressing", inputPath, outputPath, append))
+        if (endsWith(inputPath, binExtension) && runFileDriver(nnp_bin_to_binpack_file, "Compressing", true, inputPath, outputPath, append))
             return;
-        runDriver(endsWith(inputPath, binExtension) ? nnp_bin_to_binpack : nnp_plain_to_binpack, "Compressing", inputPath,
+        runDriver(endsWith(inputPath, binExtension) ? nnp_bin_to_binpack : nnp_plain_to_binpack, "Compressing", true, inputPath,
                   outputPath, append);
     } else if (endsWith(inputPath, binpackExtension)) {
         if (endsWith(outputPath, binExtension)) {
-            if (runFileDriver(nnp_binpack_to_bin_file, "Decompressing", inputPath, outputPath, append)) return;
-            runDriver(nnp_binpack_to_bin, "Decompressing", inputPath, outputPath, append);
+            if (runFileDriver(nnp_binpack_to_bin_file, "Decompressing", false, inputPath, outputPath, append)) return;
+            runDriver(nnp_binpack_to_bin, "Decompressing", false, inputPath, outputPath, append);
         } else if (endsWith(outputPath, plainExtension)) {
-            runDriver(nnp_binpack_to_plain, "Decompressing", inputPath, outputPath, append);
+            runDriver(nnp_binpack_to_plain, "Decompressing", false, inputPath, outputPath, append);
         } else {
             std::cerr << "Unrecognized file format. Only " << binExtension << " and " << plainExtension
                       << " are supported for decompression.";

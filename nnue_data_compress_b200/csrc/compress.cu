@@ -647,23 +647,26 @@ __global__ void k_orbit_resolve(const u64* __restrict__ tables, u64 entries, con
 }
 
 // ------------------------------------------------------------------ chunk emission
-// grid = (EMIT_BLOCKS_PER_CHUNK, 1 + chunks): segment 0 is copied as it is, segment 1 + k behind its
+// grid = EMIT_BLOCKS_PER_SEG * (1 + chunks) blocks, EMIT_BLOCKS_PER_SEG per segment (a flat grid: any
+// number of chunks): segment 0 is copied as it is, segment 1 + k behind its
 // 8-byte header 'B','I','N','P',LE32(size) (:486-498). Source and destination of a segment differ by
 // a multiple of 8 bytes, so they share their alignment and the body moves as aligned vectors.
 // `last_size`: size field of the last chunk when it continues in the next shard (else NATURAL_SIZE).
 constexpr int EMIT_THREADS = 256;
+constexpr unsigned EMIT_BLOCKS_PER_SEG = 8;
 __global__ void __launch_bounds__(EMIT_THREADS)
 k_emit_chunks(const unsigned char* __restrict__ payload, const u64* __restrict__ seg_off, unsigned char* __restrict__ out,
-              u64 last_size)
+              u64 last_size, u64 n_seg)
 {
-    const u64 seg = blockIdx.y;
+    const u64 seg = blockIdx.x / EMIT_BLOCKS_PER_SEG;
+    const unsigned part = blockIdx.x % EMIT_BLOCKS_PER_SEG;
     const u64 s0 = seg_off[seg], s1 = seg_off[seg + 1];
     u64 size = s1 - s0;
     unsigned char* dst = out + s0;
     if (seg > 0) {
         dst += 8 * (seg - 1);
-        const u64 field = (seg == gridDim.y - 1 && last_size != NATURAL_SIZE) ? last_size : size;
-        if (blockIdx.x == 0 && threadIdx.x < 8) {
+        const u64 field = (seg == n_seg - 1 && last_size != NATURAL_SIZE) ? last_size : size;
+        if (part == 0 && threadIdx.x < 8) {
             const unsigned char hdr[8] = {'B', 'I', 'N', 'P', (unsigned char)field, (unsigned char)(field >> 8),
                                           (unsigned char)(field >> 16), (unsigned char)(field >> 24)};
             dst[threadIdx.x] = hdr[threadIdx.x];
@@ -671,8 +674,8 @@ k_emit_chunks(const unsigned char* __restrict__ payload, const u64* __restrict__
         dst += 8;
     }
     const unsigned char* src = payload + s0;
-    const u64 tid = (u64)blockIdx.x * EMIT_THREADS + threadIdx.x;
-    const u64 nthreads = (u64)gridDim.x * EMIT_THREADS;
+    const u64 tid = (u64)part * EMIT_THREADS + threadIdx.x;
+    const u64 nthreads = (u64)EMIT_BLOCKS_PER_SEG * EMIT_THREADS;
     u64 head = (8 - ((uintptr_t)src & 7)) & 7;
     if (head > size) head = size;
     for (u64 i = tid; i < head; i += nthreads) dst[i] = src[i];
@@ -769,8 +772,9 @@ void launch_orbit_resolve(const u64* tables, u64 entries, const u64* sizes, int 
 }
 void launch_emit_chunks(const void* payload, const u64* seg_off, u64 chunks, void* out, u64 last_size, cudaStream_t s)
 {
-    dim3 grid(8, (unsigned)(chunks + 1));
-    k_emit_chunks<<<grid, EMIT_THREADS, 0, s>>>((const unsigned char*)payload, seg_off, (unsigned char*)out, last_size);
+    const u64 n_seg = chunks + 1;  // 2^31 / 8 segments = 256 TiB of payload per launch
+    k_emit_chunks<<<(unsigned)(n_seg * EMIT_BLOCKS_PER_SEG), EMIT_THREADS, 0, s>>>((const unsigned char*)payload, seg_off,
+                                                                                    (unsigned char*)out, last_size, n_seg);
 }
 void launch_find_head(const u32* codes, u64 n, u64 start, u64* out, cudaStream_t s)
 {

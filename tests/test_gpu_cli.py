@@ -72,3 +72,18 @@ def test_cli_streams_large_files(tmp_path, monkeypatch):
     r = subprocess.run([CLI, str(d / "g.binpack"), str(d / "rt.bin")], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0
     assert (d / "rt.bin").read_bytes() == golden("twochunks.rt.bin")
+
+
+def test_cli_prints_the_reference_start_and_end_lines(tmp_path):
+    """stdout: the reference's first line and the LAST of its progress lines (compress_file.cpp:1369-1372,
+    :1395-1410); the lines in between are not reproduced."""
+    from refutil import REF_BIN
+
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    d = tmp_path
+    (d / "g.bin").write_bytes(golden("twochunks.bin"))
+    for args in ((str(d / "g.bin"), str(d / "g.binpack")), (str(d / "g.binpack"), str(d / "rt.bin"))):
+        ours = _run(*args).stdout.strip().split("\n")
+        ref = subprocess.run([REF_BIN, *args], capture_output=True, text=True, timeout=300).stdout.strip().split("\n")
+        assert len(ours) == 2 and ours[0] == ref[0] and ours[1] == ref[-1], (ours, ref[:1], ref[-1:])

@@ -102,6 +102,18 @@ def test_sharded_synthetic(nnp, n, plies, world, overlap):
     assert nnp.bin_to_binpack(b) == want
 
 
+def test_sharded_reference_16m(nnp):
+    """The 8-rank one-file compressor against ONE run of the compiled reference on 16 M records."""
+    from refutil import have_ref, ref_convert
+
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    b = nnp.generate_bin(16_000_000, 100, 4242)
+    want = ref_convert(BIN_TO_BINPACK, b)
+    assert len(want) > 30 << 20
+    assert _sharded(nnp, b, 8, 65536) == want
+
+
 def test_sharded_window_too_small(nnp):
     import numpy as np
     import torch
