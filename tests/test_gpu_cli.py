@@ -66,24 +66,28 @@ def test_cli_streams_large_files(tmp_path, monkeypatch):
     (d / "g.bin").write_bytes(golden("twochunks.bin"))
     env = dict(os.environ, NNP_STREAM_THRESHOLD="1000", NNP_SLAB_BYTES=str(40 * 7000))
     r = subprocess.run([CLI, str(d / "g.bin"), str(d / "g.binpack")], capture_output=True, text=True, timeout=300, env=env)
-    assert r.returncode == 0 and "positions" in r.stdout
+    assert r.returncode == 0 and r.stdout.startswith("Compressing")
     assert (d / "g.binpack").read_bytes() == golden("twochunks.binpack")
     env["NNP_SLAB_BYTES"] = str(700_000)
     r = subprocess.run([CLI, str(d / "g.binpack"), str(d / "rt.bin")], capture_output=True, text=True, timeout=300, env=env)
-    assert r.returncode == 0
+    assert r.returncode == 0 and "positions" in r.stdout
     assert (d / "rt.bin").read_bytes() == golden("twochunks.rt.bin")
 
 
-def test_cli_prints_the_reference_start_and_end_lines(tmp_path):
+def test_cli_prints_the_reference_start_and_end_lines(tmp_path, nnp):
     """stdout: the reference's first line and the LAST of its progress lines (compress_file.cpp:1369-1372,
-    :1395-1410); the lines in between are not reproduced."""
+    :1395-1410); the lines in between are not reproduced. Whole-buffer and slab-wise drivers alike."""
     from refutil import REF_BIN
 
     if not have_ref():
         pytest.skip("oracle/_ref not built")
     d = tmp_path
-    (d / "g.bin").write_bytes(golden("twochunks.bin"))
-    for args in ((str(d / "g.bin"), str(d / "g.binpack")), (str(d / "g.binpack"), str(d / "rt.bin"))):
-        ours = _run(*args).stdout.strip().split("\n")
-        ref = subprocess.run([REF_BIN, *args], capture_output=True, text=True, timeout=300).stdout.strip().split("\n")
-        assert len(ours) == 2 and ours[0] == ref[0] and ours[1] == ref[-1], (ours, ref[:1], ref[-1:])
+    (d / "g.bin").write_bytes(nnp.generate_bin(250_000, 100, 5))
+    (d / "s.bin").write_bytes(golden("games100.bin"))
+    for stream in ("1", str(1 << 40)):
+        env = dict(os.environ, NNP_STREAM_THRESHOLD=stream)
+        for stem in ("g", "s"):
+            for args in ((str(d / f"{stem}.bin"), str(d / f"{stem}.binpack")), (str(d / f"{stem}.binpack"), str(d / f"{stem}.rt.bin"))):
+                ours = subprocess.run([CLI, *args], capture_output=True, text=True, timeout=300, env=env).stdout.strip().split("\n")
+                ref = subprocess.run([REF_BIN, *args], capture_output=True, text=True, timeout=300).stdout.strip().split("\n")
+                assert ours == ref[:1] + (ref[-1:] if len(ref) > 1 else []), (ours, ref[:1], ref[-1:])
