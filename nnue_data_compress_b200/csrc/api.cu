@@ -1200,6 +1200,13 @@ int init_device(int device)
     for (auto& ev : C.pipe_ev)
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return NNP_ERR_CUDA;
     if (cudaMallocHost(&C.pinned, 4096) != cudaSuccess) return NNP_ERR_NOMEM;
+    // the device-side lookup tables: the counterpart of the reference's static initialisation
+    // (src/chess/Bitboard.cpp:460-464)
+    init_tables_compress(C.own_stream);
+    init_tables_decompress(C.own_stream);
+    init_tables_halfkp(C.own_stream);
+    if (cudaStreamSynchronize(C.own_stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return NNP_ERR_CUDA;
+    C.launches += 3;
     const char* dbg = std::getenv("NNP_DEBUG_REJECT_MOD");
     C.debug_reject_mod = dbg ? (uint32_t)std::strtoul(dbg, nullptr, 10) : 0u;
     const char* dbg2 = std::getenv("NNP_DEBUG_EXHAUSTIVE");

@@ -27,7 +27,7 @@ __device__ __forceinline__ bool chain_step(ChainCursor& c, BitReader& r, bool st
                                            const StepTables* T = nullptr)
 {
     if (strict && (c.mv.from > 63 || c.mv.to > 63)) return false;  // null move followed by plies
-    pos_do_move(c.pos, c.mv, moved);
+    pos_do_move(c.pos, c.mv, moved, T);
     Move m;
     int sc;
     if (!decode_ply(r, c.pos, c.last_score, m, sc, strict, T)) return false;
@@ -77,7 +77,7 @@ __device__ __forceinline__ bool emit_chain_bin(const unsigned char* s, u32 bytes
         s, bytes_after_stem,
         [&](const ChainCursor& cc) {
             const int moved = pos_piece_at(cc.pos, cc.mv.from);
-            spliced = stream_apply_move(W, cc.pos, cc.mv, moved);
+            spliced = stream_apply_move(W, cc.pos, cc.mv, moved, T);
             return moved;
         },
         [&](const ChainCursor& cc, u32 k) {

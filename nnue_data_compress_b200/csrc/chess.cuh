@@ -146,28 +146,71 @@ __device__ __forceinline__ u64 piece_attacks(int pt, int sq, u64 occ)
     return a;
 }
 
-// Step attacks from a 1 KB table in shared memory (filled by the block from the functions above): one
-// 8-byte load instead of ~35 ALU-pipe instructions per knight or king lane.
+// Lookup tables in shared memory (filled by the block from the functions above and below). The chain
+// kernels are bound by the integer ALU pipe, so everything that is a pure function of a square or of a
+// bit position is looked up (LSU pipe) instead of computed: knight / king step attacks, pawn capture
+// sets, the two diagonal masks, 1 << sq and (1 << sq) - 1 and the castling rights a move from / to a
+// square preserves. (A 7 KB table of the splice's "bits below stream position p" masks was measured
+// too: it costs the L1 cache more than it saves)
+constexpr int STEP_TABLE_ROWS = 65;
 struct StepTables {
     u64 knight[64], king[64];
+    u64 pawn[2][64];     // pawn_attacks(bit64(sq), colour)
+    u64 diag[64], anti[64];
+    u64 bit[64], before[65];
+    unsigned char keep_cr[64];  // preserved_cr(sq)
+    alignas(16) u32 pad[2];
 };
+__device__ __forceinline__ u64 diag_mask(int sq);
+__device__ __forceinline__ u64 anti_mask(int sq);
+__device__ __forceinline__ int preserved_cr(int sq);
+__device__ __forceinline__ void step_tables_entry(StepTables& T, int i)
+{
+    if (i < 64) {
+        T.knight[i] = knight_attacks(i);
+        T.king[i] = king_attacks(i);
+        T.pawn[0][i] = pawn_attacks(bit64(i), 0);
+        T.pawn[1][i] = pawn_attacks(bit64(i), 1);
+        T.diag[i] = diag_mask(i);
+        T.anti[i] = anti_mask(i);
+        T.bit[i] = bit64(i);
+        T.keep_cr[i] = (unsigned char)preserved_cr(i);
+    }
+    if (i < 65) T.before[i] = before64(i);
+}
 #ifdef __CUDACC__
+// One copy per translation unit and device, computed once (k_step_tables_init, at nnp_init) and then
+// copied into every block's shared memory with 16-byte loads: computing the tables per block would
+// cost more than one percent of a block's work.
+static __device__ StepTables g_step_tables;
+static __global__ void k_step_tables_init()
+{
+    for (int i = threadIdx.x; i < STEP_TABLE_ROWS; i += blockDim.x) step_tables_entry(g_step_tables, i);
+}
+static_assert(sizeof(StepTables) % 16 == 0, "copied as uint4");
 __device__ __forceinline__ void step_tables_fill(StepTables& T)  // whole block; call before any early return
 {
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) {
-        if (i < 64) T.knight[i] = knight_attacks(i);
-        else T.king[i - 64] = king_attacks(i - 64);
-    }
+    const uint4* src = reinterpret_cast<const uint4*>(&g_step_tables);
+    uint4* dst = reinterpret_cast<uint4*>(&T);
+    for (int i = threadIdx.x; i < (int)(sizeof(StepTables) / 16); i += blockDim.x) dst[i] = src[i];
     __syncthreads();
 }
 #endif
+__device__ __forceinline__ u64 bishop_attacks(int sq, u64 occ, const StepTables* T)
+{
+#ifdef NNP_NO_SMALL_LUT
+    T = nullptr;
+#endif
+    if (!T) return bishop_attacks(sq, occ);
+    return line_attacks(occ, T->diag[sq], sq) | line_attacks(occ, T->anti[sq], sq);
+}
 __device__ __forceinline__ u64 piece_attacks(int pt, int sq, u64 occ, const StepTables* T)
 {
     if (!T) return piece_attacks(pt, sq, occ);
     u64 a = 0;
     if (pt == PT_KNIGHT || pt == PT_KING) a = pt == PT_KNIGHT ? T->knight[sq] : T->king[sq];
     else {
-        if (pt == PT_BISHOP || pt == PT_QUEEN) a = bishop_attacks(sq, occ);
+        if (pt == PT_BISHOP || pt == PT_QUEEN) a = bishop_attacks(sq, occ, T);
         if (pt == PT_ROOK || pt == PT_QUEEN) a |= rook_attacks(sq, occ);
     }
     return a;
@@ -272,7 +315,8 @@ __device__ __forceinline__ bool ep_possible(const Pos& p, int ep, int side)
 {
     u64 attackers = pawn_attacks(bit64(ep), side ^ 1) & pos_type_bb(p, PT_PAWN) & pos_occ(p, side);
     if (!attackers) return false;
-    return ep_possible_cold(p, ep, attackers, side);
+    const Pos copy = p;  // the out-of-line test gets its own copy: the caller's position stays in registers
+    return ep_possible_cold(copy, ep, attackers, side);
 }
 
 // Board::isSquareAttacked as used by Position::trySet (Position.cpp:505) and the game generator
@@ -345,14 +389,18 @@ __device__ __forceinline__ void board_do_move(Pos& p, const Move& m, int moved)
 
 // Position::doMove (Position.cpp:626-662)
 // `moved` (optional) = pos_piece_at(p, m.from) when the caller has already looked it up
-__device__ __forceinline__ void pos_do_move(Pos& p, const Move& m, int moved = -1)
+__device__ __forceinline__ void pos_do_move(Pos& p, const Move& m, int moved = -1, const StepTables* T = nullptr)
 {
     if (moved < 0) moved = pos_piece_at(p, m.from);
     int moved_type = moved >> 1;
     p.ply = (p.ply + 1) & 0xFFFF;
     p.rule50 = (p.rule50 + 1) & 0xFF;
     if (m.type != MT_CASTLE && (moved_type == PT_PAWN || ((pos_all(p) >> m.to) & 1))) p.rule50 = 0;
-    p.cr &= preserved_cr(m.from) & preserved_cr(m.to);
+#ifdef NNP_NO_SMALL_LUT
+    T = nullptr;
+#endif
+    if (T && (m.from | m.to) < 64) p.cr &= (int)T->keep_cr[m.from] & (int)T->keep_cr[m.to];
+    else p.cr &= preserved_cr(m.from) & preserved_cr(m.to);
     p.ep = SQ_NONE;
     if (moved_type == PT_PAWN && ((m.to ^ m.from) == 16)) {
         int cand = (m.to + m.from) >> 1;
@@ -678,12 +726,15 @@ __device__ __forceinline__ void stem_unpack(ByteFn B, Pos& p, Move& mv, int& sco
 // ---------------------------------------------------------------- movetext codec
 
 // destination set of a pawn (addMoveScore :890-919 / nextMoveScore :701-730)
-__device__ __forceinline__ u64 pawn_destinations(const Pos& p, int from, u64 ours, u64 theirs)
+__device__ __forceinline__ u64 pawn_destinations(const Pos& p, int from, u64 ours, u64 theirs, const StepTables* T = nullptr)
 {
+#ifdef NNP_NO_SMALL_LUT
+    T = nullptr;
+#endif
     u64 occ = ours | theirs;
     u64 targets = theirs;
-    if (p.ep != SQ_NONE) targets |= bit64(p.ep & 63);
-    u64 dest = pawn_attacks(bit64(from), p.stm) & targets;
+    if (p.ep != SQ_NONE) targets |= T ? T->bit[p.ep & 63] : bit64(p.ep & 63);
+    u64 dest = (T ? T->pawn[p.stm & 1][from] : pawn_attacks(bit64(from), p.stm)) & targets;
     int s1 = p.stm == WHITE ? from + 8 : from - 8;
     if (s1 >= 0 && s1 < 64 && !((occ >> s1) & 1)) {
         dest |= bit64(s1);
@@ -713,7 +764,7 @@ __device__ __forceinline__ u32 encode_ply(const Pos& p, const Move& mv, int scor
     u32 extra_moves = 0;
     bool promotes = false;
     if (pt == PT_PAWN) {
-        dest = pawn_destinations(p, mv.from, ours, theirs);
+        dest = pawn_destinations(p, mv.from, ours, theirs, T);
         promotes = (mv.from >> 3) == (stm == WHITE ? 6 : 1);
     } else if (pt == PT_KING) {
         const int our_mask = stm == WHITE ? (CR_WK | CR_WQ) : (CR_BK | CR_BQ);
@@ -753,32 +804,62 @@ __device__ __forceinline__ u32 encode_ply(const Pos& p, const Move& mv, int scor
     return (u32)(acc << (32 - n));
 }
 
-// MSB-first bit reader over a byte span (PackedMoveScoreListReader::extractBitsLE8 :623-648).
-// Reads the one or two bytes a field touches straight from memory (L1 hits): a 64-bit register
-// window with 32-bit refills was measured slower in the chain decoder (more registers and 64-bit
-// shifts than the byte loads cost). `pos` counts the bits consumed (numReadBytes :815-818).
+// MSB-first bit reader over a byte span (PackedMoveScoreListReader::extractBitsLE8 :623-648): a
+// 32-bit window refilled 16 bits at a time with aligned halfword loads, the next halfword already
+// loaded one refill ahead, so that a field costs a few register operations and the load latency of
+// the movetext is off the critical path (the byte-per-field form this replaces accounted for a third
+// of the chain decoder's stall samples). `pos` counts the bits consumed (numReadBytes :815-818).
 struct BitReader {
     const unsigned char* p;
-    u32 nbits;   // bits available
+    u32 nbits;    // bits available
     u32 pos;
     bool overrun;
+    u32 win;      // the next `have` bits of the stream in its top bits, zeros below
+    u32 have;
+    u32 next16;   // the two bytes behind the window as loaded (little-endian halfword): swapped when they enter it,
+                  // so that nothing waits for the load before the next refill
+    u32 fetched;  // bytes behind the span's start that are in win or next16
+    u32 nbytes;
+    __device__ __forceinline__ u32 load16(u32 idx) const  // bytes idx (low) and idx + 1 (high), zeros past the span
+    {
+        if (idx + 1 < nbytes) return *reinterpret_cast<const unsigned short*>(p + idx);  // p + idx is even (init)
+        return idx < nbytes ? (u32)p[idx] : 0u;
+    }
     __device__ __forceinline__ void init(const unsigned char* p0, u64 bytes)
     {
         p = p0;
         const u64 bits = bytes * 8;
         nbits = bits > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)bits;
+        nbytes = nbits >> 3;
         pos = 0;
         overrun = false;
+        win = 0;
+        have = 0;
+        fetched = 0;
+        if ((reinterpret_cast<uintptr_t>(p0) & 1) && nbytes > 0) {  // an odd start: one byte, then aligned halfwords
+            win = (u32)p0[0] << 24;
+            have = 8;
+            fetched = 1;
+        }
+        next16 = load16(fetched);
+        fetched += 2;
     }
     __device__ __forceinline__ u32 get(int n)  // n <= 8
     {
         if (n == 0) return 0;
         if (pos + (u32)n > nbits) { overrun = true; pos += n; return 0; }
-        u32 byte = pos >> 3, sh = pos & 7;
-        u32 v = ((u32)p[byte] << 16);
-        if (((pos + n - 1) >> 3) > byte) v |= ((u32)p[byte + 1] << 8);
+        if (have < 16) {  // room for 16 more bits (and n <= 8 <= have afterwards)
+            const u32 be = ((next16 & 0xFFu) << 8) | (next16 >> 8);  // stream order: byte idx first
+            win |= be << (16 - have);
+            have += 16;
+            next16 = load16(fetched);
+            fetched += 2;
+        }
+        const u32 v = win >> (32 - n);
+        win <<= n;
+        have -= n;
         pos += n;
-        return (v >> (24 - sh - n)) & ((1u << n) - 1u);
+        return v;
     }
 };
 
@@ -809,7 +890,7 @@ __device__ __forceinline__ bool decode_ply(BitReader& r, const Pos& p, int& last
     u32 n, att_n = 0;
     bool promotes = false;
     if (pt == PT_PAWN) {
-        dest = pawn_destinations(p, from, ours, theirs);
+        dest = pawn_destinations(p, from, ours, theirs, T);
         n = (u32)popc64(dest);
         promotes = (from >> 3) == (stm == WHITE ? 6 : 1);
         if (promotes) n *= 4;

@@ -188,26 +188,30 @@ __device__ __forceinline__ void park_append(u32 parked, u32* __restrict__ list, 
     if (parked != KW_NONE) list[base + __popc(m & ((1u << lane) - 1u))] = parked;
 }
 
+// Persistent form: the grid is sized to the machine (launch_walk_runs) and every block loops over tiles of
+// KW_THREADS runs, so the lookup tables are staged in shared memory once per block, not once per tile.
 __global__ void __launch_bounds__(KW_THREADS, KW_MIN_BLOCKS)
 k_walk_runs(const unsigned char* __restrict__ bin, u64 n, u64 run_lo, u64 run_hi, u32* __restrict__ codes,
             u32* __restrict__ stems, CompressTotals* tot, u32* __restrict__ park_list, u64* park_count)
 {
     __shared__ StepTables T;
     step_tables_fill(T);
-    const u64 run = run_lo + (u64)blockIdx.x * KW_THREADS + threadIdx.x;
-    const u64 r0 = run * KW_RUN;
-    u32 parked = KW_NONE;
-    if (run < run_hi && r0 < n) {
-        const u64 e = r0 + KW_RUN < n ? r0 + KW_RUN : n;
-        bool head = r0 == 0;
-        if (!head) {
-            const u32* w = reinterpret_cast<const u32*>(bin + (r0 - 1) * 40);
-            head = !fields_link(w[9], w[19]);
+    for (u64 tile = blockIdx.x; run_lo + tile * KW_THREADS < run_hi; tile += gridDim.x) {
+        const u64 run = run_lo + tile * KW_THREADS + threadIdx.x;
+        const u64 r0 = run * KW_RUN;
+        u32 parked = KW_NONE;
+        if (run < run_hi && r0 < n) {
+            const u64 e = r0 + KW_RUN < n ? r0 + KW_RUN : n;
+            bool head = r0 == 0;
+            if (!head) {
+                const u32* w = reinterpret_cast<const u32*>(bin + (r0 - 1) * 40);
+                head = !fields_link(w[9], w[19]);
+            }
+            walk_item(bin, head ? r0 : r0 - 1, head, e, codes, stems, [&](u64 rec) { atomicMin(&tot->error_index, rec); },
+                      [&](u64 rec) { parked = (u32)rec; }, &T);
         }
-        walk_item(bin, head ? r0 : r0 - 1, head, e, codes, stems, [&](u64 rec) { atomicMin(&tot->error_index, rec); },
-                  [&](u64 rec) { parked = (u32)rec; }, &T);
+        park_append(parked, park_list, park_count);
     }
-    park_append(parked, park_list, park_count);
 }
 
 __global__ void __launch_bounds__(KW_THREADS, KW_MIN_BLOCKS)
@@ -703,6 +707,9 @@ __global__ void __launch_bounds__(32) k_find_head(const u32* __restrict__ codes,
 
 // ------------------------------------------------------------------ host launchers
 
+void init_tables_compress(cudaStream_t s) { k_step_tables_init<<<1, 256, 0, s>>>(); }
+
+
 void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, cudaStream_t s)
 {
     if (n == 0) return;
@@ -714,6 +721,20 @@ void launch_sample_heads(const void* d_bin, u64 n, u64 stride, u64 samples, u64*
     if (samples == 0) return;
     k_sample_heads<<<(unsigned)((samples + 255) / 256), 256, 0, s>>>((const unsigned char*)d_bin, n, stride, samples, heads);
 }
+// SMs of the current device (148 on a B200), asked once per device
+static int sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
 u64 walk_runs(u64 n) { return (n + KW_RUN - 1) / KW_RUN; }
 int walk_run_records() { return KW_RUN; }
 // runs [run_lo, run_hi) of the n records at d_bin (the records before run_lo * KW_RUN must be there too)
@@ -721,7 +742,9 @@ void launch_walk_runs(const void* d_bin, u64 n, u64 run_lo, u64 run_hi, u32* cod
                       u32* park_list, u64* park_count, cudaStream_t s)
 {
     if (run_hi <= run_lo) return;
-    const u64 blocks = (run_hi - run_lo + KW_THREADS - 1) / KW_THREADS;
+    u64 blocks = (run_hi - run_lo + KW_THREADS - 1) / KW_THREADS;
+    const u64 resident = (u64)sm_count() * KW_MIN_BLOCKS;  // one wave of persistent blocks
+    if (blocks > resident) blocks = resident;
     k_walk_runs<<<(unsigned)blocks, KW_THREADS, 0, s>>>((const unsigned char*)d_bin, n, run_lo, run_hi, codes, stems, tot,
                                                        park_list, park_count);
 }

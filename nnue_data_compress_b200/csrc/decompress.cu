@@ -761,6 +761,9 @@ __global__ void k_slow_emit_text(const unsigned char* __restrict__ in, ChunkTabl
 
 // ------------------------------------------------------------------ host launchers
 
+void init_tables_decompress(cudaStream_t s) { k_step_tables_init<<<1, 256, 0, s>>>(); }
+
+
 void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks, u32 world, u32 rank, cudaStream_t s)
 {
     k_walk_chunks<<<1, 32, 0, s>>>((const unsigned char*)d_in, n, tab, max_chunks, world, rank);

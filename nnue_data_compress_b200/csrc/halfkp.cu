@@ -191,6 +191,9 @@ k_bin_halfkp(const unsigned char* __restrict__ bin, u64 n, HalfKpOut out, Compre
 
 // ------------------------------------------------------------------ host launchers
 
+void init_tables_halfkp(cudaStream_t s) { k_step_tables_init<<<1, 256, 0, s>>>(); }
+
+
 static HalfKpOut make_out(int* white, int* black, void* meta) { return HalfKpOut{white, black, reinterpret_cast<uint2*>(meta)}; }
 
 void launch_emit_chains_halfkp_verify(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off,

@@ -4,6 +4,11 @@
 
 namespace nnp {
 
+// ---- lookup tables (chess.cuh: one copy per translation unit), filled once per device at nnp_init
+void init_tables_compress(cudaStream_t s);
+void init_tables_decompress(cudaStream_t s);
+void init_tables_halfkp(cudaStream_t s);
+
 // ---- compress (.bin -> .binpack), compress.cu
 void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, cudaStream_t s);
 u64 walk_runs(u64 n);  // number of runs = upper bound of the parked heads of any round

@@ -90,7 +90,9 @@ __device__ __forceinline__ int stream_from_pos(const Pos& p, u32* col, int strid
 
 // Applies move `m`, made in position `p` (the position BEFORE the move), to the stream of `p`.
 // The token changes mirror Board::doMove (Position.h:300-439) as restated in board_do_move.
-__device__ __forceinline__ bool stream_apply_move(u32 (&W)[8], const Pos& p, const Move& m, int moved = -1)
+// General form: up to four token edits applied one after the other (castling, en passant, and the
+// reference for the fused form below in the CPU suite).
+__device__ __forceinline__ bool stream_apply_move_generic(u32 (&W)[8], const Pos& p, const Move& m, int moved = -1)
 {
     const u64 all = pos_all(p);
     const u64 kings = pos_type_bb(p, PT_KING);
@@ -168,6 +170,101 @@ __device__ __forceinline__ bool stream_apply_move(u32 (&W)[8], const Pos& p, con
     if (new_king_sq >= 0) {
         const int f = (pc & 1) ? 7 : 1;
         w0 = (w0 & ~(63u << f)) | ((u32)new_king_sq << f);
+    }
+    W[0] = w0;
+    return true;
+}
+
+// the eight-word mask "bits below stream position pos"
+__device__ __forceinline__ void stream_low_masks(int pos, u32 (&M)[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) M[k] = stream_low_mask(pos, k);
+}
+
+// Normal moves and promotions (everything but castling and en passant: 99.7 % of the plies of a game)
+// change exactly two tokens, and both edits are applied in ONE pass over the seven board words:
+//
+//   new = old[0, X1) ++ v1 ++ old[X1 + wo1, X2) ++ v2 ++ old[X2 + wo2, ...)
+//
+// with X1 < X2 the stream positions of the two squares in the OLD stream, wo the old and wn the new
+// token widths (a non-king piece leaves '0' behind: 5 -> 1; it arrives as a 5-bit token on an empty
+// square or on a captured piece: 1 | 5 -> 5; a king occupies no stream bits, so it leaves a '0':
+// 0 -> 1, and its destination token disappears: 1 | 5 -> 0). The bits between the edits move by
+// d1 = wn1 - wo1, the bits above the second edit by d1 + d2, which is 0 for a quiet move and -4 for a
+// capture. Each output word is therefore a masked merge of the old word, the old stream shifted by d1
+// and the old stream shifted by d1 + d2; the at most one 5-bit token is OR-ed in last, and the '0'
+// bits are simply left uncovered by the three masks.
+__device__ __forceinline__ bool stream_apply_move(u32 (&W)[8], const Pos& p, const Move& m, int moved = -1,
+                                                  const StepTables* T = nullptr)
+{
+#ifdef NNP_SPLICE_GENERIC
+    return stream_apply_move_generic(W, p, m, moved);
+#endif
+    if (m.type == MT_CASTLE || m.type == MT_ENPASSANT) return stream_apply_move_generic(W, p, m, moved);
+    const u64 all = pos_all(p);
+    const u64 kings = pos_type_bb(p, PT_KING);
+    const u64 wkb = kings & p.occ[0], bkb = kings & p.occ[1];
+    if (popc64(wkb) != 1 || popc64(bkb) != 1 || popc64(all) > 34) return false;
+    const int from = m.from, to = m.to;
+    if (from > 63 || to > 63 || from == to) return false;
+    const int pc = moved >= 0 ? moved : pos_piece_at(p, from);
+    if (pc == NO_PIECE) return false;
+    if ((kings >> to) & 1) return false;
+    const bool king_moves = (pc >> 1) == PT_KING;
+    const int placed = m.type == MT_PROMOTION ? m.promo : pc;
+    if (king_moves ? m.type != MT_NORMAL : placed == NO_PIECE) return false;
+    const int wto = (int)((all >> to) & 1) * 4 + 1;  // old width of the destination token: 1 or 5
+
+    // stream squares and their positions in the old stream (see stream_apply_move_generic)
+    const u64 s_all = bswap64(all);
+    const int ks1 = lsb64(wkb) ^ 56, ks2 = lsb64(bkb) ^ 56;
+    const int sf = from ^ 56, st = to ^ 56;
+#ifdef NNP_NO_SMALL_LUT
+    const u64 bf = before64(sf), bt = before64(st);
+#else
+    const u64 bf = T ? T->before[sf] : before64(sf), bt = T ? T->before[st] : before64(st);
+#endif
+    const int xf = 13 + sf + 4 * popc64(s_all & bf) - 5 * ((sf > ks1) + (sf > ks2));
+    const int xt = 13 + st + 4 * popc64(s_all & bt) - 5 * ((st > ks1) + (st > ks2));
+    const int wof = king_moves ? 0 : 5, wnt = king_moves ? 0 : 5;  // the from-square always becomes '0' (width 1)
+    const bool from_first = sf < st;
+    const int X1 = from_first ? xf : xt, X2 = from_first ? xt : xf;
+    const int wo1 = from_first ? wof : wto, wn1 = from_first ? 1 : wnt;
+    const int wn2 = from_first ? wnt : 1;
+    const int d1 = wn1 - wo1;                       // -5 .. +4
+    const int dd = 1 - wof + wnt - wto;             // d1 + d2: 0 or -4
+    const int X2n = X2 + d1;                        // second edit in the new stream
+    u32 M1[8], M1e[8], M2[8], M2e[8];
+    stream_low_masks(X1, M1);
+    stream_low_masks(X1 + wn1, M1e);
+    stream_low_masks(X2n, M2);
+    stream_low_masks(X2n + wn2, M2e);
+    // the arriving piece's token (none for a king) at its position in the new stream
+    const int Xtok = from_first ? X2n : X1;
+    const u32 tok = king_moves ? 0u : stream_token(placed);
+    const int wi = Xtok >> 5, sb = Xtok & 31;
+    const u32 vlo = tok << sb, vhi = __funnelshift_l(tok, 0u, sb);
+    const u32 upA = (u32)(d1 + 8), upB = (u32)(dd + 8);
+    u32 N[STREAM_BOARD_WORDS];
+    u32 below = W[0] << 24;
+#pragma unroll
+    for (int k = 0; k < STREAM_BOARD_WORDS; ++k) {
+        const u32 b8 = __byte_perm(W[k], W[k + 1], 0x4321);  // stream bits 32k+8 .. 32k+39
+        const u32 A = __funnelshift_l(below, b8, upA);        // old stream moved by d1
+        const u32 B = __funnelshift_l(below, b8, upB);        // old stream moved by d1 + d2
+        below = b8;
+        u32 v = (W[k] & M1[k]) | (A & M2[k] & ~M1e[k]) | (B & ~M2e[k]);
+        if (k == wi) v |= vlo;
+        if (k == wi + 1) v |= vhi;
+        N[k] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < STREAM_BOARD_WORDS; ++k) W[k] = N[k];
+    u32 w0 = W[0] ^ 1u;  // side to move
+    if (king_moves) {
+        const int f = (pc & 1) ? 7 : 1;
+        w0 = (w0 & ~(63u << f)) | ((u32)to << f);
     }
     W[0] = w0;
     return true;

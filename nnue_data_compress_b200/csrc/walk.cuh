@@ -88,13 +88,20 @@ __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin,
             Wp[0] = v0.x; Wp[1] = v0.y; Wp[2] = v1.x; Wp[3] = v1.y; Wp[4] = v2.x; Wp[5] = v2.y; Wp[6] = v3.x; Wp[7] = v3.y;
             p8 = v4.x; p9 = v4.y;
         }
+        // The out-of-line helpers take a position by reference; they get a copy of their own so that the
+        // walk's position P never has its address taken and stays in registers through the loop.
         Pos P;
-        bool valid = decode_record(bin, a, P);
-        if (!valid) on_error(a);
-        if (a_is_head) {
-            codes[a] = 0u;
-            store_stem_cold(P, p8, p9, stems + a * 8);
+        bool valid;
+        {
+            Pos anchor;
+            valid = decode_record(bin, a, anchor);
+            if (a_is_head) {
+                codes[a] = 0u;
+                store_stem_cold(anchor, p8, p9, stems + a * 8);
+            }
+            P = anchor;
         }
+        if (!valid) on_error(a);
         Move pmv = sfmove_to_move(p8 >> 16);  // the move of the record in front, decoded once
         u64 rec = a + 1;
         // software pipeline: the loads of record rec + 1 are in flight while record rec is processed
@@ -116,8 +123,8 @@ __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin,
             const Move pm = pmv;
             const Move cm = sfmove_to_move(c8 >> 16);
             const int moved = pm.from < 64 ? pos_piece_at(P, pm.from) : NO_PIECE;
-            const bool spliced = stream_apply_move(Wp, P, pm, moved);  // Wp becomes the expected stream
-            pos_do_move(P, pm, moved);                                  // Position::afterMove
+            const bool spliced = stream_apply_move(Wp, P, pm, moved, T);  // Wp becomes the expected stream
+            pos_do_move(P, pm, moved, T);                               // Position::afterMove
             bool cont = false;
             if (spliced) {
                 const int end = stream_board_end(P);
@@ -140,7 +147,9 @@ __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin,
             }
             if (!cont) {
                 bool ok;
-                cont = walk_slow(bin, rec, P, c8, c9, stems, ok);
+                Pos Q = P;
+                cont = walk_slow(bin, rec, Q, c8, c9, stems, ok);
+                P = Q;
                 if (!ok) on_error(rec);
                 valid = ok;
             }

@@ -26,6 +26,32 @@ Rec load(const unsigned char* bin, size_t i)
     std::memcpy(r.w, bin + 40 * i, 40);
     return r;
 }
+// the lookup tables the kernels keep in shared memory, filled with the same per-entry function
+const StepTables* tables()
+{
+    static StepTables* T = nullptr;
+    if (!T) {
+        T = new StepTables();
+        for (int i = 0; i < STEP_TABLE_ROWS; ++i) step_tables_entry(*T, i);
+    }
+    return T;
+}
+// every form of the splice on one move: the fused two-edit pass with and without the tables and the
+// general edit-by-edit form must accept the same moves and give the same stream
+bool splice_all_forms(const u32 (&W)[8], const Pos& p, const Move& m, u32 (&out)[8], bool& agree)
+{
+    u32 a[8], b[8], c[8];
+    std::memcpy(a, W, 32);
+    std::memcpy(b, W, 32);
+    std::memcpy(c, W, 32);
+    const bool oa = stream_apply_move(a, p, m, -1, tables());
+    const bool ob = stream_apply_move(b, p, m, -1, nullptr);
+    const bool oc = stream_apply_move_generic(c, p, m);
+    agree = oa == ob && ob == oc;
+    if (oa && agree) agree = std::memcmp(a, b, 28) == 0 && std::memcmp(a, c, 28) == 0;  // the seven board words
+    std::memcpy(out, a, 32);
+    return oa;
+}
 }  // namespace
 
 extern "C" {
@@ -56,12 +82,18 @@ int sim_stream_check(const unsigned char* bin, size_t n, uint64_t* enc_mismatch,
         }
         const Move m = sfmove_to_move(r.w[8] >> 16);
         u32 W2[8];
-        std::memcpy(W2, W, 32);
-        const bool ok = stream_apply_move(W2, p, m);
+        bool agree;
+        const bool ok = splice_all_forms(W, p, m, W2, agree);
+        if (!agree) {
+            ++*splice_mismatch;
+            if (*first_bad == ~0ull) *first_bad = i;
+        }
         if (!ok) continue;
         ++*spliced;
-        Pos q = p;
+        Pos q = p, q2 = p;
         pos_do_move(q, m);
+        pos_do_move(q2, m, -1, tables());
+        if (!pos_equal(q, q2) || q.rule50 != q2.rule50 || q.ply != q2.ply) ++*splice_mismatch;
         u32 c[8], d[8];
         sfen_encode(q, c);
         stream_with_tail(W2, stream_board_end(q), q, d);
@@ -107,11 +139,15 @@ uint64_t sim_stream_fuzz(const unsigned char* bin, size_t n, int moves_per_pos, 
             }
             if (m.type == MT_PROMOTION) m.promo = ((PT_KNIGHT + (int)((v >> 17) & 3)) << 1) | (int)((v >> 19) & 1);
             u32 W2[8];
-            std::memcpy(W2, W, 32);
-            if (!stream_apply_move(W2, p, m)) continue;
+            bool agree;
+            const bool ok = splice_all_forms(W, p, m, W2, agree);
+            if (!agree) ++*mismatch;
+            if (!ok) continue;
             ++accepted;
-            Pos q = p;
+            Pos q = p, q2 = p;
             pos_do_move(q, m);
+            pos_do_move(q2, m, -1, tables());
+            if (!pos_equal(q, q2) || q.rule50 != q2.rule50) ++*mismatch;
             u32 c[8], d[8];
             sfen_encode(q, c);
             stream_with_tail(W2, stream_board_end(q), q, d);
@@ -159,7 +195,7 @@ uint64_t sim_walk_check(const unsigned char* bin, size_t n, int run, uint64_t* p
         bool head = r0 == 0;
         if (!head) head = !fields_link(load(bin, r0 - 1).w[9], load(bin, r0).w[9]);
         walk_item(bin, head ? r0 : r0 - 1, head, e, codes_b.data(), stems_b.data(), on_error,
-                  [&](u64 rec) { queue.push_back(rec); });
+                  [&](u64 rec) { queue.push_back(rec); }, (r0 / run) % 2 ? tables() : nullptr);
     }
     while (!queue.empty()) {
         *parked += queue.size();
@@ -167,7 +203,8 @@ uint64_t sim_walk_check(const unsigned char* bin, size_t n, int run, uint64_t* p
         for (uint64_t rec : queue) {
             size_t e = (rec / run + 1) * run;
             if (e > n) e = n;
-            walk_item(bin, rec, true, e, codes_b.data(), stems_b.data(), on_error, [&](u64 r) { next.push_back(r); });
+            walk_item(bin, rec, true, e, codes_b.data(), stems_b.data(), on_error, [&](u64 r) { next.push_back(r); },
+                      (rec / run) % 2 ? nullptr : tables());
         }
         queue.swap(next);
     }
@@ -199,7 +236,9 @@ long long sim_decode_binpack(const unsigned char* in, size_t n, unsigned char* o
         while ((unsigned long long)cur + 34 <= size) {
             const u32 plies = ((u32)chunk[cur + 32] << 8) | chunk[cur + 33];
             u32 consumed = 0;
-            if (!emit_chain_bin(chunk + cur, size - cur - 34, out, rec, out_cap_records, col, 1, consumed)) return -1;
+            if (!emit_chain_bin(chunk + cur, size - cur - 34, out, rec, out_cap_records, col, 1, consumed,
+                                (rec & 1) ? tables() : nullptr))
+                return -1;
             rec += 1ull + plies;
             cur += consumed;
         }
