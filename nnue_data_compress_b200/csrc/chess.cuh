@@ -791,15 +791,16 @@ __device__ __forceinline__ u32 encode_ply(const Pos& p, const Move& mv, int scor
     int n = 0;
     acc = (acc << w1) | (piece_id & ((1u << w1) - 1u)); n += w1;
     acc = (acc << w2) | (move_id & ((1u << w2) - 1u)); n += w2;
-    // addBitsVle16 (:864-874): 4-bit groups, low group first, continuation flag on top
-    u32 v = zz_enc((int)(short)(score - last_score));
-    for (;;) {
-        u32 block = (v & 15u) | ((v > 15u) ? 16u : 0u);
-        acc = (acc << 5) | block;
-        n += 5;
-        v >>= 4;
-        if (v == 0) break;
-    }
+    // addBitsVle16 (:864-874): 4-bit groups, low group first, continuation flag on top. All four possible
+    // blocks are laid out first group leftmost and the unused ones shifted out, without a loop.
+    const u32 v = zz_enc((int)(short)(score - last_score));
+    const int nb = 1 + (v > 0xFu) + (v > 0xFFu) + (v > 0xFFFu);
+    u32 blocks = ((v & 15u) << 15) | (((v >> 4) & 15u) << 10) | (((v >> 8) & 15u) << 5) | (v >> 12);
+    blocks |= nb > 1 ? (16u << 15) : 0u;
+    blocks |= nb > 2 ? (16u << 10) : 0u;
+    blocks |= nb > 3 ? (16u << 5) : 0u;
+    acc = (acc << (5 * nb)) | (blocks >> (5 * (4 - nb)));
+    n += 5 * nb;
     nbits = n;
     return (u32)(acc << (32 - n));
 }
@@ -844,6 +845,32 @@ struct BitReader {
         next16 = load16(fetched);
         fetched += 2;
     }
+    // The decoder's reads: ensure16() makes at least 16 bits visible (one refill at most), take(n) removes
+    // n <= 16 visible bits (n = 0 gives 0) without any test. Bits past the span read as zeros and are
+    // noticed by the caller afterwards (past_end()), which is what get() reports field by field.
+    __device__ __forceinline__ void ensure16()
+    {
+        if (have < 16) {
+            const u32 be = ((next16 & 0xFFu) << 8) | (next16 >> 8);
+            win |= be << (16 - have);
+            have += 16;
+            next16 = load16(fetched);
+            fetched += 2;
+        }
+    }
+    __device__ __forceinline__ u32 take(int n)
+    {
+        const u32 v = __funnelshift_l(win, 0u, (u32)n);  // win >> (32 - n), 0 for n = 0
+        win <<= n;
+        have -= n;
+        pos += n;
+        return v;
+    }
+    __device__ __forceinline__ bool past_end()
+    {
+        if (pos > nbits) overrun = true;
+        return overrun;
+    }
     __device__ __forceinline__ u32 get(int n)  // n <= 8
     {
         if (n == 0) return 0;
@@ -873,7 +900,8 @@ __device__ __forceinline__ bool decode_ply(BitReader& r, const Pos& p, int& last
     u64 ours = pos_occ(p, stm), theirs = pos_occ(p, stm ^ 1);
     u64 occ = ours | theirs;
     u32 n_ours = (u32)popc64(ours);
-    u32 piece_id = r.get(used_bits(n_ours));
+    r.ensure16();  // piece id (<= 6 bits) and move id (<= 8 bits) come out of one refill
+    u32 piece_id = r.take(used_bits(n_ours));
     if (strict && piece_id >= n_ours) return false;
     // an id beyond the count (corrupted movetext; the reference indexes its lookup table out of range,
     // ArithmeticUtility.h:186-209) selects square 0, as the oracle does
@@ -903,7 +931,7 @@ __device__ __forceinline__ bool decode_ply(BitReader& r, const Pos& p, int& last
         dest = piece_attacks(pt, from, occ, T) & ~ours;
         n = (u32)popc64(dest);
     }
-    const u32 id = r.get(used_bits(n));
+    const u32 id = r.take(min(used_bits(n), 8));
     if (strict && id >= n) return false;
     if (pt == PT_KING && id >= att_n) {
         const int long_right = stm == WHITE ? CR_WQ : CR_BQ;
@@ -920,16 +948,23 @@ __device__ __forceinline__ bool decode_ply(BitReader& r, const Pos& p, int& last
             mv.type = MT_ENPASSANT;
         }
     }
-    // extractVle16 (:650-667)
+    // extractVle16 (:650-667): 5-bit blocks, 4 payload bits (low group first) under a continuation flag.
+    // Two blocks are looked at per refill, without a loop: nearly every score delta fits them.
     u32 v = 0;
     int off = 0;
     for (;;) {
-        u32 block = r.get(5);
-        v |= (block & 15u) << off;
-        if (!(block >> 4) || r.overrun) break;
-        off += 4;
-        if (off > 28) return false;  // a ninth block: the reference shifts a 16-bit value by 32 (undefined); no encoder emits it
+        r.ensure16();
+        const u32 two = r.win >> 22;                 // the next two blocks
+        const u32 b0 = two >> 5, b1 = two & 31u;
+        const bool more0 = (b0 >> 4) != 0;
+        v |= (b0 & 15u) << off;
+        if (more0) v |= (b1 & 15u) << (off + 4);
+        r.take(more0 ? 10 : 5);
+        if (!more0 || !(b1 >> 4) || r.pos > r.nbits) break;
+        off += 8;
+        if (off > 24) return false;  // a ninth block: the reference shifts a 16-bit value by 32 (undefined); no encoder emits it
     }
+    if (r.past_end()) return false;
     score = (int)(short)(last_score + zz_dec(v & 0xFFFFu));
     last_score = (int)(short)(-score);
     return !r.overrun;
