@@ -67,8 +67,9 @@ int nnp_init(int device);
 int nnp_init_all(int n_devices);
 /* Binds the calling host thread to an initialised device: its further calls run there. */
 int nnp_bind_device(int device);
-/* number of initialised devices */
+/* number of initialised devices, and the CUDA ordinal of the index-th of them (-1 past the end) */
 int nnp_device_count(void);
+int nnp_device_at(int index);
 /* Releases every device of the process. */
 void nnp_shutdown(void);
 const char* nnp_strerror(int status);
@@ -196,16 +197,24 @@ int nnp_binpack_chunk_range_dev(const void* d_binpack, size_t binpack_bytes, int
 int nnp_shard_decompress_dev(const void* d_binpack, size_t binpack_bytes, int world, int rank, void* d_out, size_t out_cap,
                              size_t* out_bytes, nnp_chunk_range* range);
 
-/* ---- whole files of any size -----------------------------------------------------
- * File-to-file forms of the two headline drivers for inputs that do not fit the device: the input is
- * processed in slabs of about `slab_bytes` (0 = default: 2 GiB of records / 256 MiB of chunks).
- * .bin -> .binpack visits the slabs with the sharded compressor above, one slab after the other, and
- * writes exactly the file one reference run writes, whatever the slab size; .binpack -> .bin decodes
- * groups of whole chunks. `append` != 0 appends to the output file (the tool's -a). *positions (may be
- * NULL) receives the number of positions converted. The reference errors return their status after
- * leaving in the file what the reference tool would have left. */
+/* ---- whole files of any size, on every device of the process ------------------
+ * File-to-file forms of the two headline drivers: the input is processed in slabs of about
+ * `slab_bytes` (0 = default: 512 MiB of records / 64 MiB of chunks) that are dealt to all initialised
+ * devices (nnp_init_all); per device a loader, a compute and a drainer thread work on double buffers,
+ * so that reading + H2D, the kernels and D2H + writing of consecutive slabs overlap and neither host nor
+ * device memory has to hold the file. .bin -> .binpack runs the heavy part of every slab (the sharded
+ * compressor's begin) concurrently and replays the chunk-flush rule slab after slab in file order in
+ * host memory: it writes exactly the file one reference run writes, whatever the slab size and the
+ * number of devices; .binpack -> .bin decodes groups of whole chunks. `append` != 0 appends to the
+ * output file (the tool's -a). *positions (may be NULL) receives the number of positions converted.
+ * The reference errors return their status after leaving in the file what the reference tool would
+ * have left.
+ * The *_multi forms are the same pipelines between host buffers (the whole-buffer host drivers above
+ * use one device): out == NULL is the capacity query (for .binpack -> .bin a count pass). */
 int nnp_bin_to_binpack_file(const char* in_path, const char* out_path, int append, size_t slab_bytes, uint64_t* positions);
 int nnp_binpack_to_bin_file(const char* in_path, const char* out_path, int append, size_t slab_bytes, uint64_t* positions);
+int nnp_bin_to_binpack_multi(const void* bin, size_t bin_bytes, void* out, size_t out_cap, size_t* out_bytes);
+int nnp_binpack_to_bin_multi(const void* binpack, size_t binpack_bytes, void* out, size_t out_cap, size_t* out_bytes);
 
 /* ---- decode fused into its consumer: HalfKP feature rows ------------ */
 

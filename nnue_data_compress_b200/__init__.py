@@ -63,7 +63,8 @@ EXPORTS = [
     "nnp_shard_compress_table_dev", "nnp_shard_compress_resolve_dev",
     "nnp_bin_to_binpack_file", "nnp_binpack_to_bin_file",
     "nnp_binpack_to_halfkp_dev", "nnp_bin_to_halfkp_dev",
-    "nnp_init_all", "nnp_bind_device", "nnp_device_count",
+    "nnp_init_all", "nnp_bind_device", "nnp_device_count", "nnp_device_at",
+    "nnp_bin_to_binpack_multi", "nnp_binpack_to_bin_multi",
     "nnp_binpack_chunk_range", "nnp_binpack_chunk_range_dev", "nnp_shard_decompress_dev",
     "nnp_last_dominant_kernel", "nnp_last_positions",
 ]
@@ -108,7 +109,7 @@ def lib() -> ctypes.CDLL:
         conv = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         for name in EXPORTS:
             fn = getattr(L, name)
-            if name.endswith(("_to_binpack", "_to_bin", "_to_plain", "_dev")) and not name.endswith("_file") and name not in (
+            if name.endswith(("_to_binpack", "_to_bin", "_to_plain", "_dev", "_multi")) and not name.endswith("_file") and name not in (
                 "nnp_binpack_count_dev",
                 "nnp_generate_bin_dev",
                 "nnp_shard_compress_begin_dev",
@@ -159,7 +160,7 @@ def lib() -> ctypes.CDLL:
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
             getattr(L, name).restype = ctypes.c_int
-        for name in ("nnp_init_all", "nnp_bind_device"):
+        for name in ("nnp_init_all", "nnp_bind_device", "nnp_device_at"):
             getattr(L, name).argtypes = [ctypes.c_int]
             getattr(L, name).restype = ctypes.c_int
         L.nnp_device_count.restype = ctypes.c_int
@@ -193,6 +194,27 @@ def init(device: int | None = None) -> None:
     if rc != 0:
         raise NnpError(rc, lib().nnp_strerror(rc).decode() + " / " + lib().nnp_last_cuda_error().decode())
     _initialised = True
+
+
+def init_all(n_devices: int = 0) -> int:
+    """nnp_init_all: every visible GPU (or the first `n_devices`) in this one process; the slab-wise file
+    drivers and the *_multi drivers then spread their slabs over all of them. Returns the device count."""
+    global _initialised
+    rc = lib().nnp_init_all(n_devices)
+    if rc <= 0:
+        raise NnpError(rc, lib().nnp_strerror(rc).decode() + " / " + lib().nnp_last_cuda_error().decode())
+    _initialised = True
+    return rc
+
+
+def bin_to_binpack_multi(data: bytes) -> bytes:
+    """compressBin over every initialised device (nnp_bin_to_binpack_multi)."""
+    return _convert_host("nnp_bin_to_binpack_multi", data)
+
+
+def binpack_to_bin_multi(data: bytes) -> bytes:
+    """decompressBin over every initialised device (nnp_binpack_to_bin_multi)."""
+    return _convert_host("nnp_binpack_to_bin_multi", data)
 
 
 def convert_file(direction: str, input_path: str, output_path: str, append: bool = False, slab_bytes: int = 0) -> int:

@@ -1266,6 +1266,13 @@ int nnp_bind_device(int device)
     return NNP_OK;
 }
 
+int nnp_device_at(int index)
+{
+    for (int d = 0; d < MAX_DEVICES; ++d)
+        if (g_ctxs[d].ready && index-- == 0) return d;
+    return -1;
+}
+
 int nnp_device_count(void)
 {
     int n = 0;
@@ -1273,9 +1280,12 @@ int nnp_device_count(void)
     return n;
 }
 
+void nnp_internal_release_buffers(void);  // files.cu: the pinned staging buffers of the file drivers
+
 void nnp_shutdown(void)
 {
     std::lock_guard<std::mutex> lock(g_init_mutex);
+    nnp_internal_release_buffers();
     for (Context& C : g_ctxs) {
         if (!C.ready) continue;
         std::lock_guard<std::mutex> dev_lock(C.mutex);

@@ -198,8 +198,17 @@ int main(int argc, char** argv)
         return 1;
     }
     const bool append = flags.count("a") == 1 || flags.count("append") == 1;
+    // NNP_DEVICES = "all" or a count: every slab-wise conversion is spread over that many GPUs (one loader,
+    // compute and drainer thread per GPU, csrc/files.cu); otherwise one GPU, NNP_DEVICE (default 0)
+    const char* devs = std::getenv("NNP_DEVICES");
     const char* dev = std::getenv("NNP_DEVICE");
-    const int rc = nnp_init(dev ? std::atoi(dev) : 0);
+    int rc;
+    if (devs && *devs) {
+        rc = nnp_init_all(std::string(devs) == "all" ? 0 : std::atoi(devs));
+        if (rc > 0) rc = NNP_OK;
+    } else {
+        rc = nnp_init(dev ? std::atoi(dev) : 0);
+    }
     if (rc != NNP_OK) {
         std::cerr << nnp_strerror(rc) << " " << nnp_last_cuda_error() << "\n";
         return 2;
