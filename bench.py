@@ -409,6 +409,54 @@ def plain_leg(torch, L, check, ptr, timed, d_bin, n, dev, peak):
     return out
 
 
+def file_leg(torch, L, check, d_bin, d_pack, pack_bytes, n_pos):
+    """File to file from tmpfs through the slab pipeline (csrc/files.cu: reader, H2D, kernels, D2H and
+    writer overlap on double buffers): wall-clock seconds of the whole call, best of three (the first call
+    also page-locks the staging buffers, which the library keeps). Output compared with the device path."""
+    import numpy as np
+
+    work = scratch_dir()
+    try:
+        p_in, p_pack, p_back = (os.path.join(work, x) for x in ("in.bin", "out.binpack", "back.bin"))
+        slab = 256 << 20
+        with open(p_in, "wb") as f:
+            for off in range(0, n_pos * 40, slab):
+                f.write(d_bin[off:off + slab].cpu().numpy().tobytes())
+        pos = ctypes.c_uint64(0)
+        tc = td = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            check(L.nnp_bin_to_binpack_file(p_in.encode(), p_pack.encode(), 0, 0, ctypes.byref(pos)), "file bin->binpack")
+            t1 = time.perf_counter()
+            assert pos.value == n_pos, (pos.value, n_pos)
+            check(L.nnp_binpack_to_bin_file(p_pack.encode(), p_back.encode(), 0, 0, ctypes.byref(pos)), "file binpack->bin")
+            t2 = time.perf_counter()
+            assert pos.value == n_pos, (pos.value, n_pos)
+            tc = t1 - t0 if tc is None else min(tc, t1 - t0)
+            td = t2 - t1 if td is None else min(td, t2 - t1)
+        same = os.path.getsize(p_pack) == pack_bytes and os.path.getsize(p_back) == n_pos * 40
+        if same:
+            with open(p_pack, "rb") as f:
+                same = np.array_equal(np.frombuffer(f.read(), dtype=np.uint8), d_pack[:pack_bytes].cpu().numpy())
+        # what one thread reads from the same tmpfs file, for scale
+        t0 = time.perf_counter()
+        with open(p_in, "rb", buffering=0) as f:
+            buf = bytearray(slab)
+            while f.readinto(buf):
+                pass
+        t_read = time.perf_counter() - t0
+        return {
+            "storage": "tmpfs " + os.path.dirname(work), "devices": int(L.nnp_device_count()),
+            "bin_to_binpack": {"s": tc, "mpos_s": n_pos / tc / 1e6, "input_gbs": n_pos * 40 / tc / 1e9},
+            "binpack_to_bin": {"s": td, "mpos_s": n_pos / td / 1e6, "output_gbs": n_pos * 40 / td / 1e9},
+            "value": 2 * n_pos / (tc + td) / 1e6, "unit": "Mpos/s",
+            "binpack_identical_to_device_path": bool(same),
+            "one_thread_read_of_the_input_gbs": n_pos * 40 / t_read / 1e9,
+        }
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def sweep_leg(torch, L, check, ptr, n, seed, dev, peak, d_bin, d_out):
     """BASELINE configs[4]: chain lengths 1, 8, 64 and 400 plies, `n` positions each, device-resident
     round trip (best of 3 per direction, the library's CUDA events), generated into the bench's own
@@ -836,6 +884,13 @@ def main():
             plain = plain_leg(torch, L, check, ptr, timed, d_bin, min(args.plain_positions, n_pos), dev, peak)
         except Exception as e:  # noqa: BLE001
             plain = {"error": str(e)[:300]}
+
+    if world == 1 and not args.no_file:
+        try:
+            log("file to file")
+            e2e_file = file_leg(torch, L, check, d_bin, d_pack, pack_bytes, n_pos)
+        except Exception as e:  # noqa: BLE001
+            e2e_file = {"error": str(e)[:300]}
 
     if world == 1 and not args.no_sweep:
         try:

@@ -199,7 +199,7 @@ int nnp_shard_decompress_dev(const void* d_binpack, size_t binpack_bytes, int wo
 
 /* ---- whole files of any size, on every device of the process ------------------
  * File-to-file forms of the two headline drivers: the input is processed in slabs of about
- * `slab_bytes` (0 = default: 512 MiB of records / 64 MiB of chunks) that are dealt to all initialised
+ * `slab_bytes` (0 = default: 256 MiB of records / 32 MiB of chunks) that are dealt to all initialised
  * devices (nnp_init_all); per device a loader, a compute and a drainer thread work on double buffers,
  * so that reading + H2D, the kernels and D2H + writing of consecutive slabs overlap and neither host nor
  * device memory has to hold the file. .bin -> .binpack runs the heavy part of every slab (the sharded

@@ -34,6 +34,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -154,13 +155,19 @@ struct MemSink : Sink {  // p == nullptr: nothing is kept (size queries)
 struct PinnedPool {
     std::mutex m;
     std::vector<std::pair<void*, size_t>> free_list;
+    std::atomic<uint64_t> allocs{0}, alloc_bytes{0};
+    double alloc_seconds = 0;  // diagnostics (nnp_internal_pool_stats)
     void* get(size_t bytes, size_t* cap)
     {
         {
             std::lock_guard<std::mutex> lock(m);
             size_t best = free_list.size();
+            // best fit, but a small request leaves the large buffers to the large requests
+            const size_t limit = 2 * bytes + ((size_t)64 << 20);
             for (size_t i = 0; i < free_list.size(); ++i)
-                if (free_list[i].second >= bytes && (best == free_list.size() || free_list[i].second < free_list[best].second)) best = i;
+                if (free_list[i].second >= bytes && free_list[i].second <= limit &&
+                    (best == free_list.size() || free_list[i].second < free_list[best].second))
+                    best = i;
             if (best != free_list.size()) {
                 void* p = free_list[best].first;
                 *cap = free_list[best].second;
@@ -168,8 +175,12 @@ struct PinnedPool {
                 return p;
             }
         }
+        const auto t0 = std::chrono::steady_clock::now();
         void* p = nnp_host_alloc(bytes + 64);
         *cap = p ? bytes : 0;
+        allocs += 1;
+        alloc_bytes += bytes;
+        alloc_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         return p;
     }
     void put(void* p, size_t cap)
@@ -187,6 +198,13 @@ struct PinnedPool {
 };
 PinnedPool g_pool;
 
+// slabs of one run differ a little in size: buffers grow in generous steps so that they are made once
+size_t roomy(size_t bytes)
+{
+    const size_t step = (size_t)32 << 20;
+    return bytes < step ? bytes : ((bytes + bytes / 8 + step - 1) / step) * step;
+}
+
 struct PinnedBuffer {
     void* p = nullptr;
     size_t cap = 0;
@@ -195,7 +213,7 @@ struct PinnedBuffer {
     {
         if (bytes <= cap && p) return true;
         g_pool.put(p, cap);
-        p = g_pool.get(bytes, &cap);
+        p = g_pool.get(roomy(bytes), &cap);
         return p != nullptr;
     }
 };
@@ -209,6 +227,7 @@ struct DeviceBuffer {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
+        bytes = roomy(bytes);
         if (cudaMalloc(&p, bytes + 64) != cudaSuccess) { (void)cudaGetLastError(); return false; }
         cap = bytes;
         return true;
@@ -357,7 +376,7 @@ int compress_pipeline(Source& src, uint64_t n_total, Sink& sink, size_t slab_byt
     if (devices.empty()) return NNP_ERR_NOT_INITIALISED;
     const size_t G = devices.size();
 
-    uint64_t slab_records = (slab_bytes ? slab_bytes : ((size_t)512 << 20)) / 40;
+    uint64_t slab_records = (slab_bytes ? slab_bytes : ((size_t)256 << 20)) / 40;
     if (slab_records < 16) slab_records = 16;
     const uint64_t overlap0 = std::min<uint64_t>(65536, slab_records);
     std::vector<Slab> slabs;
@@ -546,7 +565,7 @@ int decompress_pipeline(Source& src, uint64_t total, Sink& sink, size_t slab_byt
     const std::vector<int> devices = bound_devices();
     if (devices.empty()) return NNP_ERR_NOT_INITIALISED;
     const size_t G = devices.size();
-    const uint64_t slab = slab_bytes ? slab_bytes : ((size_t)64 << 20);
+    const uint64_t slab = slab_bytes ? slab_bytes : ((size_t)32 << 20);
 
     // groups of whole chunks (:500-521 for the header checks)
     std::vector<Slab> slabs;
@@ -653,6 +672,12 @@ struct Fd {
 extern "C" {
 
 void nnp_internal_release_buffers(void) { g_pool.release(); }
+void nnp_internal_pool_stats(uint64_t* allocs, uint64_t* bytes, double* seconds)
+{
+    *allocs = g_pool.allocs;
+    *bytes = g_pool.alloc_bytes;
+    *seconds = g_pool.alloc_seconds;
+}
 
 int nnp_bin_to_binpack_file(const char* in_path, const char* out_path, int append, size_t slab_bytes, uint64_t* positions)
 {
