@@ -522,6 +522,7 @@ int parse_plain_dev(const void* d_text, size_t text_bytes, bool count_only, Pars
     PlainTotals* h_tot = reinterpret_cast<PlainTotals*>((char*)C.pinned + 1280);
     h_tot->error_pos = NO_ERROR_IDX;
     h_tot->committed = 0;
+    h_tot->inherit = 0;
     CK(cudaMemcpyAsync(d_tot, h_tot, sizeof(PlainTotals), cudaMemcpyHostToDevice, s));
     launch_find_records(false, d_text, text_bytes, tile_count, tile_prefix, nullptr, d_tot, s);
     launch_exclusive_sum(tile_count, tiles, tile_prefix, s);
@@ -541,6 +542,15 @@ int parse_plain_dev(const void* d_text, size_t text_bytes, bool count_only, Pars
     CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(PlainTotals), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (h_tot->error_pos != NO_ERROR_IDX) return NNP_ERR_BAD_TEXT;
+    if (h_tot->inherit) {  // some record inherits a field from an earlier one (:1254): resolved in linear time
+        WS(WS_TEXT_C, P.nrec * 40 + 64, u64, defs);
+        WS(WS_TEXT_D, defs_tiles(P.nrec) * 40 + 64, u64, tile_max);
+        launch_parse_inherited(d_text, text_bytes, rec_pos, P.nrec, defs, tile_max, entries, d_tot, s);
+        LAUNCHED(5, "k_parse_inherited");
+        CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(PlainTotals), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h_tot->error_pos != NO_ERROR_IDX) return NNP_ERR_BAD_TEXT;
+    }
     P.entries = entries;
     return NNP_OK;
 }

@@ -96,6 +96,7 @@ struct Entry {
 struct PlainTotals {
     u64 error_pos;  // byte offset of the first construct the parser rejects, or NO_ERROR_IDX
     u64 committed;  // scratch for the flush-boundary orbit
+    u64 inherit;    // some record does not define all five keys itself: the inheritance passes are needed
 };
 
 #ifdef __CUDACC__

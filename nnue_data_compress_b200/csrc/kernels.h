@@ -100,6 +100,9 @@ void launch_find_records(bool write, const void* text, u64 n, u32* tile_count, c
                          PlainTotals* tot, cudaStream_t s);
 void launch_parse_records(const void* text, u64 n, const u64* rec_pos, u64 nrec, Entry* entries, PlainTotals* tot,
                           cudaStream_t s);
+u64 defs_tiles(u64 nrec);
+void launch_parse_inherited(const void* text, u64 n, const u64* rec_pos, u64 nrec, u64* defs, u64* tile_max, Entry* entries,
+                            PlainTotals* tot, cudaStream_t s);
 void launch_entries_link_encode(const Entry* entries, u64 n, u32* codes, u32* stems, cudaStream_t s);
 void launch_entries_to_bin(const Entry* entries, u64 n, void* out, cudaStream_t s);
 void launch_bin_text(bool write, const void* bin, u64 n, u32* lens, const u64* offs, void* out, CompressTotals* tot,

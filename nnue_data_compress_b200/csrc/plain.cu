@@ -193,6 +193,35 @@ __device__ __forceinline__ bool key_is(const Span& k, const char* lit, int n)
     return true;
 }
 
+// The five values of a record (nullptr = never defined: the default of `TrainingDataEntry e;`) -> Entry.
+// Returns false where the reference would throw or misbehave (std::stoi on a non-number, no move).
+__device__ __forceinline__ bool parse_entry(const Span& fen, const Span& move, const Span& score, const Span& ply,
+                                            const Span& result, Entry& out)
+{
+    bool ok = true;
+    Pos p;
+    pos_clear(p);  // TrainingDataEntry e; -> Position()
+    Move mv;
+    mv.from = mv.to = 0; mv.type = MT_NORMAL; mv.promo = NO_PIECE;
+    long long v;
+    int sc = 0, pl = 0, res = 0;
+    if (fen.p && !parse_fen(fen.p, fen.p + fen.n, p)) ok = false;
+    if (!move.p || !parse_uci(p, move.p, move.n, mv)) ok = false;
+    if (score.p) { if (parse_int(score.p, score.p + score.n, v)) sc = (int)(short)v; else ok = false; }
+    if (ply.p) { if (parse_int(ply.p, ply.p + ply.n, v)) pl = (int)(v & 0xFFFF); else ok = false; }
+    if (result.p) { if (parse_int(result.p, result.p + result.n, v)) res = (int)(short)v; else ok = false; }
+    Entry e;
+    e.occ0 = p.occ[0]; e.occ1 = p.occ[1]; e.t0 = p.t0; e.t1 = p.t1; e.t2 = p.t2;
+    e.meta = (u32)p.stm | ((u32)p.ep << 1) | ((u32)p.cr << 8) | (((u32)p.rule50 & 0xFF) << 12);
+    e.pos_ply = (u32)p.ply & 0xFFFF;
+    e.mv = (u32)mv.from | ((u32)mv.to << 6) | ((u32)mv.type << 12) | ((u32)mv.promo << 14);
+    e.score_ply = ((u32)sc & 0xFFFF) | ((u32)pl << 16);
+    e.result = (u32)res & 0xFFFF;
+    e.pad = 0;
+    out = e;
+    return ok;
+}
+
 // The block's records are contiguous text (about 105 bytes each): it is staged in shared memory with
 // 16-byte loads and parsed there, because byte-wise walking of global memory costs one sector
 // request per character and lane. Lines in front of the staged region (a record that inherits a
@@ -230,14 +259,17 @@ k_parse_records(const unsigned char* __restrict__ text, u64 n, const u64* __rest
     const u64 r = r0 + threadIdx.x;
     if (r >= nrec) return;
     const u64 epos = rec_pos[r];
-    const u64 stop_validate = r > 0 ? rec_pos[r - 1] : 0;  // every line down to here is checked
+    const u64 stop_validate = r > 0 ? rec_pos[r - 1] : 0;  // the record's own lines end here
     Span fen{nullptr, 0}, move{nullptr, 0}, score{nullptr, 0}, ply{nullptr, 0}, result{nullptr, 0};
     int found = 0;
     bool bad = false;
     // start of the terminator's line
     u64 cur = epos;
     while (cur > 0 && *at(cur - 1) != '\n') --cur;
-    while (cur > 0 && (found != 31 || cur > stop_validate)) {
+    // Only the record's own lines are walked: a key it does not define is inherited from an earlier
+    // record ("fields persist", :1254), which the inheritance passes below resolve in linear time
+    // (k_record_defs, a running maximum over the records, k_parse_inherited).
+    while (cur > 0 && cur > stop_validate) {
         const u64 le = cur - 1;  // the '\n' that ends the previous line
         u64 ls = le;
         while (ls > 0 && *at(ls - 1) != '\n') --ls;
@@ -256,27 +288,136 @@ k_parse_records(const unsigned char* __restrict__ text, u64 n, const u64* __rest
         }
         cur = ls;
     }
-    Pos p;
-    pos_clear(p);  // TrainingDataEntry e; -> Position()
-    Move mv;
-    mv.from = mv.to = 0; mv.type = MT_NORMAL; mv.promo = NO_PIECE;
-    long long v;
-    int sc = 0, pl = 0, res = 0;
-    if (fen.p && !parse_fen(fen.p, fen.p + fen.n, p)) bad = true;
-    if (!move.p || !parse_uci(p, move.p, move.n, mv)) bad = true;
-    if (score.p) { if (parse_int(score.p, score.p + score.n, v)) sc = (int)(short)v; else bad = true; }
-    if (ply.p) { if (parse_int(ply.p, ply.p + ply.n, v)) pl = (int)(v & 0xFFFF); else bad = true; }
-    if (result.p) { if (parse_int(result.p, result.p + result.n, v)) res = (int)(short)v; else bad = true; }
+    if (found != 31 && r > 0) {  // inherits a field from an earlier record: parsed by k_parse_inherited
+        tot->inherit = 1;
+        if (bad) atomicMin(&tot->error_pos, epos);
+        return;
+    }
+    if (!parse_entry(fen, move, score, ply, result, entries[r])) bad = true;
     if (bad) atomicMin(&tot->error_pos, epos);
-    Entry e;
-    e.occ0 = p.occ[0]; e.occ1 = p.occ[1]; e.t0 = p.t0; e.t1 = p.t1; e.t2 = p.t2;
-    e.meta = (u32)p.stm | ((u32)p.ep << 1) | ((u32)p.cr << 8) | (((u32)p.rule50 & 0xFF) << 12);
-    e.pos_ply = (u32)p.ply & 0xFFFF;
-    e.mv = (u32)mv.from | ((u32)mv.to << 6) | ((u32)mv.type << 12) | ((u32)mv.promo << 14);
-    e.score_ply = ((u32)sc & 0xFFFF) | ((u32)pl << 16);
-    e.result = (u32)res & 0xFFFF;
-    e.pad = 0;
-    entries[r] = e;
+}
+
+// ---- fields that persist across records (:1254), in linear time
+//
+// k_record_defs: for every record and each of the five keys, the start of the line that defines it inside
+// the record (+ 1; 0 = the record does not define it; the line nearest to the terminator wins, as in the
+// stream). An inclusive running maximum over the records turns that into "the last definition at or
+// before this record" (line offsets grow with the record index): three small kernels over 40 bytes
+// per record. k_parse_inherited then parses the records that do not define all five keys themselves from
+// those lines. The passes only run for files in which some record inherits a field.
+constexpr int DEF_KEYS = 5;
+__global__ void __launch_bounds__(PARSE_THREADS)
+k_record_defs(const unsigned char* __restrict__ text, u64 n, const u64* __restrict__ rec_pos, u64 nrec, u64* __restrict__ defs)
+{
+    const u64 r = (u64)blockIdx.x * PARSE_THREADS + threadIdx.x;
+    if (r >= nrec) return;
+    const u64 stop = r > 0 ? rec_pos[r - 1] : 0;
+    u64 d[DEF_KEYS] = {0, 0, 0, 0, 0};
+    u64 cur = rec_pos[r];
+    while (cur > 0 && text[cur - 1] != '\n') --cur;
+    while (cur > 0 && cur > stop) {
+        const u64 le = cur - 1;
+        u64 ls = le;
+        while (ls > 0 && text[ls - 1] != '\n') --ls;
+        Span key, val;
+        if (split_line(text + ls, text + le, key, val) == 2) {
+            const int k = key_is(key, "fen", 3) ? 0 : key_is(key, "move", 4) ? 1 : key_is(key, "score", 5) ? 2
+                        : key_is(key, "ply", 3) ? 3 : key_is(key, "result", 6) ? 4 : -1;
+            if (k >= 0 && d[k] == 0) d[k] = ls + 1;
+        }
+        cur = ls;
+    }
+#pragma unroll
+    for (int k = 0; k < DEF_KEYS; ++k) defs[r * DEF_KEYS + k] = d[k];
+}
+
+constexpr int MAXSCAN_THREADS = 256;
+// tile_max[t][k] = maximum of defs[.][k] over the MAXSCAN_THREADS records of tile t
+__global__ void __launch_bounds__(MAXSCAN_THREADS) k_defs_tile_max(const u64* __restrict__ defs, u64 nrec, u64* __restrict__ tile_max)
+{
+    __shared__ u64 sm[MAXSCAN_THREADS / 32][DEF_KEYS];
+    const u64 r = (u64)blockIdx.x * MAXSCAN_THREADS + threadIdx.x;
+    u64 v[DEF_KEYS];
+#pragma unroll
+    for (int k = 0; k < DEF_KEYS; ++k) v[k] = r < nrec ? defs[r * DEF_KEYS + k] : 0;
+#pragma unroll
+    for (int k = 0; k < DEF_KEYS; ++k)
+        for (int d = 16; d > 0; d >>= 1) {
+            const u64 o = __shfl_xor_sync(0xffffffffu, v[k], d);
+            v[k] = o > v[k] ? o : v[k];
+        }
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < DEF_KEYS; ++k) sm[threadIdx.x >> 5][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < DEF_KEYS) {
+        u64 m = 0;
+        for (int w = 0; w < MAXSCAN_THREADS / 32; ++w) m = sm[w][threadIdx.x] > m ? sm[w][threadIdx.x] : m;
+        tile_max[(u64)blockIdx.x * DEF_KEYS + threadIdx.x] = m;
+    }
+}
+// exclusive running maximum over the tiles, in place (one thread per key: a few thousand tiles)
+__global__ void k_defs_tile_scan(u64* __restrict__ tile_max, u64 tiles)
+{
+    if (threadIdx.x >= DEF_KEYS || blockIdx.x != 0) return;
+    u64 run = 0;
+    for (u64 t = 0; t < tiles; ++t) {
+        const u64 v = tile_max[t * DEF_KEYS + threadIdx.x];
+        tile_max[t * DEF_KEYS + threadIdx.x] = run;
+        run = v > run ? v : run;
+    }
+}
+// defs[r][k] = max(defs[0..r][k]): inclusive, in place
+__global__ void __launch_bounds__(MAXSCAN_THREADS) k_defs_apply(u64* __restrict__ defs, u64 nrec, const u64* __restrict__ tile_excl)
+{
+    __shared__ u64 sm[MAXSCAN_THREADS][DEF_KEYS + 1];
+    const u64 r = (u64)blockIdx.x * MAXSCAN_THREADS + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < DEF_KEYS; ++k) sm[threadIdx.x][k] = r < nrec ? defs[r * DEF_KEYS + k] : 0;
+    __syncthreads();
+    for (int d = 1; d < MAXSCAN_THREADS; d <<= 1) {
+        u64 o[DEF_KEYS];
+#pragma unroll
+        for (int k = 0; k < DEF_KEYS; ++k) o[k] = (int)threadIdx.x >= d ? sm[threadIdx.x - d][k] : 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < DEF_KEYS; ++k)
+            if (o[k] > sm[threadIdx.x][k]) sm[threadIdx.x][k] = o[k];
+        __syncthreads();
+    }
+    if (r < nrec) {
+#pragma unroll
+        for (int k = 0; k < DEF_KEYS; ++k) {
+            const u64 e = tile_excl[(u64)blockIdx.x * DEF_KEYS + k], v = sm[threadIdx.x][k];
+            defs[r * DEF_KEYS + k] = e > v ? e : v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PARSE_THREADS)
+k_parse_inherited(const unsigned char* __restrict__ text, u64 n, const u64* __restrict__ rec_pos, u64 nrec,
+                  const u64* __restrict__ defs, Entry* __restrict__ entries, PlainTotals* tot)
+{
+    const u64 r = (u64)blockIdx.x * PARSE_THREADS + threadIdx.x;
+    if (r >= nrec || r == 0) return;
+    const u64 stop = rec_pos[r - 1];
+    Span sp[DEF_KEYS];
+    bool own = true;
+#pragma unroll
+    for (int k = 0; k < DEF_KEYS; ++k) {
+        const u64 d = defs[r * DEF_KEYS + k];
+        sp[k].p = nullptr;
+        sp[k].n = 0;
+        if (d == 0 || d - 1 < stop) own = false;  // not defined by the record itself
+        if (d != 0) {
+            const u64 ls = d - 1;
+            u64 le = ls;
+            while (le < n && text[le] != '\n') ++le;
+            Span key;
+            split_line(text + ls, text + le, key, sp[k]);
+        }
+    }
+    if (own) return;  // parsed by k_parse_records
+    if (!parse_entry(sp[0], sp[1], sp[2], sp[3], sp[4], entries[r])) atomicMin(&tot->error_pos, rec_pos[r]);
 }
 
 __device__ __forceinline__ void entry_unpack(const Entry& e, Pos& p, RecordFields& f)
@@ -396,6 +537,19 @@ void launch_parse_records(const void* text, u64 n, const u64* rec_pos, u64 nrec,
 {
     if (nrec == 0) return;
     k_parse_records<<<(unsigned)((nrec + PARSE_THREADS - 1) / PARSE_THREADS), PARSE_THREADS, 0, s>>>((const unsigned char*)text, n, rec_pos, nrec, entries, tot);
+}
+u64 defs_tiles(u64 nrec) { return (nrec + MAXSCAN_THREADS - 1) / MAXSCAN_THREADS; }
+// the inheritance passes: defs [nrec * 5] u64 and tile_max [defs_tiles(nrec) * 5] u64 are scratch
+void launch_parse_inherited(const void* text, u64 n, const u64* rec_pos, u64 nrec, u64* defs, u64* tile_max, Entry* entries,
+                            PlainTotals* tot, cudaStream_t s)
+{
+    if (nrec == 0) return;
+    const unsigned pb = (unsigned)((nrec + PARSE_THREADS - 1) / PARSE_THREADS), tb = (unsigned)defs_tiles(nrec);
+    k_record_defs<<<pb, PARSE_THREADS, 0, s>>>((const unsigned char*)text, n, rec_pos, nrec, defs);
+    k_defs_tile_max<<<tb, MAXSCAN_THREADS, 0, s>>>(defs, nrec, tile_max);
+    k_defs_tile_scan<<<1, 32, 0, s>>>(tile_max, tb);
+    k_defs_apply<<<tb, MAXSCAN_THREADS, 0, s>>>(defs, nrec, tile_max);
+    k_parse_inherited<<<pb, PARSE_THREADS, 0, s>>>((const unsigned char*)text, n, rec_pos, nrec, defs, entries, tot);
 }
 void launch_entries_link_encode(const Entry* entries, u64 n, u32* codes, u32* stems, cudaStream_t s)
 {

@@ -298,6 +298,50 @@ def test_plain_layout_variants(nnp):
     assert nnp.plain_to_bin(b"") == b"" and nnp.plain_to_binpack(b"\n\n") == b""
 
 
+def test_plain_inherited_fields_in_linear_time(nnp):
+    """A key that (almost) never appears: every record inherits it from far back (fields persist,
+    compress_file.cpp:1254). The parser resolves that with a running maximum over the records, not by
+    walking back through the file; 300 000 records with no `result` line at all and `ply` only in the
+    first record take milliseconds and match the oracle."""
+    import time
+
+    b = nnp.generate_bin(300_000, 100, 77)
+    rc, text = oracle_convert(BIN_TO_PLAIN, b)
+    assert rc == 0
+    lines = text.split(b"\n")
+    seen_ply = False
+    kept = []
+    for ln in lines:
+        if ln.startswith(b"result "):
+            continue
+        if ln.startswith(b"ply "):
+            if seen_ply:
+                continue
+            seen_ply = True
+        kept.append(ln)
+    data = b"\n".join(kept)
+    assert len(data) < len(text) - 300_000 * 8
+    for mode, fn in ((PLAIN_TO_BIN, nnp.plain_to_bin), (PLAIN_TO_BINPACK, nnp.plain_to_binpack)):
+        rc, want = oracle_convert(mode, data)
+        assert rc == 0
+        t0 = time.time()
+        got = fn(data)
+        assert time.time() - t0 < 20
+        assert got == want
+    # every second record drops its fen line: the position persists, the move is read in it
+    kept, k = [], 0
+    for ln in lines:
+        if ln.startswith(b"fen "):
+            k += 1
+            if k % 2 == 0:
+                continue
+        kept.append(ln)
+    data = b"\n".join(kept)
+    rc, want = oracle_convert(PLAIN_TO_BIN, data)
+    if rc == 0:  # (the oracle refuses what the reference would crash on)
+        assert nnp.plain_to_bin(data) == want
+
+
 def test_plain_rejected_layouts(nnp):
     for text in (b"fen\nrnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1\nmove e2e4\nscore 1\nply 0\nresult 0\ne\n",
                  b"fen rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1\nmove e2e4\nscore x\nply 0\nresult 0\ne\n",
