@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -24,7 +25,7 @@ enum WsSlot {
     WS_CODES = 0, WS_STEMS, WS_TILE_AGG, WS_PAYLOAD, WS_HEAD_OFF, WS_CHUNK_OFF, WS_TOTALS,
     WS_CHUNK_START, WS_CHUNK_LEN, WS_CHUNK_TILE_BASE, WS_CHUNK_INFO, WS_TILE_COUNT, WS_TILE_PREFIX,
     WS_CAND_CHUNK, WS_CAND_OFF, WS_CAND_NEXT, WS_CAND_BASE, WS_CAND_CNT, WS_CHUNK_COUNT, WS_CHUNK_SLOW, WS_CHUNK_BASE,
-    WS_DTOTALS, WS_AGG_TOP, WS_HEAD_NEXT, WS_PARK_A, WS_PARK_B, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_COUNT
+    WS_DTOTALS, WS_AGG_TOP, WS_HEAD_NEXT, WS_PARK_A, WS_PARK_B, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_BLEED, WS_COUNT
 };
 
 // codes/stems of n records -> payload scan and payload write; leaves the headerless payload stream
@@ -157,7 +158,8 @@ size_t binpack_capacity_for_records(size_t n)
 
 // ---------------------------------------------------------------- shared tail of both compressors
 
-int build_payload(const u32* codes, const u32* stems, u64 n, PayloadPlan& P)
+// `rec_base`: index of codes[0] in the record numbering of the K1 pass (the bleed list uses it)
+int build_payload(const u32* codes, const u32* stems, u64 n, PayloadPlan& P, u64 rec_base = 0)
 {
     Context& C = g_ctx;
     cudaStream_t s = C.stream;
@@ -186,6 +188,25 @@ int build_payload(const u32* codes, const u32* stems, u64 n, PayloadPlan& P)
     launch_write_payload(codes, stems, n, tile_agg, payload, head_off, s);
     launch_head_next(head_off, P.heads, head_next, d_tot, s);
     LAUNCHED(2, "k_write_payload");
+    if (h_tot->bleeds > 0) {
+        // stored moves that are not pseudo-legal: their ids overflow their fields and the reference ORs the
+        // excess into the byte the field starts in (addBitsLE8 :840-862). Sort the few plies by record
+        // (host) and let a second pass of the writer's scan add exactly those bits.
+        const u64 count = h_tot->bleeds;
+        if (count > BLEED_LIST_CAP) {
+            C.last_cuda_error = "more than 2^20 stored moves are not pseudo-legal in their positions";
+            return NNP_ERR_BAD_ARG;
+        }
+        WS(WS_BLEED, BLEED_LIST_CAP * 8, u64, bleed_list);
+        std::vector<u64> host(count);
+        CK(cudaMemcpyAsync(host.data(), bleed_list, count * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        std::sort(host.begin(), host.end(), [](u64 a, u64 b) { return (a & 0xFFFFFFFFull) < (b & 0xFFFFFFFFull); });
+        CK(cudaMemcpyAsync(bleed_list, host.data(), count * 8, cudaMemcpyHostToDevice, s));
+        launch_write_bleed(codes, n, tile_agg, payload, bleed_list, count, rec_base, s);
+        LAUNCHED(1, "k_write_payload<bleed>");
+        CK(cudaStreamSynchronize(s));  // `host` is pageable and goes out of scope
+    }
     return NNP_OK;
 }
 
@@ -231,6 +252,7 @@ int reset_compress_totals(CompressTotals** d_tot_out)
     h_tot->chunks = 0;
     h_tot->error_index = NO_ERROR_IDX;
     h_tot->parked[0] = h_tot->parked[1] = 0;
+    h_tot->bleeds = 0;
     CK(cudaMemcpyAsync(d_tot, h_tot, sizeof(CompressTotals), cudaMemcpyHostToDevice, C.stream));
     *d_tot_out = d_tot;
     return NNP_OK;
@@ -246,6 +268,7 @@ int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** ste
     cudaStream_t s = C.stream;
     WS(WS_CODES, n_all * 4, u32, codes);
     WS(WS_STEMS, n_all * 32, u32, stems);
+    WS(WS_BLEED, BLEED_LIST_CAP * 8, u64, bleed_list);
     *codes_out = codes;
     *stems_out = stems;
     CompressTotals* d_tot = nullptr;
@@ -269,7 +292,7 @@ int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** ste
     }
     if (per_record) {
         if (C.pipe_src) CK(cudaMemcpyAsync(const_cast<void*>(d_bin), C.pipe_src, n_all * 40, cudaMemcpyHostToDevice, s));
-        launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, s);
+        launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, bleed_list, s);
         LAUNCHED(1, "k_decode_link_encode");
         C.last_kernel = "k_decode_link_encode";
         CK(cudaEventRecord(C.ev[3], s));
@@ -298,11 +321,11 @@ int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** ste
                                    cudaMemcpyHostToDevice, C.copy_stream));
                 CK(cudaEventRecord(C.pipe_ev[k % 16], C.copy_stream));
                 CK(cudaStreamWaitEvent(s, C.pipe_ev[k % 16], 0));
-                launch_walk_runs(d_bin, n_all, lo, hi, codes, stems, d_tot, lists[0], &d_tot->parked[0], s);
+                launch_walk_runs(d_bin, n_all, lo, hi, codes, stems, d_tot, lists[0], &d_tot->parked[0], bleed_list, s);
                 LAUNCHED(1, "k_walk_runs");
             }
         } else {
-            launch_walk_runs(d_bin, n_all, 0, runs, codes, stems, d_tot, lists[0], &d_tot->parked[0], s);
+            launch_walk_runs(d_bin, n_all, 0, runs, codes, stems, d_tot, lists[0], &d_tot->parked[0], bleed_list, s);
             LAUNCHED(1, "k_walk_runs");
         }
         CK(cudaEventRecord(C.ev[3], s));
@@ -312,7 +335,8 @@ int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** ste
             const u64 n_items = h_tot->parked[cur];
             if (n_items == 0) break;
             CK(cudaMemsetAsync(&d_tot->parked[cur ^ 1], 0, 8, s));
-            launch_walk_items(d_bin, n_all, codes, stems, d_tot, lists[cur], n_items, lists[cur ^ 1], &d_tot->parked[cur ^ 1], s);
+            launch_walk_items(d_bin, n_all, codes, stems, d_tot, lists[cur], n_items, lists[cur ^ 1], &d_tot->parked[cur ^ 1],
+                              bleed_list, s);
             LAUNCHED(1, "k_walk_items");
         }
     }
@@ -408,7 +432,7 @@ int shard_begin_dev(const void* d_bin, u64 n_records, u64 own_lo, u64 own_hi, in
     info->end_owned_record = end;
     g_ctx.shard.active = true;
     if (first == end) return NNP_OK;
-    rc = build_payload(codes + first, stems + first * 8, end - first, g_ctx.shard.plan);
+    rc = build_payload(codes + first, stems + first * 8, end - first, g_ctx.shard.plan, first);
     if (rc != NNP_OK) return rc;
     info->payload_bytes = g_ctx.shard.plan.payload_bytes;
     info->chains = g_ctx.shard.plan.heads;
@@ -574,7 +598,8 @@ int plain_to_binpack_dev(const void* d_text, size_t text_bytes, void* d_out, siz
     CompressTotals* d_tot = nullptr;
     rc = reset_compress_totals(&d_tot);
     if (rc != NNP_OK) return rc;
-    launch_entries_link_encode(P.entries, P.nrec, codes, stems, s);
+    WS(WS_BLEED, BLEED_LIST_CAP * 8, u64, bleed_list);
+    launch_entries_link_encode(P.entries, P.nrec, codes, stems, d_tot, bleed_list, s);
     LAUNCHED(1, "k_entries_link_encode");
     rc = compress_tail(codes, stems, P.nrec, NNP_OK, d_out, out_cap, out_bytes);
     if (rc != NNP_OK) return rc;

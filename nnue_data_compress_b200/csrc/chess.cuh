@@ -747,10 +747,14 @@ __device__ __forceinline__ u64 pawn_destinations(const Pos& p, int from, u64 our
 
 // PackedMoveScoreList::addMoveScore (compress_file.cpp:877-989) for one continuation ply.
 // Returns the ply's bit string left-aligned in 32 bits; nbits <= 31 (6 + 5 + 20).
-// Field values are masked to their widths (the reference lets an out-of-range id bleed into
-// neighbouring bits, which only happens for stored moves that are not pseudo-legal).
+// Field values are masked to their widths here. The reference does not mask (addBitsLE8 :840-862 takes
+// a std::uint8_t and ORs it in): an id that does not fit its field -- possible only for a stored move
+// that is not pseudo-legal in its position -- sets bits of the byte the field starts in, above the
+// field. Where that lands depends on the byte alignment of the chain, which only the payload writer
+// knows, so such a ply is reported through `bleed` (packed raw ids and widths, 0 = none) and the
+// writer ORs the stray bits in (k_write_payload<true>).
 __device__ __forceinline__ u32 encode_ply(const Pos& p, const Move& mv, int score, int last_score, int& nbits,
-                                          const StepTables* T = nullptr)
+                                          const StepTables* T = nullptr, u32* bleed = nullptr)
 {
     int stm = p.stm;
     u64 ours = pos_occ(p, stm), theirs = pos_occ(p, stm ^ 1);
@@ -787,6 +791,10 @@ __device__ __forceinline__ u32 encode_ply(const Pos& p, const Move& mv, int scor
         if ((mv.to & 7) == 7) move_id += 1;
     }
     int w1 = used_bits((u32)popc64(ours)), w2 = used_bits(num_moves);
+    if (bleed) {
+        const u32 rp = piece_id & 0xFFu, rm = move_id & 0xFFu;  // the reference's std::uint8_t argument
+        *bleed = ((rp >> w1) | (rm >> w2)) ? (rp | ((u32)w1 << 8) | (rm << 12) | ((u32)w2 << 20) | (1u << 31)) : 0u;
+    }
     u64 acc = 0;  // bits accumulate at the low end, MSB-first order == append order
     int n = 0;
     acc = (acc << w1) | (piece_id & ((1u << w1) - 1u)); n += w1;

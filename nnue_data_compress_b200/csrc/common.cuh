@@ -71,7 +71,9 @@ struct CompressTotals {
     u64 chunks;         // written by the chunk-orbit kernel
     u64 error_index;    // first record whose sfen is malformed, or NO_ERROR_IDX
     u64 parked[2];      // chain heads parked by the current / next round of the chain walk
+    u64 bleeds;         // plies whose ids do not fit their fields (see encode_ply); listed in BleedLog::list
 };
+
 
 struct DecompressTotals {
     u64 positions;

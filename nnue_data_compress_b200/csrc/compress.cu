@@ -67,7 +67,7 @@ __device__ __forceinline__ void k1_load(const K1Shared& sh, int t, Pos& p, Recor
 #endif
 __global__ void __launch_bounds__(K1_THREADS, K1_MIN_BLOCKS)
 k_decode_link_encode(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ codes,
-                     u32* __restrict__ stems, CompressTotals* tot)
+                     u32* __restrict__ stems, CompressTotals* tot, u64* __restrict__ bleed_list)
 {
     __shared__ K1Shared sh;
     const int t = threadIdx.x;
@@ -116,8 +116,10 @@ k_decode_link_encode(const unsigned char* __restrict__ bin, u64 n, u32* __restri
         bool prev_ok;
         k1_load(sh, t - 1, a, pf, prev_ok);
         const bool has_prev = rec > 0 && ok && prev_ok;
-        const u32 code = link_code(has_prev, a, pf, p, cf);
+        u32 bleed = 0;
+        const u32 code = link_code(has_prev, a, pf, p, cf, &bleed);
         codes[rec] = code;
+        if (bleed) bleed_report(BleedLog{bleed_list, &tot->bleeds}, (u64)rec, bleed);
         if (code == 0u) sh.heads[atomicAdd(&sh.nheads, 1u)] = (u32)t;
     }
     __syncthreads();
@@ -192,10 +194,12 @@ __device__ __forceinline__ void park_append(u32 parked, u32* __restrict__ list, 
 // KW_THREADS runs, so the lookup tables are staged in shared memory once per block, not once per tile.
 __global__ void __launch_bounds__(KW_THREADS, KW_MIN_BLOCKS)
 k_walk_runs(const unsigned char* __restrict__ bin, u64 n, u64 run_lo, u64 run_hi, u32* __restrict__ codes,
-            u32* __restrict__ stems, CompressTotals* tot, u32* __restrict__ park_list, u64* park_count)
+            u32* __restrict__ stems, CompressTotals* tot, u32* __restrict__ park_list, u64* park_count,
+            u64* __restrict__ bleed_list)
 {
     __shared__ StepTables T;
     step_tables_fill(T);
+    const BleedLog B{bleed_list, &tot->bleeds};
     for (u64 tile = blockIdx.x; run_lo + tile * KW_THREADS < run_hi; tile += gridDim.x) {
         const u64 run = run_lo + tile * KW_THREADS + threadIdx.x;
         const u64 r0 = run * KW_RUN;
@@ -208,7 +212,7 @@ k_walk_runs(const unsigned char* __restrict__ bin, u64 n, u64 run_lo, u64 run_hi
                 head = !fields_link(w[9], w[19]);
             }
             walk_item(bin, head ? r0 : r0 - 1, head, e, codes, stems, [&](u64 rec) { atomicMin(&tot->error_index, rec); },
-                      [&](u64 rec) { parked = (u32)rec; }, &T);
+                      [&](u64 rec) { parked = (u32)rec; }, &T, &B);
         }
         park_append(parked, park_list, park_count);
     }
@@ -216,10 +220,12 @@ k_walk_runs(const unsigned char* __restrict__ bin, u64 n, u64 run_lo, u64 run_hi
 
 __global__ void __launch_bounds__(KW_THREADS, KW_MIN_BLOCKS)
 k_walk_items(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ codes, u32* __restrict__ stems,
-             CompressTotals* tot, const u32* __restrict__ items, u64 n_items, u32* __restrict__ park_list, u64* park_count)
+             CompressTotals* tot, const u32* __restrict__ items, u64 n_items, u32* __restrict__ park_list, u64* park_count,
+             u64* __restrict__ bleed_list)
 {
     __shared__ StepTables T;
     step_tables_fill(T);
+    const BleedLog B{bleed_list, &tot->bleeds};
     const u64 i = (u64)blockIdx.x * KW_THREADS + threadIdx.x;
     u32 parked = KW_NONE;
     if (i < n_items) {
@@ -227,7 +233,7 @@ k_walk_items(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ cod
         u64 e = (rec / KW_RUN + 1) * KW_RUN;
         if (e > n) e = n;
         walk_item(bin, rec, true, e, codes, stems, [&](u64 r) { atomicMin(&tot->error_index, r); },
-                  [&](u64 r) { parked = (u32)r; }, &T);
+                  [&](u64 r) { parked = (u32)r; }, &T, &B);
     }
     park_append(parked, park_list, park_count);
 }
@@ -447,9 +453,26 @@ __device__ __forceinline__ void or_words8(u32* payload, u64 bytepos, const uint4
     }
 }
 
+// first entry of the sorted bleed list with record index >= rec
+__device__ __forceinline__ u64 bleed_lower_bound(const u64* __restrict__ list, u64 count, u64 rec)
+{
+    u64 lo = 0, hi = count;
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if ((list[mid] & 0xFFFFFFFFull) < rec) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// BLEED = false: the writer. BLEED = true: the same scan, writing nothing but the stray bits of the plies
+// in `bleed_list` (sorted by record index, indices relative to `rec_base`): an unmasked id ORs
+// (id >> width) << bitsLeft into the byte its field starts in when that byte is already in use
+// (addBitsLE8 :840-862; a field that opens a new byte is truncated by the byte store).
+template <bool BLEED>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_write_payload(const u32* __restrict__ codes, const u32* __restrict__ stems, u64 n,
-                const Agg* __restrict__ tile_prefix, u32* __restrict__ payload, u64* __restrict__ head_off)
+                const Agg* __restrict__ tile_prefix, u32* __restrict__ payload, u64* __restrict__ head_off,
+                const u64* __restrict__ bleed_list, u64 bleed_count, u64 rec_base)
 {
     __shared__ Agg warp_tot[SCAN_THREADS / 32];
     const u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
@@ -477,23 +500,42 @@ k_write_payload(const u32* __restrict__ codes, const u32* __restrict__ stems, u6
             if (h > 0) {
                 P = M + ceil8(ob);
                 // numPlies of the chain that just ended, big-endian (:1118-1119)
-                or_byte(payload, M - 2, op >> 8);
-                or_byte(payload, M - 1, op);
+                if (!BLEED) {
+                    or_byte(payload, M - 2, op >> 8);
+                    or_byte(payload, M - 1, op);
+                }
             }
-            const uint4* s = reinterpret_cast<const uint4*>(stems + rec * 8);
-            or_words8(payload, P, s[0], s[1]);
-            head_off[h] = P;
+            if (!BLEED) {
+                const uint4* s = reinterpret_cast<const uint4*>(stems + rec * 8);
+                or_words8(payload, P, s[0], s[1]);
+                head_off[h] = P;
+            }
             M = P + 34;
             ob = 0;
             op = 0;
             ++h;
         } else {
             const int nb = code_bits(c[i]);
-            or_bits(payload, M * 8 + ob, c[i] & ~(1u << (31 - nb)), nb);
+            if (!BLEED) {
+                or_bits(payload, M * 8 + ob, c[i] & ~(1u << (31 - nb)), nb);
+            } else {
+                const u64 j = bleed_lower_bound(bleed_list, bleed_count, rec_base + rec);
+                if (j < bleed_count && (bleed_list[j] & 0xFFFFFFFFull) == rec_base + rec) {
+                    const u32 pk = (u32)(bleed_list[j] >> 32);
+                    const u32 raw[2] = {pk & 0xFFu, (pk >> 12) & 0xFFu}, width[2] = {(pk >> 8) & 15u, (pk >> 20) & 15u};
+                    u32 q = ob;  // bit offset of the field in the chain's movetext
+                    for (int f = 0; f < 2; ++f) {
+                        const u32 left = (8u - (q & 7u)) & 7u;  // m_bitsLeft when the field is added
+                        const u32 stray = ((raw[f] >> width[f]) << left) & 0xFFu;
+                        if (width[f] != 0 && left != 0 && stray != 0) or_byte(payload, M + (q >> 3), stray);
+                        q += width[f];
+                    }
+                }
+            }
             ob += nb;
             op = (op + 1) & 0xFFFF;  // std::uint16_t numPlies
         }
-        if (rec == n - 1) {  // ~CompressedTrainingDataEntryWriter (:1094-1106): last movelist
+        if (!BLEED && rec == n - 1) {  // ~CompressedTrainingDataEntryWriter (:1094-1106): last movelist
             or_byte(payload, M - 2, op >> 8);
             or_byte(payload, M - 1, op);
         }
@@ -710,11 +752,12 @@ __global__ void __launch_bounds__(32) k_find_head(const u32* __restrict__ codes,
 void init_tables_compress(cudaStream_t s) { k_step_tables_init<<<1, 256, 0, s>>>(); }
 
 
-void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, cudaStream_t s)
+void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u64* bleed_list,
+                               cudaStream_t s)
 {
     if (n == 0) return;
     const u64 blocks = (n + K1_TILE - 1) / K1_TILE;
-    k_decode_link_encode<<<(unsigned)blocks, K1_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems, tot);
+    k_decode_link_encode<<<(unsigned)blocks, K1_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems, tot, bleed_list);
 }
 void launch_sample_heads(const void* d_bin, u64 n, u64 stride, u64 samples, u64* heads, cudaStream_t s)
 {
@@ -739,22 +782,22 @@ u64 walk_runs(u64 n) { return (n + KW_RUN - 1) / KW_RUN; }
 int walk_run_records() { return KW_RUN; }
 // runs [run_lo, run_hi) of the n records at d_bin (the records before run_lo * KW_RUN must be there too)
 void launch_walk_runs(const void* d_bin, u64 n, u64 run_lo, u64 run_hi, u32* codes, u32* stems, CompressTotals* tot,
-                      u32* park_list, u64* park_count, cudaStream_t s)
+                      u32* park_list, u64* park_count, u64* bleed_list, cudaStream_t s)
 {
     if (run_hi <= run_lo) return;
     u64 blocks = (run_hi - run_lo + KW_THREADS - 1) / KW_THREADS;
     const u64 resident = (u64)sm_count() * KW_MIN_BLOCKS;  // one wave of persistent blocks
     if (blocks > resident) blocks = resident;
     k_walk_runs<<<(unsigned)blocks, KW_THREADS, 0, s>>>((const unsigned char*)d_bin, n, run_lo, run_hi, codes, stems, tot,
-                                                       park_list, park_count);
+                                                       park_list, park_count, bleed_list);
 }
 void launch_walk_items(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, const u32* items, u64 n_items,
-                       u32* park_list, u64* park_count, cudaStream_t s)
+                       u32* park_list, u64* park_count, u64* bleed_list, cudaStream_t s)
 {
     if (n_items == 0) return;
     const u64 blocks = (n_items + KW_THREADS - 1) / KW_THREADS;
     k_walk_items<<<(unsigned)blocks, KW_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems, tot, items, n_items,
-                                                        park_list, park_count);
+                                                        park_list, park_count, bleed_list);
 }
 u64 scan_tiles(u64 n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
 void launch_tile_aggregate(const u32* codes, u64 n, Agg* tile_agg, cudaStream_t s)
@@ -774,7 +817,15 @@ void launch_write_payload(const u32* codes, const u32* stems, u64 n, const Agg* 
                           u64* head_off, cudaStream_t s)
 {
     if (n == 0) return;
-    k_write_payload<<<(unsigned)scan_tiles(n), SCAN_THREADS, 0, s>>>(codes, stems, n, tile_prefix, payload, head_off);
+    k_write_payload<false><<<(unsigned)scan_tiles(n), SCAN_THREADS, 0, s>>>(codes, stems, n, tile_prefix, payload, head_off,
+                                                                             nullptr, 0, 0);
+}
+void launch_write_bleed(const u32* codes, u64 n, const Agg* tile_prefix, u32* payload, const u64* bleed_list, u64 bleed_count,
+                        u64 rec_base, cudaStream_t s)
+{
+    if (n == 0 || bleed_count == 0) return;
+    k_write_payload<true><<<(unsigned)scan_tiles(n), SCAN_THREADS, 0, s>>>(codes, nullptr, n, tile_prefix, payload, nullptr,
+                                                                            bleed_list, bleed_count, rec_base);
 }
 void launch_head_next(const u64* head_off, u64 heads, u32* next, CompressTotals* tot, cudaStream_t s)
 {

@@ -10,14 +10,18 @@ void init_tables_decompress(cudaStream_t s);
 void init_tables_halfkp(cudaStream_t s);
 
 // ---- compress (.bin -> .binpack), compress.cu
-void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, cudaStream_t s);
+void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u64* bleed_list,
+                               cudaStream_t s);
 u64 walk_runs(u64 n);  // number of runs = upper bound of the parked heads of any round
 void launch_sample_heads(const void* d_bin, u64 n, u64 stride, u64 samples, u64* heads, cudaStream_t s);
 int walk_run_records();
 void launch_walk_runs(const void* d_bin, u64 n, u64 run_lo, u64 run_hi, u32* codes, u32* stems, CompressTotals* tot,
-                      u32* park_list, u64* park_count, cudaStream_t s);
+                      u32* park_list, u64* park_count, u64* bleed_list, cudaStream_t s);
 void launch_walk_items(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, const u32* items, u64 n_items,
-                       u32* park_list, u64* park_count, cudaStream_t s);
+                       u32* park_list, u64* park_count, u64* bleed_list, cudaStream_t s);
+constexpr u64 BLEED_LIST_CAP = 1u << 20;  // = BLEED_CAP (link.cuh)
+void launch_write_bleed(const u32* codes, u64 n, const Agg* tile_prefix, u32* payload, const u64* bleed_list, u64 bleed_count,
+                        u64 rec_base, cudaStream_t s);
 u64 scan_tiles(u64 n);
 void launch_tile_aggregate(const u32* codes, u64 n, Agg* tile_agg, cudaStream_t s);
 u64 scan_blocks(u64 ntiles);  // entries of the block_tot scratch
@@ -103,7 +107,8 @@ void launch_parse_records(const void* text, u64 n, const u64* rec_pos, u64 nrec,
 u64 defs_tiles(u64 nrec);
 void launch_parse_inherited(const void* text, u64 n, const u64* rec_pos, u64 nrec, u64* defs, u64* tile_max, Entry* entries,
                             PlainTotals* tot, cudaStream_t s);
-void launch_entries_link_encode(const Entry* entries, u64 n, u32* codes, u32* stems, cudaStream_t s);
+void launch_entries_link_encode(const Entry* entries, u64 n, u32* codes, u32* stems, CompressTotals* tot, u64* bleed_list,
+                                cudaStream_t s);
 void launch_entries_to_bin(const Entry* entries, u64 n, void* out, cudaStream_t s);
 void launch_bin_text(bool write, const void* bin, u64 n, u32* lens, const u64* offs, void* out, CompressTotals* tot,
                      cudaStream_t s);

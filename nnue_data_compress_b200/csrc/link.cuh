@@ -7,6 +7,23 @@
 
 namespace nnp {
 
+// plies whose ids do not fit their fields (see encode_ply): record index | packed ids << 32, appended in
+// no particular order; *count may run past the capacity (the host then refuses the input)
+constexpr u64 BLEED_CAP = 1u << 20;
+struct BleedLog {
+    u64* list;
+    u64* count;
+};
+__device__ __forceinline__ void bleed_report(const BleedLog& B, u64 rec, u32 packed)
+{
+#ifdef NNP_HOST_SIM
+    const u64 i = (*B.count)++;
+#else
+    const u64 i = atomicAdd(reinterpret_cast<unsigned long long*>(B.count), 1ull);
+#endif
+    if (i < BLEED_CAP) B.list[i] = (rec & 0xFFFFFFFFull) | ((u64)packed << 32);
+}
+
 struct RecordFields {
     Move mv;
     int score;   // int16
@@ -17,8 +34,9 @@ struct RecordFields {
 // Returns the record's code word: 0 for a chain head, otherwise the ply's bits left-aligned and
 // terminated by a single 1 bit (never zero), so that the bit count is 32 - ffs(code).
 __device__ __forceinline__ u32 link_code(bool has_prev, const Pos& prev, const RecordFields& pf, const Pos& cur,
-                                         const RecordFields& cf)
+                                         const RecordFields& cf, u32* bleed = nullptr)
 {
+    if (bleed) *bleed = 0u;
     bool cont = false;
     if (has_prev && pf.result == -cf.result && pf.ply + 1 == cf.ply) {  // short-circuit order of :589-592
         Pos a = prev;
@@ -28,7 +46,7 @@ __device__ __forceinline__ u32 link_code(bool has_prev, const Pos& prev, const R
     if (!cont) return 0u;
     int nbits;
     const int last_score = (int)(short)(-pf.score);  // m_lastScore (:838, :986)
-    const u32 bits = encode_ply(cur, cf.mv, cf.score, last_score, nbits);
+    const u32 bits = encode_ply(cur, cf.mv, cf.score, last_score, nbits, nullptr, bleed);
     return bits | (1u << (31 - nbits));
 }
 
@@ -43,9 +61,9 @@ __device__ __forceinline__ void store_stem(const Pos& cur, const RecordFields& c
 }
 
 __device__ __forceinline__ u32 link_and_encode(bool has_prev, const Pos& prev, const RecordFields& pf, const Pos& cur,
-                                               const RecordFields& cf, u32* stem_out)
+                                               const RecordFields& cf, u32* stem_out, u32* bleed = nullptr)
 {
-    const u32 code = link_code(has_prev, prev, pf, cur, cf);
+    const u32 code = link_code(has_prev, prev, pf, cur, cf, bleed);
     if (code == 0u) store_stem(cur, cf, stem_out);
     return code;
 }

@@ -432,7 +432,8 @@ __device__ __forceinline__ void entry_unpack(const Entry& e, Pos& p, RecordField
 }
 
 __global__ void __launch_bounds__(128)
-k_entries_link_encode(const Entry* __restrict__ entries, u64 n, u32* __restrict__ codes, u32* __restrict__ stems)
+k_entries_link_encode(const Entry* __restrict__ entries, u64 n, u32* __restrict__ codes, u32* __restrict__ stems,
+                      CompressTotals* tot, u64* __restrict__ bleed_list)
 {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -442,7 +443,9 @@ k_entries_link_encode(const Entry* __restrict__ entries, u64 n, u32* __restrict_
     pos_clear(prev);
     pf = cf;
     if (i > 0) entry_unpack(entries[i - 1], prev, pf);
-    codes[i] = link_and_encode(i > 0, prev, pf, cur, cf, stems + i * 8);
+    u32 bleed = 0;
+    codes[i] = link_and_encode(i > 0, prev, pf, cur, cf, stems + i * 8, &bleed);
+    if (bleed) bleed_report(BleedLog{bleed_list, &tot->bleeds}, i, bleed);
 }
 
 // trainingDataEntryToPackedSfenValue (:570-585) for parsed text records
@@ -551,10 +554,11 @@ void launch_parse_inherited(const void* text, u64 n, const u64* rec_pos, u64 nre
     k_defs_apply<<<tb, MAXSCAN_THREADS, 0, s>>>(defs, nrec, tile_max);
     k_parse_inherited<<<pb, PARSE_THREADS, 0, s>>>((const unsigned char*)text, n, rec_pos, nrec, defs, entries, tot);
 }
-void launch_entries_link_encode(const Entry* entries, u64 n, u32* codes, u32* stems, cudaStream_t s)
+void launch_entries_link_encode(const Entry* entries, u64 n, u32* codes, u32* stems, CompressTotals* tot, u64* bleed_list,
+                                cudaStream_t s)
 {
     if (n == 0) return;
-    k_entries_link_encode<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(entries, n, codes, stems);
+    k_entries_link_encode<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(entries, n, codes, stems, tot, bleed_list);
 }
 void launch_entries_to_bin(const Entry* entries, u64 n, void* out, cudaStream_t s)
 {

@@ -78,7 +78,7 @@ static __device__ __noinline__ bool walk_slow(const unsigned char* __restrict__ 
 template <typename ErrFn, typename ParkFn>
 __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin, u64 a, bool a_is_head, u64 e,
                                           u32* __restrict__ codes, u32* __restrict__ stems, ErrFn on_error, ParkFn park,
-                                          const StepTables* T = nullptr)
+                                          const StepTables* T = nullptr, const BleedLog* B = nullptr)
 {
     for (;;) {
         u32 Wp[8], p8, p9;
@@ -156,9 +156,11 @@ __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin,
             u32 code = 0u;
             if (cont) {
                 int nbits;
+                u32 bleed = 0;
                 const u32 bits = encode_ply(P, cm, (int)(short)(c8 & 0xFFFF),
-                                            (int)(short)(-(int)(short)(p8 & 0xFFFF)), nbits, T);
+                                            (int)(short)(-(int)(short)(p8 & 0xFFFF)), nbits, T, &bleed);
                 code = bits | (1u << (31 - nbits));
+                if (bleed && B) bleed_report(*B, rec, bleed);
             }
             codes[rec] = code;
 #pragma unroll

@@ -374,3 +374,67 @@ def test_plain_error_partial_outputs(nnp):
     with pytest.raises(nnp.NnpError) as ei:
         nnp.binpack_to_plain(data)
     assert ei.value.status == -1 and ei.value.partial == want
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_fuzz_differential_against_the_oracle(nnp, seed):
+    """Random bit flips in .bin and .binpack inputs: wherever the oracle (= the reference's semantics)
+    gives a result -- OK or one of the three reference errors -- status and bytes agree. This includes
+    stored moves that are not pseudo-legal, whose ids the reference does not mask (addBitsLE8
+    :840-862): the payload writer adds the same stray bits (k_write_payload<true>)."""
+    import random
+
+    rng = random.Random(seed)
+
+    def ours(fn, data):
+        try:
+            return 0, fn(data)
+        except nnp.NnpError as e:
+            return e.status, (e.partial or b"")
+
+    packs = [golden(n + ".binpack") for n in ("games100", "long400", "restart", "heads")]
+    bins = [golden(n + ".bin") for n in ("games100", "long400", "restart")]
+    agree = skipped = 0
+    for it in range(300):
+        if it & 1:
+            b = bytearray(rng.choice(packs))
+            for _ in range(rng.randrange(1, 4)):
+                b[rng.randrange(8, len(b))] ^= 1 << rng.randrange(8)
+            mode, fn = BINPACK_TO_BIN, nnp.binpack_to_bin
+        else:
+            b = bytearray(rng.choice(bins))
+            for _ in range(rng.randrange(1, 4)):
+                b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+            mode, fn = BIN_TO_BINPACK, nnp.bin_to_binpack
+        rc_o, out_o = oracle_convert(mode, bytes(b))
+        if rc_o not in (0, -1, -2, -3):
+            skipped += 1
+            continue
+        rc, out = ours(fn, bytes(b))
+        assert (rc, out) == (rc_o, out_o), (seed, it, mode, rc_o, rc, len(out_o), len(out))
+        agree += 1
+    assert agree > 150
+
+
+def test_illegal_stored_moves_bleed_like_the_reference(nnp):
+    """Every stored move replaced by a random one (mostly not pseudo-legal): ids overflow their fields in
+    many plies; bytes must still be the oracle's, through both forms of K1 and through the .plain path."""
+    import random
+
+    rng = random.Random(11)
+    b = bytearray(golden("games100.bin"))
+    for r in range(len(b) // 40):
+        if rng.random() < 0.5:
+            mv = rng.randrange(1 << 16)
+            b[40 * r + 34] = mv & 0xFF
+            b[40 * r + 35] = mv >> 8
+    data = bytes(b)
+    rc, want = oracle_convert(BIN_TO_BINPACK, data)
+    assert rc == 0
+    L = nnp.lib()
+    for key in (b"k1_walk", b"k1_per_record"):
+        L.nnp_debug_config(key, 1)
+        try:
+            assert nnp.bin_to_binpack(data) == want
+        finally:
+            L.nnp_debug_config(key, 0)
