@@ -211,8 +211,11 @@ k_walk_runs(const unsigned char* __restrict__ bin, u64 n, u64 run_lo, u64 run_hi
                 const u32* w = reinterpret_cast<const u32*>(bin + (r0 - 1) * 40);
                 head = !fields_link(w[9], w[19]);
             }
+            // a head right behind the anchor (files of single positions) is decoded on the spot, where all
+            // lanes of the warp do the same thing anyway; any other head is parked for a dense round
             walk_item(bin, head ? r0 : r0 - 1, head, e, codes, stems, [&](u64 rec) { atomicMin(&tot->error_index, rec); },
-                      [&](u64 rec) { parked = (u32)rec; }, &T, &B);
+                      [&](u64 rec, u64 a) { if (rec == a + 1) return true; parked = (u32)rec; return false; },
+                      [](u64) {}, &T, &B);
         }
         park_append(parked, park_list, park_count);
     }
@@ -233,9 +236,82 @@ k_walk_items(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ cod
         u64 e = (rec / KW_RUN + 1) * KW_RUN;
         if (e > n) e = n;
         walk_item(bin, rec, true, e, codes, stems, [&](u64 r) { atomicMin(&tot->error_index, r); },
-                  [&](u64 r) { parked = (u32)r; }, &T, &B);
+                  [&](u64 r, u64 a) { if (r == a + 1) return true; parked = (u32)r; return false; }, [](u64) {}, &T, &B);
     }
     park_append(parked, park_list, park_count);
+}
+
+// ------------------------------------------------------------------ K1, chain-owning form
+//
+// k_walk_chains: every thread owns the chains whose HEADS lie in its range of `range` consecutive records
+// and walks each of them from its head to its end, wherever that is (the tail of its last chain runs
+// into the next thread's range; that thread starts at the first head of its own range, which it finds
+// from the ply / result fields alone). Compared with k_walk_runs: the only from-scratch decodes are the
+// chain heads, which need one anyway for their stem (one per ~100 records instead of one per 16), no
+// head is parked and no item rounds follow. The warp stays dense because decode-then-walk is a nested
+// loop: lanes that finish a chain early wait at the loop exit, so the warp decodes the next heads of
+// all its lanes together and walks the next chains together -- efficient as long as the chains of a
+// file are of similar length, which the density sample checks (launch site). A thread that would
+// walk more than WALK_CHAINS_CAP records (a file with giant chains) gives up and raises
+// tot->parked[1]: the host then runs the file through k_walk_runs, whose cost does not depend on
+// chain length.
+constexpr u64 WALK_CHAINS_CAP = 16384;
+__global__ void __launch_bounds__(KW_THREADS, KW_MIN_BLOCKS)
+k_walk_chains(const unsigned char* __restrict__ bin, u64 n, u64 range, u64 n_ranges, u32* __restrict__ codes,
+              u32* __restrict__ stems, CompressTotals* tot, u64* __restrict__ bleed_list)
+{
+    __shared__ StepTables T;
+    step_tables_fill(T);
+    const BleedLog B{bleed_list, &tot->bleeds};
+    for (u64 tile = blockIdx.x; tile * KW_THREADS < n_ranges; tile += gridDim.x) {
+        const u64 g = tile * KW_THREADS + threadIdx.x;
+        const u64 r0 = g * range, r1 = g < n_ranges ? (r0 + range < n ? r0 + range : n) : 0;
+        // the first chain head at or behind r0, from the field tests of isContinuation (:589-590) alone
+        u64 h = r0;
+        bool active = g < n_ranges;
+        if (active && r0 > 0) {
+            u32 prev = reinterpret_cast<const u32*>(bin + (r0 - 1) * 40)[9];
+            bool found = false;
+            while (!found && h < r1) {  // eight records per step: the loads of a step are independent
+                u32 w[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] = h + j < n ? reinterpret_cast<const u32*>(bin + (h + j) * 40)[9] : 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (!found && h + j < r1) {
+                        if (!fields_link(prev, w[j])) { found = true; h += j; }
+                        prev = w[j];
+                    }
+                }
+                if (!found) h += 8;
+            }
+            active = found;  // else the whole range continues a chain of an earlier thread
+        }
+        const u64 stop = h + WALK_CHAINS_CAP < n ? h + WALK_CHAINS_CAP : n;
+        auto on_error = [&](u64 rec) { atomicMin(&tot->error_index, rec); };
+        // Both loops are warp-uniform (every lane takes part in the votes, lanes without work idle inside):
+        // the warp opens the next chains of all its lanes together and walks them together. Left to the
+        // compiler's reconvergence, a lane that finishes its chain early runs ahead into the next head's
+        // from-scratch decode alone, and the warp pays that decode once per lane.
+        WalkState S;
+        while (__any_sync(0xffffffffu, active)) {
+            if (active) walk_open(S, bin, h, true, stop, codes, stems, on_error);
+            bool walking = active;
+            while (__any_sync(0xffffffffu, walking)) {
+                if (walking) walking = S.rec < stop && walk_step(S, bin, stop, codes, stems, on_error, &T, &B);
+            }
+            if (active) {
+                if (S.rec >= stop) {
+                    if (S.rec < n) tot->parked[1] = 1;  // gave up inside a chain: the file goes to k_walk_runs
+                    active = false;
+                } else if (S.rec < r1) {
+                    h = S.rec;  // the next chain of this range
+                } else {
+                    active = false;  // the next head belongs to the next thread
+                }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------ payload scan
@@ -779,6 +855,20 @@ static int sm_count()
     return cached[dev];
 }
 u64 walk_runs(u64 n) { return (n + KW_RUN - 1) / KW_RUN; }
+// ranges of k_walk_chains: a few per resident thread, at least 128 and at most 1024 records each
+void launch_walk_chains(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u64* bleed_list, cudaStream_t s)
+{
+    if (n == 0) return;
+    const u64 resident = (u64)sm_count() * KW_MIN_BLOCKS;
+    u64 range = (n + resident * KW_THREADS * 2 - 1) / (resident * KW_THREADS * 2);
+    range = range < 128 ? 128 : range > 1024 ? 1024 : range;
+    range = (range + 7) & ~(u64)7;
+    const u64 n_ranges = (n + range - 1) / range;
+    u64 blocks = (n_ranges + KW_THREADS - 1) / KW_THREADS;
+    if (blocks > resident) blocks = resident;
+    k_walk_chains<<<(unsigned)blocks, KW_THREADS, 0, s>>>((const unsigned char*)d_bin, n, range, n_ranges, codes, stems, tot,
+                                                         bleed_list);
+}
 int walk_run_records() { return KW_RUN; }
 // runs [run_lo, run_hi) of the n records at d_bin (the records before run_lo * KW_RUN must be there too)
 void launch_walk_runs(const void* d_bin, u64 n, u64 run_lo, u64 run_hi, u32* codes, u32* stems, CompressTotals* tot,

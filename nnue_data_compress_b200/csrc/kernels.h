@@ -19,6 +19,7 @@ void launch_walk_runs(const void* d_bin, u64 n, u64 run_lo, u64 run_hi, u32* cod
                       u32* park_list, u64* park_count, u64* bleed_list, cudaStream_t s);
 void launch_walk_items(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, const u32* items, u64 n_items,
                        u32* park_list, u64* park_count, u64* bleed_list, cudaStream_t s);
+void launch_walk_chains(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u64* bleed_list, cudaStream_t s);
 constexpr u64 BLEED_LIST_CAP = 1u << 20;  // = BLEED_CAP (link.cuh)
 void launch_write_bleed(const u32* codes, u64 n, const Agg* tile_prefix, u32* payload, const u64* bleed_list, u64 bleed_count,
                         u64 rec_base, cudaStream_t s);

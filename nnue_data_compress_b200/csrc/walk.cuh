@@ -68,113 +68,139 @@ static __device__ __noinline__ bool walk_slow(const unsigned char* __restrict__ 
     return cont;
 }
 
-// One work item: decode record `a` from scratch (the anchor; when it is a chain head also emit
-// its code 0 and its stem), then produce the codes of records a+1 .. e-1 by walking. The walk
-// stops at the first record whose ply / result fields rule out a continuation: such a record is a
-// chain head whatever its position, and park(rec) hands it to a later, dense round of items --
-// unless it directly follows the anchor: back-to-back heads (files of single positions) are
-// decoded on the spot, where all lanes of the warp do the same thing anyway.
+// The state a thread carries along a chain: the previous record's raw stream, score / move / ply words
+// and decoded position, and the next record's words already on their way from memory.
+struct WalkState {
+    u32 Wp[8], p8, p9;
+    Pos P;
+    bool valid;
+    Move pmv;               // the move of the record in front, decoded once
+    uint2 n0, n1, n2, n3, n4;  // record `rec` (software pipeline: loaded while the record before it is processed)
+    u64 rec;                // the next record to look at
+};
+
+// Opens a walk at record `a`: decodes it from scratch (the anchor; when it is a chain head also emits its
+// code 0 and its stem) and starts the loads of record a + 1 (records at or behind `e` are never touched).
 // on_error(rec) reports "Improperly encoded bin sfen" (:407-408, :441-442).
-template <typename ErrFn, typename ParkFn>
+template <typename ErrFn>
+__device__ __forceinline__ void walk_open(WalkState& S, const unsigned char* __restrict__ bin, u64 a, bool a_is_head, u64 e,
+                                          u32* __restrict__ codes, u32* __restrict__ stems, ErrFn on_error)
+{
+    {
+        const uint2* src = reinterpret_cast<const uint2*>(bin + a * 40);
+        const uint2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
+        S.Wp[0] = v0.x; S.Wp[1] = v0.y; S.Wp[2] = v1.x; S.Wp[3] = v1.y; S.Wp[4] = v2.x; S.Wp[5] = v2.y; S.Wp[6] = v3.x; S.Wp[7] = v3.y;
+        S.p8 = v4.x; S.p9 = v4.y;
+    }
+    // The out-of-line helpers take a position by reference; they get a copy of their own so that the
+    // walk's position never has its address taken and stays in registers through the loop.
+    {
+        Pos anchor;
+        S.valid = decode_record(bin, a, anchor);
+        if (a_is_head) {
+            codes[a] = 0u;
+            store_stem_cold(anchor, S.p8, S.p9, stems + a * 8);
+        }
+        S.P = anchor;
+    }
+    if (!S.valid) on_error(a);
+    S.pmv = sfmove_to_move(S.p8 >> 16);
+    S.rec = a + 1;
+    S.n0 = S.n1 = S.n2 = S.n3 = S.n4 = make_uint2(0u, 0u);
+    if (S.rec < e) {
+        const uint2* src = reinterpret_cast<const uint2*>(bin + S.rec * 40);
+        S.n0 = src[0]; S.n1 = src[1]; S.n2 = src[2]; S.n3 = src[3]; S.n4 = src[4];
+    }
+}
+
+// One record (S.rec < e): false when its ply / result fields rule out a continuation -- it is a chain head
+// whatever its position and is left untouched -- otherwise the record gets its code (and its stem when its
+// position turns out not to continue the chain) and S moves on to the next one.
+template <typename ErrFn>
+__device__ __forceinline__ bool walk_step(WalkState& S, const unsigned char* __restrict__ bin, u64 e, u32* __restrict__ codes,
+                                          u32* __restrict__ stems, ErrFn on_error, const StepTables* T, const BleedLog* B)
+{
+    const u64 rec = S.rec;
+    u32 Wc[8], c8, c9;
+    Wc[0] = S.n0.x; Wc[1] = S.n0.y; Wc[2] = S.n1.x; Wc[3] = S.n1.y; Wc[4] = S.n2.x; Wc[5] = S.n2.y; Wc[6] = S.n3.x; Wc[7] = S.n3.y;
+    c8 = S.n4.x; c9 = S.n4.y;
+    if (!S.valid || !fields_link(S.p9, c9)) return false;  // rec starts a chain
+    if (rec + 1 < e) {
+        const uint2* src = reinterpret_cast<const uint2*>(bin + (rec + 1) * 40);
+        S.n0 = src[0]; S.n1 = src[1]; S.n2 = src[2]; S.n3 = src[3]; S.n4 = src[4];
+    }
+    const Move pm = S.pmv;
+    const Move cm = sfmove_to_move(c8 >> 16);
+    const int moved = pm.from < 64 ? pos_piece_at(S.P, pm.from) : NO_PIECE;
+    const bool spliced = stream_apply_move(S.Wp, S.P, pm, moved, T);  // Wp becomes the expected stream
+    pos_do_move(S.P, pm, moved, T);                                   // Position::afterMove
+    bool cont = false;
+    if (spliced) {
+        const int end = stream_board_end(S.P);
+        u32 diff = 0;
+#pragma unroll
+        for (int k = 0; k < STREAM_BOARD_WORDS; ++k) diff |= (S.Wp[k] ^ Wc[k]) & stream_low_mask(end, k);
+        if (diff == 0) {
+            // same side to move, kings and board; castling(4) and ep(1[+6]) follow the board bits
+            const u32* cw = reinterpret_cast<const u32*>(bin + rec * 40);
+            const int wi = end >> 5;  // end <= 203: wi + 1 <= 7
+            const u32 t = __funnelshift_r(cw[wi], cw[wi + 1], end & 31);
+            const int cr = (int)(t & 15u);
+            int ep = SQ_NONE;
+            if (t & 16u) {
+                const int sq = (int)((t >> 5) & 63u);
+                if (ep_possible(S.P, sq, S.P.stm)) ep = sq;  // setEpSquare Position.h:868-872
+            }
+            cont = cr == S.P.cr && ep == S.P.ep;
+        }
+    }
+    if (!cont) {
+        bool ok;
+        Pos Q = S.P;
+        cont = walk_slow(bin, rec, Q, c8, c9, stems, ok);
+        S.P = Q;
+        if (!ok) on_error(rec);
+        S.valid = ok;
+    }
+    u32 code = 0u;
+    if (cont) {
+        int nbits;
+        u32 bleed = 0;
+        const u32 bits = encode_ply(S.P, cm, (int)(short)(c8 & 0xFFFF), (int)(short)(-(int)(short)(S.p8 & 0xFFFF)), nbits, T,
+                                    &bleed);
+        code = bits | (1u << (31 - nbits));
+        if (bleed && B) bleed_report(*B, rec, bleed);
+    }
+    codes[rec] = code;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) S.Wp[k] = Wc[k];
+    S.p8 = c8;
+    S.p9 = c9;
+    S.pmv = cm;
+    S.rec = rec + 1;
+    return true;
+}
+
+// One work item: open at record `a`, then produce the codes of records a+1 .. e-1 by walking. The walk
+// stops at the first chain head. at_head(rec, a) decides what happens to it: true = the walk goes on from it
+// (it becomes the next anchor), false = the walk ends (the caller parked it for a later round, or it
+// belongs to another thread). at_end(rec) is called when the walk reaches `e` without having met a head
+// there.
+template <typename ErrFn, typename HeadFn, typename EndFn>
 __device__ __forceinline__ void walk_item(const unsigned char* __restrict__ bin, u64 a, bool a_is_head, u64 e,
-                                          u32* __restrict__ codes, u32* __restrict__ stems, ErrFn on_error, ParkFn park,
-                                          const StepTables* T = nullptr, const BleedLog* B = nullptr)
+                                          u32* __restrict__ codes, u32* __restrict__ stems, ErrFn on_error, HeadFn at_head,
+                                          EndFn at_end, const StepTables* T = nullptr, const BleedLog* B = nullptr)
 {
     for (;;) {
-        u32 Wp[8], p8, p9;
-        {
-            const uint2* src = reinterpret_cast<const uint2*>(bin + a * 40);
-            const uint2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3], v4 = src[4];
-            Wp[0] = v0.x; Wp[1] = v0.y; Wp[2] = v1.x; Wp[3] = v1.y; Wp[4] = v2.x; Wp[5] = v2.y; Wp[6] = v3.x; Wp[7] = v3.y;
-            p8 = v4.x; p9 = v4.y;
-        }
-        // The out-of-line helpers take a position by reference; they get a copy of their own so that the
-        // walk's position P never has its address taken and stays in registers through the loop.
-        Pos P;
-        bool valid;
-        {
-            Pos anchor;
-            valid = decode_record(bin, a, anchor);
-            if (a_is_head) {
-                codes[a] = 0u;
-                store_stem_cold(anchor, p8, p9, stems + a * 8);
-            }
-            P = anchor;
-        }
-        if (!valid) on_error(a);
-        Move pmv = sfmove_to_move(p8 >> 16);  // the move of the record in front, decoded once
-        u64 rec = a + 1;
-        // software pipeline: the loads of record rec + 1 are in flight while record rec is processed
-        uint2 n0, n1, n2, n3, n4;
-        n0 = n1 = n2 = n3 = n4 = make_uint2(0u, 0u);
-        if (rec < e) {
-            const uint2* src = reinterpret_cast<const uint2*>(bin + rec * 40);
-            n0 = src[0]; n1 = src[1]; n2 = src[2]; n3 = src[3]; n4 = src[4];
-        }
-        for (; rec < e; ++rec) {
-            u32 Wc[8], c8, c9;
-            Wc[0] = n0.x; Wc[1] = n0.y; Wc[2] = n1.x; Wc[3] = n1.y; Wc[4] = n2.x; Wc[5] = n2.y; Wc[6] = n3.x; Wc[7] = n3.y;
-            c8 = n4.x; c9 = n4.y;
-            if (rec + 1 < e) {
-                const uint2* src = reinterpret_cast<const uint2*>(bin + (rec + 1) * 40);
-                n0 = src[0]; n1 = src[1]; n2 = src[2]; n3 = src[3]; n4 = src[4];
-            }
-            if (!valid || !fields_link(p9, c9)) break;  // rec starts a chain
-            const Move pm = pmv;
-            const Move cm = sfmove_to_move(c8 >> 16);
-            const int moved = pm.from < 64 ? pos_piece_at(P, pm.from) : NO_PIECE;
-            const bool spliced = stream_apply_move(Wp, P, pm, moved, T);  // Wp becomes the expected stream
-            pos_do_move(P, pm, moved, T);                               // Position::afterMove
-            bool cont = false;
-            if (spliced) {
-                const int end = stream_board_end(P);
-                u32 diff = 0;
-#pragma unroll
-                for (int k = 0; k < STREAM_BOARD_WORDS; ++k) diff |= (Wp[k] ^ Wc[k]) & stream_low_mask(end, k);
-                if (diff == 0) {
-                    // same side to move, kings and board; castling(4) and ep(1[+6]) follow the board bits
-                    const u32* cw = reinterpret_cast<const u32*>(bin + rec * 40);
-                    const int wi = end >> 5;  // end <= 203: wi + 1 <= 7
-                    const u32 t = __funnelshift_r(cw[wi], cw[wi + 1], end & 31);
-                    const int cr = (int)(t & 15u);
-                    int ep = SQ_NONE;
-                    if (t & 16u) {
-                        const int sq = (int)((t >> 5) & 63u);
-                        if (ep_possible(P, sq, P.stm)) ep = sq;  // setEpSquare Position.h:868-872
-                    }
-                    cont = cr == P.cr && ep == P.ep;
-                }
-            }
-            if (!cont) {
-                bool ok;
-                Pos Q = P;
-                cont = walk_slow(bin, rec, Q, c8, c9, stems, ok);
-                P = Q;
-                if (!ok) on_error(rec);
-                valid = ok;
-            }
-            u32 code = 0u;
-            if (cont) {
-                int nbits;
-                u32 bleed = 0;
-                const u32 bits = encode_ply(P, cm, (int)(short)(c8 & 0xFFFF),
-                                            (int)(short)(-(int)(short)(p8 & 0xFFFF)), nbits, T, &bleed);
-                code = bits | (1u << (31 - nbits));
-                if (bleed && B) bleed_report(*B, rec, bleed);
-            }
-            codes[rec] = code;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) Wp[k] = Wc[k];
-            p8 = c8;
-            p9 = c9;
-            pmv = cm;
-        }
-        if (rec >= e) return;
-        if (rec != a + 1) {
-            park(rec);
+        WalkState S;
+        walk_open(S, bin, a, a_is_head, e, codes, stems, on_error);
+        while (S.rec < e && walk_step(S, bin, e, codes, stems, on_error, T, B)) {}
+        if (S.rec >= e) {
+            at_end(S.rec);
             return;
         }
-        a = rec;
+        if (!at_head(S.rec, a)) return;
+        a = S.rec;
         a_is_head = true;
     }
 }

@@ -190,12 +190,27 @@ uint64_t sim_walk_check(const unsigned char* bin, size_t n, int run, uint64_t* p
     // (b) chain walk
     std::vector<uint64_t> queue, next;
     auto on_error = [&](u64 rec) { if (rec < err_b) err_b = rec; };
+    if (run < 0) {
+        // the chain-owning form (k_walk_chains): a range's thread walks the chains whose heads lie in it
+        const size_t range = (size_t)-run;
+        for (size_t r0 = 0; r0 < n; r0 += range) {
+            const size_t r1 = r0 + range < n ? r0 + range : n;
+            size_t h = r0;
+            if (r0 > 0)
+                while (h < r1 && fields_link(load(bin, h - 1).w[9], load(bin, h).w[9])) ++h;
+            if (h >= r1) continue;
+            walk_item(bin, h, true, n, codes_b.data(), stems_b.data(), on_error, [&](u64 rec, u64) { return rec < r1; },
+                      [](u64) {}, (r0 / range) % 2 ? tables() : nullptr);
+        }
+        run = 1;  // nothing queued
+    } else
     for (size_t r0 = 0; r0 < n; r0 += (size_t)run) {
         const size_t e = r0 + run < n ? r0 + run : n;
         bool head = r0 == 0;
         if (!head) head = !fields_link(load(bin, r0 - 1).w[9], load(bin, r0).w[9]);
         walk_item(bin, head ? r0 : r0 - 1, head, e, codes_b.data(), stems_b.data(), on_error,
-                  [&](u64 rec) { queue.push_back(rec); }, (r0 / run) % 2 ? tables() : nullptr);
+                  [&](u64 rec, u64 a) { if (rec == a + 1) return true; queue.push_back(rec); return false; }, [](u64) {},
+                  (r0 / run) % 2 ? tables() : nullptr);
     }
     while (!queue.empty()) {
         *parked += queue.size();
@@ -203,7 +218,8 @@ uint64_t sim_walk_check(const unsigned char* bin, size_t n, int run, uint64_t* p
         for (uint64_t rec : queue) {
             size_t e = (rec / run + 1) * run;
             if (e > n) e = n;
-            walk_item(bin, rec, true, e, codes_b.data(), stems_b.data(), on_error, [&](u64 r) { next.push_back(r); },
+            walk_item(bin, rec, true, e, codes_b.data(), stems_b.data(), on_error,
+                      [&](u64 r, u64 a) { if (r == a + 1) return true; next.push_back(r); return false; }, [](u64) {},
                       (rec / run) % 2 ? nullptr : tables());
         }
         queue.swap(next);

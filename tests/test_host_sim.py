@@ -47,9 +47,11 @@ def test_stream_splice_fuzz(sim):
     assert accepted > 50_000 and mm.value == 0
 
 
-@pytest.mark.parametrize("run", [1, 5, 16, 64])
+@pytest.mark.parametrize("run", [1, 5, 16, 64, -7, -128, -1000])
 def test_chain_walk_equals_record_parallel_step(sim, run):
-    """walk_item (chain-walking K1) produces the codes and stems of link_code (record-parallel K1)."""
+    """walk_item (chain-walking K1) produces the codes and stems of link_code (record-parallel K1); run > 0:
+    runs with parked heads (k_walk_runs), run < 0: threads owning the chains whose heads lie in their range
+    of -run records (k_walk_chains)."""
     for name, b in _inputs():
         parked, err = ctypes.c_uint64(), ctypes.c_uint64()
         bad = sim.sim_walk_check(b, len(b) // 40, run, ctypes.byref(parked), ctypes.byref(err))
