@@ -758,9 +758,10 @@ int decode_front(const void* d_in, size_t in_bytes, DecodePlan& P)
     WS(WS_TILE_PREFIX, (P.tiles + 2) * 8, u64, tile_prefix);
     WS(WS_TILE_FLAGS, P.tiles * (CAND_TILE / 32) * 4, u32, tile_flags);
     P.tile_prefix = tile_prefix;
-    launch_candidates_scan(d_in, in_bytes, P.tab, P.tiles, tile_count, tile_flags, C.debug_reject_mod, s);
+    WS(WS_CHUNK_SLOW, (P.chunks + 1) * 4, u32, chunk_flag);  // (the exhaustive strategy reuses the slot afterwards)
+    launch_candidates_scan(d_in, in_bytes, P.tab, P.chunks, P.tiles, tile_count, tile_flags, C.debug_reject_mod, chunk_flag, s);
     launch_exclusive_sum(tile_count, P.tiles, tile_prefix, s);
-    LAUNCHED(2, "k_candidates_scan");
+    LAUNCHED(3, "k_candidates_scan");
     u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
     CK(cudaMemcpyAsync(h_u64, tile_prefix + P.tiles, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

@@ -509,7 +509,9 @@ __device__ __forceinline__ void or_byte(u32* payload, u64 bytepos, u32 v)
 {
     atomicOr(payload + (bytepos >> 2), (v & 0xFF) << ((bytepos & 3) * 8));
 }
-// eight memory-order words at an arbitrary byte offset
+// eight memory-order words (a stem) at an arbitrary byte offset. The 32 bytes are the stem's alone: payload
+// words that lie entirely inside them are stored plainly, only the two ragged edge words, which the
+// neighbouring movetext / numPlies bytes share, are OR-ed.
 __device__ __forceinline__ void or_words8(u32* payload, u64 bytepos, const uint4& a, const uint4& b)
 {
     const u32 w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -517,12 +519,13 @@ __device__ __forceinline__ void or_words8(u32* payload, u64 bytepos, const uint4
     const int sh = (int)(bytepos & 3) * 8;
     if (sh == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) atomicOr(dst + i, w[i]);
+        for (int i = 0; i < 8; ++i) dst[i] = w[i];
     } else {
-        u32 carry = 0;
+        atomicOr(dst, w[0] << sh);
+        u32 carry = w[0] >> (32 - sh);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            atomicOr(dst + i, (w[i] << sh) | carry);
+        for (int i = 1; i < 8; ++i) {
+            dst[i] = (w[i] << sh) | carry;
             carry = w[i] >> (32 - sh);
         }
         atomicOr(dst + 8, carry);
@@ -576,7 +579,7 @@ k_write_payload(const u32* __restrict__ codes, const u32* __restrict__ stems, u6
             if (h > 0) {
                 P = M + ceil8(ob);
                 // numPlies of the chain that just ended, big-endian (:1118-1119)
-                if (!BLEED) {
+                if (!BLEED && op != 0) {
                     or_byte(payload, M - 2, op >> 8);
                     or_byte(payload, M - 1, op);
                 }
@@ -663,6 +666,31 @@ k_head_next(const u64* __restrict__ head_off, const CompressTotals* __restrict__
     const u64 target = head_off[h] + CHUNK_THRESHOLD;
     u64 lo = h + 1, hi = H;  // first index in [lo, hi) with head_off >= target, hi if none
     if (target > tot->payload_bytes) lo = hi;
+    if (lo < hi) {
+        // gallop from where the successor lies at the file's mean chain size: a handful of probes instead
+        // of log2(heads) (files of short chains have tens of millions of heads)
+        const u64 mean = tot->payload_bytes / H + 1;
+        u64 g = h + CHUNK_THRESHOLD / mean;
+        g = g < lo ? lo : g >= hi ? hi - 1 : g;
+        u64 step = 16;
+        if (head_off[g] >= target) {
+            hi = g;
+            while (hi > lo) {
+                const u64 p = hi - lo > step ? hi - step : lo;
+                if (head_off[p] >= target) hi = p; else { lo = p + 1; break; }
+                step <<= 1;
+                if (p == lo) break;
+            }
+        } else {
+            lo = g + 1;
+            while (lo < hi) {
+                const u64 p = hi - lo > step ? lo + step - 1 : hi - 1;
+                if (head_off[p] >= target) { hi = p; break; }
+                lo = p + 1;
+                step <<= 1;
+            }
+        }
+    }
     while (lo < hi) {
         const u64 mid = (lo + hi) >> 1;
         if (head_off[mid] >= target) hi = mid; else lo = mid + 1;

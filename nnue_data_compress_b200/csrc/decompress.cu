@@ -309,6 +309,37 @@ __device__ __forceinline__ u64 find_chunk(const u64* base, u64 chunks, u64 tile)
     return lo;
 }
 
+// Chunks that hold nothing but single positions (files of chain length 1: every chain is a stem with
+// numPlies == 0, 34 bytes): the reader's walk (Reader::next :1154-1190) then visits the multiples of 34,
+// whatever the bytes say, so the candidates are known without looking at every offset. One block per
+// chunk tests "numPlies == 0 at every multiple of 34"; an ordinary chunk fails at one of its first
+// stems and the block leaves at once. k_candidates_scan lists the multiples of 34 for a flagged chunk;
+// the emit kernel verifies the walk as for any other candidate set.
+constexpr int HEADS_ONLY_THREADS = 256;
+__global__ void __launch_bounds__(HEADS_ONLY_THREADS)
+k_chunk_heads_only(const unsigned char* __restrict__ in, ChunkTable tab, u32* __restrict__ chunk_flag)
+{
+    __shared__ int fail;
+    const u64 c = blockIdx.x;
+    const unsigned char* s = in + tab.start[c];
+    const u32 stems = tab.len[c] / 34;
+    if (threadIdx.x == 0) {
+        int f = stems < 4;
+        for (u32 k = 0; k < 4 && k < stems; ++k) f |= s[34 * k + 32] | s[34 * k + 33];
+        fail = f;
+    }
+    __syncthreads();
+    if (fail) {
+        if (threadIdx.x == 0) chunk_flag[c] = 0;
+        return;
+    }
+    int bad = 0;
+    for (u32 k = threadIdx.x; k < stems; k += HEADS_ONLY_THREADS) bad |= s[34 * (u64)k + 32] | s[34 * (u64)k + 33];
+    if (bad) fail = 1;  // benign race: every writer stores 1
+    __syncthreads();
+    if (threadIdx.x == 0) chunk_flag[c] = fail ? 0u : 1u;
+}
+
 // pass 0: tests every offset of the tile, stores the tile's flag bitmap (CAND_TILE / 32 words) and
 //         tile_count[tile].
 // Stage 1 looks at one byte per offset -- the high byte of the stem's rule50 field, which packEntry
@@ -317,7 +348,7 @@ __device__ __forceinline__ u64 find_chunk(const u64* base, u64 chunks, u64 tile)
 // with dense warps.
 __global__ void __launch_bounds__(CAND_THREADS)
 k_candidates_scan(const unsigned char* __restrict__ in, u64 n_in, ChunkTable tab, u32* __restrict__ tile_count,
-                  u32* __restrict__ tile_flags, u32 debug_reject_mod)
+                  u32* __restrict__ tile_flags, u32 debug_reject_mod, const u32* __restrict__ chunk_flag)
 {
     __shared__ __align__(16) unsigned char sm[CAND_TILE + 96];  // the tile from its 16-byte aligned base
     __shared__ u32 flags[CAND_TILE / 32];
@@ -331,6 +362,25 @@ k_candidates_scan(const unsigned char* __restrict__ in, u64 n_in, ChunkTable tab
     const u64 off0 = (tile - tab.tile_base[c]) * CAND_TILE;
     const unsigned char* src = in + tab.start[c] + off0;
     const u64 avail = clen - off0;  // > 0 by construction
+    if (chunk_flag[c]) {
+        // a chunk of single positions: the chains start at the multiples of 34 (at most one per bitmap word)
+        u32 mine = 0;
+        if (t < CAND_TILE / 32) {
+            const u64 base = off0 + 32ull * t;
+            const u64 m = (base + 33) / 34 * 34;
+            u32 word = 0;
+            if (m < base + 32 && m + 34 <= clen) {
+                word = 1u << (u32)(m - base);
+                if (debug_reject_mod && (u32)((m * 2654435761ull) >> 11) % debug_reject_mod == 0) word = 0;  // test hook
+            }
+            tile_flags[tile * (CAND_TILE / 32) + t] = word;
+            mine = word != 0;
+        }
+        u32 total;
+        block_exclusive_sum<CAND_THREADS>(mine, total, warp_tot);
+        if (t == 0) tile_count[tile] = total;
+        return;
+    }
     const int nload = (int)(avail < (u64)(CAND_TILE + 34) ? avail : (u64)(CAND_TILE + 34));
     const unsigned char* base = reinterpret_cast<const unsigned char*>((uintptr_t)src & ~(uintptr_t)15);
     const int delta = (int)(src - base);
@@ -768,12 +818,13 @@ void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks,
 {
     k_walk_chunks<<<1, 32, 0, s>>>((const unsigned char*)d_in, n, tab, max_chunks, world, rank);
 }
-void launch_candidates_scan(const void* d_in, u64 n_in, ChunkTable tab, u64 tiles, u32* tile_count, u32* tile_flags,
-                            u32 debug_reject_mod, cudaStream_t s)
+void launch_candidates_scan(const void* d_in, u64 n_in, ChunkTable tab, u64 chunks, u64 tiles, u32* tile_count, u32* tile_flags,
+                            u32 debug_reject_mod, u32* chunk_flag, cudaStream_t s)
 {
-    if (tiles == 0) return;
+    if (tiles == 0 || chunks == 0) return;
+    k_chunk_heads_only<<<(unsigned)chunks, HEADS_ONLY_THREADS, 0, s>>>((const unsigned char*)d_in, tab, chunk_flag);
     k_candidates_scan<<<(unsigned)tiles, CAND_THREADS, 0, s>>>((const unsigned char*)d_in, n_in, tab, tile_count, tile_flags,
-                                                             debug_reject_mod);
+                                                             debug_reject_mod, chunk_flag);
 }
 void launch_mark_conflicts(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u32* cand_cnt,
                            u64 ncand, cudaStream_t s)
