@@ -64,16 +64,89 @@ __device__ __forceinline__ bool walk_chain(const unsigned char* s, u32 bytes_aft
     return walk_chain(s, bytes_after_stem, [](const ChainCursor&) { return -1; }, emit, consumed);
 }
 
+// Staging of a chain's 40-byte records (k_emit_chains_verify). A record is 40 bytes at a 40-byte stride:
+// written as five 8-byte stores when it is made, it leaves a partial 32-byte sector at its end that
+// the next record of the chain completes a whole step later, by which time L2 has usually written
+// it back: the DRAM interface then sees 1.3x the bytes and reads back what it merges. Four records
+// starting at a record index that is a multiple of four are 160 bytes = five whole sectors, 16-byte
+// aligned at both ends: a lane gathers them in its shared-memory slot and writes them with ten 16-byte
+// stores (or, with NNP_BULK_STORE, hands them to the copy engine as one cp.async.bulk, bulk.cuh --
+// measured slower here: the copy is a uniform-datapath instruction, so a warp issues its 32 lanes'
+// copies one after the other). Records in front of the first multiple of four and behind
+// the last whole group of a chain go out with plain stores.
+constexpr int OUT_GROUP = 4;
+constexpr int OUT_SLOT_BYTES = OUT_GROUP * 40 + 16;  // + 16: the slots of a quarter-warp start in different banks
+struct OutStage {
+    unsigned char* slot;  // 16-byte aligned, OUT_GROUP * 40 bytes; nullptr = plain stores only
+    u64 first;            // record index of slot record 0
+    int staged;
+};
+__device__ __forceinline__ void store_record(unsigned char* out, u64 rec, const u32 (&w)[8], u32 w8, u32 w9)
+{
+    uint2* d = reinterpret_cast<uint2*>(out + rec * 40);
+    d[0] = make_uint2(w[0], w[1]);
+    d[1] = make_uint2(w[2], w[3]);
+    d[2] = make_uint2(w[4], w[5]);
+    d[3] = make_uint2(w[6], w[7]);
+    d[4] = make_uint2(w8, w9);
+}
+// what is left in the slot at the end of a chain (fewer than OUT_GROUP records)
+__device__ __forceinline__ void out_stage_finish(OutStage& st, unsigned char* out)
+{
+    for (int m = 0; m < st.staged; ++m) {
+        const uint2* sp = reinterpret_cast<const uint2*>(st.slot + m * 40);
+        uint2* d = reinterpret_cast<uint2*>(out + (st.first + m) * 40);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) d[i] = sp[i];
+    }
+    st.staged = 0;
+#if defined(NNP_BULK_STORE) && defined(__CUDACC__)
+    if (st.slot) bulk_store_wait_read();  // the slot must outlive the copy engine's reads of it
+#endif
+}
+__device__ __forceinline__ void out_stage_put(OutStage& st, unsigned char* out, u64 rec, const u32 (&w)[8], u32 w8, u32 w9)
+{
+    if (!st.slot || (st.staged == 0 && (rec & (OUT_GROUP - 1)))) {  // no staging, or in front of a group boundary
+        store_record(out, rec, w, w8, w9);
+        return;
+    }
+    if (st.staged == 0) {
+#if defined(NNP_BULK_STORE) && defined(__CUDACC__)
+        bulk_store_wait_read();  // the copy engine is done with the slot's previous content
+#endif
+        st.first = rec;
+    }
+    uint2* d = reinterpret_cast<uint2*>(st.slot + st.staged * 40);
+    d[0] = make_uint2(w[0], w[1]);
+    d[1] = make_uint2(w[2], w[3]);
+    d[2] = make_uint2(w[4], w[5]);
+    d[3] = make_uint2(w[6], w[7]);
+    d[4] = make_uint2(w8, w9);
+    if (++st.staged == OUT_GROUP) {
+#if defined(NNP_BULK_STORE) && defined(__CUDACC__)
+        bulk_store(out + st.first * 40, st.slot, OUT_GROUP * 40);
+#else
+        const uint4* sp = reinterpret_cast<const uint4*>(st.slot);
+        uint4* g = reinterpret_cast<uint4*>(out + st.first * 40);  // 160 * (first / 4): 32-byte aligned
+#pragma unroll
+        for (int i = 0; i < OUT_GROUP * 40 / 16; ++i) g[i] = sp[i];
+#endif
+        st.staged = 0;
+    }
+}
+
 // walk_chain writing 40-byte .bin records rec0, rec0 + 1, ... (below rec_limit). The Huffman stream
 // of the position is carried along the chain (stream.cuh): built once for the chain head, then
-// spliced per move. `col` is the thread's 8-word scratch column in shared memory.
+// spliced per move. `col` is the thread's 8-word scratch column in shared memory; `slot` (optional)
+// its record staging slot for bulk stores.
 __device__ __forceinline__ bool emit_chain_bin(const unsigned char* s, u32 bytes_after_stem, unsigned char* out, u64 rec0,
                                                u64 rec_limit, u32* col, int stride, u32& consumed,
-                                               const StepTables* T = nullptr)
+                                               const StepTables* T = nullptr, unsigned char* slot = nullptr)
 {
     u32 W[8];
     bool spliced = false;
-    return walk_chain(
+    OutStage st{slot, 0, 0};
+    const bool ok = walk_chain(
         s, bytes_after_stem,
         [&](const ChainCursor& cc) {
             const int moved = pos_piece_at(cc.pos, cc.mv.from);
@@ -88,14 +161,11 @@ __device__ __forceinline__ bool emit_chain_bin(const unsigned char* s, u32 bytes
             // trainingDataEntryToPackedSfenValue (:570-585): score, move, gamePly, result, padding 0xFF
             const u32 w8 = ((u32)cc.score & 0xFFFFu) | (move_to_sfmove(cc.mv) << 16);
             const u32 w9 = ((u32)cc.ply & 0xFFFFu) | (((u32)cc.result & 0xFFu) << 16) | 0xFF000000u;
-            uint2* d = reinterpret_cast<uint2*>(out + (rec0 + k) * 40);
-            d[0] = make_uint2(w[0], w[1]);
-            d[1] = make_uint2(w[2], w[3]);
-            d[2] = make_uint2(w[4], w[5]);
-            d[3] = make_uint2(w[6], w[7]);
-            d[4] = make_uint2(w8, w9);
+            out_stage_put(st, out, rec0 + k, w, w8, w9);
         },
         consumed, T);
+    if (slot) out_stage_finish(st, out);
+    return ok;
 }
 
 }  // namespace nnp

@@ -14,6 +14,7 @@
 #include "host_sim.h"  // tests/host_sim: CPU stand-ins for the intrinsics, test harness only
 #else
 #include <cuda_runtime.h>
+#include "bulk.cuh"
 #endif
 
 namespace nnp {
@@ -187,13 +188,19 @@ static __global__ void k_step_tables_init()
 {
     for (int i = threadIdx.x; i < STEP_TABLE_ROWS; i += blockDim.x) step_tables_entry(g_step_tables, i);
 }
-static_assert(sizeof(StepTables) % 16 == 0, "copied as uint4");
-__device__ __forceinline__ void step_tables_fill(StepTables& T)  // whole block; call before any early return
+static_assert(sizeof(StepTables) % 16 == 0, "moved as one bulk copy");
+// whole block; call before any early return. One thread asks the copy engine for the 4 KB (cp.async.bulk,
+// bulk.cuh); everybody waits on the mbarrier the copy completes on.
+__device__ __forceinline__ void step_tables_fill(StepTables& T)
 {
-    const uint4* src = reinterpret_cast<const uint4*>(&g_step_tables);
-    uint4* dst = reinterpret_cast<uint4*>(&T);
-    for (int i = threadIdx.x; i < (int)(sizeof(StepTables) / 16); i += blockDim.x) dst[i] = src[i];
+    __shared__ alignas(8) unsigned long long bar;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (unsigned)sizeof(StepTables));
+        bulk_load(&T, &g_step_tables, (unsigned)sizeof(StepTables), &bar);
+    }
+    mbar_wait(&bar, 0);
 }
 #endif
 __device__ __forceinline__ u64 bishop_attacks(int sq, u64 occ, const StepTables* T)

@@ -701,6 +701,17 @@ k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const
 {
     __shared__ u32 scratch[8 * EMITC_THREADS];
     __shared__ StepTables T;
+    // Record staging (chain.cuh: OutStage) is a build option, -DNNP_OUT_STAGE (160-byte vector drain) or
+    // -DNNP_OUT_STAGE -DNNP_BULK_STORE (cp.async.bulk): both bring the kernel's DRAM traffic from 1.59x to
+    // 1.11x / 1.17x of its algorithmic bytes and both make it 5-6 % slower, because the kernel is bound by
+    // the integer pipe, not by memory (100 M positions: 4.80 ms plain, 5.05 ms staged, 5.09 ms bulk).
+#ifdef NNP_OUT_STAGE
+    __shared__ alignas(16) unsigned char stage[EMITC_THREADS * OUT_SLOT_BYTES];
+    // (an output buffer that is only 8-byte aligned keeps the plain stores)
+    unsigned char* const slot = (reinterpret_cast<uintptr_t>(out) & 15) ? nullptr : stage + threadIdx.x * OUT_SLOT_BYTES;
+#else
+    unsigned char* const slot = nullptr;
+#endif
     step_tables_fill(T);
     const u64 i = cand_lo + (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
     if (i >= cand_hi) return;
@@ -710,7 +721,7 @@ k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const
     const u64 rec0 = cand_rec[i];
     const unsigned char* s = in + tab.start[c] + off;
     u32 consumed = 0;
-    bool ok = emit_chain_bin(s, clen - off - 34, out, rec0, ~0ull, scratch + threadIdx.x, EMITC_THREADS, consumed, &T);
+    bool ok = emit_chain_bin(s, clen - off - 34, out, rec0, ~0ull, scratch + threadIdx.x, EMITC_THREADS, consumed, &T, slot);
     if (!reader_links_hold(cand_chunk, cand_off, cand_cnt, ncand, i, off + consumed, clen)) ok = false;
     if (!ok) atomicAdd(violations, 1ull);
 }
