@@ -10,6 +10,7 @@ namespace nnp {
 struct ChainCursor {
     Pos pos;
     Move mv;
+    int moved;  // the piece on mv.from in pos when the ply decoder looked it up, else -1
     int score, ply, result;
     int last_score;
     u32 num_plies;
@@ -19,6 +20,7 @@ __device__ __forceinline__ void chain_open(const unsigned char* s, ChainCursor& 
 {
     stem_unpack([&](int i) { return (u32)s[i]; }, c.pos, c.mv, c.score, c.ply, c.result);
     c.num_plies = ((u32)s[32] << 8) | (u32)s[33];
+    c.moved = -1;
     c.last_score = (int)(short)(-c.score);  // PackedMoveScoreListReader ctor (:618)
 }
 
@@ -30,8 +32,10 @@ __device__ __forceinline__ bool chain_step(ChainCursor& c, BitReader& r, bool st
     pos_do_move(c.pos, c.mv, moved, T);
     Move m;
     int sc;
-    if (!decode_ply(r, c.pos, c.last_score, m, sc, strict, T)) return false;
+    int looked_up = -1;
+    if (!decode_ply(r, c.pos, c.last_score, m, sc, strict, T, &looked_up)) return false;
     c.mv = m;
+    c.moved = looked_up;
     c.score = sc;
     c.ply = (c.ply + 1) & 0xFFFF;
     c.result = (int)(short)(-c.result);
@@ -149,7 +153,7 @@ __device__ __forceinline__ bool emit_chain_bin(const unsigned char* s, u32 bytes
     const bool ok = walk_chain(
         s, bytes_after_stem,
         [&](const ChainCursor& cc) {
-            const int moved = pos_piece_at(cc.pos, cc.mv.from);
+            const int moved = cc.moved >= 0 ? cc.moved : pos_piece_at(cc.pos, cc.mv.from);
             spliced = stream_apply_move(W, cc.pos, cc.mv, moved, T);
             return moved;
         },

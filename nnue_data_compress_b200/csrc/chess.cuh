@@ -238,6 +238,8 @@ struct Pos {
 struct Move {
     int from, to, type, promo;  // promo = piece code or NO_PIECE
 };
+// (the piece standing on `from`, which decode_ply / encode_ply look up anyway, travels next to the move
+// as a separate `moved` value: -1 = not looked up)
 
 __device__ __forceinline__ void pos_clear(Pos& p)  // Position() Position.h:828-836
 {
@@ -761,13 +763,14 @@ __device__ __forceinline__ u64 pawn_destinations(const Pos& p, int from, u64 our
 // knows, so such a ply is reported through `bleed` (packed raw ids and widths, 0 = none) and the
 // writer ORs the stray bits in (k_write_payload<true>).
 __device__ __forceinline__ u32 encode_ply(const Pos& p, const Move& mv, int score, int last_score, int& nbits,
-                                          const StepTables* T = nullptr, u32* bleed = nullptr)
+                                          const StepTables* T = nullptr, u32* bleed = nullptr, int* moved_out = nullptr)
 {
     int stm = p.stm;
     u64 ours = pos_occ(p, stm), theirs = pos_occ(p, stm ^ 1);
     u64 occ = ours | theirs;
     u32 piece_id = (u32)popc64(ours & before64(mv.from));
     int pc = pos_piece_at(p, mv.from);
+    if (moved_out) *moved_out = pc;
     int pt = pc >> 1;
     // every mover type yields a destination set; counting it and ranking the destination happen
     // once behind the branches (a warp usually holds movers of all types)
@@ -909,7 +912,7 @@ struct BitReader {
 // `strict` rejects ids the reference encoder can never produce (used by the speculative
 // chain discovery to kill false candidates early); returns false on such an id.
 __device__ __forceinline__ bool decode_ply(BitReader& r, const Pos& p, int& last_score, Move& mv, int& score, bool strict,
-                                           const StepTables* T = nullptr)
+                                           const StepTables* T = nullptr, int* moved_out = nullptr)
 {
     int stm = p.stm;
     u64 ours = pos_occ(p, stm), theirs = pos_occ(p, stm ^ 1);
@@ -921,7 +924,9 @@ __device__ __forceinline__ bool decode_ply(BitReader& r, const Pos& p, int& last
     // an id beyond the count (corrupted movetext; the reference indexes its lookup table out of range,
     // ArithmeticUtility.h:186-209) selects square 0, as the oracle does
     int from = piece_id < n_ours ? nth_set_bit(ours, piece_id) : 0;
-    int pt = pos_piece_at(p, from) >> 1;
+    const int pc_from = pos_piece_at(p, from);
+    int pt = pc_from >> 1;
+    if (moved_out) *moved_out = pc_from;
     mv.from = from;
     mv.type = MT_NORMAL;
     mv.promo = NO_PIECE;
@@ -954,6 +959,7 @@ __device__ __forceinline__ bool decode_ply(BitReader& r, const Pos& p, int& last
         mv.from = stm == WHITE ? 4 : 60;  // Move::castle Chess.h:1029-1040
         mv.to = (stm == WHITE ? 0 : 56) + (is_long ? 0 : 7);
         mv.type = MT_CASTLE;
+        if (moved_out && mv.from != from) *moved_out = -1;  // (a corrupted stream: the king is not on its home square)
     } else {
         mv.to = id < n ? nth_set_bit(dest, promotes ? id >> 2 : id) : 0;
         if (promotes) {

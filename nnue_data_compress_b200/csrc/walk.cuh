@@ -75,6 +75,7 @@ struct WalkState {
     Pos P;
     bool valid;
     Move pmv;               // the move of the record in front, decoded once
+    int pmoved;             // the piece on pmv.from in P if the encoder looked it up, else -1
     uint2 n0, n1, n2, n3, n4;  // record `rec` (software pipeline: loaded while the record before it is processed)
     u64 rec;                // the next record to look at
 };
@@ -105,6 +106,7 @@ __device__ __forceinline__ void walk_open(WalkState& S, const unsigned char* __r
     }
     if (!S.valid) on_error(a);
     S.pmv = sfmove_to_move(S.p8 >> 16);
+    S.pmoved = -1;
     S.rec = a + 1;
     S.n0 = S.n1 = S.n2 = S.n3 = S.n4 = make_uint2(0u, 0u);
     if (S.rec < e) {
@@ -131,7 +133,7 @@ __device__ __forceinline__ bool walk_step(WalkState& S, const unsigned char* __r
     }
     const Move pm = S.pmv;
     const Move cm = sfmove_to_move(c8 >> 16);
-    const int moved = pm.from < 64 ? pos_piece_at(S.P, pm.from) : NO_PIECE;
+    const int moved = S.pmoved >= 0 ? S.pmoved : pm.from < 64 ? pos_piece_at(S.P, pm.from) : NO_PIECE;
     const bool spliced = stream_apply_move(S.Wp, S.P, pm, moved, T);  // Wp becomes the expected stream
     pos_do_move(S.P, pm, moved, T);                                   // Position::afterMove
     bool cont = false;
@@ -163,11 +165,12 @@ __device__ __forceinline__ bool walk_step(WalkState& S, const unsigned char* __r
         S.valid = ok;
     }
     u32 code = 0u;
+    int cmoved = -1;
     if (cont) {
         int nbits;
         u32 bleed = 0;
         const u32 bits = encode_ply(S.P, cm, (int)(short)(c8 & 0xFFFF), (int)(short)(-(int)(short)(S.p8 & 0xFFFF)), nbits, T,
-                                    &bleed);
+                                    &bleed, &cmoved);
         code = bits | (1u << (31 - nbits));
         if (bleed && B) bleed_report(*B, rec, bleed);
     }
@@ -177,6 +180,7 @@ __device__ __forceinline__ bool walk_step(WalkState& S, const unsigned char* __r
     S.p8 = c8;
     S.p9 = c9;
     S.pmv = cm;
+    S.pmoved = cmoved;
     S.rec = rec + 1;
     return true;
 }
