@@ -633,7 +633,7 @@ k_resolve_chunks(ChunkTable tab, const u64* __restrict__ tile_prefix, const u32*
 // ------------------------------------------------------------------ record emission
 
 #ifndef EMIT_MIN_BLOCKS
-#define EMIT_MIN_BLOCKS 6
+#define EMIT_MIN_BLOCKS 5
 #endif
 constexpr int EMITC_THREADS = 128;
 __global__ void __launch_bounds__(EMITC_THREADS, EMIT_MIN_BLOCKS)
