@@ -940,7 +940,7 @@ def main():
         # scaled from the capture's position count to this run's (both recorded in profiles/traffic.json)
         t = traffic.get(kernel)
         if not t or t.get("plies") != args.plies:
-            return None
+            return None  # no capture of this kernel at this chain length
         return int((t["dram_read_bytes"] + t["dram_write_bytes"]) * (n_pos / t["positions"]))
 
     def roof(kernel, ms, share_of):
