@@ -25,7 +25,7 @@ enum WsSlot {
     WS_CODES = 0, WS_STEMS, WS_TILE_AGG, WS_PAYLOAD, WS_HEAD_OFF, WS_CHUNK_OFF, WS_TOTALS,
     WS_CHUNK_START, WS_CHUNK_LEN, WS_CHUNK_TILE_BASE, WS_CHUNK_INFO, WS_TILE_COUNT, WS_TILE_PREFIX,
     WS_CAND_CHUNK, WS_CAND_OFF, WS_CAND_NEXT, WS_CAND_BASE, WS_CAND_CNT, WS_CHUNK_COUNT, WS_CHUNK_SLOW, WS_CHUNK_BASE,
-    WS_DTOTALS, WS_AGG_TOP, WS_HEAD_NEXT, WS_PARK_A, WS_PARK_B, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_BLEED, WS_COUNT
+    WS_DTOTALS, WS_AGG_TOP, WS_HEAD_NEXT, WS_PARK_A, WS_PARK_B, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_BLEED, WS_WALK, WS_COUNT
 };
 
 // codes/stems of n records -> payload scan and payload write; leaves the headerless payload stream
@@ -736,7 +736,8 @@ int decode_front(const void* d_in, size_t in_bytes, DecodePlan& P)
         P.tab.len = len;
         P.tab.tile_base = tile_base;
         P.tab.info = d_info;
-        launch_walk_chunks(d_in, in_bytes, P.tab, table_cap, 1, 0, s);
+        WS(WS_WALK, walk_scratch_bytes(), unsigned char, walk_scratch);
+        launch_walk_chunks(d_in, in_bytes, P.tab, table_cap, 1, 0, walk_scratch, s);
         LAUNCHED(1, "k_walk_chunks");
         CK(cudaMemcpyAsync(h_info, d_info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -992,7 +993,8 @@ int chunk_range_dev(const void* d_in, size_t in_bytes, int world, int rank, nnp_
         tab.len = len;
         tab.tile_base = tile_base;
         tab.info = d_info;
-        launch_walk_chunks(d_in, in_bytes, tab, table_cap, (u32)world, (u32)rank, s);
+        WS(WS_WALK, walk_scratch_bytes(), unsigned char, walk_scratch);
+        launch_walk_chunks(d_in, in_bytes, tab, table_cap, (u32)world, (u32)rank, walk_scratch, s);
         LAUNCHED(1, "k_walk_chunks");
         CK(cudaMemcpyAsync(h_info, d_info, sizeof(ChunkInfo), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -1646,6 +1648,7 @@ int nnp_debug_config(const char* key, uint64_t value)
     else if (!std::strcmp(key, "k1_walk")) g_ctx.debug_k1_walk = value != 0;
     else if (!std::strcmp(key, "k1_runs")) g_ctx.debug_k1_runs = value != 0;
     else if (!std::strcmp(key, "reject_mod")) g_ctx.debug_reject_mod = (uint32_t)value;
+    else if (!std::strcmp(key, "walk_seg_bytes")) set_walk_segment_bytes(value);
     else return NNP_ERR_BAD_ARG;
     return NNP_OK;
 }

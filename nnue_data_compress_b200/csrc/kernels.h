@@ -55,7 +55,9 @@ struct ChunkTable {
     ChunkInfo* info;
 };
 
-void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks, u32 world, u32 rank, cudaStream_t s);
+size_t walk_scratch_bytes();
+void set_walk_segment_bytes(u64 v);  // test hook (0 = default)
+void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks, u32 world, u32 rank, void* scratch, cudaStream_t s);
 void launch_candidates_scan(const void* d_in, u64 n_in, ChunkTable tab, u64 chunks, u64 tiles, u32* tile_count, u32* tile_flags,
                             u32 debug_reject_mod, u32* chunk_flag, cudaStream_t s);
 void launch_mark_conflicts(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u32* cand_cnt,

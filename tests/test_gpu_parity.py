@@ -438,3 +438,46 @@ def test_illegal_stored_moves_bleed_like_the_reference(nnp):
             assert nnp.bin_to_binpack(data) == want
         finally:
             L.nnp_debug_config(key, 0)
+
+
+def test_segmented_header_walk(nnp):
+    """The chunk headers of large files are walked in parallel segments (k_seg_find / k_seg_walk) and only
+    believed when every segment's walk ends on the next segment's start; tiny segments force that path on
+    small files, and a broken header or a "BINP" inside a payload must leave the file to the sequential walk."""
+    import numpy as np
+    import torch
+
+    L = nnp.lib()
+    b = nnp.generate_bin(1_500_000, 2, 41)  # ~25 chunks
+    pack = nnp.bin_to_binpack(b)
+    rc, want = oracle_convert(BINPACK_TO_BIN, pack)
+    assert rc == 0 and pack.count(b"BINP") >= 20
+    L.nnp_debug_config(b"walk_seg_bytes", 1 << 20)
+    try:
+        assert nnp.binpack_to_bin(pack) == want
+        d = torch.from_numpy(np.frombuffer(pack, dtype=np.uint8).copy()).cuda()
+        for world in (1, 3, 8):
+            pieces = []
+            for r in range(world):
+                out = torch.empty(len(want) + 64, dtype=torch.uint8, device="cuda")
+                got, rng = nnp.shard_decompress(d, world, r, out)
+                pieces.append(out[:got].cpu().numpy().tobytes())
+            assert b"".join(pieces) == want
+        # a false header inside a payload, behind a segment boundary: the walk in front of it steps over it
+        fake = bytearray(pack)
+        at = (len(pack) // 2 // 16) * 16 + 64
+        fake[at:at + 8] = b"BINP" + (40).to_bytes(4, "little")
+        rc, want2 = oracle_convert(BINPACK_TO_BIN, bytes(fake))
+        if rc == 0:
+            assert nnp.binpack_to_bin(bytes(fake)) == want2
+        # a broken header: the reference's error and partial output
+        bad = bytearray(pack)
+        third = [i for i in range(len(pack) - 4) if pack[i:i + 4] == b"BINP"][12]
+        bad[third] = ord("X")
+        rc, want3 = oracle_convert(BINPACK_TO_BIN, bytes(bad))
+        assert rc == -1
+        with pytest.raises(nnp.NnpError) as ei:
+            nnp.binpack_to_bin(bytes(bad))
+        assert ei.value.status == -1 and ei.value.partial == want3
+    finally:
+        L.nnp_debug_config(b"walk_seg_bytes", 0)
