@@ -717,6 +717,7 @@ struct DecodePlan {
     u64* chunk_base = nullptr;
     u64* chunk_tbase = nullptr;
     u64* tile_prefix = nullptr;
+    u32* tile_flags = nullptr;
     DecompressTotals* d_tot = nullptr;
 };
 
@@ -759,6 +760,7 @@ int decode_front(const void* d_in, size_t in_bytes, DecodePlan& P)
     WS(WS_TILE_PREFIX, (P.tiles + 2) * 8, u64, tile_prefix);
     WS(WS_TILE_FLAGS, P.tiles * (CAND_TILE / 32) * 4, u32, tile_flags);
     P.tile_prefix = tile_prefix;
+    P.tile_flags = tile_flags;
     WS(WS_CHUNK_SLOW, (P.chunks + 1) * 4, u32, chunk_flag);  // (the exhaustive strategy reuses the slot afterwards)
     launch_candidates_scan(d_in, in_bytes, P.tab, P.chunks, P.tiles, tile_count, tile_flags, C.debug_reject_mod, chunk_flag, s);
     launch_exclusive_sum(tile_count, P.tiles, tile_prefix, s);
@@ -780,7 +782,8 @@ int decode_front(const void* d_in, size_t in_bytes, DecodePlan& P)
 // Exhaustive strategy after decode_front: probe every candidate, resolve the reader's walk per
 // chunk (false candidates are skipped, unresolvable chunks go to the sequential kernels) and
 // produce the per-chunk position counts (and text sizes when `text`).
-int decode_plan(const void* d_in, size_t in_bytes, bool text, DecodePlan& P, bool have_front = false)
+// `have_next`: WS_CAND_NEXT already holds the chain ends (the optimistic walk wrote them): no probe pass
+int decode_plan(const void* d_in, size_t in_bytes, bool text, DecodePlan& P, bool have_front = false, bool have_next = false)
 {
     Context& C = g_ctx;
     cudaStream_t s = C.stream;
@@ -813,7 +816,7 @@ int decode_plan(const void* d_in, size_t in_bytes, bool text, DecodePlan& P, boo
     P.cand_tbase = cand_tbase; P.chunk_tbase = chunk_tbase;
     P.chunk_count = chunk_count; P.chunk_slow = chunk_slow; P.chunk_base = chunk_base;
 
-    launch_probe_chains(d_in, P.tab, cand_chunk, cand_off, P.ncand, cand_next, cand_cnt, cand_tlen, s);
+    if (!have_next) launch_probe_chains(d_in, P.tab, cand_chunk, cand_off, P.ncand, cand_next, cand_cnt, cand_tlen, s);
     launch_resolve_chunks(P.tab, P.chunks, tile_prefix, cand_off, cand_next, cand_cnt, cand_base, chunk_count, chunk_slow,
                           cand_tlen, cand_tbase, chunk_tbytes, s);
     launch_slow_count(d_in, P.tab, P.chunks, chunk_slow, chunk_count, chunk_tbytes, d_tot, s);
@@ -858,6 +861,9 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
     if (rc != NNP_OK) return rc;
     DecompressTotals* h_tot = reinterpret_cast<DecompressTotals*>((char*)C.pinned + 512);
     u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+    const u64* placed_rec = nullptr;
+    const u32* placed_next = nullptr;
+    bool repaired = false;
 
     // Optimistic strategy: on files the reference wrote, the candidates are exactly the chains, so
     // every chain can be emitted at the record index its header count implies while the kernel
@@ -866,6 +872,9 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
         WS(WS_CAND_REC, (P.ncand + 2) * 8, u64, cand_rec);
         WS(WS_LSUM_A, (large_sum_tiles(P.ncand) + 1) * 4, u32, lsum_a);
         WS(WS_LSUM_B, (large_sum_tiles(P.ncand) + 2) * 8, u64, lsum_b);
+        WS(WS_CAND_NEXT, (P.ncand + 1) * 4, u32, cand_next);
+        placed_rec = cand_rec;
+        placed_next = cand_next;
         launch_mark_conflicts(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_cnt, P.ncand, s);
         launch_exclusive_sum_large(P.cand_cnt, P.ncand, cand_rec, lsum_a, lsum_b, s);
         LAUNCHED(4, "candidate record offsets");
@@ -875,11 +884,14 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
         C.last_candidates = P.ncand;
         C.last_tentative_positions = positions;
         C.last_violations = ~0ull;
-        if (positions * 40 <= out_cap) {
+        // (a false candidate's count may push the tentative total past the buffer: the walk is attempted
+        // anyway, records behind the buffer's end are not written, and the repair below finds the real total)
+        const u64 rec_limit = out_cap / 40;
+        {
             CK(cudaEventRecord(C.ev[1], s));
             launch_check_chunks(P.tab, P.chunks, P.tile_prefix, &P.d_tot->violations, s);
             LAUNCHED(1, "k_check_chunks");
-            if (C.pipe_dst && positions * 40 <= C.pipe_dst_cap) {
+            if (C.pipe_dst && positions * 40 <= C.pipe_dst_cap && positions * 40 <= out_cap) {
                 // host output: emit in groups of chains and copy every group's records out while the
                 // next group is decoded (the record index of a chain is the prefix sum cand_rec)
                 constexpr u64 PIPE_GROUPS = 16;
@@ -893,7 +905,7 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
                 for (u64 g = 0; g < n_groups; ++g) {
                     const u64 lo = g * per, hi = lo + per < P.ncand ? lo + per : P.ncand;
                     launch_emit_chains_verify(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_cnt, cand_rec, P.ncand, lo, hi, d_out,
-                                              &P.d_tot->violations, s);
+                                              rec_limit, cand_next, &P.d_tot->violations, s);
                     LAUNCHED(1, "k_emit_chains_verify");
                     CK(cudaEventRecord(C.pipe_ev[g % 16], s));
                     CK(cudaStreamWaitEvent(C.copy_stream, C.pipe_ev[g % 16], 0));
@@ -907,7 +919,7 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
                 C.pipe_dst_done = true;
             } else {
                 launch_emit_chains_verify(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_cnt, cand_rec, P.ncand, 0, P.ncand, d_out,
-                                          &P.d_tot->violations, s);
+                                          rec_limit, cand_next, &P.d_tot->violations, s);
                 LAUNCHED(1, "k_emit_chains_verify");
             }
             CK(cudaEventRecord(C.ev[2], s));
@@ -931,9 +943,16 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
         }
         ++C.optimistic_misses;
         C.pipe_dst_done = false;  // whatever was copied out is overwritten by the exhaustive result
+        // Repair instead of starting over: every candidate was decoded by the walk above, so its chain end
+        // is known (cand_next) and the reader's walk can be resolved per chunk without a probe pass; the
+        // header counts that k_mark_conflicts zeroed are listed again; and chains that already lie where the
+        // resolved walk wants them (everything in front of the first false candidate) are not written twice.
+        launch_candidates_list(d_in, P.tab, P.tiles, P.tile_flags, P.tile_prefix, P.cand_chunk, P.cand_off, P.cand_cnt, s);
+        LAUNCHED(1, "k_candidates_list");
+        repaired = true;
     }
 
-    rc = decode_plan(d_in, in_bytes, false, P, true);
+    rc = decode_plan(d_in, in_bytes, false, P, true, repaired);
     if (rc != NNP_OK) return rc;
     CK(cudaEventRecord(C.ev[1], s));
     if (!d_out) {
@@ -945,7 +964,8 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
     C.last_positions = positions;
     if (positions * 40 > out_cap) return NNP_ERR_CAPACITY;
     if (P.chunks > 0) {
-        launch_emit_chains(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_base, P.ncand, P.chunk_base, d_out, P.d_tot, s);
+        launch_emit_chains(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_base, P.ncand, P.chunk_base, d_out, P.d_tot,
+                           repaired ? placed_rec : nullptr, repaired ? placed_next : nullptr, s);
         launch_slow_emit(d_in, P.tab, P.chunks, P.chunk_slow, P.chunk_base, d_out, s);
         LAUNCHED(2, "k_emit_chains");
     }

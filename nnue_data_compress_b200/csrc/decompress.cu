@@ -770,7 +770,8 @@ constexpr int EMITC_THREADS = 128;
 __global__ void __launch_bounds__(EMITC_THREADS, EMIT_MIN_BLOCKS)
 k_emit_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
               const u32* __restrict__ cand_off, const u32* __restrict__ cand_base, u64 ncand,
-              const u64* __restrict__ chunk_base, unsigned char* __restrict__ out, DecompressTotals* tot)
+              const u64* __restrict__ chunk_base, unsigned char* __restrict__ out, DecompressTotals* tot,
+              const u64* __restrict__ placed_rec, const u32* __restrict__ placed_next)
 {
     __shared__ u32 scratch[8 * EMITC_THREADS];
     const u64 i = (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
@@ -783,6 +784,8 @@ k_emit_chains(const unsigned char* __restrict__ in, ChunkTable tab, const u32* _
         return;
     }
     const u64 rec0 = chunk_base[c] + b;
+    // after a failed optimistic walk: the chain was decoded then and already lies where it belongs
+    if (placed_rec && placed_rec[i] == rec0 && placed_next[i] != 0xFFFFFFFFu) return;
     const unsigned char* s = in + tab.start[c] + off;
     u32 consumed = 0;
     const bool ok = emit_chain_bin(s, tab.len[c] - off - 34, out, rec0, ~0ull, scratch + threadIdx.x, EMITC_THREADS, consumed);
@@ -828,7 +831,8 @@ k_mark_conflicts(const unsigned char* __restrict__ in, ChunkTable tab, const u32
 __global__ void __launch_bounds__(EMITC_THREADS, EMIT_MIN_BLOCKS)
 k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
                      const u32* __restrict__ cand_off, const u32* __restrict__ cand_cnt, const u64* __restrict__ cand_rec,
-                     u64 ncand, u64 cand_lo, u64 cand_hi, unsigned char* __restrict__ out, u64* __restrict__ violations)
+                     u64 ncand, u64 cand_lo, u64 cand_hi, unsigned char* __restrict__ out, u64 rec_limit,
+                     u32* __restrict__ cand_next, u64* __restrict__ violations)
 {
     __shared__ u32 scratch[8 * EMITC_THREADS];
     __shared__ StepTables T;
@@ -846,13 +850,20 @@ k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const
     step_tables_fill(T);
     const u64 i = cand_lo + (u64)blockIdx.x * EMITC_THREADS + threadIdx.x;
     if (i >= cand_hi) return;
-    if (cand_cnt[i] == 0) return;  // marked by k_mark_conflicts
+    if (cand_cnt[i] == 0) {  // marked by k_mark_conflicts
+        cand_next[i] = 0xFFFFFFFFu;
+        return;
+    }
     const u32 c = cand_chunk[i], off = cand_off[i];
     const u32 clen = tab.len[c];
     const u64 rec0 = cand_rec[i];
     const unsigned char* s = in + tab.start[c] + off;
     u32 consumed = 0;
-    bool ok = emit_chain_bin(s, clen - off - 34, out, rec0, ~0ull, scratch + threadIdx.x, EMITC_THREADS, consumed, &T, slot);
+    bool ok = emit_chain_bin(s, clen - off - 34, out, rec0, rec_limit, scratch + threadIdx.x, EMITC_THREADS, consumed, &T, slot);
+    // where the chain ends: should a link not hold anywhere, the reader's walk is resolved from these
+    // (k_resolve_chunks) without decoding every candidate a second time
+    cand_next[i] = ok ? off + consumed : 0xFFFFFFFFu;
+    if (rec0 + cand_cnt[i] > rec_limit) ok = false;  // (a false candidate's count pushed records past the buffer)
     if (!reader_links_hold(cand_chunk, cand_off, cand_cnt, ncand, i, off + consumed, clen)) ok = false;
     if (!ok) atomicAdd(violations, 1ull);
 }
@@ -1005,12 +1016,12 @@ void launch_check_chunks(ChunkTable tab, u64 chunks, const u64* tile_prefix, u64
 }
 void launch_emit_chains_verify(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off,
                                const u32* cand_cnt, const u64* cand_rec, u64 ncand, u64 cand_lo, u64 cand_hi, void* out,
-                               u64* violations, cudaStream_t s)
+                               u64 rec_limit, u32* cand_next, u64* violations, cudaStream_t s)
 {
     if (cand_hi <= cand_lo) return;
     k_emit_chains_verify<<<(unsigned)((cand_hi - cand_lo + EMITC_THREADS - 1) / EMITC_THREADS), EMITC_THREADS, 0, s>>>(
         (const unsigned char*)d_in, tab, cand_chunk, cand_off, cand_cnt, cand_rec, ncand, cand_lo, cand_hi, (unsigned char*)out,
-        violations);
+        rec_limit, cand_next, violations);
 }
 void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s)
 {
@@ -1063,11 +1074,13 @@ void launch_slow_emit_text(const void* d_in, ChunkTable tab, u64 chunks, const u
                                                                    (unsigned char*)out);
 }
 void launch_emit_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, const u32* cand_base,
-                        u64 ncand, const u64* chunk_base, void* out, DecompressTotals* tot, cudaStream_t s)
+                        u64 ncand, const u64* chunk_base, void* out, DecompressTotals* tot, const u64* placed_rec,
+                        const u32* placed_next, cudaStream_t s)
 {
     if (ncand == 0) return;
     k_emit_chains<<<(unsigned)((ncand + EMITC_THREADS - 1) / EMITC_THREADS), EMITC_THREADS, 0, s>>>(
-        (const unsigned char*)d_in, tab, cand_chunk, cand_off, cand_base, ncand, chunk_base, (unsigned char*)out, tot);
+        (const unsigned char*)d_in, tab, cand_chunk, cand_off, cand_base, ncand, chunk_base, (unsigned char*)out, tot, placed_rec,
+        placed_next);
 }
 void launch_slow_emit(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, const u64* chunk_base, void* out,
                       cudaStream_t s)

@@ -68,7 +68,7 @@ void launch_check_chunks(ChunkTable tab, u64 chunks, const u64* tile_prefix, u64
 // candidates [cand_lo, cand_hi)
 void launch_emit_chains_verify(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off,
                                const u32* cand_cnt, const u64* cand_rec, u64 ncand, u64 cand_lo, u64 cand_hi, void* out,
-                               u64* violations, cudaStream_t s);
+                               u64 rec_limit, u32* cand_next, u64* violations, cudaStream_t s);
 void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s);
 void launch_exclusive_sum64(const u64* in, u64 n, u64* out, cudaStream_t s);
 void launch_probe_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u64 ncand,
@@ -84,7 +84,8 @@ void launch_emit_chains_text(const void* d_in, ChunkTable tab, const u32* cand_c
 void launch_slow_emit_text(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, const u64* chunk_tbase,
                            void* out, cudaStream_t s);
 void launch_emit_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, const u32* cand_base,
-                        u64 ncand, const u64* chunk_base, void* out, DecompressTotals* tot, cudaStream_t s);
+                        u64 ncand, const u64* chunk_base, void* out, DecompressTotals* tot, const u64* placed_rec,
+                        const u32* placed_next, cudaStream_t s);
 void launch_slow_emit(const void* d_in, ChunkTable tab, u64 chunks, const u32* chunk_slow, const u64* chunk_base, void* out,
                       cudaStream_t s);
 
