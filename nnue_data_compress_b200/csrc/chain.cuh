@@ -139,6 +139,112 @@ __device__ __forceinline__ void out_stage_put(OutStage& st, unsigned char* out, 
     }
 }
 
+// A chain of a single position (numPlies == 0: all of a file of chain length 1) needs no position at all:
+// its 40-byte record is the stem transcoded. The stem lists the occupied squares a1 -> h8 with one nibble
+// each (CompressedPosition, Position.h:1374-1406), the PackedSfen stream wants a token per non-king
+// square rank 8 first (SfenPacker::pack :266-312): the pieces are visited in stream order, each one's
+// nibble looked up by its rank among the occupied squares, and its token dropped at 13 + stream square
+// - kings so far + 4 * pieces so far. Same bytes as stem_unpack + stream_from_pos + stream_with_tail
+// (one white and one black king, at most 32 pieces; anything else returns false and takes that route),
+// at a fifth of the instructions. `col` is the thread's 8-word scratch column in shared memory.
+__device__ __forceinline__ bool stem_to_record(const unsigned char* s, u32* col, int stride, u32 (&w)[8], u32& w8, u32& w9)
+{
+    // the 32 stem bytes as eight little-endian words, from aligned loads
+    u32 v[8];
+    {
+        const u32* wp = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(s) & ~(uintptr_t)3);
+        const int sh = (int)(reinterpret_cast<uintptr_t>(s) & 3) * 8;
+        u32 prev = wp[0];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const u32 next = (sh || j < 7) ? wp[j + 1] : 0u;  // (aligned stems end with wp[7])
+            v[j] = __funnelshift_r(prev, next, sh);
+            prev = next;
+        }
+    }
+    const u64 occ = ((u64)__byte_perm(v[0], 0, 0x0123) << 32) | __byte_perm(v[1], 0, 0x0123);  // big-endian (:1245-1257)
+    if (popc64(occ) > 32) return false;
+    const u64 nlo = ((u64)v[3] << 32) | v[2], nhi = ((u64)v[5] << 32) | v[4];  // nibble k: bits 4k.. of nlo (k < 16) / nhi
+#pragma unroll
+    for (int k = 0; k < 8; ++k) col[k * stride] = 0;
+    int stm = WHITE, cr = 0, ep = SQ_NONE, wk = 0, bk = 0, nwk = 0, nbk = 0, np = 0, nk = 0, n12 = 0;
+    u64 rest = bswap64(occ);  // bit i = stream square i (square i ^ 56)
+    while (rest) {
+        const int ss = lsb64(rest);
+        rest &= rest - 1;
+        const int sq = ss ^ 56;
+        const int k = popc64(occ & before64(sq));
+        const int nib = (int)(((k & 16) ? nhi : nlo) >> ((k & 15) * 4)) & 15;
+        if (nib == 10) { wk = sq; ++nwk; ++nk; continue; }
+        if (nib == 11 || nib == 15) {
+            bk = sq; ++nbk; ++nk;
+            if (nib == 15) stm = BLACK;
+            continue;
+        }
+        int pc = nib;  // 0..11: Piece ordinal
+        if (nib == 12) {  // the pawn that just made a double push (Position.h:1440-1456)
+            ++n12;
+            if ((sq >> 3) == 3) { pc = (PT_PAWN << 1) | WHITE; ep = (sq - 8) & 0xFF; }
+            else { pc = (PT_PAWN << 1) | BLACK; ep = (sq + 8) & 0xFF; }
+        } else if (nib == 13) {
+            pc = (PT_ROOK << 1) | WHITE;
+            cr |= (sq == 0) ? CR_WQ : CR_WK;
+        } else if (nib == 14) {
+            pc = (PT_ROOK << 1) | BLACK;
+            cr |= (sq == 56) ? CR_BQ : CR_BK;
+        }
+        const int pos = 13 + ss - nk + 4 * np;
+        ++np;
+        const u32 tok = stream_token(pc);
+        const int wi = pos >> 5, sb = pos & 31;
+        col[wi * stride] |= tok << sb;
+        if (sb > 27) col[(wi + 1) * stride] |= tok >> (32 - sb);
+    }
+    // (several ep nibbles -- corrupted input only -- are visited in a different order by stem_unpack, where the
+    // last one counts: the other route)
+    if (nwk != 1 || nbk != 1 || n12 > 1) return false;
+    // header, then castling / ep / rule50 / full move behind the board (stream_with_tail)
+    u32 T = (u32)cr & 15u;
+    int n = 5;
+    if (ep != SQ_NONE) {
+        T |= 16u | ((u32)(ep & 63) << 5);
+        n = 11;
+    }
+    const u32 pr = __byte_perm(v[7], 0, 0x4401) & 0xFFFFu;  // bytes 28, 29 big-endian
+    const int ply = (int)(pr & 0x3FFF);
+    const u32 rule50 = v[7] >> 24;                       // byte 31
+    T |= (rule50 & 63u) << n;
+    T |= (u32)(((ply + 1) >> 1) & 0xFF) << (n + 6);
+    const int end = 13 + 62 + 4 * np;
+    {
+        const int wi = end >> 5, sb = end & 31;
+        col[wi * stride] |= T << sb;
+        if (wi < 7) col[(wi + 1) * stride] |= __funnelshift_l(T, 0u, sb);
+    }
+    col[0] |= (u32)stm | ((u32)wk << 1) | ((u32)bk << 7);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = col[k * stride];
+    // score, move, ply, result (unpackEntry :1022-1043, trainingDataEntryToPackedSfenValue :570-585)
+    const u32 cm = __byte_perm(v[6], 0, 0x4401) & 0xFFFFu;   // bytes 24, 25 big-endian
+    const u32 sc = __byte_perm(v[6], 0, 0x4423) & 0xFFFFu;   // bytes 26, 27 big-endian
+    Move mv;
+    if (cm == 0) {
+        mv.from = mv.to = SQ_NONE;  // Move::null()
+        mv.type = MT_NORMAL;
+        mv.promo = NO_PIECE;
+    } else {
+        mv.type = (int)(cm >> 14);
+        mv.from = (int)((cm >> 8) & 63);
+        mv.to = (int)((cm >> 2) & 63);
+        mv.promo = NO_PIECE;
+        if (mv.type == MT_PROMOTION) mv.promo = ((PT_KNIGHT + (int)(cm & 3)) << 1) | ((mv.to >> 3) == 0 ? BLACK : WHITE);
+    }
+    const int score = zz_dec(sc), result = zz_dec(pr >> 14);
+    w8 = ((u32)score & 0xFFFFu) | (move_to_sfmove(mv) << 16);
+    w9 = ((u32)ply & 0xFFFFu) | (((u32)result & 0xFFu) << 16) | 0xFF000000u;
+    return true;
+}
+
 // walk_chain writing 40-byte .bin records rec0, rec0 + 1, ... (below rec_limit). The Huffman stream
 // of the position is carried along the chain (stream.cuh): built once for the chain head, then
 // spliced per move. `col` is the thread's 8-word scratch column in shared memory; `slot` (optional)
@@ -147,6 +253,14 @@ __device__ __forceinline__ bool emit_chain_bin(const unsigned char* s, u32 bytes
                                                u64 rec_limit, u32* col, int stride, u32& consumed,
                                                const StepTables* T = nullptr, unsigned char* slot = nullptr)
 {
+    if ((((u32)s[32] << 8) | (u32)s[33]) == 0u) {  // a single position: transcode the stem
+        u32 w[8], w8, w9;
+        if (stem_to_record(s, col, stride, w, w8, w9)) {
+            if (rec0 < rec_limit) store_record(out, rec0, w, w8, w9);
+            consumed = 34;
+            return true;
+        }
+    }
     u32 W[8];
     bool spliced = false;
     OutStage st{slot, 0, 0};
