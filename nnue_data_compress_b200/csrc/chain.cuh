@@ -167,38 +167,60 @@ __device__ __forceinline__ bool stem_to_record(const unsigned char* s, u32* col,
     const u64 nlo = ((u64)v[3] << 32) | v[2], nhi = ((u64)v[5] << 32) | v[4];  // nibble k: bits 4k.. of nlo (k < 16) / nhi
 #pragma unroll
     for (int k = 0; k < 8; ++k) col[k * stride] = 0;
-    int stm = WHITE, cr = 0, ep = SQ_NONE, wk = 0, bk = 0, nwk = 0, nbk = 0, np = 0, nk = 0, n12 = 0;
-    u64 rest = bswap64(occ);  // bit i = stream square i (square i ^ 56)
-    while (rest) {
-        const int ss = lsb64(rest);
-        rest &= rest - 1;
-        const int sq = ss ^ 56;
-        const int k = popc64(occ & before64(sq));
-        const int nib = (int)(((k & 16) ? nhi : nlo) >> ((k & 15) * 4)) & 15;
-        if (nib == 10) { wk = sq; ++nwk; ++nk; continue; }
-        if (nib == 11 || nib == 15) {
-            bk = sq; ++nbk; ++nk;
-            if (nib == 15) stm = BLACK;
-            continue;
+    int stm = WHITE, cr = 0, ep = SQ_NONE, wk = 0, bk = 0, nwk = 0, nbk = 0, n12 = 0;
+    int cursor = 13;  // stream position of the next token
+    // Rank by rank, rank 8 first: the rank's nibbles are consecutive in the stem (its pieces in file order), so
+    // a 64-bit window over them is shifted once per rank and by one nibble per piece; the rank's tokens are
+    // gathered in a 64-bit register (at most 8 x 5 bits) and dropped into the stream column once per rank.
+#pragma unroll 1
+    for (int r = 7; r >= 0; --r) {
+        u32 rb = (u32)(occ >> (8 * r)) & 0xFFu;
+        const int first = popc64(occ & before64(8 * r));  // nibble index of the rank's first piece (< 32)
+        // nibbles first .. first + 7 as one 32-bit window
+        const u64 hi_part = first >= 16 ? 0ull : nhi, lo_part = first >= 16 ? nhi : nlo;
+        const int sh = (first & 15) * 4;
+        u32 nw = sh == 0 ? (u32)lo_part : (u32)((lo_part >> sh) | (hi_part << (64 - sh)));
+        u64 bits = 0;  // the rank's tokens, first square lowest
+        int nbits = 0, prev_f = -1;
+        while (rb) {
+            const int f = __ffs((int)rb) - 1;
+            rb &= rb - 1;
+            const int sq = 8 * r + f;
+            const int nib = (int)(nw & 15u);
+            nw >>= 4;
+            nbits += f - prev_f - 1;  // the empty squares in between: '0' bits
+            prev_f = f;
+            if (nib == 10) { wk = sq; ++nwk; continue; }  // kings occupy no stream bits
+            if (nib == 11 || nib == 15) {
+                bk = sq; ++nbk;
+                if (nib == 15) stm = BLACK;
+                continue;
+            }
+            int pc = nib;  // 0..11: Piece ordinal
+            if (nib == 12) {  // the pawn that just made a double push (Position.h:1440-1456)
+                ++n12;
+                if (r == 3) { pc = (PT_PAWN << 1) | WHITE; ep = (sq - 8) & 0xFF; }
+                else { pc = (PT_PAWN << 1) | BLACK; ep = (sq + 8) & 0xFF; }
+            } else if (nib == 13) {
+                pc = (PT_ROOK << 1) | WHITE;
+                cr |= (sq == 0) ? CR_WQ : CR_WK;
+            } else if (nib == 14) {
+                pc = (PT_ROOK << 1) | BLACK;
+                cr |= (sq == 56) ? CR_BQ : CR_BK;
+            }
+            bits |= (u64)stream_token(pc) << nbits;
+            nbits += 5;
         }
-        int pc = nib;  // 0..11: Piece ordinal
-        if (nib == 12) {  // the pawn that just made a double push (Position.h:1440-1456)
-            ++n12;
-            if ((sq >> 3) == 3) { pc = (PT_PAWN << 1) | WHITE; ep = (sq - 8) & 0xFF; }
-            else { pc = (PT_PAWN << 1) | BLACK; ep = (sq + 8) & 0xFF; }
-        } else if (nib == 13) {
-            pc = (PT_ROOK << 1) | WHITE;
-            cr |= (sq == 0) ? CR_WQ : CR_WK;
-        } else if (nib == 14) {
-            pc = (PT_ROOK << 1) | BLACK;
-            cr |= (sq == 56) ? CR_BQ : CR_BK;
+        nbits += 7 - prev_f;  // the empty squares behind the rank's last piece
+        {
+            const int wi = cursor >> 5, sb = cursor & 31;
+            const u32 b0 = (u32)bits, b1 = (u32)(bits >> 32);
+            col[wi * stride] |= b0 << sb;
+            const u32 mid = __funnelshift_l(b0, b1, sb);  // bits 32 - sb .. 63 - sb
+            if (wi < 7) col[(wi + 1) * stride] |= mid;
+            if (wi < 6 && sb) col[(wi + 2) * stride] |= b1 >> (32 - sb);
         }
-        const int pos = 13 + ss - nk + 4 * np;
-        ++np;
-        const u32 tok = stream_token(pc);
-        const int wi = pos >> 5, sb = pos & 31;
-        col[wi * stride] |= tok << sb;
-        if (sb > 27) col[(wi + 1) * stride] |= tok >> (32 - sb);
+        cursor += nbits;
     }
     // (several ep nibbles -- corrupted input only -- are visited in a different order by stem_unpack, where the
     // last one counts: the other route)
@@ -215,7 +237,7 @@ __device__ __forceinline__ bool stem_to_record(const unsigned char* s, u32* col,
     const u32 rule50 = v[7] >> 24;                       // byte 31
     T |= (rule50 & 63u) << n;
     T |= (u32)(((ply + 1) >> 1) & 0xFF) << (n + 6);
-    const int end = 13 + 62 + 4 * np;
+    const int end = cursor;  // 13 + 62 + 4 * pieces
     {
         const int wi = end >> 5, sb = end & 31;
         col[wi * stride] |= T << sb;

@@ -433,4 +433,60 @@ uint64_t sim_halfkp_tokens(const unsigned char* bin, size_t n)
     return bad;
 }
 
+
+// stem_to_record (the direct transcode of single-position chains) against the general route (stem_unpack +
+// stream_from_pos + stream_with_tail + the record fields) on every stem of a .binpack and on `mutations`
+// randomly damaged copies of each: whatever the direct route accepts must be the same 40 bytes.
+uint64_t sim_stem_transcode_fuzz(const unsigned char* in, size_t n, int mutations, uint64_t seed, uint64_t* mismatch)
+{
+    uint64_t accepted = 0, xs = seed * 0x9E3779B97F4A7C15ull + 1;
+    *mismatch = 0;
+    size_t pos = 0;
+    u32 col[8];
+    auto check = [&](const unsigned char* stem) {
+        alignas(8) unsigned char buf[48];
+        for (int shift = 0; shift < 4; ++shift) {  // every alignment of the stem within a word
+            std::memset(buf, 0xEE, sizeof buf);
+            std::memcpy(buf + 4 + shift, stem, 34);
+            const unsigned char* sp = buf + 4 + shift;
+            u32 w[8], w8, w9;
+            if (!stem_to_record(sp, col, 1, w, w8, w9)) continue;
+            ++accepted;
+            ChainCursor cc;
+            chain_open(sp, cc);
+            u32 W[8], g[8];
+            const int end = stream_from_pos(cc.pos, col, 1, W);
+            stream_with_tail(W, end, cc.pos, g);
+            const u32 g8 = ((u32)cc.score & 0xFFFFu) | (move_to_sfmove(cc.mv) << 16);
+            const u32 g9 = ((u32)cc.ply & 0xFFFFu) | (((u32)cc.result & 0xFFu) << 16) | 0xFF000000u;
+            if (std::memcmp(w, g, 32) != 0 || w8 != g8 || w9 != g9) ++*mismatch;
+        }
+    };
+    while (pos < n) {
+        if (n - pos < 8 || std::memcmp(in + pos, "BINP", 4) != 0) break;
+        u32 size;
+        std::memcpy(&size, in + pos + 4, 4);
+        if (n - pos - 8 < size) break;
+        const unsigned char* chunk = in + pos + 8;
+        u32 cur = 0;
+        while ((unsigned long long)cur + 34 <= size) {
+            check(chunk + cur);
+            for (int m = 0; m < mutations; ++m) {
+                unsigned char stem[34];
+                std::memcpy(stem, chunk + cur, 34);
+                for (int k = 0; k < 1 + (m & 3); ++k) {
+                    xs = xs * 6364136223846793005ull + 1442695040888963407ull;
+                    stem[(xs >> 33) % 32] ^= (unsigned char)(1u << ((xs >> 60) & 7));
+                }
+                check(stem);
+            }
+            u32 consumed = 0;
+            if (!walk_chain(chunk + cur, size - cur - 34, [](const ChainCursor&, u32) {}, consumed)) break;
+            cur += consumed;
+        }
+        pos += 8 + (size_t)size;
+    }
+    return accepted;
+}
+
 }  // extern "C"

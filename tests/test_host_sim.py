@@ -138,3 +138,16 @@ def test_halfkp_row_listed_from_sfen_tokens(sim):
     entries of the row rebuilt from the decoded position."""
     for name, b in _inputs():
         assert sim.sim_halfkp_tokens(b, len(b) // 40) == 0, name
+
+
+def test_stem_transcode_equals_the_general_route(sim):
+    """stem_to_record (single-position chains: stem nibbles -> PackedSfen tokens, no position in between) gives
+    the bytes of stem_unpack + stream_from_pos + stream_with_tail on every stem of the golden files, at every
+    byte alignment, and on randomly damaged stems whenever it accepts them."""
+    total = 0
+    for name in GOLDEN_SETS:
+        b = golden(name + ".binpack")
+        mm = ctypes.c_uint64()
+        total += sim.sim_stem_transcode_fuzz(b, len(b), 6 if name in ("heads", "shuffled", "restart") else 1, 5, ctypes.byref(mm))
+        assert mm.value == 0, name
+    assert total > 100_000
