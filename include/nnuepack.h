@@ -271,8 +271,9 @@ int nnp_decode_stats(uint64_t* out14);
 /* Test hooks (the environment variables NNP_DEBUG_EXHAUSTIVE / NNP_DEBUG_REJECT_MOD set the same
  * switches at nnp_init): "exhaustive" != 0 skips the optimistic decode strategy; "reject_mod" = m
  * drops the chain-start candidates whose hashed offset is 0 mod m (0 = off), which forces the
- * fallback strategies; "k1_per_record" / "k1_walk" / "k1_runs" != 0 pin the compressor's first kernel to
- * its record-parallel, chain-owning or run-based form (by default a sample of the chain-head density picks);
+ * fallback strategies; "k1_per_record" / "k1_walk" / "k1_runs" / "k1_heads" != 0 pin the compressor's first
+ * kernel to its record-parallel, chain-owning, run-based or chain-head-transcoding form (by default a sample of
+ * the chain-head density picks);
  * "walk_seg_bytes" = v sets the segment size of the parallel chunk-header walk (0 = default 8 MiB; files
  * shorter than eight segments are walked sequentially).
  * Results never depend on these switches. */

@@ -68,6 +68,7 @@ struct Context {
     cudaEvent_t pipe_ev[16] = {};
     uint32_t debug_reject_mod = 0;
     bool debug_k1_per_record = false;  // "k1_per_record": always the record-parallel K1
+    bool debug_k1_heads = false;       // "k1_heads": always the chain-head transcoder (k_heads_transcode)
     bool debug_k1_walk = false;        // "k1_walk": always the chain-owning walk (no density sample)
     bool debug_k1_runs = false;        // "k1_runs": always the run-based walk with parked heads
     bool debug_exhaustive = false;     // NNP_DEBUG_EXHAUSTIVE: skip the optimistic decode strategy
@@ -282,6 +283,7 @@ int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** ste
     // three forms of K1: record-parallel for files of (nearly) single positions, chain-owning threads for
     // ordinary files, runs with parked heads when chains are enormous (or the input is still arriving)
     bool per_record = C.debug_k1_per_record;
+    bool heads_only = C.debug_k1_heads;
     bool by_chains = !C.pipe_src && !C.debug_k1_runs && n_all < 0xFFFFFFFFull;
     if (!per_record && !C.debug_k1_walk && !C.debug_k1_runs && !C.pipe_src && n_all >= 4096) {
         const u64 samples = n_all / 2 < 65536 ? n_all / 2 : 65536;
@@ -292,11 +294,13 @@ int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** ste
         CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         per_record = h_tot->parked[1] * 3 > samples;     // more than one record in three starts a chain
+        heads_only = h_tot->parked[1] * 10 > samples * 9;  // nearly all of them do: stems are transcoded (heads.cuh)
         // chains of hundreds of records: a thread owns too few of them to keep its warp busy (measured at
         // 400 plies per chain: 9.7 ms against 5.1 ms for the run-based walk), see DESIGN.md 4.1
         if (h_tot->parked[1] * 200 < samples) by_chains = false;
         CK(cudaMemsetAsync(&d_tot->parked[1], 0, 8, s));
     }
+    if (heads_only) per_record = true;
     if (!per_record && by_chains) {
         launch_walk_chains(d_bin, n_all, codes, stems, d_tot, bleed_list, s);
         LAUNCHED(1, "k_walk_chains");
@@ -316,9 +320,10 @@ int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** ste
     }
     if (per_record) {
         if (C.pipe_src) CK(cudaMemcpyAsync(const_cast<void*>(d_bin), C.pipe_src, n_all * 40, cudaMemcpyHostToDevice, s));
-        launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, bleed_list, s);
-        LAUNCHED(1, "k_decode_link_encode");
-        C.last_kernel = "k_decode_link_encode";
+        if (heads_only) launch_heads_transcode(d_bin, n_all, codes, stems, d_tot, bleed_list, s);
+        else launch_decode_link_encode(d_bin, n_all, codes, stems, d_tot, bleed_list, s);
+        LAUNCHED(1, heads_only ? "k_heads_transcode" : "k_decode_link_encode");
+        C.last_kernel = heads_only ? "k_heads_transcode" : "k_decode_link_encode";
         CK(cudaEventRecord(C.ev[3], s));
         CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -1665,6 +1670,7 @@ int nnp_debug_config(const char* key, uint64_t value)
     if (!key) return NNP_ERR_BAD_ARG;
     if (!std::strcmp(key, "exhaustive")) g_ctx.debug_exhaustive = value != 0;
     else if (!std::strcmp(key, "k1_per_record")) g_ctx.debug_k1_per_record = value != 0;
+    else if (!std::strcmp(key, "k1_heads")) g_ctx.debug_k1_heads = value != 0;
     else if (!std::strcmp(key, "k1_walk")) g_ctx.debug_k1_walk = value != 0;
     else if (!std::strcmp(key, "k1_runs")) g_ctx.debug_k1_runs = value != 0;
     else if (!std::strcmp(key, "reject_mod")) g_ctx.debug_reject_mod = (uint32_t)value;

@@ -27,6 +27,7 @@
 #include "kernels.h"
 #include "link.cuh"
 #include "walk.cuh"
+#include "heads.cuh"
 
 namespace nnp {
 
@@ -134,6 +135,72 @@ k_decode_link_encode(const unsigned char* __restrict__ bin, u64 n, u32* __restri
         k1_load(sh, th, hp, hf, hok);
         store_stem(hp, hf, stems + (u64)(first + th) * 8);
     }
+}
+
+// ------------------------------------------------------------------ K1 for files of single positions
+//
+// k_heads_transcode: when (nearly) every record starts a chain -- shuffled training data, the L = 1 end of
+// the sweep -- K1 only has to produce stems, and a stem is the record's own token stream in another order
+// (heads.cuh). One thread per record: the ply / result fields of the record in front decide whether it
+// can continue a chain at all (isContinuation :589-590); if not, it is transcoded without building a
+// position. The few records that pass the field test, and the streams the transcoder leaves alone, take
+// the reference's route (decode both positions, compare, encode) out of line.
+
+constexpr int KH_THREADS = 128;
+
+static __device__ __noinline__ void heads_other(const unsigned char* __restrict__ bin, u64 rec, bool linked,
+                                                u32* __restrict__ codes, u32* __restrict__ stems, CompressTotals* tot,
+                                                u64* __restrict__ bleed_list)
+{
+    const u32* w = reinterpret_cast<const u32*>(bin + rec * 40);
+    Pos cur, prev;
+    const bool ok = decode_record(bin, rec, cur);
+    if (!ok) atomicMin(&tot->error_index, rec);
+    bool prev_ok = false;
+    RecordFields pf = record_fields(0u, 0u);
+    if (linked) {
+        prev_ok = decode_record(bin, rec - 1, prev);
+        pf = record_fields(w[-2], w[-1]);
+    }
+    u32 bleed = 0;
+    codes[rec] = link_and_encode(linked && ok && prev_ok, prev, pf, cur, record_fields(w[8], w[9]), stems + rec * 8, &bleed);
+    if (bleed) bleed_report(BleedLog{bleed_list, &tot->bleeds}, rec, bleed);
+}
+
+__global__ void __launch_bounds__(KH_THREADS, 8)
+k_heads_transcode(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ codes, u32* __restrict__ stems,
+                  CompressTotals* tot, u64* __restrict__ bleed_list)
+{
+    __shared__ __align__(16) u32 raw[KH_THREADS * 10];
+    const int t = threadIdx.x;
+    const u64 first = (u64)blockIdx.x * KH_THREADS;
+    const u64 count = n - first < (u64)KH_THREADS ? n - first : (u64)KH_THREADS;
+    {
+        const uint2* src = reinterpret_cast<const uint2*>(bin + first * 40);
+        uint2* dst = reinterpret_cast<uint2*>(raw);
+        for (int i = t; i < (int)count * 5; i += KH_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    if ((u64)t >= count) return;
+    const u64 rec = first + t;
+    const u32* w = raw + t * 10;
+    bool linked = false;
+    if (rec > 0) {
+        const u32 prev9 = t > 0 ? w[-1] : reinterpret_cast<const u32*>(bin + rec * 40)[-1];
+        linked = fields_link(prev9, w[9]);
+    }
+    int st = HEADS_OTHER;
+    if (!linked) {
+        u32 s[8];
+        st = record_to_stem([&](int j) { return w[j]; }, s);
+        if (st == HEADS_OK) {
+            codes[rec] = 0u;
+            uint4* d = reinterpret_cast<uint4*>(stems + rec * 8);
+            d[0] = make_uint4(s[0], s[1], s[2], s[3]);
+            d[1] = make_uint4(s[4], s[5], s[6], s[7]);
+        }
+    }
+    if (st != HEADS_OK) heads_other(bin, rec, linked, codes, stems, tot, bleed_list);  // also reports malformed streams
 }
 
 // ------------------------------------------------------------------ K1, chain-walking form
@@ -862,6 +929,13 @@ void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems,
     if (n == 0) return;
     const u64 blocks = (n + K1_TILE - 1) / K1_TILE;
     k_decode_link_encode<<<(unsigned)blocks, K1_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems, tot, bleed_list);
+}
+void launch_heads_transcode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u64* bleed_list,
+                            cudaStream_t s)
+{
+    if (n == 0) return;
+    k_heads_transcode<<<(unsigned)((n + KH_THREADS - 1) / KH_THREADS), KH_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems,
+                                                                                         tot, bleed_list);
 }
 void launch_sample_heads(const void* d_bin, u64 n, u64 stride, u64 samples, u64* heads, cudaStream_t s)
 {

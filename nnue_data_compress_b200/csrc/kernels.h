@@ -10,6 +10,8 @@ void init_tables_decompress(cudaStream_t s);
 void init_tables_halfkp(cudaStream_t s);
 
 // ---- compress (.bin -> .binpack), compress.cu
+void launch_heads_transcode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u64* bleed_list,
+                            cudaStream_t s);
 void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u64* bleed_list,
                                cudaStream_t s);
 u64 walk_runs(u64 n);  // number of runs = upper bound of the parked heads of any round

@@ -10,6 +10,7 @@
 #include "../../nnue_data_compress_b200/csrc/stream.cuh"
 #include "../../nnue_data_compress_b200/csrc/walk.cuh"
 #include "../../nnue_data_compress_b200/csrc/chain.cuh"
+#include "../../nnue_data_compress_b200/csrc/heads.cuh"
 #include "../../nnue_data_compress_b200/csrc/halfkp.cuh"
 #include <algorithm>
 #include <vector>
@@ -485,6 +486,45 @@ uint64_t sim_stem_transcode_fuzz(const unsigned char* in, size_t n, int mutation
             cur += consumed;
         }
         pos += 8 + (size_t)size;
+    }
+    return accepted;
+}
+
+
+// record_to_stem (the direct transcode of chain heads, heads.cuh) against the general route (sfen_decode +
+// stem_pack) on every record of a .bin and on `mutations` randomly damaged copies of each: where the direct
+// route answers, it must give the same 32 bytes, and it must call malformed exactly what the decoder does.
+uint64_t sim_heads_transcode_fuzz(const unsigned char* bin, size_t n, int mutations, uint64_t seed, uint64_t* mismatch)
+{
+    uint64_t accepted = 0, xs = seed * 0x9E3779B97F4A7C15ull + 1;
+    *mismatch = 0;
+    auto check = [&](const Rec& r) {
+        Pos p;
+        pos_clear(p);
+        const bool ok = sfen_decode([&](int j) { return r.w[j]; }, p);
+        alignas(32) u32 g[8];
+        if (ok) store_stem(p, record_fields(r.w[8], r.w[9]), g);
+        u32 d[8];
+        const int st = record_to_stem([&](int j) { return r.w[j]; }, d);
+        if (st == HEADS_OTHER) return;
+        if (st == HEADS_BAD) {
+            if (ok) ++*mismatch;
+            return;
+        }
+        ++accepted;
+        if (!ok || std::memcmp(d, g, 32) != 0) ++*mismatch;
+    };
+    for (size_t i = 0; i < n; ++i) {
+        Rec r = load(bin, i);
+        check(r);
+        for (int m = 0; m < mutations; ++m) {
+            Rec q = r;
+            for (int k = 0; k < 1 + (m & 3); ++k) {
+                xs = xs * 6364136223846793005ull + 1442695040888963407ull;
+                q.w[(xs >> 33) % 10] ^= 1u << ((xs >> 58) & 31);
+            }
+            check(q);
+        }
     }
     return accepted;
 }

@@ -167,7 +167,7 @@ def host_sim():
         so = os.path.join(sim_dir, "libsim.so")
         csrc = os.path.join(ROOT, "nnue_data_compress_b200", "csrc")
         srcs = [os.path.join(sim_dir, "sim.cpp"), os.path.join(sim_dir, "host_sim.h")] + [
-            os.path.join(csrc, f) for f in ("chess.cuh", "stream.cuh", "walk.cuh", "link.cuh", "chain.cuh", "halfkp.cuh")]
+            os.path.join(csrc, f) for f in ("chess.cuh", "stream.cuh", "walk.cuh", "link.cuh", "chain.cuh", "heads.cuh", "halfkp.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in srcs):
             subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-DNNP_HOST_SIM", "-I" + sim_dir,
                             "-shared", "-fPIC", "-o", so, srcs[0]], check=True)
@@ -188,6 +188,8 @@ def host_sim():
         L.sim_halfkp_rows.restype = ctypes.c_longlong
         L.sim_stem_transcode_fuzz.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, u64p]
         L.sim_stem_transcode_fuzz.restype = ctypes.c_uint64
+        L.sim_heads_transcode_fuzz.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, u64p]
+        L.sim_heads_transcode_fuzz.restype = ctypes.c_uint64
         L.sim_halfkp_tokens.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
         L.sim_halfkp_tokens.restype = ctypes.c_uint64
         _sim = L

@@ -81,11 +81,12 @@ def test_many_chunks(nnp, n, plies):
     assert nnp.binpack_to_bin(got) == oracle_convert(BINPACK_TO_BIN, want)[1]
 
 
-@pytest.mark.parametrize("force", ["k1_walk", "k1_per_record"])
+@pytest.mark.parametrize("force", ["k1_walk", "k1_per_record", "k1_heads"])
 @pytest.mark.parametrize("n,plies", [(400_000, 100), (400_000, 1), (300_000, 5)])
 def test_both_forms_of_k1(nnp, force, n, plies):
-    """The compressor's first kernel exists in a chain-walking and a record-parallel form (a sample
-    of the chain-head density picks one); both must give the oracle's bytes on long and short chains."""
+    """The compressor's first kernel exists in a chain-walking and a record-parallel form, and as a transcoder
+    for files of chain heads (a sample of the chain-head density picks one); each must give the oracle's
+    bytes on long and short chains."""
     b = nnp.generate_bin(n, plies, 31)
     rc, want = oracle_convert(BIN_TO_BINPACK, b)
     assert rc == 0
@@ -432,7 +433,7 @@ def test_illegal_stored_moves_bleed_like_the_reference(nnp):
     rc, want = oracle_convert(BIN_TO_BINPACK, data)
     assert rc == 0
     L = nnp.lib()
-    for key in (b"k1_walk", b"k1_per_record"):
+    for key in (b"k1_walk", b"k1_per_record", b"k1_heads"):
         L.nnp_debug_config(key, 1)
         try:
             assert nnp.bin_to_binpack(data) == want

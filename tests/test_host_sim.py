@@ -151,3 +151,16 @@ def test_stem_transcode_equals_the_general_route(sim):
         total += sim.sim_stem_transcode_fuzz(b, len(b), 6 if name in ("heads", "shuffled", "restart") else 1, 5, ctypes.byref(mm))
         assert mm.value == 0, name
     assert total > 100_000
+
+
+def test_heads_transcode_equals_the_general_route(sim):
+    """record_to_stem (chain heads: PackedSfen tokens -> stem nibbles, no position in between) gives the bytes of
+    sfen_decode + stem_pack on every record of the golden files and on randomly damaged records, and reports
+    exactly the streams the decoder reports as malformed."""
+    total = 0
+    for name in GOLDEN_SETS:
+        b = golden(name + ".bin")
+        mm = ctypes.c_uint64()
+        total += sim.sim_heads_transcode_fuzz(b, len(b) // 40, 4, 11, ctypes.byref(mm))
+        assert mm.value == 0, name
+    assert total > 100_000

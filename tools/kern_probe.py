@@ -18,7 +18,8 @@ cap = n * 40 // 8 + (1 << 20) if plies > 20 else n * 36 + (1 << 20)
 d_pack = torch.empty(cap, dtype=torch.uint8, device="cuda")
 d_out = torch.empty(n * 40, dtype=torch.uint8, device="cuda")
 sz, o = ctypes.c_size_t(0), ctypes.c_size_t(0)
-L.nnp_debug_config(b"k1_walk", 1)
+if len(sys.argv) <= 3 or sys.argv[3] != "auto":
+    L.nnp_debug_config(b"k1_walk", 1)  # third argument "auto": let the density sample pick K1
 for _ in range(2):
     assert L.nnp_bin_to_binpack_dev(ctypes.c_void_p(d_bin.data_ptr()), n * 40, ctypes.c_void_p(d_pack.data_ptr()), cap, ctypes.byref(sz)) == 0
     assert L.nnp_binpack_to_bin_dev(ctypes.c_void_p(d_pack.data_ptr()), sz.value, ctypes.c_void_p(d_out.data_ptr()), n * 40, ctypes.byref(o)) == 0
