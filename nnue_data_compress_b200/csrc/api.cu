@@ -69,6 +69,11 @@ struct Context {
     uint32_t debug_reject_mod = 0;
     bool debug_k1_per_record = false;  // "k1_per_record": always the record-parallel K1
     bool debug_k1_heads = false;       // "k1_heads": always the chain-head transcoder (k_heads_transcode)
+    int debug_dec_direct = 0;          // "dec_direct": 2 = never take the candidate-free route for files of single positions
+    int debug_k1_direct = 0;           // "k1_direct": 1 = always try the one-kernel route for files of chain heads, 2 = never
+    const void* sampled_bin = nullptr;  // the last head-density sample (sample_head_density)
+    u64 sampled_n = 0, sampled_heads = 0, sampled_count = 0;
+    bool sampled_valid = false;
     bool debug_k1_walk = false;        // "k1_walk": always the chain-owning walk (no density sample)
     bool debug_k1_runs = false;        // "k1_runs": always the run-based walk with parked heads
     bool debug_exhaustive = false;     // NNP_DEBUG_EXHAUSTIVE: skip the optimistic decode strategy
@@ -262,6 +267,70 @@ int reset_compress_totals(CompressTotals** d_tot_out)
 
 // ---------------------------------------------------------------- .bin -> .binpack
 
+// The share of records whose ply / result fields rule out a continuation (isContinuation :589-590), on a sample
+// of up to 65 536 record pairs of a device-resident file; one launch and one readback. `keep` holds the answer
+// for the next question about the same file (compress_dev asks for the direct route, then K1 asks again).
+int sample_head_density(const void* d_bin, u64 n_all, u64* heads, u64* samples, bool keep = false)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    if (C.sampled_bin == d_bin && C.sampled_n == n_all && C.sampled_valid) {
+        *heads = C.sampled_heads;
+        *samples = C.sampled_count;
+        C.sampled_valid = false;  // one reuse: the buffer may hold another file next time
+        return NNP_OK;
+    }
+    WS(WS_TOTALS, sizeof(CompressTotals), CompressTotals, d_tot);
+    CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
+    *samples = n_all / 2 < 65536 ? n_all / 2 : 65536;
+    const u64 stride = (n_all - 1) / *samples;
+    CK(cudaMemsetAsync(&d_tot->parked[1], 0, 8, s));
+    launch_sample_heads(d_bin, n_all, stride, *samples, &d_tot->parked[1], s);
+    LAUNCHED(1, "k_sample_heads");
+    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *heads = h_tot->parked[1];
+    CK(cudaMemsetAsync(&d_tot->parked[1], 0, 8, s));
+    C.sampled_bin = d_bin;
+    C.sampled_n = n_all;
+    C.sampled_heads = *heads;
+    C.sampled_count = *samples;
+    C.sampled_valid = keep;
+    return NNP_OK;
+}
+
+// A .bin of nothing but chain heads -> .binpack in one kernel (k_heads_direct, compress.cu). *done = false
+// when the file turns out not to be of that kind, or does not fit: the caller then takes the general route,
+// which overwrites whatever the attempt wrote.
+int heads_direct_dev(const void* d_bin, u64 n, void* d_out, size_t out_cap, size_t* out_bytes, bool* done)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    *done = false;
+    const u64 total = heads_direct_bytes(n);
+    if (total > out_cap) return NNP_OK;
+    CompressTotals* d_tot = nullptr;
+    int rc = reset_compress_totals(&d_tot);
+    if (rc != NNP_OK) return rc;
+    CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
+    CK(cudaEventRecord(C.ev[0], s));
+    launch_heads_direct(d_bin, n, d_out, reinterpret_cast<u32*>(&d_tot->parked[0]), s);
+    LAUNCHED(1, "k_heads_direct");
+    CK(cudaEventRecord(C.ev[3], s));
+    CK(cudaEventRecord(C.ev[1], s));
+    CK(cudaEventRecord(C.ev[2], s));
+    CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h_tot->parked[0] != 0) return NNP_OK;  // a possible continuation, a malformed or irregular stream
+    *out_bytes = total;
+    *done = true;
+    C.last_kernel = "k_heads_direct";
+    C.last_positions = n;
+    CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
+    C.last_dominant_ms = C.last_stage_ms = C.last_total_ms;
+    return NNP_OK;
+}
+
 // K1: codes and stems of all n records (the chain walk, or the record-parallel kernel under the
 // "k1_per_record" switch); *error_index = first malformed record or NO_ERROR_IDX
 int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** stems_out, u64* error_index)
@@ -285,20 +354,15 @@ int link_encode_records(const void* d_bin, u64 n_all, u32** codes_out, u32** ste
     bool per_record = C.debug_k1_per_record;
     bool heads_only = C.debug_k1_heads;
     bool by_chains = !C.pipe_src && !C.debug_k1_runs && n_all < 0xFFFFFFFFull;
-    if (!per_record && !C.debug_k1_walk && !C.debug_k1_runs && !C.pipe_src && n_all >= 4096) {
-        const u64 samples = n_all / 2 < 65536 ? n_all / 2 : 65536;
-        const u64 stride = (n_all - 1) / samples;
-        CK(cudaMemsetAsync(&d_tot->parked[1], 0, 8, s));
-        launch_sample_heads(d_bin, n_all, stride, samples, &d_tot->parked[1], s);
-        LAUNCHED(1, "k_sample_heads");
-        CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        per_record = h_tot->parked[1] * 3 > samples;     // more than one record in three starts a chain
-        heads_only = h_tot->parked[1] * 10 > samples * 9;  // nearly all of them do: stems are transcoded (heads.cuh)
+    if (!per_record && !heads_only && !C.debug_k1_walk && !C.debug_k1_runs && !C.pipe_src && n_all >= 4096) {
+        u64 heads = 0, samples = 0;
+        rc = sample_head_density(d_bin, n_all, &heads, &samples);
+        if (rc != NNP_OK) return rc;
+        per_record = heads * 3 > samples;       // more than one record in three starts a chain
+        heads_only = heads * 10 > samples * 9;  // nearly all of them do: stems are transcoded (heads.cuh)
         // chains of hundreds of records: a thread owns too few of them to keep its warp busy (measured at
         // 400 plies per chain: 9.7 ms against 5.1 ms for the run-based walk), see DESIGN.md 4.1
-        if (h_tot->parked[1] * 200 < samples) by_chains = false;
-        CK(cudaMemsetAsync(&d_tot->parked[1], 0, 8, s));
+        if (heads * 200 < samples) by_chains = false;
     }
     if (heads_only) per_record = true;
     if (!per_record && by_chains) {
@@ -387,9 +451,28 @@ int compress_dev(const void* d_bin, size_t bin_bytes, void* d_out, size_t out_ca
     if (((uintptr_t)d_bin & 7) || ((uintptr_t)d_out & 7)) return NNP_ERR_BAD_ARG;
 
     cudaStream_t s = C.stream;
+    int rc = NNP_OK;
+    // a file of single positions (every sampled record fails the field test of isContinuation) is first tried
+    // in one kernel; the attempt itself notices if a record might continue a chain after all
+    bool direct = C.debug_k1_direct == 1;
+    const bool pinned_k1 = C.debug_k1_per_record || C.debug_k1_heads || C.debug_k1_walk || C.debug_k1_runs;
+    if (C.debug_k1_direct == 0 && !pinned_k1 && !C.pipe_src && n_all >= 4096) {
+        u64 heads = 0, samples = 0;
+        rc = sample_head_density(d_bin, n_all, &heads, &samples, true);
+        if (rc != NNP_OK) return rc;
+        direct = heads == samples;
+    }
+    if (direct && !C.pipe_src) {
+        bool done = false;
+        rc = heads_direct_dev(d_bin, n_all, d_out, out_cap, out_bytes, &done);
+        if (rc != NNP_OK || done) {
+            C.sampled_valid = false;
+            return rc;
+        }
+    }
     u32 *codes = nullptr, *stems = nullptr;
     u64 error_index = NO_ERROR_IDX;
-    int rc = link_encode_records(d_bin, n_all, &codes, &stems, &error_index);
+    rc = link_encode_records(d_bin, n_all, &codes, &stems, &error_index);
     if (rc != NNP_OK) return rc;
     int status = NNP_OK;
     u64 n = n_all;
@@ -724,10 +807,13 @@ struct DecodePlan {
     u64* tile_prefix = nullptr;
     u32* tile_flags = nullptr;
     DecompressTotals* d_tot = nullptr;
+    bool walked = false;          // decode_walk has run
+    u32* chunk_flag = nullptr;    // decode_heads_only has run: 1 = the chunk holds nothing but single positions
+    u64 heads_only_chunks = 0;
 };
 
-// chunk table + candidate list: the part both decode strategies share
-int decode_front(const void* d_in, size_t in_bytes, DecodePlan& P)
+// chunk table: the header walk (:500-521) and the zeroed totals
+int decode_walk(const void* d_in, size_t in_bytes, DecodePlan& P)
 {
     Context& C = g_ctx;
     cudaStream_t s = C.stream;
@@ -759,14 +845,43 @@ int decode_front(const void* d_in, size_t in_bytes, DecodePlan& P)
     std::memset(h_tot, 0, sizeof(DecompressTotals));
     h_tot->error_chunk = NO_ERROR_IDX;
     CK(cudaMemcpyAsync(d_tot, h_tot, sizeof(DecompressTotals), cudaMemcpyHostToDevice, s));
+    P.walked = true;
+    return NNP_OK;
+}
+
+// which chunks hold nothing but single positions (their stem counts go to WS_CHUNK_COUNT)
+int decode_heads_only(const void* d_in, DecodePlan& P)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    WS(WS_CHUNK_SLOW, (P.chunks + 1) * 4, u32, chunk_flag);  // (the exhaustive strategy reuses the slot afterwards)
+    WS(WS_CHUNK_COUNT, (P.chunks + 1) * 4, u32, chunk_stems);
+    launch_chunk_heads_only(d_in, P.tab, P.chunks, chunk_flag, chunk_stems, &P.d_tot->heads_only_chunks, s);
+    LAUNCHED(1, "k_chunk_heads_only");
+    P.chunk_flag = chunk_flag;
+    P.chunk_count = chunk_stems;
+    return NNP_OK;
+}
+
+// chunk table + candidate list: the part both decode strategies share
+int decode_front(const void* d_in, size_t in_bytes, DecodePlan& P)
+{
+    Context& C = g_ctx;
+    cudaStream_t s = C.stream;
+    int rc = P.walked ? NNP_OK : decode_walk(d_in, in_bytes, P);
+    if (rc != NNP_OK) return rc;
     if (P.chunks == 0) return NNP_OK;
+    if (!P.chunk_flag) {
+        rc = decode_heads_only(d_in, P);
+        if (rc != NNP_OK) return rc;
+    }
+    u32* chunk_flag = P.chunk_flag;
 
     WS(WS_TILE_COUNT, (P.tiles + 1) * 4, u32, tile_count);
     WS(WS_TILE_PREFIX, (P.tiles + 2) * 8, u64, tile_prefix);
     WS(WS_TILE_FLAGS, P.tiles * (CAND_TILE / 32) * 4, u32, tile_flags);
     P.tile_prefix = tile_prefix;
     P.tile_flags = tile_flags;
-    WS(WS_CHUNK_SLOW, (P.chunks + 1) * 4, u32, chunk_flag);  // (the exhaustive strategy reuses the slot afterwards)
     launch_candidates_scan(d_in, in_bytes, P.tab, P.chunks, P.tiles, tile_count, tile_flags, C.debug_reject_mod, chunk_flag, s);
     launch_exclusive_sum(tile_count, P.tiles, tile_prefix, s);
     LAUNCHED(3, "k_candidates_scan");
@@ -862,10 +977,49 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
     if (d_out && ((uintptr_t)d_out & 7)) return NNP_ERR_BAD_ARG;
     CK(cudaEventRecord(C.ev[0], s));
     DecodePlan P;
-    int rc = decode_front(d_in, in_bytes, P);
+    int rc = decode_walk(d_in, in_bytes, P);
     if (rc != NNP_OK) return rc;
     DecompressTotals* h_tot = reinterpret_cast<DecompressTotals*>((char*)C.pinned + 512);
     u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+
+    // A file of single positions (shuffled training data): when every chunk holds nothing but 34-byte chains
+    // the reader's walk is known without looking for it -- no candidates, no verification (k_emit_heads_only).
+    if (d_out && P.chunks > 0 && !C.debug_exhaustive && C.debug_dec_direct != 2) {
+        rc = decode_heads_only(d_in, P);
+        if (rc != NNP_OK) return rc;
+        CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(DecompressTotals), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h_tot->heads_only_chunks == P.chunks) {
+            WS(WS_CHUNK_BASE, (P.chunks + 2) * 8, u64, chunk_base);
+            launch_exclusive_sum(P.chunk_count, P.chunks, chunk_base, s);
+            LAUNCHED(1, "k_exclusive_sum");
+            CK(cudaMemcpyAsync(h_u64, chunk_base + P.chunks, 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            const u64 positions = h_u64[0];
+            *out_bytes = positions * 40;
+            C.last_positions = positions;
+            if (positions * 40 > out_cap) return NNP_ERR_CAPACITY;
+            CK(cudaEventRecord(C.ev[1], s));
+            launch_emit_heads_only(d_in, P.tab, P.chunks, chunk_base, positions, d_out, out_cap / 40, s);
+            LAUNCHED(1, "k_emit_heads_only");
+            CK(cudaEventRecord(C.ev[2], s));
+            CK(cudaStreamSynchronize(s));
+            C.last_kernel = "k_emit_heads_only";
+            C.last_candidates = positions;
+            C.last_tentative_positions = positions;
+            C.last_violations = 0;
+            CK(cudaEventElapsedTime(&C.last_total_ms, C.ev[0], C.ev[2]));
+            CK(cudaEventElapsedTime(&C.last_dominant_ms, C.ev[1], C.ev[2]));
+            if (P.walk_status != 0) {
+                *out_bytes = committed_bin_records(positions) * 40;
+                C.last_positions = *out_bytes / 40;
+                return P.walk_status;
+            }
+            return NNP_OK;
+        }
+    }
+    rc = decode_front(d_in, in_bytes, P);
+    if (rc != NNP_OK) return rc;
     const u64* placed_rec = nullptr;
     const u32* placed_next = nullptr;
     bool repaired = false;
@@ -1671,6 +1825,8 @@ int nnp_debug_config(const char* key, uint64_t value)
     if (!std::strcmp(key, "exhaustive")) g_ctx.debug_exhaustive = value != 0;
     else if (!std::strcmp(key, "k1_per_record")) g_ctx.debug_k1_per_record = value != 0;
     else if (!std::strcmp(key, "k1_heads")) g_ctx.debug_k1_heads = value != 0;
+    else if (!std::strcmp(key, "k1_direct")) g_ctx.debug_k1_direct = (int)value;
+    else if (!std::strcmp(key, "dec_direct")) g_ctx.debug_dec_direct = (int)value;
     else if (!std::strcmp(key, "k1_walk")) g_ctx.debug_k1_walk = value != 0;
     else if (!std::strcmp(key, "k1_runs")) g_ctx.debug_k1_runs = value != 0;
     else if (!std::strcmp(key, "reject_mod")) g_ctx.debug_reject_mod = (uint32_t)value;

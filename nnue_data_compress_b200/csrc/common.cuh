@@ -82,6 +82,7 @@ struct DecompressTotals {
     u64 violations;    // links of the optimistic walk that did not hold
     u64 false_candidates;      // candidates the exhaustive walk found not to be chain starts
     u64 false_sample[8];       // the first few of them: chunk << 32 | offset (diagnostics)
+    u64 heads_only_chunks;     // chunks that hold nothing but single positions (k_chunk_heads_only)
 };
 
 // one parsed .plain record (TrainingDataEntry, compress_file.cpp:548-555), 64 bytes

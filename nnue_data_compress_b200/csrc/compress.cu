@@ -203,6 +203,102 @@ k_heads_transcode(const unsigned char* __restrict__ bin, u64 n, u32* __restrict_
     if (st != HEADS_OK) heads_other(bin, rec, linked, codes, stems, tot, bleed_list);  // also reports malformed streams
 }
 
+// k_heads_direct: the whole conversion in one kernel for a file in which EVERY record starts a chain. Then every
+// chain is 34 bytes (stem + numPlies 0), the writer's flush rule (:1076-1080) closes a chunk after exactly
+// HEADS_PER_CHUNK = ceil(2^20 / 34) chains, and record r's bytes lie at a position that depends on r alone:
+//   (r / HEADS_PER_CHUNK) * (8 + 34 * HEADS_PER_CHUNK) + 8 + 34 * (r % HEADS_PER_CHUNK).
+// No codes, no stems array, no payload stream, no scan, no orbit, no chunk copy: a block transcodes 128
+// records (record_to_stem), lays their 34-byte chains (and a chunk header where one falls among them) out in
+// shared memory and writes the 4.3 KB image with whole-word stores. The premise is checked on the way: a
+// record whose ply / result fields link to its predecessor AND whose occupancy differs from it in at most four
+// squares (what a move can change) might continue a chain; that, a malformed stream or a stream the
+// transcoder leaves alone raises *fallback and the host runs the general pipeline instead.
+constexpr u32 HEADS_PER_CHUNK = (CHUNK_THRESHOLD + 33) / 34;
+constexpr u64 HEADS_CHUNK_BYTES = (u64)HEADS_PER_CHUNK * 34;
+constexpr int HD_THREADS = 128;
+
+__host__ __device__ __forceinline__ u64 heads_direct_offset(u64 rec)
+{
+    return (rec / HEADS_PER_CHUNK) * (HEADS_CHUNK_BYTES + 8) + 8 + (rec % HEADS_PER_CHUNK) * 34;
+}
+
+// occupancy of record `rec` for the first thread of a block (its predecessor is in another block's tile)
+static __device__ __noinline__ bool heads_occupancy(const unsigned char* __restrict__ bin, u64 rec, u64& occ)
+{
+    const u32* w = reinterpret_cast<const u32*>(bin + rec * 40);
+    u32 s[8];
+    if (record_to_stem([&](int j) { return w[j]; }, s) != HEADS_OK) return false;
+    occ = bswap64((u64)s[0] | ((u64)s[1] << 32));
+    return true;
+}
+
+__global__ void __launch_bounds__(HD_THREADS, 8)
+k_heads_direct(const unsigned char* __restrict__ bin, u64 n, unsigned char* __restrict__ out, u32* __restrict__ fallback)
+{
+    __shared__ __align__(16) u32 raw[HD_THREADS * 10];
+    __shared__ __align__(16) u32 image[(HD_THREADS * 34 + 8 + 8) / 4 + 2];
+    __shared__ u64 occs[HD_THREADS];
+    const int t = threadIdx.x;
+    const u64 first = (u64)blockIdx.x * HD_THREADS;
+    const int count = (int)(n - first < (u64)HD_THREADS ? n - first : (u64)HD_THREADS);
+    {
+        const uint2* src = reinterpret_cast<const uint2*>(bin + first * 40);
+        uint2* dst = reinterpret_cast<uint2*>(raw);
+        for (int i = t; i < count * 5; i += HD_THREADS) dst[i] = src[i];
+    }
+    // the block's bytes of the file: its chains, and in front of them the header of a chunk its first record opens
+    const u64 g_lo = heads_direct_offset(first) - (first % HEADS_PER_CHUNK == 0 ? 8 : 0);
+    const u64 g_hi = heads_direct_offset(first + count - 1) + 34;
+    const u64 img_base = g_lo & ~3ull;
+    __syncthreads();
+    const u64 rec = first + t;
+    const u32* w = raw + t * 10;
+    u32 s[8] = {};
+    int st = HEADS_OK;
+    if (t < count) {
+        st = record_to_stem([&](int j) { return w[j]; }, s);
+        occs[t] = bswap64((u64)s[0] | ((u64)s[1] << 32));
+    }
+    __syncthreads();
+    if (t < count) {
+        bool doubt = st != HEADS_OK;
+        if (!doubt && rec > 0) {
+            const u32 prev9 = t > 0 ? w[-1] : reinterpret_cast<const u32*>(bin + rec * 40)[-1];
+            if (fields_link(prev9, w[9])) {
+                u64 po = t > 0 ? occs[t - 1] : 0ull;
+                const bool have = t > 0 ? true : heads_occupancy(bin, rec - 1, po);
+                doubt = !have || popc64(po ^ occs[t]) <= 4;
+            }
+        }
+        if (doubt) atomicOr(fallback, 1u);
+        unsigned short* img = reinterpret_cast<unsigned short*>(image) + ((heads_direct_offset(rec) - img_base) >> 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            img[2 * k] = (unsigned short)(s[k] & 0xFFFFu);
+            img[2 * k + 1] = (unsigned short)(s[k] >> 16);
+        }
+        img[16] = 0;  // numPlies, big-endian
+        if (rec % HEADS_PER_CHUNK == 0) {
+            // "BINP" + LE32 payload size of the chunk this record opens (:486-498)
+            const u64 left = n - rec;
+            const u32 size = (u32)((left < HEADS_PER_CHUNK ? left : (u64)HEADS_PER_CHUNK) * 34);
+            img[-4] = 0x4942; img[-3] = 0x504E;  // 'B','I' / 'N','P'
+            img[-2] = (unsigned short)(size & 0xFFFFu);
+            img[-1] = (unsigned short)(size >> 16);
+        }
+    }
+    __syncthreads();
+    // whole words of [g_lo, g_hi); a first / last halfword when the range starts / ends in the middle of a word
+    const u64 w_lo = (g_lo + 3) & ~3ull, w_hi = g_hi & ~3ull;
+    u32* gw = reinterpret_cast<u32*>(out + w_lo);
+    const u32* iw = image + ((w_lo - img_base) >> 2);
+    const int words = (int)((w_hi - w_lo) >> 2);
+    for (int i = t; i < words; i += HD_THREADS) gw[i] = iw[i];
+    if (t == 0 && (g_lo & 2)) *reinterpret_cast<unsigned short*>(out + g_lo) = reinterpret_cast<const unsigned short*>(image)[1];
+    if (t == 32 && (g_hi & 2))
+        *reinterpret_cast<unsigned short*>(out + w_hi) = reinterpret_cast<const unsigned short*>(image)[(w_hi - img_base) >> 1];
+}
+
 // ------------------------------------------------------------------ K1, chain-walking form
 //
 // k_walk_runs: every thread owns a run of KW_RUN consecutive records and walks it with walk_item
@@ -936,6 +1032,13 @@ void launch_heads_transcode(const void* d_bin, u64 n, u32* codes, u32* stems, Co
     if (n == 0) return;
     k_heads_transcode<<<(unsigned)((n + KH_THREADS - 1) / KH_THREADS), KH_THREADS, 0, s>>>((const unsigned char*)d_bin, n, codes, stems,
                                                                                          tot, bleed_list);
+}
+u64 heads_direct_bytes(u64 n) { return n == 0 ? 0 : heads_direct_offset(n - 1) + 34; }
+void launch_heads_direct(const void* d_bin, u64 n, void* d_out, u32* fallback, cudaStream_t s)
+{
+    if (n == 0) return;
+    k_heads_direct<<<(unsigned)((n + HD_THREADS - 1) / HD_THREADS), HD_THREADS, 0, s>>>((const unsigned char*)d_bin, n,
+                                                                                        (unsigned char*)d_out, fallback);
 }
 void launch_sample_heads(const void* d_bin, u64 n, u64 stride, u64 samples, u64* heads, cudaStream_t s)
 {

@@ -448,14 +448,15 @@ __device__ __forceinline__ u64 find_chunk(const u64* base, u64 chunks, u64 tile)
 // the emit kernel verifies the walk as for any other candidate set.
 constexpr int HEADS_ONLY_THREADS = 256;
 __global__ void __launch_bounds__(HEADS_ONLY_THREADS)
-k_chunk_heads_only(const unsigned char* __restrict__ in, ChunkTable tab, u32* __restrict__ chunk_flag)
+k_chunk_heads_only(const unsigned char* __restrict__ in, ChunkTable tab, u32* __restrict__ chunk_flag,
+                   u32* __restrict__ chunk_stems, u64* __restrict__ flagged)
 {
     __shared__ int fail;
     const u64 c = blockIdx.x;
     const unsigned char* s = in + tab.start[c];
     const u32 stems = tab.len[c] / 34;
     if (threadIdx.x == 0) {
-        int f = stems < 4;
+        int f = stems < 1;
         for (u32 k = 0; k < 4 && k < stems; ++k) f |= s[34 * k + 32] | s[34 * k + 33];
         fail = f;
     }
@@ -468,7 +469,45 @@ k_chunk_heads_only(const unsigned char* __restrict__ in, ChunkTable tab, u32* __
     for (u32 k = threadIdx.x; k < stems; k += HEADS_ONLY_THREADS) bad |= s[34 * (u64)k + 32] | s[34 * (u64)k + 33];
     if (bad) fail = 1;  // benign race: every writer stores 1
     __syncthreads();
-    if (threadIdx.x == 0) chunk_flag[c] = fail ? 0u : 1u;
+    if (threadIdx.x == 0) {
+        chunk_flag[c] = fail ? 0u : 1u;
+        if (!fail) {
+            chunk_stems[c] = stems;  // the reader's record count for this chunk
+            atomicAdd(flagged, 1ull);
+        }
+    }
+}
+
+// k_emit_heads_only: a file whose chunks ALL hold nothing but single positions needs no candidates at all --
+// record r of chunk c is the stem at byte 34 * r of the chunk, whatever it contains (Reader::next :1154-1213
+// reads 32 + 2 bytes, finds numPlies == 0 and is at the next stem). One thread per record; the chunk is found
+// from the prefix sums of the chunks' stem counts (one search per block, then a step or two per thread).
+constexpr int HEADS_EMIT_THREADS = 128;
+__global__ void __launch_bounds__(HEADS_EMIT_THREADS, 5)
+k_emit_heads_only(const unsigned char* __restrict__ in, ChunkTable tab, u64 chunks, const u64* __restrict__ chunk_base,
+                  unsigned char* __restrict__ out, u64 rec_limit)
+{
+    __shared__ u32 scratch[8 * HEADS_EMIT_THREADS];
+    __shared__ StepTables T;
+    __shared__ u64 first_chunk;
+    step_tables_fill(T);
+    const u64 r0 = (u64)blockIdx.x * HEADS_EMIT_THREADS;
+    if (threadIdx.x == 0) {
+        u64 lo = 0, hi = chunks;  // the last chunk whose first record is <= r0
+        while (hi - lo > 1) {
+            const u64 mid = (lo + hi) >> 1;
+            if (chunk_base[mid] <= r0) lo = mid; else hi = mid;
+        }
+        first_chunk = lo;
+    }
+    __syncthreads();
+    const u64 r = r0 + threadIdx.x;
+    if (r >= chunk_base[chunks]) return;
+    u64 c = first_chunk;
+    while (chunk_base[c + 1] <= r) ++c;
+    const unsigned char* s = in + tab.start[c] + 34 * (r - chunk_base[c]);
+    u32 consumed = 0;
+    emit_chain_bin(s, 0u, out, r, rec_limit, scratch + threadIdx.x, HEADS_EMIT_THREADS, consumed, &T, nullptr);
 }
 
 // pass 0: tests every offset of the tile, stores the tile's flag bitmap (CAND_TILE / 32 words) and
@@ -987,11 +1026,25 @@ void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks,
     }
     k_walk_chunks<<<1, 32, 0, s>>>(in, n, tab, max_chunks, world, rank, done);
 }
+void launch_chunk_heads_only(const void* d_in, ChunkTable tab, u64 chunks, u32* chunk_flag, u32* chunk_stems, u64* flagged,
+                             cudaStream_t s)
+{
+    if (chunks == 0) return;
+    k_chunk_heads_only<<<(unsigned)chunks, HEADS_ONLY_THREADS, 0, s>>>((const unsigned char*)d_in, tab, chunk_flag, chunk_stems,
+                                                                       flagged);
+}
+void launch_emit_heads_only(const void* d_in, ChunkTable tab, u64 chunks, const u64* chunk_base, u64 positions, void* d_out,
+                            u64 rec_limit, cudaStream_t s)
+{
+    if (positions == 0) return;
+    k_emit_heads_only<<<(unsigned)((positions + HEADS_EMIT_THREADS - 1) / HEADS_EMIT_THREADS), HEADS_EMIT_THREADS, 0, s>>>(
+        (const unsigned char*)d_in, tab, chunks, chunk_base, (unsigned char*)d_out, rec_limit);
+}
+// (chunk_flag: filled by launch_chunk_heads_only beforehand)
 void launch_candidates_scan(const void* d_in, u64 n_in, ChunkTable tab, u64 chunks, u64 tiles, u32* tile_count, u32* tile_flags,
-                            u32 debug_reject_mod, u32* chunk_flag, cudaStream_t s)
+                            u32 debug_reject_mod, const u32* chunk_flag, cudaStream_t s)
 {
     if (tiles == 0 || chunks == 0) return;
-    k_chunk_heads_only<<<(unsigned)chunks, HEADS_ONLY_THREADS, 0, s>>>((const unsigned char*)d_in, tab, chunk_flag);
     k_candidates_scan<<<(unsigned)tiles, CAND_THREADS, 0, s>>>((const unsigned char*)d_in, n_in, tab, tile_count, tile_flags,
                                                              debug_reject_mod, chunk_flag);
 }

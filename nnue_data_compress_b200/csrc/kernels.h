@@ -12,6 +12,8 @@ void init_tables_halfkp(cudaStream_t s);
 // ---- compress (.bin -> .binpack), compress.cu
 void launch_heads_transcode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u64* bleed_list,
                             cudaStream_t s);
+u64 heads_direct_bytes(u64 n);  // size of the .binpack of n single-position chains
+void launch_heads_direct(const void* d_bin, u64 n, void* d_out, u32* fallback, cudaStream_t s);
 void launch_decode_link_encode(const void* d_bin, u64 n, u32* codes, u32* stems, CompressTotals* tot, u64* bleed_list,
                                cudaStream_t s);
 u64 walk_runs(u64 n);  // number of runs = upper bound of the parked heads of any round
@@ -60,8 +62,12 @@ struct ChunkTable {
 size_t walk_scratch_bytes();
 void set_walk_segment_bytes(u64 v);  // test hook (0 = default)
 void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks, u32 world, u32 rank, void* scratch, cudaStream_t s);
+void launch_chunk_heads_only(const void* d_in, ChunkTable tab, u64 chunks, u32* chunk_flag, u32* chunk_stems, u64* flagged,
+                             cudaStream_t s);
+void launch_emit_heads_only(const void* d_in, ChunkTable tab, u64 chunks, const u64* chunk_base, u64 positions, void* d_out,
+                            u64 rec_limit, cudaStream_t s);
 void launch_candidates_scan(const void* d_in, u64 n_in, ChunkTable tab, u64 chunks, u64 tiles, u32* tile_count, u32* tile_flags,
-                            u32 debug_reject_mod, u32* chunk_flag, cudaStream_t s);
+                            u32 debug_reject_mod, const u32* chunk_flag, cudaStream_t s);
 void launch_mark_conflicts(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u32* cand_cnt,
                            u64 ncand, cudaStream_t s);
 void launch_candidates_list(const void* d_in, ChunkTable tab, u64 tiles, const u32* tile_flags, const u64* tile_prefix,

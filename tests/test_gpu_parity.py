@@ -81,6 +81,100 @@ def test_many_chunks(nnp, n, plies):
     assert nnp.binpack_to_bin(got) == oracle_convert(BINPACK_TO_BIN, want)[1]
 
 
+HEADS_PER_CHUNK = ((1 << 20) + 33) // 34  # a chunk of single positions closes after this many chains
+
+
+@pytest.mark.parametrize("n", [4096, HEADS_PER_CHUNK - 1, HEADS_PER_CHUNK, HEADS_PER_CHUNK + 1, 2 * HEADS_PER_CHUNK,
+                               2 * HEADS_PER_CHUNK + 127, 400_003])
+def test_files_of_single_positions_take_one_kernel(nnp, n):
+    """A .bin in which every record starts a chain is converted by one kernel (k_heads_direct: the stem is the
+    record's token stream in another order, and every byte's place in the file follows from its record index);
+    the bytes are the oracle's, whole chunks and a ragged last one alike."""
+    b = nnp.generate_bin(n, 1, 77)
+    rc, want = oracle_convert(BIN_TO_BINPACK, b)
+    assert rc == 0
+    assert nnp.bin_to_binpack(b) == want
+    assert nnp.lib().nnp_last_dominant_kernel() == b"k_heads_direct"
+    nnp.lib().nnp_debug_config(b"k1_direct", 2)
+    try:
+        assert nnp.bin_to_binpack(b) == want
+        assert nnp.lib().nnp_last_dominant_kernel() != b"k_heads_direct"
+    finally:
+        nnp.lib().nnp_debug_config(b"k1_direct", 0)
+    # and back: chunks of nothing but 34-byte chains are read without looking for chain starts
+    rc, back = oracle_convert(BINPACK_TO_BIN, want)
+    assert rc == 0
+    assert nnp.binpack_to_bin(want) == back
+    assert nnp.lib().nnp_last_dominant_kernel() == b"k_emit_heads_only"
+    nnp.lib().nnp_debug_config(b"dec_direct", 2)
+    try:
+        assert nnp.binpack_to_bin(want) == back
+        assert nnp.lib().nnp_last_dominant_kernel() != b"k_emit_heads_only"
+    finally:
+        nnp.lib().nnp_debug_config(b"dec_direct", 0)
+
+
+def test_single_position_chunks_with_damaged_stems(nnp):
+    """The candidate-free reader takes every 34 bytes as a stem whatever they hold, as the reference does: stems
+    with flipped bits (irregular nibbles, stray special codes) decode to the oracle's records; a flipped
+    numPlies byte sends the file back through the general reader."""
+    import random
+
+    rng = random.Random(5)
+    pack = bytearray(nnp.bin_to_binpack(nnp.generate_bin(70_000, 1, 12)))
+    starts = [8]  # payload starts of the chunks
+    while starts[-1] - 8 + 8 + int.from_bytes(pack[starts[-1] - 4:starts[-1]], "little") < len(pack):
+        starts.append(starts[-1] + int.from_bytes(pack[starts[-1] - 4:starts[-1]], "little") + 8)
+    for trial in range(6):
+        b = bytearray(pack)
+        for _ in range(400):
+            c = rng.choice(starts)
+            size = int.from_bytes(b[c - 4:c], "little")
+            k = rng.randrange(size // 34)
+            byte = rng.randrange(34 if trial == 5 else 32)
+            b[c + 34 * k + byte] ^= 1 << rng.randrange(8)
+        rc, want = oracle_convert(BINPACK_TO_BIN, bytes(b))
+        if rc != 0:
+            continue
+        try:
+            got = nnp.binpack_to_bin(bytes(b))
+        except nnp.NnpError as e:
+            assert e.status == -4, e.status
+            continue
+        assert got == want
+        if trial < 5:
+            assert nnp.lib().nnp_last_dominant_kernel() == b"k_emit_heads_only"
+
+
+def test_one_kernel_route_gives_way(nnp):
+    """The one-kernel route checks its premise while it runs: shuffled game positions (chain heads, but some with
+    ply / result fields that happen to link), real chains, and a malformed record all end in the general
+    pipeline's bytes and status when the route is forced on them."""
+    import numpy as np
+
+    L = nnp.lib()
+    games = np.frombuffer(nnp.generate_bin(300_000, 100, 9), dtype=np.uint8).reshape(-1, 40)
+    shuffled = games[np.random.default_rng(4).permutation(len(games))].tobytes()
+    bad = bytearray(nnp.generate_bin(50_000, 1, 3))
+    bad[40 * 31_000 + 2:40 * 31_000 + 32] = b"\xff" * 30  # every square a 5-bit token of type 7
+    cases = [shuffled, games.tobytes(), golden("heads.bin"), golden("shuffled.bin"), golden("restart.bin"), bytes(bad)]
+    for data in cases:
+        rc, want = oracle_convert(BIN_TO_BINPACK, data)
+        L.nnp_debug_config(b"k1_direct", 1)
+        try:
+            if rc == 0:
+                assert nnp.bin_to_binpack(data) == want
+            else:
+                with pytest.raises(nnp.NnpError) as ei:
+                    nnp.bin_to_binpack(data)
+                assert ei.value.status == rc and ei.value.partial == want
+        finally:
+            L.nnp_debug_config(b"k1_direct", 0)
+    # left to itself the shuffled file is sampled, found to be nearly all heads and transcoded by K1
+    assert nnp.bin_to_binpack(shuffled) == oracle_convert(BIN_TO_BINPACK, shuffled)[1]
+    assert L.nnp_last_dominant_kernel() in (b"k_heads_transcode", b"k_heads_direct")
+
+
 @pytest.mark.parametrize("force", ["k1_walk", "k1_per_record", "k1_heads"])
 @pytest.mark.parametrize("n,plies", [(400_000, 100), (400_000, 1), (300_000, 5)])
 def test_both_forms_of_k1(nnp, force, n, plies):
