@@ -464,8 +464,21 @@ def sweep_leg(torch, L, check, ptr, n, seed, dev, peak, d_bin, d_out):
     size = ctypes.c_size_t(0)
     t_total, t_dom = ctypes.c_float(0), ctypes.c_float(0)
     rows = []
-    for plies in (1, 8, 64, 400):
-        check(L.nnp_generate_bin_dev(ptr(d_bin), n, plies, seed + plies), "sweep generate")
+    for plies in (1, "shuffled", 8, 64, 400):
+        shuffled = plies == "shuffled"
+        if shuffled:
+            # chain length 1 as training pipelines produce it: the positions of 100-ply games in random order
+            # (the generator's own chain-length-1 file is the start position over and over); some records
+            # happen to continue their predecessor, which is what keeps this file on the general route
+            check(L.nnp_generate_bin_dev(ptr(d_bin), n, 100, seed + 7), "sweep generate")
+            g = torch.Generator(device=dev)
+            g.manual_seed(seed)
+            rows40 = d_bin[: n * 40].view(torch.int64).view(n, 5)
+            rows40.copy_(rows40[torch.randperm(n, device=dev, generator=g)])
+            torch.cuda.synchronize()
+            plies = 1
+        else:
+            check(L.nnp_generate_bin_dev(ptr(d_bin), n, plies, seed + plies), "sweep generate")
         cap = n * 40 // 8 + (1 << 20)
         d = torch.empty(cap, dtype=torch.uint8, device=dev)
         rc = L.nnp_bin_to_binpack_dev(ptr(d_bin), n * 40, ptr(d), cap, ctypes.byref(size))
@@ -491,7 +504,7 @@ def sweep_leg(torch, L, check, ptr, n, seed, dev, peak, d_bin, d_out):
             assert size.value == n * 40
         alg = n * 40 + pk
         rows.append({
-            "plies": plies, "positions": n, "binpack_bytes": pk, "bytes_per_position": alg / n,
+            "plies": plies, "input": "shuffled game positions" if shuffled else "games", "positions": n, "binpack_bytes": pk, "bytes_per_position": alg / n,
             "compress_ms": c_best, "decompress_ms": d_best, "round_trip_mpos_s": 2 * n / ((c_best + d_best) * 1e-3) / 1e6,
             "compress_frac": alg / (c_best * 1e-3) / 1e9 / peak, "decompress_frac": alg / (d_best * 1e-3) / 1e9 / peak,
             "compress_kernel": c_name, "compress_kernel_ms": ck, "decompress_kernel": d_name, "decompress_kernel_ms": dk,

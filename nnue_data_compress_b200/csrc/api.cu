@@ -25,7 +25,7 @@ enum WsSlot {
     WS_CODES = 0, WS_STEMS, WS_TILE_AGG, WS_PAYLOAD, WS_HEAD_OFF, WS_CHUNK_OFF, WS_TOTALS,
     WS_CHUNK_START, WS_CHUNK_LEN, WS_CHUNK_TILE_BASE, WS_CHUNK_INFO, WS_TILE_COUNT, WS_TILE_PREFIX,
     WS_CAND_CHUNK, WS_CAND_OFF, WS_CAND_NEXT, WS_CAND_BASE, WS_CAND_CNT, WS_CHUNK_COUNT, WS_CHUNK_SLOW, WS_CHUNK_BASE,
-    WS_DTOTALS, WS_AGG_TOP, WS_HEAD_NEXT, WS_PARK_A, WS_PARK_B, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_BLEED, WS_WALK, WS_COUNT
+    WS_DTOTALS, WS_AGG_TOP, WS_HEAD_NEXT, WS_PARK_A, WS_PARK_B, WS_TILE_FLAGS, WS_CAND_REC, WS_LSUM_A, WS_LSUM_B, WS_GAME_LEN, WS_GAME_BASE, WS_STAGE_IN, WS_STAGE_OUT, WS_TEXT_A, WS_TEXT_B, WS_TEXT_C, WS_TEXT_D, WS_BLEED, WS_WALK, WS_SCAN_TILES, WS_SCAN_PREFIX, WS_COUNT
 };
 
 // codes/stems of n records -> payload scan and payload write; leaves the headerless payload stream
@@ -807,6 +807,7 @@ struct DecodePlan {
     u64* tile_prefix = nullptr;
     u32* tile_flags = nullptr;
     DecompressTotals* d_tot = nullptr;
+    bool collapse = false;        // chunks of single positions are ONE entry of the candidate list (decompress_dev only)
     bool walked = false;          // decode_walk has run
     u32* chunk_flag = nullptr;    // decode_heads_only has run: 1 = the chunk holds nothing but single positions
     u64 heads_only_chunks = 0;
@@ -882,10 +883,29 @@ int decode_front(const void* d_in, size_t in_bytes, DecodePlan& P)
     WS(WS_TILE_FLAGS, P.tiles * (CAND_TILE / 32) * 4, u32, tile_flags);
     P.tile_prefix = tile_prefix;
     P.tile_flags = tile_flags;
-    launch_candidates_scan(d_in, in_bytes, P.tab, P.chunks, P.tiles, tile_count, tile_flags, C.debug_reject_mod, chunk_flag, s);
-    launch_exclusive_sum(tile_count, P.tiles, tile_prefix, s);
-    LAUNCHED(3, "k_candidates_scan");
     u64* h_u64 = reinterpret_cast<u64*>((char*)C.pinned + 768);
+    const u64* scan_prefix = nullptr;
+    u64 scan_total = 0;
+    if (P.collapse) {
+        WS(WS_SCAN_TILES, (P.chunks + 1) * 4, u32, scan_tiles);
+        WS(WS_SCAN_PREFIX, (P.chunks + 2) * 8, u64, prefix);
+        launch_collapsed_tiles(P.tab, P.chunks, chunk_flag, tile_count, tile_flags, scan_tiles, s);
+        launch_exclusive_sum(scan_tiles, P.chunks, prefix, s);
+        LAUNCHED(2, "k_collapsed_tiles");
+        CK(cudaMemcpyAsync(h_u64, prefix + P.chunks, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        scan_prefix = prefix;
+        scan_total = h_u64[0];
+    }
+    launch_candidates_scan(d_in, in_bytes, P.tab, P.chunks, P.tiles, tile_count, tile_flags, C.debug_reject_mod, chunk_flag,
+                           scan_prefix, scan_total, s);
+    {
+        // (one count per 4 KiB of file: a multi-block sum -- a file of single positions has 400 000 tiles per 100 M positions)
+        WS(WS_LSUM_A, (large_sum_tiles(P.tiles) + 1) * 4, u32, lsum_a);
+        WS(WS_LSUM_B, (large_sum_tiles(P.tiles) + 2) * 8, u64, lsum_b);
+        launch_exclusive_sum_large(tile_count, P.tiles, tile_prefix, lsum_a, lsum_b, s);
+    }
+    LAUNCHED(5, "k_candidates_scan");
     CK(cudaMemcpyAsync(h_u64, tile_prefix + P.tiles, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     P.ncand = h_u64[0];
@@ -894,7 +914,8 @@ int decode_front(const void* d_in, size_t in_bytes, DecodePlan& P)
     WS(WS_CAND_OFF, (P.ncand + 1) * 4, u32, cand_off);
     WS(WS_CAND_CNT, (P.ncand + 1) * 4, u32, cand_cnt);
     P.cand_chunk = cand_chunk; P.cand_off = cand_off; P.cand_cnt = cand_cnt;
-    launch_candidates_list(d_in, P.tab, P.tiles, tile_flags, tile_prefix, cand_chunk, cand_off, cand_cnt, s);
+    launch_candidates_list(d_in, P.tab, P.tiles, tile_flags, tile_prefix, cand_chunk, cand_off, cand_cnt,
+                           P.collapse ? chunk_flag : nullptr, s);
     LAUNCHED(1, "k_candidates_list");
     return NNP_OK;
 }
@@ -989,6 +1010,7 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
         if (rc != NNP_OK) return rc;
         CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(DecompressTotals), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        P.heads_only_chunks = h_tot->heads_only_chunks;
         if (h_tot->heads_only_chunks == P.chunks) {
             WS(WS_CHUNK_BASE, (P.chunks + 2) * 8, u64, chunk_base);
             launch_exclusive_sum(P.chunk_count, P.chunks, chunk_base, s);
@@ -1018,6 +1040,9 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
             return NNP_OK;
         }
     }
+    // chunks of single positions among ordinary ones (shuffled data in which a few records happen to continue
+    // their predecessor): each is one entry of the candidate list and k_emit_heads_chunks writes its records
+    P.collapse = d_out && P.chunk_flag && P.heads_only_chunks > 0 && C.debug_reject_mod == 0 && C.debug_dec_direct != 2;
     rc = decode_front(d_in, in_bytes, P);
     if (rc != NNP_OK) return rc;
     const u64* placed_rec = nullptr;
@@ -1050,6 +1075,11 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
             CK(cudaEventRecord(C.ev[1], s));
             launch_check_chunks(P.tab, P.chunks, P.tile_prefix, &P.d_tot->violations, s);
             LAUNCHED(1, "k_check_chunks");
+            const u32* collapsed = P.collapse ? P.chunk_flag : nullptr;
+            if (collapsed) {
+                launch_emit_heads_chunks(d_in, P.tab, P.chunks, collapsed, P.tile_prefix, cand_rec, d_out, rec_limit, s);
+                LAUNCHED(1, "k_emit_heads_chunks");
+            }
             if (C.pipe_dst && positions * 40 <= C.pipe_dst_cap && positions * 40 <= out_cap) {
                 // host output: emit in groups of chains and copy every group's records out while the
                 // next group is decoded (the record index of a chain is the prefix sum cand_rec)
@@ -1064,7 +1094,7 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
                 for (u64 g = 0; g < n_groups; ++g) {
                     const u64 lo = g * per, hi = lo + per < P.ncand ? lo + per : P.ncand;
                     launch_emit_chains_verify(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_cnt, cand_rec, P.ncand, lo, hi, d_out,
-                                              rec_limit, cand_next, &P.d_tot->violations, s);
+                                              rec_limit, cand_next, &P.d_tot->violations, collapsed, s);
                     LAUNCHED(1, "k_emit_chains_verify");
                     CK(cudaEventRecord(C.pipe_ev[g % 16], s));
                     CK(cudaStreamWaitEvent(C.copy_stream, C.pipe_ev[g % 16], 0));
@@ -1078,7 +1108,7 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
                 C.pipe_dst_done = true;
             } else {
                 launch_emit_chains_verify(d_in, P.tab, P.cand_chunk, P.cand_off, P.cand_cnt, cand_rec, P.ncand, 0, P.ncand, d_out,
-                                          rec_limit, cand_next, &P.d_tot->violations, s);
+                                          rec_limit, cand_next, &P.d_tot->violations, collapsed, s);
                 LAUNCHED(1, "k_emit_chains_verify");
             }
             CK(cudaEventRecord(C.ev[2], s));
@@ -1106,9 +1136,17 @@ int decompress_dev(const void* d_in, size_t in_bytes, void* d_out, size_t out_ca
         // is known (cand_next) and the reader's walk can be resolved per chunk without a probe pass; the
         // header counts that k_mark_conflicts zeroed are listed again; and chains that already lie where the
         // resolved walk wants them (everything in front of the first false candidate) are not written twice.
-        launch_candidates_list(d_in, P.tab, P.tiles, P.tile_flags, P.tile_prefix, P.cand_chunk, P.cand_off, P.cand_cnt, s);
-        LAUNCHED(1, "k_candidates_list");
-        repaired = true;
+        if (P.collapse) {
+            // (rare twice over: the strategies below know nothing of collapsed chunks -- list every chain start again)
+            P.collapse = false;
+            rc = decode_front(d_in, in_bytes, P);
+            if (rc != NNP_OK) return rc;
+        } else {
+            launch_candidates_list(d_in, P.tab, P.tiles, P.tile_flags, P.tile_prefix, P.cand_chunk, P.cand_off, P.cand_cnt, nullptr,
+                                   s);
+            LAUNCHED(1, "k_candidates_list");
+            repaired = true;
+        }
     }
 
     rc = decode_plan(d_in, in_bytes, false, P, true, repaired);

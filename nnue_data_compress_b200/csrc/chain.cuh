@@ -164,67 +164,136 @@ __device__ __forceinline__ bool stem_to_record(const unsigned char* s, u32* col,
     }
     const u64 occ = ((u64)__byte_perm(v[0], 0, 0x0123) << 32) | __byte_perm(v[1], 0, 0x0123);  // big-endian (:1245-1257)
     if (popc64(occ) > 32) return false;
-    const u64 nlo = ((u64)v[3] << 32) | v[2], nhi = ((u64)v[5] << 32) | v[4];  // nibble k: bits 4k.. of nlo (k < 16) / nhi
+    const int np = popc64(occ);
+    // the nibbles, np of them; what lies behind them is not looked at (stem_unpack visits occupied squares only)
+    u32 nb4[4];  // the nibble string, eight to a word
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int keep = min(max(4 * np - 32 * j, 0), 32);
+        nb4[j] = v[2 + j] & __funnelshift_lc(0xFFFFFFFFu, 0u, keep);
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) col[k * stride] = 0;
-    int stm = WHITE, cr = 0, ep = SQ_NONE, wk = 0, bk = 0, nwk = 0, nbk = 0, n12 = 0;
-    int cursor = 13;  // stream position of the next token
-    // Rank by rank, rank 8 first: the rank's nibbles are consecutive in the stem (its pieces in file order), so
-    // a 64-bit window over them is shifted once per rank and by one nibble per piece; the rank's tokens are
-    // gathered in a 64-bit register (at most 8 x 5 bits) and dropped into the stream column once per rank.
-#pragma unroll 1
-    for (int r = 7; r >= 0; --r) {
-        u32 rb = (u32)(occ >> (8 * r)) & 0xFFu;
-        const int first = popc64(occ & before64(8 * r));  // nibble index of the rank's first piece (< 32)
-        // nibbles first .. first + 7 as one 32-bit window
-        const u64 hi_part = first >= 16 ? 0ull : nhi, lo_part = first >= 16 ? nhi : nlo;
-        const int sh = (first & 15) * 4;
-        u32 nw = sh == 0 ? (u32)lo_part : (u32)((lo_part >> sh) | (hi_part << (64 - sh)));
-        u64 bits = 0;  // the rank's tokens, first square lowest
-        int nbits = 0, prev_f = -1;
-        while (rb) {
-            const int f = __ffs((int)rb) - 1;
-            rb &= rb - 1;
-            const int sq = 8 * r + f;
-            const int nib = (int)(nw & 15u);
-            nw >>= 4;
-            nbits += f - prev_f - 1;  // the empty squares in between: '0' bits
-            prev_f = f;
-            if (nib == 10) { wk = sq; ++nwk; continue; }  // kings occupy no stream bits
-            if (nib == 11 || nib == 15) {
-                bk = sq; ++nbk;
-                if (nib == 15) stm = BLACK;
-                continue;
-            }
-            int pc = nib;  // 0..11: Piece ordinal
-            if (nib == 12) {  // the pawn that just made a double push (Position.h:1440-1456)
-                ++n12;
-                if (r == 3) { pc = (PT_PAWN << 1) | WHITE; ep = (sq - 8) & 0xFF; }
-                else { pc = (PT_PAWN << 1) | BLACK; ep = (sq + 8) & 0xFF; }
-            } else if (nib == 13) {
-                pc = (PT_ROOK << 1) | WHITE;
-                cr |= (sq == 0) ? CR_WQ : CR_WK;
-            } else if (nib == 14) {
-                pc = (PT_ROOK << 1) | BLACK;
-                cr |= (sq == 56) ? CR_BQ : CR_BK;
-            }
-            bits |= (u64)stream_token(pc) << nbits;
-            nbits += 5;
-        }
-        nbits += 7 - prev_f;  // the empty squares behind the rank's last piece
-        {
-            const int wi = cursor >> 5, sb = cursor & 31;
-            const u32 b0 = (u32)bits, b1 = (u32)(bits >> 32);
-            col[wi * stride] |= b0 << sb;
-            const u32 mid = __funnelshift_l(b0, b1, sb);  // bits 32 - sb .. 63 - sb
-            if (wi < 7) col[(wi + 1) * stride] |= mid;
-            if (wi < 6 && sb) col[(wi + 2) * stride] |= b1 >> (32 - sb);
-        }
-        cursor += nbits;
+    // The nibbles above 9 carry state (Position.h:1374-1456): 10 / 11 the kings, 15 the black king with black to
+    // move, 12 the pawn that just made a double push, 13 / 14 a rook that may still castle. They are found in
+    // all 32 nibbles at once (bit-sliced compares) and rewritten to the plain piece they stand for, so that the
+    // loop over the squares below has no cases.
+    u32 k10[4], kbk[4], e12[4], e13[4], e14[4];
+    u32 any15 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const u32 M = 0x11111111u, x = nb4[j];
+        const u32 b0 = x & M, b1 = (x >> 1) & M, b2 = (x >> 2) & M, b3 = (x >> 3) & M;
+        k10[j] = b3 & ~b2 & b1 & ~b0;
+        kbk[j] = b3 & b1 & b0;  // 1011 and 1111
+        e12[j] = b3 & b2 & ~b1 & ~b0;
+        e13[j] = b3 & b2 & ~b1 & b0;
+        e14[j] = b3 & b2 & b1 & ~b0;
+        const u32 e15 = kbk[j] & b2;
+        any15 |= e15;
+        nb4[j] = x ^ (e13[j] * 0xBu) ^ (e14[j] * 0x9u) ^ (e15 * 0x4u) ^ (e12[j] * 0xCu);  // -> 6, 7, 11, 0
     }
+    const int nwk = __popc(k10[0]) + __popc(k10[1]) + __popc(k10[2]) + __popc(k10[3]);
+    const int nbk = __popc(kbk[0]) + __popc(kbk[1]) + __popc(kbk[2]) + __popc(kbk[3]);
+    const int n12 = __popc(e12[0]) + __popc(e12[1]) + __popc(e12[2]) + __popc(e12[3]);
     // (several ep nibbles -- corrupted input only -- are visited in a different order by stem_unpack, where the
     // last one counts: the other route)
     if (nwk != 1 || nbk != 1 || n12 > 1) return false;
+    // nibble index of the one marked nibble: words below the one that holds it count 8 (a zero word minus one is
+    // all ones), the word itself counts the nibbles below the mark, words above it are switched off
+    auto only = [](const u32 (&m)[4]) {
+        const u32 L = 0x11111111u;
+        const int c0 = __popc((m[0] - 1u) & L), c1 = __popc((m[1] - 1u) & L), c2 = __popc((m[2] - 1u) & L),
+                  c3 = __popc((m[3] - 1u) & L);
+        const bool s0 = m[0] != 0u, s1 = s0 || m[1] != 0u, s2 = s1 || m[2] != 0u;
+        return c0 + (s0 ? 0 : c1) + (s1 ? 0 : c2) + (s2 ? 0 : c3);
+    };
+    auto marked = [](const u32 (&m)[4], int k) {  // is nibble k marked?
+        const u64 lo = ((u64)m[1] << 32) | m[0], hi = ((u64)m[3] << 32) | m[2];
+        return (u32)(((k & 16) ? hi : lo) >> (4 * (k & 15))) & 1u;
+    };
+    const int stm = any15 ? BLACK : WHITE;
+    const int wk = nth_set_bit(occ, (u32)only(k10)), bk = nth_set_bit(occ, (u32)only(kbk));
+    // castling rights: a 13 on a1 is the queen side, anywhere else the king side; 14 likewise with a8
+    int cr = 0;
+    {
+        const u32 a1 = (u32)(occ & 1ull) & e13[0];  // nibble 0 is a1's when a1 is occupied
+        if (a1) cr |= CR_WQ;
+        if ((e13[0] ^ a1) | e13[1] | e13[2] | e13[3]) cr |= CR_WK;
+        const int q = popc64(occ & before64(56));
+        const bool a8 = ((occ >> 56) & 1ull) && marked(e14, q);
+        if (a8) cr |= CR_BQ;
+        const int n14 = __popc(e14[0]) + __popc(e14[1]) + __popc(e14[2]) + __popc(e14[3]);
+        if (n14 > (a8 ? 1 : 0)) cr |= CR_BK;
+    }
+    int ep = SQ_NONE;
+    if (n12) {  // the pawn that just made a double push (Position.h:1440-1456): white on rank 4, else black
+        const int k = only(e12), sq = nth_set_bit(occ, (u32)k);
+        if ((sq >> 3) == 3) {
+            ep = (sq - 8) & 0xFF;
+        } else {
+            ep = (sq + 8) & 0xFF;
+            const u32 bit = 1u << (4 * (k & 7));  // a black pawn is piece 1
+            if ((k >> 3) == 0) nb4[0] |= bit; else if ((k >> 3) == 1) nb4[1] |= bit; else if ((k >> 3) == 2) nb4[2] |= bit; else nb4[3] |= bit;
+        }
+    }
+    // Square by square in stream order (rank 8 first): one '0' for an empty square, 1 + type + colour for a piece,
+    // nothing for a king. The rank's nibbles are consecutive in the stem; every half rank gathers its tokens in
+    // a 32-bit register (at most 4 x 5 bits) and the rank is dropped into the stream column in one piece.
+    int cursor = 13;  // stream position of the next token
+    // the string is consumed from its top: moved up so that the last piece's nibble is the topmost one, the
+    // rank's nibbles are the top 4 * (pieces of the rank) bits, and the string moves up by as much afterwards
+    u32 t0 = nb4[0], t1 = nb4[1], t2 = nb4[2], t3 = nb4[3];
+    {
+        const int up = 4 * (32 - np);  // 0 .. 120 (a stem has at least the two kings)
+        if (up & 64) { t3 = t1; t2 = t0; t1 = 0u; t0 = 0u; }
+        if (up & 32) { t3 = t2; t2 = t1; t1 = t0; t0 = 0u; }
+        t3 = __funnelshift_l(t2, t3, up);
+        t2 = __funnelshift_l(t1, t2, up);
+        t1 = __funnelshift_l(t0, t1, up);
+        t0 <<= (up & 31);
+    }
+#pragma unroll
+    for (int r = 7; r >= 0; --r) {
+        const u32 rb = (u32)(occ >> (8 * r)) & 0xFFu;
+        const int take = 4 * __popc(rb);                 // 0 .. 32 bits
+        u32 nw = __funnelshift_rc(t3, 0u, 32 - take);    // the rank's nibbles, file a lowest
+        t3 = __funnelshift_lc(t2, t3, take);
+        t2 = __funnelshift_lc(t1, t2, take);
+        t1 = __funnelshift_lc(t0, t1, take);
+        t0 = __funnelshift_lc(0u, t0, take);
+        u32 hb[2];
+        int hn[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            // (the place of the next token is kept as a power of two and tokens are multiplied into place: the
+            // kernels that call this are bound by the integer ALU pipe, multiply-adds issue on the other one)
+            u32 b = 0, pw = 1;
+#pragma unroll
+            for (int f = 4 * h; f < 4 * h + 4; ++f) {
+                const u32 p = (rb >> f) & 1u;
+                const u32 nib = nw & 15u;
+                const u32 king = nib >= 10u ? p : 0u;
+                const u32 emit = p ^ king;
+                const u32 tok = 1u | (nib & 14u) | ((nib & 1u) << 4);  // stream_token
+                b += tok * emit * pw;
+                pw *= 30u * emit + 2u - king;  // x 32 behind a token, x 2 behind a '0', x 1 for a king
+                nw >>= 4 * p;
+            }
+            hb[h] = b;
+            hn[h] = 31 - __clz((int)pw);
+        }
+        const u64 bits = (u64)hb[0] | ((u64)hb[1] << hn[0]);
+        {
+            const int ci = cursor >> 5, sb = cursor & 31;
+            const u32 b0 = (u32)bits, b1 = (u32)(bits >> 32);
+            col[ci * stride] |= b0 << sb;
+            const u32 mid = __funnelshift_l(b0, b1, sb);  // bits 32 - sb .. 63 - sb
+            if (ci < 7) col[(ci + 1) * stride] |= mid;
+            if (ci < 6 && sb) col[(ci + 2) * stride] |= b1 >> (32 - sb);
+        }
+        cursor += hn[0] + hn[1];
+    }
     // header, then castling / ep / rule50 / full move behind the board (stream_with_tail)
     u32 T = (u32)cr & 15u;
     int n = 5;

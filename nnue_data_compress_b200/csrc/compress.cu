@@ -167,40 +167,69 @@ static __device__ __noinline__ void heads_other(const unsigned char* __restrict_
     if (bleed) bleed_report(BleedLog{bleed_list, &tot->bleeds}, rec, bleed);
 }
 
+// occupancy of record `rec`, for the first thread of a block (its predecessor is in another block's tile)
+static __device__ __noinline__ bool heads_occupancy(const unsigned char* __restrict__ bin, u64 rec, u64& occ)
+{
+    const u32* w = reinterpret_cast<const u32*>(bin + rec * 40);
+    u32 s[8];
+    if (record_to_stem([&](int j) { return w[j]; }, s) != HEADS_OK) return false;
+    occ = bswap64((u64)s[0] | ((u64)s[1] << 32));
+    return true;
+}
+
+// Can record `rec` (fields linked to its predecessor) continue it? A move changes at most four squares of the
+// occupancy (castling), so two positions that differ in more cannot be a move apart -- which settles nearly
+// every accidental field link between unrelated positions without decoding either of them. `prev_occ` is the
+// predecessor's occupancy if a neighbouring thread has it.
+__device__ __forceinline__ bool heads_may_continue(const unsigned char* __restrict__ bin, u64 rec, u64 occ, bool have_prev,
+                                                   u64 prev_occ)
+{
+    if (!have_prev && !heads_occupancy(bin, rec - 1, prev_occ)) return true;
+    return popc64(prev_occ ^ occ) <= 4;
+}
+
 __global__ void __launch_bounds__(KH_THREADS, 8)
 k_heads_transcode(const unsigned char* __restrict__ bin, u64 n, u32* __restrict__ codes, u32* __restrict__ stems,
                   CompressTotals* tot, u64* __restrict__ bleed_list)
 {
     __shared__ __align__(16) u32 raw[KH_THREADS * 10];
+    __shared__ u64 occs[KH_THREADS];
+    __shared__ unsigned char sts[KH_THREADS];
     const int t = threadIdx.x;
     const u64 first = (u64)blockIdx.x * KH_THREADS;
-    const u64 count = n - first < (u64)KH_THREADS ? n - first : (u64)KH_THREADS;
+    const int count = (int)(n - first < (u64)KH_THREADS ? n - first : (u64)KH_THREADS);
     {
         const uint2* src = reinterpret_cast<const uint2*>(bin + first * 40);
         uint2* dst = reinterpret_cast<uint2*>(raw);
-        for (int i = t; i < (int)count * 5; i += KH_THREADS) dst[i] = src[i];
+        for (int i = t; i < count * 5; i += KH_THREADS) dst[i] = src[i];
     }
     __syncthreads();
-    if ((u64)t >= count) return;
     const u64 rec = first + t;
     const u32* w = raw + t * 10;
+    u32 s[8] = {};
+    int st = HEADS_OTHER;
+    if (t < count) {
+        st = record_to_stem([&](int j) { return w[j]; }, s);
+        occs[t] = bswap64((u64)s[0] | ((u64)s[1] << 32));
+        sts[t] = (unsigned char)st;
+    }
+    __syncthreads();
+    if (t >= count) return;
     bool linked = false;
     if (rec > 0) {
         const u32 prev9 = t > 0 ? w[-1] : reinterpret_cast<const u32*>(bin + rec * 40)[-1];
         linked = fields_link(prev9, w[9]);
     }
-    int st = HEADS_OTHER;
-    if (!linked) {
-        u32 s[8];
-        st = record_to_stem([&](int j) { return w[j]; }, s);
-        if (st == HEADS_OK) {
-            codes[rec] = 0u;
-            uint4* d = reinterpret_cast<uint4*>(stems + rec * 8);
-            d[0] = make_uint4(s[0], s[1], s[2], s[3]);
-            d[1] = make_uint4(s[4], s[5], s[6], s[7]);
-        }
+    if (st == HEADS_OK && linked && !heads_may_continue(bin, rec, occs[t], t > 0 && sts[t - 1] == HEADS_OK, t > 0 ? occs[t - 1] : 0ull))
+        linked = false;
+    if (st == HEADS_OK && !linked) {
+        codes[rec] = 0u;
+        uint4* d = reinterpret_cast<uint4*>(stems + rec * 8);
+        d[0] = make_uint4(s[0], s[1], s[2], s[3]);
+        d[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    } else {
+        heads_other(bin, rec, linked, codes, stems, tot, bleed_list);  // also reports malformed streams
     }
-    if (st != HEADS_OK) heads_other(bin, rec, linked, codes, stems, tot, bleed_list);  // also reports malformed streams
 }
 
 // k_heads_direct: the whole conversion in one kernel for a file in which EVERY record starts a chain. Then every
@@ -220,16 +249,6 @@ constexpr int HD_THREADS = 128;
 __host__ __device__ __forceinline__ u64 heads_direct_offset(u64 rec)
 {
     return (rec / HEADS_PER_CHUNK) * (HEADS_CHUNK_BYTES + 8) + 8 + (rec % HEADS_PER_CHUNK) * 34;
-}
-
-// occupancy of record `rec` for the first thread of a block (its predecessor is in another block's tile)
-static __device__ __noinline__ bool heads_occupancy(const unsigned char* __restrict__ bin, u64 rec, u64& occ)
-{
-    const u32* w = reinterpret_cast<const u32*>(bin + rec * 40);
-    u32 s[8];
-    if (record_to_stem([&](int j) { return w[j]; }, s) != HEADS_OK) return false;
-    occ = bswap64((u64)s[0] | ((u64)s[1] << 32));
-    return true;
 }
 
 __global__ void __launch_bounds__(HD_THREADS, 8)
@@ -264,11 +283,8 @@ k_heads_direct(const unsigned char* __restrict__ bin, u64 n, unsigned char* __re
         bool doubt = st != HEADS_OK;
         if (!doubt && rec > 0) {
             const u32 prev9 = t > 0 ? w[-1] : reinterpret_cast<const u32*>(bin + rec * 40)[-1];
-            if (fields_link(prev9, w[9])) {
-                u64 po = t > 0 ? occs[t - 1] : 0ull;
-                const bool have = t > 0 ? true : heads_occupancy(bin, rec - 1, po);
-                doubt = !have || popc64(po ^ occs[t]) <= 4;
-            }
+            // (a predecessor the transcoder refused raises the fallback itself)
+            if (fields_link(prev9, w[9])) doubt = heads_may_continue(bin, rec, occs[t], t > 0, t > 0 ? occs[t - 1] : 0ull);
         }
         if (doubt) atomicOr(fallback, 1u);
         unsigned short* img = reinterpret_cast<unsigned short*>(image) + ((heads_direct_offset(rec) - img_base) >> 1);
@@ -733,6 +749,55 @@ k_write_payload(const u32* __restrict__ codes, const u32* __restrict__ stems, u6
     u64 M = st.bytes;
     u32 ob = st.post_bits, op = st.post_plies;
     u64 h = st.heads;
+    if (!BLEED) {
+        // A warp whose 256 records all start chains (files of single positions) writes 256 x 34 contiguous
+        // bytes: the stems go through shared memory 64 at a time and leave as whole words, each lane
+        // assembling the words it owns; only the two ragged edge words of a batch are OR-ed. Per record this
+        // replaces two atomics and nine scattered stores of one thread by a share of coalesced ones.
+        __shared__ __align__(16) u32 stage[SCAN_THREADS / 32][64 * 8];
+        const bool mine = base + SCAN_ITEMS <= n && local.heads == (u32)SCAN_ITEMS;
+        if (__all_sync(0xffffffffu, mine)) {
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            u64 P0 = 0;
+            if (lane == 0 && h > 0) {
+                P0 = M + ceil8(ob);
+                if (op != 0) {  // numPlies of the chain that ends in front of the warp's first record (:1118-1119)
+                    or_byte(payload, M - 2, op >> 8);
+                    or_byte(payload, M - 1, op);
+                }
+            }
+            P0 = __shfl_sync(0xffffffffu, P0, 0);
+            const u64 h0 = __shfl_sync(0xffffffffu, h, 0), rec0 = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) head_off[h0 + 32 * k + lane] = P0 + 34ull * (32 * k + lane);
+            const unsigned char* sb = reinterpret_cast<const unsigned char*>(stage[warp]);
+            for (int q = 0; q < 4; ++q) {
+                const uint4* src = reinterpret_cast<const uint4*>(stems + (rec0 + 64 * q) * 8);
+                uint4* dst = reinterpret_cast<uint4*>(stage[warp]);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dst[32 * k + lane] = src[32 * k + lane];
+                __syncwarp();
+                const u64 lo = P0 + 2176ull * q, hi = lo + 2176;  // the batch's bytes of the payload
+                const u64 w_lo = lo >> 2, w_hi = (hi + 3) >> 2;
+                for (u64 wd = w_lo + lane; wd < w_hi; wd += 32) {
+                    u32 v = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const long long rel = (long long)(4 * wd + i) - (long long)lo;
+                        if (rel >= 0 && rel < 2176) {
+                            const u32 r = (u32)rel / 34u, within = (u32)rel - 34u * r;
+                            if (within < 32u) v |= (u32)sb[32u * r + within] << (8 * i);  // (numPlies stays 0)
+                        }
+                    }
+                    if (4 * wd >= lo && 4 * wd + 4 <= hi) payload[wd] = v;
+                    else if (v) atomicOr(payload + wd, v);
+                }
+            }
+            // (should the file end with this warp, its last chain has no plies and its numPlies stays 0)
+            return;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
         const u64 rec = base + i;
@@ -881,14 +946,27 @@ k_chunk_orbit(const u64* __restrict__ head_off, const u32* __restrict__ next, Co
             if (target <= total) cur = orbit_search(head_off, 0, H, target, lane);
         }
     }
+    // One hop is one dependent load (0.5 us from HBM). Where chains are all alike -- files of single positions:
+    // 3242 chunks per 100 M of them -- the next chunk starts as many heads further on as the last one did, so the
+    // lanes load the 32 heads that lie 0, 1, 2 ... strides ahead at once and the longest prefix whose links
+    // confirm each other is taken in one round trip; anywhere else the prefix is one hop long, as before.
+    u64 stride = 0;
+    while (cur < H) {
+        const u64 idx = cur + (u64)lane * stride;
+        const bool in = idx < H;
+        const u64 nx = in ? (u64)next[idx] : H;
+        const u64 off = in ? head_off[idx] : 0;
+        const u64 idx_up = __shfl_down_sync(0xffffffffu, idx, 1);
+        const bool linked = in && lane < 31 && nx == idx_up && nx < H;  // the lane above looked at the right head
+        const u32 votes = __ballot_sync(0xffffffffu, linked);
+        const int m = 1 + (__ffs((int)~votes) - 1);  // lanes 0 .. m-1 are on the orbit
+        if (lane < m && k + lane < max_chunks) seg_off[1 + k + lane] = off;
+        k += (u64)m;
+        const u64 last_nx = __shfl_sync(0xffffffffu, nx, m - 1), last_idx = __shfl_sync(0xffffffffu, idx, m - 1);
+        stride = last_nx - last_idx;
+        cur = last_nx;
+    }
     if (lane == 0) {
-        while (cur < H) {
-            const u64 off = head_off[cur];
-            const u64 nx = next[cur];
-            if (k < max_chunks) seg_off[1 + k] = off;
-            ++k;
-            cur = nx;
-        }
         seg_off[1 + (k < max_chunks ? k : max_chunks)] = total;
         tot->chunks = k;
     }

@@ -518,7 +518,8 @@ k_emit_heads_only(const unsigned char* __restrict__ in, ChunkTable tab, u64 chun
 // with dense warps.
 __global__ void __launch_bounds__(CAND_THREADS)
 k_candidates_scan(const unsigned char* __restrict__ in, u64 n_in, ChunkTable tab, u32* __restrict__ tile_count,
-                  u32* __restrict__ tile_flags, u32 debug_reject_mod, const u32* __restrict__ chunk_flag)
+                  u32* __restrict__ tile_flags, u32 debug_reject_mod, const u32* __restrict__ chunk_flag,
+                  const u64* __restrict__ scan_prefix)
 {
     __shared__ __align__(16) unsigned char sm[CAND_TILE + 96];  // the tile from its 16-byte aligned base
     __shared__ u32 flags[CAND_TILE / 32];
@@ -526,8 +527,9 @@ k_candidates_scan(const unsigned char* __restrict__ in, u64 n_in, ChunkTable tab
     __shared__ u32 warp_tot[CAND_THREADS / 32];
     __shared__ u32 nq, nq2;
     const int t = threadIdx.x, lane = t & 31;
-    const u64 tile = blockIdx.x;
-    const u64 c = find_chunk(tab.tile_base, tab.info->chunks, tile);
+    // `scan_prefix` (collapse mode): the grid only covers the tiles of the chunks that are not collapsed
+    const u64 c = scan_prefix ? find_chunk(scan_prefix, tab.info->chunks, blockIdx.x) : find_chunk(tab.tile_base, tab.info->chunks, blockIdx.x);
+    const u64 tile = scan_prefix ? tab.tile_base[c] + (blockIdx.x - scan_prefix[c]) : blockIdx.x;
     const u64 clen = tab.len[c];
     const u64 off0 = (tile - tab.tile_base[c]) * CAND_TILE;
     const unsigned char* src = in + tab.start[c] + off0;
@@ -543,6 +545,7 @@ k_candidates_scan(const unsigned char* __restrict__ in, u64 n_in, ChunkTable tab
                 word = 1u << (u32)(m - base);
                 if (debug_reject_mod && (u32)((m * 2654435761ull) >> 11) % debug_reject_mod == 0) word = 0;  // test hook
             }
+
             tile_flags[tile * (CAND_TILE / 32) + t] = word;
             mine = word != 0;
         }
@@ -642,7 +645,7 @@ constexpr int LIST_THREADS = CAND_TILE / 32;  // one thread per bitmap word
 __global__ void __launch_bounds__(LIST_THREADS)
 k_candidates_list(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ tile_flags,
                   const u64* __restrict__ tile_prefix, u32* __restrict__ cand_chunk, u32* __restrict__ cand_off,
-                  u32* __restrict__ cand_cnt)
+                  u32* __restrict__ cand_cnt, const u32* __restrict__ collapsed)
 {
     __shared__ u32 warp_tot[LIST_THREADS / 32];
     const u64 tile = blockIdx.x;
@@ -660,7 +663,7 @@ k_candidates_list(const unsigned char* __restrict__ in, ChunkTable tab, const u3
         const u32 o = threadIdx.x * 32 + b;
         cand_chunk[slot] = (u32)c;
         cand_off[slot] = (u32)(off0 + o);
-        cand_cnt[slot] = 1u + (((u32)src[o + 32] << 8) | (u32)src[o + 33]);
+        cand_cnt[slot] = collapsed && collapsed[c] ? tab.len[c] / 34u : 1u + (((u32)src[o + 32] << 8) | (u32)src[o + 33]);
         ++slot;
     }
 }
@@ -871,7 +874,7 @@ __global__ void __launch_bounds__(EMITC_THREADS, EMIT_MIN_BLOCKS)
 k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ cand_chunk,
                      const u32* __restrict__ cand_off, const u32* __restrict__ cand_cnt, const u64* __restrict__ cand_rec,
                      u64 ncand, u64 cand_lo, u64 cand_hi, unsigned char* __restrict__ out, u64 rec_limit,
-                     u32* __restrict__ cand_next, u64* __restrict__ violations)
+                     u32* __restrict__ cand_next, u64* __restrict__ violations, const u32* __restrict__ collapsed)
 {
     __shared__ u32 scratch[8 * EMITC_THREADS];
     __shared__ StepTables T;
@@ -898,7 +901,11 @@ k_emit_chains_verify(const unsigned char* __restrict__ in, ChunkTable tab, const
     const u64 rec0 = cand_rec[i];
     const unsigned char* s = in + tab.start[c] + off;
     u32 consumed = 0;
-    bool ok = emit_chain_bin(s, clen - off - 34, out, rec0, rec_limit, scratch + threadIdx.x, EMITC_THREADS, consumed, &T, slot);
+    bool ok = true;
+    if (collapsed && collapsed[c])
+        consumed = clen / 34u * 34u;  // a chunk of single positions, listed as one entry: k_emit_heads_chunks writes it
+    else
+        ok = emit_chain_bin(s, clen - off - 34, out, rec0, rec_limit, scratch + threadIdx.x, EMITC_THREADS, consumed, &T, slot);
     // where the chain ends: should a link not hold anywhere, the reader's walk is resolved from these
     // (k_resolve_chunks) without decoding every candidate a second time
     cand_next[i] = ok ? off + consumed : 0xFFFFFFFFu;
@@ -1026,6 +1033,47 @@ void launch_walk_chunks(const void* d_in, u64 n, ChunkTable tab, u64 max_chunks,
     }
     k_walk_chunks<<<1, 32, 0, s>>>(in, n, tab, max_chunks, world, rank, done);
 }
+// k_collapsed_tiles: in collapse mode a chunk of single positions is ONE entry of the candidate list (offset 0, as
+// many positions as the chunk has stems; k_emit_heads_chunks writes its records): its first tile lists bit 0, its
+// other tiles nothing, and k_candidates_scan is not launched for any of them (scan_tiles[c] = 0).
+__global__ void __launch_bounds__(CAND_TILE / 32)
+k_collapsed_tiles(ChunkTable tab, const u32* __restrict__ chunk_flag, u32* __restrict__ tile_count,
+                  u32* __restrict__ tile_flags, u32* __restrict__ scan_tiles)
+{
+    const u64 c = blockIdx.x;
+    const u64 tb = tab.tile_base[c], ntiles = tab.tile_base[c + 1] - tb;
+    if (!chunk_flag[c]) {
+        if (threadIdx.x == 0) scan_tiles[c] = (u32)ntiles;
+        return;
+    }
+    if (threadIdx.x == 0) scan_tiles[c] = 0;
+    tile_flags[tb * (CAND_TILE / 32) + threadIdx.x] = threadIdx.x == 0 ? 1u : 0u;
+    for (u64 j = threadIdx.x; j < ntiles; j += CAND_TILE / 32) tile_count[tb + j] = j == 0 ? 1u : 0u;
+}
+
+// k_emit_heads_chunks: the records of the chunks that the candidate list holds as one entry each (`collapsed`):
+// record k of chunk c is the stem at byte 34 * k, its index the entry's record offset + k. blockIdx.x = chunk,
+// blockIdx.y strides over the chunk's stems.
+__global__ void __launch_bounds__(HEADS_EMIT_THREADS, 5)
+k_emit_heads_chunks(const unsigned char* __restrict__ in, ChunkTable tab, const u32* __restrict__ collapsed,
+                    const u64* __restrict__ tile_prefix, const u64* __restrict__ cand_rec, unsigned char* __restrict__ out,
+                    u64 rec_limit)
+{
+    __shared__ u32 scratch[8 * HEADS_EMIT_THREADS];
+    __shared__ StepTables T;
+    const u64 c = blockIdx.x;
+    if (!collapsed[c]) return;
+    const u32 stems = tab.len[c] / 34u;
+    if ((u64)blockIdx.y * HEADS_EMIT_THREADS >= stems) return;
+    step_tables_fill(T);
+    const u64 rec0 = cand_rec[tile_prefix[tab.tile_base[c]]];  // the chunk's entry is the first of its first tile
+    const unsigned char* s = in + tab.start[c];
+    for (u32 k = blockIdx.y * HEADS_EMIT_THREADS + threadIdx.x; k < stems; k += gridDim.y * HEADS_EMIT_THREADS) {
+        u32 consumed = 0;
+        emit_chain_bin(s + 34ull * k, 0u, out, rec0 + k, rec_limit, scratch + threadIdx.x, HEADS_EMIT_THREADS, consumed, &T, nullptr);
+    }
+}
+
 void launch_chunk_heads_only(const void* d_in, ChunkTable tab, u64 chunks, u32* chunk_flag, u32* chunk_stems, u64* flagged,
                              cudaStream_t s)
 {
@@ -1040,13 +1088,31 @@ void launch_emit_heads_only(const void* d_in, ChunkTable tab, u64 chunks, const 
     k_emit_heads_only<<<(unsigned)((positions + HEADS_EMIT_THREADS - 1) / HEADS_EMIT_THREADS), HEADS_EMIT_THREADS, 0, s>>>(
         (const unsigned char*)d_in, tab, chunks, chunk_base, (unsigned char*)d_out, rec_limit);
 }
-// (chunk_flag: filled by launch_chunk_heads_only beforehand)
+// (chunk_flag: filled by launch_chunk_heads_only beforehand; scan_prefix / scan_total: collapse mode, see
+// launch_collapsed_tiles)
 void launch_candidates_scan(const void* d_in, u64 n_in, ChunkTable tab, u64 chunks, u64 tiles, u32* tile_count, u32* tile_flags,
-                            u32 debug_reject_mod, const u32* chunk_flag, cudaStream_t s)
+                            u32 debug_reject_mod, const u32* chunk_flag, const u64* scan_prefix, u64 scan_total, cudaStream_t s)
 {
     if (tiles == 0 || chunks == 0) return;
-    k_candidates_scan<<<(unsigned)tiles, CAND_THREADS, 0, s>>>((const unsigned char*)d_in, n_in, tab, tile_count, tile_flags,
-                                                             debug_reject_mod, chunk_flag);
+    const u64 blocks = scan_prefix ? scan_total : tiles;
+    if (blocks == 0) return;
+    k_candidates_scan<<<(unsigned)blocks, CAND_THREADS, 0, s>>>((const unsigned char*)d_in, n_in, tab, tile_count, tile_flags,
+                                                              debug_reject_mod, chunk_flag, scan_prefix);
+}
+void launch_collapsed_tiles(ChunkTable tab, u64 chunks, const u32* chunk_flag, u32* tile_count, u32* tile_flags, u32* scan_tiles,
+                            cudaStream_t s)
+{
+    if (chunks == 0) return;
+    k_collapsed_tiles<<<(unsigned)chunks, CAND_TILE / 32, 0, s>>>(tab, chunk_flag, tile_count, tile_flags, scan_tiles);
+}
+void launch_emit_heads_chunks(const void* d_in, ChunkTable tab, u64 chunks, const u32* collapsed, const u64* tile_prefix,
+                              const u64* cand_rec, void* d_out, u64 rec_limit, cudaStream_t s)
+{
+    if (chunks == 0) return;
+    // 256 blocks of 128 stems cover the 30 841 stems of an ordinary chunk in one pass; larger chunks are strided
+    k_emit_heads_chunks<<<dim3((unsigned)chunks, 256), HEADS_EMIT_THREADS, 0, s>>>((const unsigned char*)d_in, tab, collapsed,
+                                                                                   tile_prefix, cand_rec, (unsigned char*)d_out,
+                                                                                   rec_limit);
 }
 void launch_mark_conflicts(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u32* cand_cnt,
                            u64 ncand, cudaStream_t s)
@@ -1056,11 +1122,11 @@ void launch_mark_conflicts(const void* d_in, ChunkTable tab, const u32* cand_chu
                                                                     cand_cnt, ncand);
 }
 void launch_candidates_list(const void* d_in, ChunkTable tab, u64 tiles, const u32* tile_flags, const u64* tile_prefix,
-                            u32* cand_chunk, u32* cand_off, u32* cand_cnt, cudaStream_t s)
+                            u32* cand_chunk, u32* cand_off, u32* cand_cnt, const u32* collapsed, cudaStream_t s)
 {
     if (tiles == 0) return;
     k_candidates_list<<<(unsigned)tiles, LIST_THREADS, 0, s>>>((const unsigned char*)d_in, tab, tile_flags, tile_prefix,
-                                                             cand_chunk, cand_off, cand_cnt);
+                                                             cand_chunk, cand_off, cand_cnt, collapsed);
 }
 void launch_check_chunks(ChunkTable tab, u64 chunks, const u64* tile_prefix, u64* violations, cudaStream_t s)
 {
@@ -1069,12 +1135,12 @@ void launch_check_chunks(ChunkTable tab, u64 chunks, const u64* tile_prefix, u64
 }
 void launch_emit_chains_verify(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off,
                                const u32* cand_cnt, const u64* cand_rec, u64 ncand, u64 cand_lo, u64 cand_hi, void* out,
-                               u64 rec_limit, u32* cand_next, u64* violations, cudaStream_t s)
+                               u64 rec_limit, u32* cand_next, u64* violations, const u32* collapsed, cudaStream_t s)
 {
     if (cand_hi <= cand_lo) return;
     k_emit_chains_verify<<<(unsigned)((cand_hi - cand_lo + EMITC_THREADS - 1) / EMITC_THREADS), EMITC_THREADS, 0, s>>>(
         (const unsigned char*)d_in, tab, cand_chunk, cand_off, cand_cnt, cand_rec, ncand, cand_lo, cand_hi, (unsigned char*)out,
-        rec_limit, cand_next, violations);
+        rec_limit, cand_next, violations, collapsed);
 }
 void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s)
 {

@@ -67,16 +67,23 @@ void launch_chunk_heads_only(const void* d_in, ChunkTable tab, u64 chunks, u32* 
 void launch_emit_heads_only(const void* d_in, ChunkTable tab, u64 chunks, const u64* chunk_base, u64 positions, void* d_out,
                             u64 rec_limit, cudaStream_t s);
 void launch_candidates_scan(const void* d_in, u64 n_in, ChunkTable tab, u64 chunks, u64 tiles, u32* tile_count, u32* tile_flags,
-                            u32 debug_reject_mod, const u32* chunk_flag, cudaStream_t s);
+                            u32 debug_reject_mod, const u32* chunk_flag, const u64* scan_prefix, u64 scan_total, cudaStream_t s);
+// collapse mode: the tiles of the chunks of single positions get their (one) entry here, scan_tiles[c] = tiles of
+// chunk c that k_candidates_scan still has to look at (its grid is their sum, `scan_prefix` their exclusive sum)
+void launch_collapsed_tiles(ChunkTable tab, u64 chunks, const u32* chunk_flag, u32* tile_count, u32* tile_flags, u32* scan_tiles,
+                            cudaStream_t s);
+// `collapsed` (nullable, per chunk): the chunk is one entry of the candidate list (see k_candidates_scan)
+void launch_emit_heads_chunks(const void* d_in, ChunkTable tab, u64 chunks, const u32* collapsed, const u64* tile_prefix,
+                              const u64* cand_rec, void* d_out, u64 rec_limit, cudaStream_t s);
 void launch_mark_conflicts(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u32* cand_cnt,
                            u64 ncand, cudaStream_t s);
 void launch_candidates_list(const void* d_in, ChunkTable tab, u64 tiles, const u32* tile_flags, const u64* tile_prefix,
-                            u32* cand_chunk, u32* cand_off, u32* cand_cnt, cudaStream_t s);
+                            u32* cand_chunk, u32* cand_off, u32* cand_cnt, const u32* collapsed, cudaStream_t s);
 void launch_check_chunks(ChunkTable tab, u64 chunks, const u64* tile_prefix, u64* violations, cudaStream_t s);
 // candidates [cand_lo, cand_hi)
 void launch_emit_chains_verify(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off,
                                const u32* cand_cnt, const u64* cand_rec, u64 ncand, u64 cand_lo, u64 cand_hi, void* out,
-                               u64 rec_limit, u32* cand_next, u64* violations, cudaStream_t s);
+                               u64 rec_limit, u32* cand_next, u64* violations, const u32* collapsed, cudaStream_t s);
 void launch_exclusive_sum(const u32* in, u64 n, u64* out, cudaStream_t s);
 void launch_exclusive_sum64(const u64* in, u64 n, u64* out, cudaStream_t s);
 void launch_probe_chains(const void* d_in, ChunkTable tab, const u32* cand_chunk, const u32* cand_off, u64 ncand,

@@ -114,6 +114,39 @@ def test_files_of_single_positions_take_one_kernel(nnp, n):
         nnp.lib().nnp_debug_config(b"dec_direct", 0)
 
 
+def test_single_position_chunks_among_game_chunks(nnp):
+    """Chunks of nothing but single positions between ordinary chunks (shuffled data in which a few records
+    continue their predecessor; files concatenated from both kinds): the decoder lists such a chunk as one entry
+    and writes its records without looking for chain starts, the rest takes the verified walk; the records and
+    the strategy's outcome are the oracle's. With a damaged numPlies in one of them the file still decodes."""
+    import numpy as np
+
+    games = np.frombuffer(nnp.generate_bin(300_000, 100, 9), dtype=np.uint8).reshape(-1, 40)
+    shuffled = games[np.random.default_rng(4).permutation(len(games))].tobytes()
+    singles = nnp.generate_bin(100_000, 1, 5)
+    for data in (shuffled, singles + games.tobytes()[:40 * 120_000] + singles, games.tobytes()[:40 * 50_000] + singles):
+        rc, pack = oracle_convert(BIN_TO_BINPACK, data)
+        assert rc == 0
+        assert nnp.bin_to_binpack(data) == pack
+        rc, want = oracle_convert(BINPACK_TO_BIN, pack)
+        assert rc == 0
+        before = nnp.decode_stats()["optimistic_hits"]
+        assert nnp.binpack_to_bin(pack) == want
+        if data is shuffled:  # (every chunk may be of the single-position kind: then nothing is verified)
+            assert nnp.lib().nnp_last_dominant_kernel() in (b"k_emit_chains_verify", b"k_emit_heads_only")
+        else:
+            assert nnp.decode_stats()["optimistic_hits"] == before + 1
+            assert nnp.lib().nnp_last_dominant_kernel() == b"k_emit_chains_verify"
+        bad = bytearray(pack)
+        bad[8 + 34 * 1000 + 33] ^= 1  # numPlies of a chain in the first chunk
+        rc, want = oracle_convert(BINPACK_TO_BIN, bytes(bad))
+        if rc == 0:
+            try:
+                assert nnp.binpack_to_bin(bytes(bad)) == want
+            except nnp.NnpError as e:
+                assert e.status == -4, e.status
+
+
 def test_single_position_chunks_with_damaged_stems(nnp):
     """The candidate-free reader takes every 34 bytes as a stem whatever they hold, as the reference does: stems
     with flipped bits (irregular nibbles, stray special codes) decode to the oracle's records; a flipped

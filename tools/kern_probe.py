@@ -9,11 +9,16 @@ sys.path.insert(0, ".")
 import nnue_data_compress_b200 as nnp
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
-plies = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+shuffled = len(sys.argv) > 2 and sys.argv[2] == "shuffled"  # positions of 100-ply games in random order
+plies = 100 if shuffled or len(sys.argv) <= 2 else int(sys.argv[2])
 nnp.init(0)
 L = nnp.lib()
 d_bin = torch.empty(n * 40, dtype=torch.uint8, device="cuda")
 assert L.nnp_generate_bin_dev(ctypes.c_void_p(d_bin.data_ptr()), n, plies, 42) == 0
+if shuffled:
+    rows = d_bin.view(torch.int64).view(n, 5)
+    rows.copy_(rows[torch.randperm(n, device="cuda")])
+    plies = 1
 cap = n * 40 // 8 + (1 << 20) if plies > 20 else n * 36 + (1 << 20)
 d_pack = torch.empty(cap, dtype=torch.uint8, device="cuda")
 d_out = torch.empty(n * 40, dtype=torch.uint8, device="cuda")
