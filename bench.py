@@ -24,7 +24,8 @@ configs[2] beside it: the same 100 M-position file decoded by 1/2/4/8 ranks (str
 
 Auxiliary keys at N = 1, all outside the timed regions of `value` and `e2e`: `parity_checked` (the
 compiled reference run on the first records of this run's own input, compared with the GPU output),
-`plain` (BASELINE configs[3]), `sweep` (configs[4] chain lengths), `halfkp`, `e2e_file`.
+`plain` (BASELINE configs[3]), `sweep` (configs[4] chain lengths 1 / 8 / 64 / 400, plus chain length 1 as training
+pipelines produce it: the positions of 100-ply games in random order), `halfkp`, `e2e_file`.
 """
 import argparse
 import ctypes

@@ -273,7 +273,8 @@ int nnp_decode_stats(uint64_t* out14);
  * drops the chain-start candidates whose hashed offset is 0 mod m (0 = off), which forces the
  * fallback strategies; "k1_per_record" / "k1_walk" / "k1_runs" / "k1_heads" != 0 pin the compressor's first
  * kernel to its record-parallel, chain-owning, run-based or chain-head-transcoding form (by default a sample of
- * the chain-head density picks);
+ * the chain-head density picks); "k1_direct" = 1 always tries / = 2 never tries the one-kernel route for .bin files of
+ * single positions, "dec_direct" = 2 never takes the candidate-free routes for .binpack chunks of single positions;
  * "walk_seg_bytes" = v sets the segment size of the parallel chunk-header walk (0 = default 8 MiB; files
  * shorter than eight segments are walked sequentially).
  * Results never depend on these switches. */

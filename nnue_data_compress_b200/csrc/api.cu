@@ -32,6 +32,7 @@ enum WsSlot {
 // and the head offsets in the workspaces
 struct PayloadPlan {
     u64 payload_bytes = 0, heads = 0, max_chunks = 0;
+    bool dense = false;  // more than half of the records start a chain (picks the writer / orbit forms made for that)
     u32* payload = nullptr;
     u64* head_off = nullptr;
     u64* seg_off = nullptr;
@@ -192,7 +193,8 @@ int build_payload(const u32* codes, const u32* stems, u64 n, PayloadPlan& P, u64
     P.head_off = head_off;
     P.seg_off = seg_off;
     CK(cudaMemsetAsync(payload, 0, P.payload_bytes + 64, s));
-    launch_write_payload(codes, stems, n, tile_agg, payload, head_off, s);
+    P.dense = P.heads * 2 > n;
+    launch_write_payload(codes, stems, n, tile_agg, payload, head_off, P.dense, s);
     launch_head_next(head_off, P.heads, head_next, d_tot, s);
     LAUNCHED(2, "k_write_payload");
     if (h_tot->bleeds > 0) {
@@ -223,7 +225,7 @@ int run_orbit(const PayloadPlan& P, u64 base, u64 carry, u64* chunks)
     Context& C = g_ctx;
     cudaStream_t s = C.stream;
     CompressTotals* h_tot = reinterpret_cast<CompressTotals*>(C.pinned);
-    launch_chunk_orbit(P.head_off, P.head_next, P.d_tot, P.seg_off, P.max_chunks, base, carry, s);
+    launch_chunk_orbit(P.head_off, P.head_next, P.d_tot, P.seg_off, P.max_chunks, base, carry, P.dense, s);
     LAUNCHED(1, "k_chunk_orbit");
     CK(cudaMemcpyAsync(h_tot, P.d_tot, sizeof(CompressTotals), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));

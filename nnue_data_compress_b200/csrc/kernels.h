@@ -32,10 +32,10 @@ void launch_tile_aggregate(const u32* codes, u64 n, Agg* tile_agg, cudaStream_t 
 u64 scan_blocks(u64 ntiles);  // entries of the block_tot scratch
 void launch_scan_aggregates(Agg* tile_agg, u64 ntiles, Agg* block_tot, CompressTotals* tot, cudaStream_t s);
 void launch_write_payload(const u32* codes, const u32* stems, u64 n, const Agg* tile_prefix, u32* payload,
-                          u64* head_off, cudaStream_t s);
+                          u64* head_off, bool dense, cudaStream_t s);
 void launch_head_next(const u64* head_off, u64 heads, u32* next, CompressTotals* tot, cudaStream_t s);
 void launch_chunk_orbit(const u64* head_off, const u32* next, CompressTotals* tot, u64* seg_off, u64 max_chunks, u64 base,
-                        u64 carry, cudaStream_t s);
+                        u64 carry, bool speculate, cudaStream_t s);
 void launch_orbit_table(const u64* head_off, const u32* next, const CompressTotals* tot, u64* table, u64 entries, cudaStream_t s);
 void launch_orbit_resolve(const u64* tables, u64 entries, const u64* sizes, int world, int rank, u64* out, cudaStream_t s);
 void launch_emit_chunks(const void* payload, const u64* seg_off, u64 chunks, void* out, u64 last_size, cudaStream_t s);

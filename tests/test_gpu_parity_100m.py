@@ -92,3 +92,61 @@ def test_reference_parity_112m(nnp):
               f"binpack {n_pack.value} bytes identical, .bin {bin_bytes} bytes identical")
     finally:
         shutil.rmtree(work, ignore_errors=True)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("kind,n", [("shuffled", 24_000_000), ("startpos", 12_000_000)])
+def test_reference_parity_single_positions(nnp, kind, n):
+    """Files of single positions at a scale with hundreds of chunks, against the reference binary: the
+    positions of 100-ply games in random order (what a shuffled training set looks like: nearly every record starts a
+    chain, a few happen to continue their predecessor -- K1 transcodes, the decoder collapses the chunks that hold
+    nothing but 34-byte chains) and the generator's own chain-length-1 file (every record a head: one kernel each
+    way). Both files of the reference are compared byte for byte."""
+    import torch
+
+    if not have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    bin_bytes = n * 40
+    work = _scratch_dir(3 * bin_bytes)
+    if work is None:
+        pytest.skip("no scratch space")
+    L = nnp.lib()
+    try:
+        d_bin = torch.empty(bin_bytes, dtype=torch.uint8, device="cuda")
+        assert L.nnp_generate_bin_dev(ctypes.c_void_p(d_bin.data_ptr()), n, 100 if kind == "shuffled" else 1, 77) == 0
+        if kind == "shuffled":
+            g = torch.Generator(device="cuda")
+            g.manual_seed(5)
+            rows = d_bin.view(torch.int64).view(n, 5)
+            rows.copy_(rows[torch.randperm(n, device="cuda", generator=g)])
+            torch.cuda.synchronize()
+        cap = n * 34 + (1 << 20)
+        d_pack = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        n_pack = ctypes.c_size_t(0)
+        assert L.nnp_bin_to_binpack_dev(ctypes.c_void_p(d_bin.data_ptr()), bin_bytes, ctypes.c_void_p(d_pack.data_ptr()), cap,
+                                        ctypes.byref(n_pack)) == 0
+        k_compress = L.nnp_last_dominant_kernel()
+        d_rt = torch.empty(bin_bytes, dtype=torch.uint8, device="cuda")
+        n_rt = ctypes.c_size_t(0)
+        assert L.nnp_binpack_to_bin_dev(ctypes.c_void_p(d_pack.data_ptr()), n_pack.value, ctypes.c_void_p(d_rt.data_ptr()),
+                                        bin_bytes, ctypes.byref(n_rt)) == 0
+        k_decompress = L.nnp_last_dominant_kernel()
+        assert n_rt.value == bin_bytes
+        if kind == "startpos":
+            assert (k_compress, k_decompress) == (b"k_heads_direct", b"k_emit_heads_only")
+        else:
+            assert k_compress in (b"k_heads_transcode", b"k_heads_direct")
+            assert k_decompress in (b"k_emit_chains_verify", b"k_emit_heads_only")
+
+        p_bin, p_pack, p_rt = (os.path.join(work, x) for x in ("in.bin", "out.binpack", "rt.bin"))
+        with open(p_bin, "wb") as f:
+            for off in range(0, bin_bytes, SLAB):
+                f.write(d_bin[off:off + SLAB].cpu().numpy().tobytes())
+        subprocess.run([REF_BIN, p_bin, p_pack], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        ok, why = _file_equals_device(p_pack, d_pack, n_pack.value)
+        assert ok, ".bin -> .binpack differs from the reference: " + why
+        subprocess.run([REF_BIN, p_pack, p_rt], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        ok, why = _file_equals_device(p_rt, d_rt, bin_bytes)
+        assert ok, ".binpack -> .bin differs from the reference: " + why
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
