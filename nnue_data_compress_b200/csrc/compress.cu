@@ -8,9 +8,14 @@
 //                         continuation plies get their move/score bit string (:877-989), chain
 //                         heads their 32-byte stem (:997-1020). Heads met inside a run are parked
 //                         and worked off in dense rounds.
+//   k_walk_chains         K1, chain-owning form: a thread owns the chains whose heads lie in its range and
+//                         walks each from head to end, the warp opening and walking in lock-step
 //   k_decode_link_encode  K1, record-parallel form: one thread per record decodes it and tests it
-//                         against its predecessor (:587-593). Chosen for files of (nearly) single
-//                         positions (k_sample_heads) and kept as a cross-check of the walk.
+//                         against its predecessor (:587-593). Chosen when more than a third of the
+//                         records start a chain (k_sample_heads) and kept as a cross-check of the walk.
+//   k_heads_transcode     K1 for files of (nearly) single positions: a chain head's stem is its record's
+//                         token stream in another order (heads.cuh), nothing is decoded
+//   k_heads_direct        the whole conversion in one kernel when EVERY record starts a chain
 //   k_tile_aggregate      per-tile summary of the segmented payload scan
 //   k_scan_aggregates_*   exclusive scan of the tile summaries (+ totals), three small launches
 //   k_write_payload       re-scans each tile with its carry-in and writes stems, numPlies

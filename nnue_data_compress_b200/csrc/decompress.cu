@@ -6,7 +6,11 @@
 // parallelism (a few hundred chunks) cannot feed 148 SMs, so the chains are found
 // speculatively and the reader's walk is verified instead of followed:
 //
-//   k_walk_chunks         one thread follows the 8-byte BINP headers (:500-521)
+//   k_walk_chunks         one thread follows the 8-byte BINP headers (:500-521); large files are walked in
+//                         parallel segments first (k_seg_find / k_seg_walk / k_seg_prefix / k_seg_finish)
+//   k_chunk_heads_only    chunks of nothing but single positions (34-byte chains) need no discovery:
+//                         k_emit_heads_only decodes a file made of them, k_emit_heads_chunks such chunks
+//                         among ordinary ones (each is ONE entry of the candidate list, k_collapsed_tiles)
 //   k_candidates_scan     every byte offset of every chunk is tested for "could be a stem the
 //                         reference writer emits", in three stages of increasing cost, each run
 //                         on the compacted survivors of the one before; result: a bitmap per tile
