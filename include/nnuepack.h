@@ -135,7 +135,10 @@ int nnp_plain_to_bin_dev(const void* d_plain, size_t plain_bytes, void* d_out, s
  *
  * nnue_data_compress_b200/sharding.py drives these calls over torch.distributed (NCCL / gloo).
  * A malformed record (NNP_ERR_BAD_SFEN) is reported with its index and ends the sharded run: the
- * partial-output rule of the single-GPU entry point is not replayed across ranks. */
+ * partial-output rule of the single-GPU entry point is not replayed across ranks.
+ * The sequence begin .. emit keeps its state in the device's context: another compressor call on the same
+ * device in between (nnp_bin_to_binpack*, nnp_plain_to_binpack*) reuses that memory and ends the sequence --
+ * its remaining calls answer NNP_ERR_BAD_ARG until the next begin. */
 typedef struct nnp_shard_info {
     uint64_t first_owned_record; /* index (in the buffer) of the first chain head >= own_lo */
     uint64_t end_owned_record;   /* index of the first chain head >= own_hi (records before it are owned) */

@@ -237,6 +237,9 @@ int run_orbit(const PayloadPlan& P, u64 base, u64 carry, u64* chunks)
 int compress_tail(const u32* codes, const u32* stems, u64 n, int status, void* d_out, size_t out_cap, size_t* out_bytes)
 {
     Context& C = g_ctx;
+    // (this call reuses the workspace slots an open nnp_shard_compress_* sequence points into: that sequence is
+    // over, its later calls answer NNP_ERR_BAD_ARG instead of emitting from overwritten memory)
+    C.shard.active = false;
     PayloadPlan P;
     int rc = build_payload(codes, stems, n, P);
     if (rc != NNP_OK) return rc;
@@ -309,6 +312,7 @@ int heads_direct_dev(const void* d_bin, u64 n, void* d_out, size_t out_cap, size
     Context& C = g_ctx;
     cudaStream_t s = C.stream;
     *done = false;
+    C.shard.active = false;  // (WS_TOTALS is shared with an open nnp_shard_compress_* sequence, see compress_tail)
     const u64 total = heads_direct_bytes(n);
     if (total > out_cap) return NNP_OK;
     CompressTotals* d_tot = nullptr;

@@ -125,6 +125,25 @@ def test_sharded_window_too_small(nnp):
     assert rc == -12  # NNP_ERR_WINDOW: the 400-ply chain does not end within 10 records of the boundary
 
 
+def test_shard_sequence_ends_when_another_compressor_call_reuses_its_buffers(nnp):
+    """begin / orbit / emit keep pointers into the context's workspace; a whole-buffer conversion in between
+    reuses those slots, so the rest of the sequence must be refused (NNP_ERR_BAD_ARG), not run on its memory."""
+    import numpy as np
+    import torch
+
+    L = nnp.lib()
+    b = golden("games100.bin")
+    d = torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()).cuda()
+    info = nnp.ShardInfo()
+    n = len(b) // 40
+    assert L.nnp_shard_compress_begin_dev(ctypes.c_void_p(d.data_ptr()), n, 0, n, 1, ctypes.byref(info)) == 0
+    assert nnp.bin_to_binpack(golden("heads.bin")) == golden("heads.binpack")
+    a, f, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+    assert L.nnp_shard_compress_orbit(0, NO_CARRY, ctypes.byref(a), ctypes.byref(f), ctypes.byref(c)) == -6  # NNP_ERR_BAD_ARG
+    assert L.nnp_shard_compress_begin_dev(ctypes.c_void_p(d.data_ptr()), n, 0, n, 1, ctypes.byref(info)) == 0
+    assert L.nnp_shard_compress_orbit(0, NO_CARRY, ctypes.byref(a), ctypes.byref(f), ctypes.byref(c)) == 0
+
+
 # ---------------------------------------------------------------------------------------------
 # ONE .binpack decoded by several ranks (nnp_shard_decompress_dev; BASELINE configs[2])
 
