@@ -905,8 +905,8 @@ k_head_next(const u64* __restrict__ head_off, const CompressTotals* __restrict__
     if (lo < hi) {
         // gallop from where the successor lies at the file's mean chain size: a handful of probes instead
         // of log2(heads) (files of short chains have tens of millions of heads)
-        const u64 mean = tot->payload_bytes / H + 1;
-        u64 g = h + CHUNK_THRESHOLD / mean;
+        // (heads per MiB = 2^20 * H / payload, rounded down: exact to within one head where chains are all alike)
+        u64 g = h + (u64)CHUNK_THRESHOLD * H / tot->payload_bytes;
         g = g < lo ? lo : g >= hi ? hi - 1 : g;
         u64 step = 16;
         if (head_off[g] >= target) {
