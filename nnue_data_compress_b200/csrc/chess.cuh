@@ -557,10 +557,104 @@ __device__ __forceinline__ bool sfen_decode(WordFn W, Pos& p, PieceFn on_piece)
     return cursor <= 256 && err == 0;
 }
 
+// x with a zero inserted at bit k (the bits at and above k move up by one)
+__device__ __forceinline__ u64 insert_zero_bit(u64 x, int k)
+{
+    const u64 below = (1ull << k) - 1;
+    return (x & below) | ((x & ~below) << 1);
+}
+
+// The same decode without a piece callback, as a flat loop: the 62 tokens of the non-king squares are read four
+// per step with the same instructions whatever the position (no count-trailing-zeros runs, no loop whose length
+// is the piece count of the busiest lane of the warp): a token's five bits -- piece, type (3), colour -- are
+// parked a byte apart in one register, and one multiply per bit plane gathers the four tokens' bits into a
+// nibble of that plane ((x & 0x01010101) * 0x01020408 >> 24). The planes are built over the token squares in
+// stream order; the kings' squares are then opened up (a zero bit inserted at each) and the byte-swapped planes
+// are the board's (stream square s is square s ^ 56). Half the instructions of the token-driven loop above.
+template <typename WordFn>
+__device__ __forceinline__ bool sfen_decode_flat(WordFn W, Pos& p)
+{
+    const u32 w0 = W(0), w1 = W(1);
+    p.stm = w0 & 1;
+    const int wk = (w0 >> 1) & 63, bk = (w0 >> 7) & 63;  // wk != bk (the caller's business)
+    u64 win = (((u64)w1 << 32) | w0) >> 13;
+    int avail = 51, nextw = 2, cursor = 13;
+    u32 lo[5] = {0, 0, 0, 0, 0}, hi[5] = {0, 0, 0, 0, 0};  // planes: piece, type bit 0 / 1 / 2, colour; bit j = token j
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+        if (avail < 32) {  // four tokens need at most 20 bits
+            const u32 nw = nextw < 10 ? W(nextw) : 0u;
+            ++nextw;
+            win |= (u64)nw << avail;
+            avail += 32;
+        }
+        u32 c = (u32)win, acc = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (4 * g + k < 62) {
+                const u32 piece = c & 1u;          // '0', or 1 + type (3 bits, LSB first) + colour
+                acc += ((c & 31u) * piece) << (8 * k);
+                c >>= 1u + 4u * piece;
+            }
+        }
+        const int used = (g < 15 ? 4 : 2) + 4 * __popc(acc & 0x01010101u);
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            const u32 nib = (((acc >> b) & 0x01010101u) * 0x01020408u) >> 24;  // token k of the group -> bit k
+            if (g < 8) lo[b] |= nib << (4 * g); else hi[b] |= nib << (4 * g - 32);
+        }
+        win >>= used;
+        avail -= used;
+        cursor += used;
+    }
+    const u32 err = (lo[3] & (lo[2] | lo[1])) | (hi[3] & (hi[2] | hi[1]));  // type codes 5..7
+    // the kings' squares: stream square = square ^ 56, the one that comes first in the stream is opened first
+    const int ka = wk ^ 56, kb = bk ^ 56;
+    const int k1 = ka < kb ? ka : kb, k2 = ka < kb ? kb : ka;
+    u64 pl[5];
+#pragma unroll
+    for (int b = 0; b < 5; ++b) pl[b] = insert_zero_bit(insert_zero_bit(((u64)hi[b] << 32) | lo[b], k1), k2);
+    const u64 kings = (1ull << ka) | (1ull << kb);
+    pl[0] |= kings;
+    pl[1] |= kings;  // PT_KING = 5: type bits 0 and 2
+    pl[3] |= kings;
+    pl[4] |= 1ull << kb;
+    p.occ[1] = bswap64(pl[4]);
+    p.occ[0] = bswap64(pl[0] ^ pl[4]);
+    p.t0 = bswap64(pl[1]);
+    p.t1 = bswap64(pl[2]);
+    p.t2 = bswap64(pl[3]);
+    p.ep = SQ_NONE;
+    // tail: castling(4) ep(1[+6]) rule50(6) fullmove(8) = at most 25 bits
+    if (avail < 32) {
+        const u32 nw = nextw < 10 ? W(nextw) : 0u;
+        ++nextw;
+        win |= (u64)nw << avail;
+        avail += 32;
+    }
+    u32 tail = (u32)win;
+    p.cr = (int)(tail & 15u);
+    tail >>= 4; cursor += 4;
+    if (tail & 1u) {
+        const int ep = (int)((tail >> 1) & 63u);
+        tail >>= 7; cursor += 7;
+        p.ep = ep_possible(p, ep, p.stm) ? ep : SQ_NONE;  // setEpSquare Position.h:868-872
+    } else {
+        tail >>= 1; cursor += 1;
+    }
+    p.rule50 = (int)(tail & 63u);
+    const int hm = (int)((tail >> 6) & 255u);
+    cursor += 14;
+    p.ply = (2 * hm - 1 + (p.stm == BLACK)) & 0xFFFF;  // setHalfMove Position.h:938-941
+    return cursor <= 256 && err == 0;
+}
+
 template <typename WordFn>
 __device__ __forceinline__ bool sfen_decode(WordFn W, Pos& p)
 {
-    return sfen_decode(W, p, [](int, u32) {});
+    const u32 w0 = W(0);
+    if (((w0 >> 1) & 63u) != ((w0 >> 7) & 63u)) return sfen_decode_flat(W, p);
+    return sfen_decode(W, p, [](int, u32) {});  // both kings on one square: 63 tokens, the black king replaces the white one
 }
 
 // SfenPacker::pack (compress_file.cpp:266-312) into eight 32-bit words out[0..7].

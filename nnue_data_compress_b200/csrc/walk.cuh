@@ -41,12 +41,15 @@ __device__ __forceinline__ bool fields_link(u32 prev_w9, u32 cur_w9)
 }
 
 // From-scratch decode of record `rec` (pos_from_packed_sfen :364-446). Not inlined: the kernels that
-// walk chains keep one copy of the Huffman loop, off their hot path.
+// walk chains keep one copy of the Huffman loop, off their hot path -- and the compact token-driven loop, not
+// the unrolled flat form (sfen_decode_flat: 900 straight-line instructions): k_walk_chains already waits for
+// instructions (no_instruction 0.47 stalls per issue), with the flat form its anchors cost 12 % more at 8 plies
+// per chain (7.47 against 6.5 ms per 100 M) although the flat form executes half the instructions.
 static __device__ __noinline__ bool decode_record(const unsigned char* __restrict__ bin, u64 rec, Pos& P)
 {
     const u32* w = reinterpret_cast<const u32*>(bin + rec * 40);
     pos_clear(P);
-    return sfen_decode([&](int j) { return w[j]; }, P);
+    return sfen_decode([&](int j) { return w[j]; }, P, [](int, u32) {});
 }
 
 static __device__ __noinline__ void store_stem_cold(const Pos& P, u32 w8, u32 w9, u32* stem_out)

@@ -529,4 +529,39 @@ uint64_t sim_heads_transcode_fuzz(const unsigned char* bin, size_t n, int mutati
     return accepted;
 }
 
+
+// sfen_decode_flat (four tokens per step, planes gathered by multiplication) against the token-driven decoder on
+// every record of a .bin and on `mutations` randomly damaged copies of each: the same verdict always, and the same
+// position whenever the record decodes.
+uint64_t sim_sfen_decode_fuzz(const unsigned char* bin, size_t n, int mutations, uint64_t seed, uint64_t* mismatch)
+{
+    uint64_t decoded = 0, xs = seed * 0x9E3779B97F4A7C15ull + 1;
+    *mismatch = 0;
+    auto check = [&](const Rec& r) {
+        if (((r.w[0] >> 1) & 63u) == ((r.w[0] >> 7) & 63u)) return;  // the flat form is not asked
+        Pos a, b;
+        pos_clear(a);
+        pos_clear(b);
+        const bool oka = sfen_decode([&](int j) { return r.w[j]; }, a, [](int, u32) {});
+        const bool okb = sfen_decode_flat([&](int j) { return r.w[j]; }, b);
+        if (oka != okb) { ++*mismatch; return; }
+        if (!oka) return;
+        ++decoded;
+        if (!pos_equal(a, b) || a.stm != b.stm || a.ep != b.ep || a.cr != b.cr || a.rule50 != b.rule50 || a.ply != b.ply) ++*mismatch;
+    };
+    for (size_t i = 0; i < n; ++i) {
+        Rec r = load(bin, i);
+        check(r);
+        for (int m = 0; m < mutations; ++m) {
+            Rec q = r;
+            for (int k = 0; k < 1 + (m & 3); ++k) {
+                xs = xs * 6364136223846793005ull + 1442695040888963407ull;
+                q.w[(xs >> 33) % 8] ^= 1u << ((xs >> 58) & 31);
+            }
+            check(q);
+        }
+    }
+    return decoded;
+}
+
 }  // extern "C"

@@ -190,6 +190,8 @@ def host_sim():
         L.sim_stem_transcode_fuzz.restype = ctypes.c_uint64
         L.sim_heads_transcode_fuzz.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, u64p]
         L.sim_heads_transcode_fuzz.restype = ctypes.c_uint64
+        L.sim_sfen_decode_fuzz.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64, u64p]
+        L.sim_sfen_decode_fuzz.restype = ctypes.c_uint64
         L.sim_halfkp_tokens.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
         L.sim_halfkp_tokens.restype = ctypes.c_uint64
         _sim = L

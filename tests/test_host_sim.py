@@ -164,3 +164,15 @@ def test_heads_transcode_equals_the_general_route(sim):
         total += sim.sim_heads_transcode_fuzz(b, len(b) // 40, 4, 11, ctypes.byref(mm))
         assert mm.value == 0, name
     assert total > 100_000
+
+
+def test_flat_sfen_decode_equals_the_token_loop(sim):
+    """sfen_decode_flat (the decoder every kernel without a piece callback uses) gives the verdict and the
+    position of the token-driven loop on every golden record and on randomly damaged copies."""
+    total = 0
+    for name in GOLDEN_SETS:
+        b = golden(name + ".bin")
+        mm = ctypes.c_uint64()
+        total += sim.sim_sfen_decode_fuzz(b, len(b) // 40, 6, 3, ctypes.byref(mm))
+        assert mm.value == 0, name
+    assert total > 150_000
