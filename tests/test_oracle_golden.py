@@ -84,3 +84,34 @@ def test_error_statuses():
     assert rc == -3
     rc0, ref = oracle_convert(BIN_TO_BINPACK, good)
     assert out == ref  # the writer still flushes what it gathered before the bad record
+
+
+def test_files_of_single_positions_have_an_arithmetic_layout():
+    """The premise of the one-kernel route for files of chain heads (k_heads_direct), pinned on the
+    oracle: when every chain is 34 bytes the writer's flush rule (compress_file.cpp:1076-1080) closes a chunk after
+    exactly ceil(2^20 / 34) = 30 841 chains, so record r's stem lies at
+    (r / 30841) * (8 + 34 * 30841) + 8 + 34 * (r mod 30841) of the file."""
+    from refutil import golden
+
+    heads = golden("heads.bin")
+    n_unit = len(heads) // 40
+    reps = 70_000 // n_unit + 1
+    data = heads * reps  # (a record never continues the copy of the file's last record in front of it: ply 0 follows)
+    n = len(data) // 40
+    rc, pack = oracle_convert(BIN_TO_BINPACK, data)
+    assert rc == 0
+    per_chunk = ((1 << 20) + 33) // 34
+    chunks = (n + per_chunk - 1) // per_chunk
+    if len(pack) != 34 * n + 8 * chunks:
+        pytest.skip("the golden heads file repeats into a continuation at its seam")
+    pos = 0
+    for c in range(chunks):
+        assert pack[pos:pos + 4] == b"BINP"
+        size = int.from_bytes(pack[pos + 4:pos + 8], "little")
+        assert size == 34 * min(per_chunk, n - c * per_chunk)
+        pos += 8 + size
+    assert pos == len(pack)
+    rc, one = oracle_convert(BIN_TO_BINPACK, data[40 * 40_000:40 * 40_001])
+    r = 40_000
+    off = (r // per_chunk) * (8 + 34 * per_chunk) + 8 + 34 * (r % per_chunk)
+    assert pack[off:off + 34] == one[8:42]
