@@ -2,13 +2,13 @@
 // compress_file.cpp:997-1020) is the record's PackedSfen transcoded. The stream names the kings in its
 // header and then has one token per non-king square, rank 8 first (pos_from_packed_sfen :364-446); the stem
 // wants the occupied squares a1 -> h8 with one nibble each (Position::compress, Position.h:1374-1406).
-// The squares are visited in stream order, every rank's nibbles are gathered in file order and pushed
-// in FRONT of the ranks already seen (rank 1 ends up first), and the three nibbles that depend on the
-// stream's tail -- rooks that still carry a castling right, the pawn an en-passant capture would take,
-// the black king when black is to move -- are patched afterwards. Same bytes as sfen_decode + stem_pack
+// The tokens are read as one flat sequence (record_to_stem below), the kings are inserted, the ranks are put
+// into the stem's order (rank 1 first), and the three nibbles that depend on the stream's tail -- rooks that
+// still carry a castling right, the pawn an en-passant capture would take, the black king when black is to
+// move -- are patched afterwards. Same bytes as sfen_decode + stem_pack
 // wherever it answers HEADS_OK; everything irregular (both kings on one square, more than 32 pieces) is
 // left to that route (HEADS_OTHER), malformed streams are reported as the decoder reports them
-// (HEADS_BAD). Files of single positions are nothing but chain heads: k_heads_transcode (compress.cu).
+// (HEADS_BAD). Files of single positions are nothing but chain heads: k_heads_transcode, k_heads_direct (compress.cu).
 #pragma once
 #include "chess.cuh"
 
