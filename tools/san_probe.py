@@ -1,5 +1,6 @@
-"""Diagnostic (GPU box): a small pass over every compressor / decoder route, meant to run under
-`compute-sanitizer --tool memcheck|racecheck|initcheck python tools/san_probe.py`."""
+"""Diagnostic (GPU box): a small pass over every compressor / decoder route with consistency checks (all K1 forms,
+the single-position routes and their fallbacks, collapsed chunks, .plain). Small enough to run under
+compute-sanitizer where a pool allows it (this round's pool does not)."""
 import sys
 
 import numpy as np
