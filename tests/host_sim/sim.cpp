@@ -477,7 +477,14 @@ uint64_t sim_stem_transcode_fuzz(const unsigned char* in, size_t n, int mutation
                 std::memcpy(stem, chunk + cur, 34);
                 for (int k = 0; k < 1 + (m & 3); ++k) {
                     xs = xs * 6364136223846793005ull + 1442695040888963407ull;
-                    stem[(xs >> 33) % 32] ^= (unsigned char)(1u << ((xs >> 60) & 7));
+                    if (m & 4) {
+                        // a nibble with a meaning of its own (kings, ep pawn, castling rooks) dropped on a random piece
+                        unsigned char& b = stem[8 + (xs >> 33) % 16];
+                        const unsigned v = 10u + (unsigned)((xs >> 50) % 6);
+                        b = (xs >> 60) & 1 ? (unsigned char)((b & 0x0F) | (v << 4)) : (unsigned char)((b & 0xF0) | v);
+                    } else {
+                        stem[(xs >> 33) % 32] ^= (unsigned char)(1u << ((xs >> 60) & 7));
+                    }
                 }
                 check(stem);
             }

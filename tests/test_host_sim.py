@@ -148,7 +148,7 @@ def test_stem_transcode_equals_the_general_route(sim):
     for name in GOLDEN_SETS:
         b = golden(name + ".binpack")
         mm = ctypes.c_uint64()
-        total += sim.sim_stem_transcode_fuzz(b, len(b), 6 if name in ("heads", "shuffled", "restart") else 1, 5, ctypes.byref(mm))
+        total += sim.sim_stem_transcode_fuzz(b, len(b), 12 if name in ("heads", "shuffled", "restart") else 8, 5, ctypes.byref(mm))
         assert mm.value == 0, name
     assert total > 100_000
 
