@@ -272,7 +272,7 @@ int nnp_generate_bin_dev(void* d_out, size_t n_positions, uint32_t max_plies, ui
 int nnp_decode_stats(uint64_t* out14);
 
 /* Test hooks (the environment variables NNP_DEBUG_EXHAUSTIVE / NNP_DEBUG_REJECT_MOD set the same
- * switches at nnp_init): "exhaustive" != 0 skips the optimistic decode strategy; "reject_mod" = m
+ * switches at nnp_init; NNP_DEBUG_SINGLES=0 sets "k1_direct" = "dec_direct" = 2): "exhaustive" != 0 skips the optimistic decode strategy; "reject_mod" = m
  * drops the chain-start candidates whose hashed offset is 0 mod m (0 = off), which forces the
  * fallback strategies; "k1_per_record" / "k1_walk" / "k1_runs" / "k1_heads" != 0 pin the compressor's first
  * kernel to its record-parallel, chain-owning, run-based or chain-head-transcoding form (by default a sample of

@@ -1496,6 +1496,12 @@ int init_device(int device)
     C.debug_reject_mod = dbg ? (uint32_t)std::strtoul(dbg, nullptr, 10) : 0u;
     const char* dbg2 = std::getenv("NNP_DEBUG_EXHAUSTIVE");
     C.debug_exhaustive = dbg2 && dbg2[0] == '1';
+    // NNP_DEBUG_SINGLES=0: none of the routes made for files of single positions (the general pipeline for everything)
+    const char* dbg3 = std::getenv("NNP_DEBUG_SINGLES");
+    if (dbg3 && dbg3[0] == '0') {
+        C.debug_k1_direct = 2;
+        C.debug_dec_direct = 2;
+    }
     C.device = device;
     C.ready = true;
     if (!g_default) g_default = &C;

@@ -313,7 +313,7 @@ def test_device_generator_vs_reference_binary(nnp):
     assert nnp.binpack_to_bin(want) == ref_convert(BINPACK_TO_BIN, want)
 
 
-@pytest.mark.parametrize("env", [{"NNP_DEBUG_REJECT_MOD": "5"}, {"NNP_DEBUG_EXHAUSTIVE": "1"}])
+@pytest.mark.parametrize("env", [{"NNP_DEBUG_REJECT_MOD": "5"}, {"NNP_DEBUG_EXHAUSTIVE": "1"}, {"NNP_DEBUG_SINGLES": "0"}])
 def test_decode_fallbacks_are_exact(nnp, env):
     """binpack -> bin has three strategies: the optimistic single walk (default), the exhaustive
     probe/resolve walk (NNP_DEBUG_EXHAUSTIVE=1, or whenever the optimistic walk sees a violation)
